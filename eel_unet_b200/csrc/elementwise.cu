@@ -1,0 +1,736 @@
+// Bandwidth-bound ops of the hot path: layout conversion, per-channel reductions, BatchNorm
+// (statistics / apply / backward), max-pool, add+interleave, GELU, squeeze-excite, Adam.
+// Everything moves 16-byte vectors along the contiguous channel axis of NHWC tensors.
+#include "common.cuh"
+
+namespace eel {
+
+static inline int ew_grid(long long work_items, int block) {
+    long long b = (work_items + block - 1) / block;
+    long long cap = (long long)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------ layout
+template <class T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, long long NHW, int C, long long HW) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < NHW; i += (long long)gridDim.x * blockDim.x) {
+        long long n = i / HW, r = i - n * HW;
+        const float* src = x + n * C * HW + r;
+        T* dst = y + i * C;
+        for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(src[(long long)c * HW]);
+    }
+}
+
+template <class TI, class TO>
+__global__ void permute4_kernel(const TI* __restrict__ in, TO* __restrict__ out, int d0, int d1, int d2, int d3,
+                                int p0, int p1, int p2, int p3) {
+    const int d[4] = {d0, d1, d2, d3};
+    const int od[4] = {d[p0], d[p1], d[p2], d[p3]};
+    const long long istr[4] = {(long long)d1 * d2 * d3, (long long)d2 * d3, d3, 1};
+    const long long total = (long long)d0 * d1 * d2 * d3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int o3 = (int)(r % od[3]); r /= od[3];
+        int o2 = (int)(r % od[2]); r /= od[2];
+        int o1 = (int)(r % od[1]); r /= od[1];
+        int o0 = (int)r;
+        long long src = o0 * istr[p0] + o1 * istr[p1] + o2 * istr[p2] + o3 * istr[p3];
+        out[i] = from_f32<TO>(to_f32(in[src]));
+    }
+}
+
+// ------------------------------------------------------------------------------------ column reductions
+// partial[b][rb][q][c] = sum over the rows of row-block rb (of image-batch b) of f.q-th quantity.
+// Threads: TX lanes across channel vectors, TY = 256/TX across rows.
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxRowBlocks = 1024;
+
+struct RedPlan { int TX, TY, ncb, nrb; long long rows_per_rb; };
+
+template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) {
+    RedPlan p;
+    int cv = C / Vec16<T>::N;
+    p.TX = cv >= 32 ? 32 : (cv >= 16 ? 16 : (cv >= 8 ? 8 : (cv >= 4 ? 4 : (cv >= 2 ? 2 : 1))));
+    p.TY = kRedThreads / p.TX;
+    p.ncb = cdiv(cv, p.TX);
+    long long want = (4LL * kNumSMs) / ((long long)p.ncb * batch);
+    if (want < 1) want = 1;
+    long long maxrb = cdiv(rows, p.TY * 4);
+    if (maxrb < 1) maxrb = 1;
+    long long nrb = want < maxrb ? want : maxrb;
+    if (nrb > kRedMaxRowBlocks) nrb = kRedMaxRowBlocks;
+    p.nrb = (int)nrb;
+    p.rows_per_rb = (rows + nrb - 1) / nrb;
+    return p;
+}
+
+template <class T, class F, int Q>
+__global__ void __launch_bounds__(kRedThreads) colreduce_kernel(const F f, long long rows, int C, int TX,
+                                                              long long rows_per_rb, float* __restrict__ partial) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float sm[kRedThreads][Q * V + 1];
+    const int TY = kRedThreads / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int cvec = blockIdx.x * TX + tx;
+    const int c0 = cvec * V;
+    const int rb = blockIdx.y, b = blockIdx.z;
+    float acc[Q][V];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[q][v] = 0.f;
+    if (c0 < C) {
+        long long r0 = rb * rows_per_rb, r1 = r0 + rows_per_rb;
+        if (r1 > rows) r1 = rows;
+        for (long long r = r0 + ty; r < r1; r += TY) f.template accum<V>(b * rows + r, c0, acc);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) sm[threadIdx.x][q * V + v] = acc[q][v];
+    __syncthreads();
+    // thread (tx, ty) sums column tx over ty for a subset of the Q*V values
+    for (int j = ty; j < Q * V; j += TY) {
+        float s = 0.f;
+        for (int y = 0; y < TY; ++y) s += sm[y * TX + tx][j];
+        if (c0 < C) {
+            int q = j / V, v = j % V;
+            partial[(((long long)b * gridDim.y + rb) * Q + q) * C + c0 + v] = s;
+        }
+    }
+}
+
+// out[b][j] = scale * sum_rb partial[b][rb][j]   (fp64 accumulation)
+__global__ void finalize_partials_kernel(const float* __restrict__ partial, int nrb, int width, float* __restrict__ out,
+                                         float scale) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (j >= width) return;
+    double s = 0.0;
+    for (int r = 0; r < nrb; ++r) s += (double)partial[((long long)b * nrb + r) * width + j];
+    out[(long long)b * width + j] = (float)(s * scale);
+}
+
+template <class T, class F, int Q>
+static int run_colreduce(const F& f, long long rows, int C, int batch, float* partial, size_t ws_bytes, RedPlan& pl,
+                         cudaStream_t st, const char* what) {
+    if (C % Vec16<T>::N != 0) {
+        set_error("%s: channel count %d not a multiple of the vector width", what, C);
+        return EEL_ERR_INVALID;
+    }
+    pl = plan_reduce<T>(rows, C, batch);
+    size_t need = sizeof(float) * (size_t)batch * pl.nrb * Q * C;
+    if (need > ws_bytes || partial == nullptr) {
+        set_error("%s: workspace too small (%zu > %zu)", what, need, ws_bytes);
+        return EEL_ERR_WORKSPACE;
+    }
+    dim3 grid(pl.ncb, pl.nrb, batch);
+    colreduce_kernel<T, F, Q><<<grid, kRedThreads, 0, st>>>(f, rows, C, pl.TX, pl.rows_per_rb, partial);
+    return check_launch(what);
+}
+
+static int run_finalize(const float* partial, int nrb, int width, int batch, float* out, float scale, cudaStream_t st,
+                        const char* what) {
+    dim3 grid(cdiv(width, 128), batch);
+    finalize_partials_kernel<<<grid, 128, 0, st>>>(partial, nrb, width, out, scale);
+    return check_launch(what);
+}
+
+template <class T> struct SumF {
+    const T* x; int C;
+    template <int V> __device__ void accum(long long r, int c0, float (&acc)[1][V]) const {
+        Vec16<T> v = ld16(x + r * C + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[0][i] += v.get(i);
+    }
+};
+
+// sum of a*b (squeeze-excite backward: d att = sum_hw dout * t)
+template <class T> struct DotF {
+    const T* a; const T* b; int C;
+    template <int V> __device__ void accum(long long r, int c0, float (&acc)[1][V]) const {
+        Vec16<T> va = ld16(a + r * C + c0), vb = ld16(b + r * C + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[0][i] += va.get(i) * vb.get(i);
+    }
+};
+
+// shifted moments for BatchNorm: d = z - z[0][c]  ->  sum d, sum d^2 (no catastrophic cancellation)
+template <class T> struct MomentF {
+    const T* z; int C;
+    template <int V> __device__ void accum(long long r, int c0, float (&acc)[2][V]) const {
+        Vec16<T> v = ld16(z + r * C + c0), p = ld16(z + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float d = v.get(i) - p.get(i);
+            acc[0][i] += d;
+            acc[1][i] += d * d;
+        }
+    }
+};
+
+// BatchNorm backward sums: g = dy * relu_mask;  sum g, sum g * xhat
+template <class T> struct BnBwdF {
+    const T* dy; const T* z; const float* mean; const float* rstd; const float* gamma; const float* beta; int C; int relu;
+    template <int V> __device__ void accum(long long r, int c0, float (&acc)[2][V]) const {
+        Vec16<T> vd = ld16(dy + r * C + c0), vz = ld16(z + r * C + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float xh = (vz.get(i) - mean[c0 + i]) * rstd[c0 + i];
+            float g = vd.get(i);
+            if (relu && !(gamma[c0 + i] * xh + beta[c0 + i] > 0.f)) g = 0.f;
+            acc[0][i] += g;
+            acc[1][i] += g * xh;
+        }
+    }
+};
+
+template <class T>
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nrb, int C, const T* __restrict__ z, double count,
+                                   float* mean, float* rstd, float* rmean, float* rvar, float momentum, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < nrb; ++r) {
+        s1 += (double)partial[((long long)r * 2 + 0) * C + c];
+        s2 += (double)partial[((long long)r * 2 + 1) * C + c];
+    }
+    double pivot = (double)to_f32(z[c]);
+    double md = s1 / count;
+    double var = s2 / count - md * md;
+    if (var < 0.0) var = 0.0;
+    double m = pivot + md;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean != nullptr) rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * m);
+    if (rvar != nullptr) {
+        double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unb);
+    }
+}
+
+__global__ void bn_eval_stats_kernel(const float* rmean, const float* rvar, float eps, float* mean, float* rstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rmean[c];
+    rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+}
+
+template <class T>
+__global__ void bn_act_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, long long nvec, int C, int relu) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)((i * V) % C);
+        Vec16<T> v = ld16(z + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float sc = gamma[c0 + j] * rstd[c0 + j];
+            float r = (v.get(j) - mean[c0 + j]) * sc + beta[c0 + j];
+            o.set(j, relu ? fmaxf(r, 0.f) : r);
+        }
+        st16(y + i * V, o);
+    }
+}
+
+// dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n)  (train)   or   gamma*rstd*g  (frozen statistics)
+template <class T>
+__global__ void bn_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ sums /* [2][C]: dbeta, dgamma */, float inv_count,
+                                  long long nvec, int C, int relu, int train) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)((i * V) % C);
+        Vec16<T> vd = ld16(dy + i * V), vz = ld16(z + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            int c = c0 + j;
+            float xh = (vz.get(j) - mean[c]) * rstd[c];
+            float g = vd.get(j);
+            if (relu && !(gamma[c] * xh + beta[c] > 0.f)) g = 0.f;
+            float r = train ? (g - sums[c] * inv_count - xh * sums[C + c] * inv_count) : g;
+            o.set(j, gamma[c] * rstd[c] * r);
+        }
+        st16(dz + i * V, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------ max-pool 2x2
+template <class T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec_out, int Ho, int Wo, int C) {
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_out; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv);
+        long long p = i / cv;
+        int xo = (int)(p % Wo);
+        long long r = p / Wo;   // n*Ho + yo
+        const T* s = x + ((r * 2) * (2LL * Wo) + 2 * xo) * C + c * V;
+        Vec16<T> a = ld16(s), b = ld16(s + C), d = ld16(s + 2LL * Wo * C), e = ld16(s + 2LL * Wo * C + C), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.set(j, fmaxf(fmaxf(a.get(j), b.get(j)), fmaxf(d.get(j), e.get(j))));
+        st16(y + i * V, o);
+    }
+}
+
+// gradient goes to the first maximum in scan order (ATen max_pool2d semantics)
+template <class T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                    long long nvec_out, int Ho, int Wo, int C) {
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_out; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv);
+        long long p = i / cv;
+        int xo = (int)(p % Wo);
+        long long r = p / Wo;
+        long long off = ((r * 2) * (2LL * Wo) + 2 * xo) * C + c * V;
+        long long o2 = 2LL * Wo * C;
+        Vec16<T> a = ld16(x + off), b = ld16(x + off + C), d = ld16(x + off + o2), e = ld16(x + off + o2 + C);
+        Vec16<T> g = ld16(dy + i * V), ga, gb, gd, ge;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float va = a.get(j), vb = b.get(j), vd = d.get(j), ve = e.get(j);
+            int k = 0; float m = va;
+            if (vb > m) { m = vb; k = 1; }
+            if (vd > m) { m = vd; k = 2; }
+            if (ve > m) { m = ve; k = 3; }
+            float gv = g.get(j);
+            ga.set(j, k == 0 ? gv : 0.f); gb.set(j, k == 1 ? gv : 0.f);
+            gd.set(j, k == 2 ? gv : 0.f); ge.set(j, k == 3 ? gv : 0.f);
+        }
+        st16(dx + off, ga); st16(dx + off + C, gb); st16(dx + off + o2, gd); st16(dx + off + o2 + C, ge);
+    }
+}
+
+// ------------------------------------------------------------------------------------ add + interleave
+template <class T>
+__global__ void add_interleave_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ e,
+                                          T* __restrict__ out, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> va = ld16(a + i * V), vb = ld16(b + i * V), ve = ld16(e + i * V), o0, o1;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float s = va.get(j) + vb.get(j);
+            if (j < V / 2) { o0.set(2 * j, s); o0.set(2 * j + 1, ve.get(j)); }
+            else { o1.set(2 * j - V, s); o1.set(2 * j + 1 - V, ve.get(j)); }
+        }
+        st16(out + i * 2 * V, o0);
+        st16(out + i * 2 * V + V, o1);
+    }
+}
+
+template <class T>
+__global__ void add_interleave_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dab, T* __restrict__ de, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> i0 = ld16(dout + i * 2 * V), i1 = ld16(dout + i * 2 * V + V), oa, oe;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (j < V / 2) { oa.set(j, i0.get(2 * j)); oe.set(j, i0.get(2 * j + 1)); }
+            else { oa.set(j, i1.get(2 * j - V)); oe.set(j, i1.get(2 * j + 1 - V)); }
+        }
+        st16(dab + i * V, oa);
+        st16(de + i * V, oe);
+    }
+}
+
+// ------------------------------------------------------------------------------------ ReLU
+template <class T>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> v = ld16(x + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.set(j, fmaxf(v.get(j), 0.f));
+        st16(y + i * V, o);
+    }
+}
+
+template <class T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> v = ld16(y + i * V), g = ld16(dy + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.set(j, v.get(j) > 0.f ? g.get(j) : 0.f);
+        st16(dx + i * V, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------ GELU (erf)
+template <class T>
+__global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> v = ld16(x + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float a = v.get(j);
+            o.set(j, 0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
+        }
+        st16(y + i * V, o);
+    }
+}
+
+template <class T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        Vec16<T> v = ld16(x + i * V), g = ld16(dy + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float a = v.get(j);
+            float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752f));
+            float pdf = 0.39894228040143268f * expf(-0.5f * a * a);
+            o.set(j, g.get(j) * (cdf + a * pdf));
+        }
+        st16(dx + i * V, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------ squeeze-excite
+// one block per image: hid = relu(W1 mean + b1), att = sigmoid(W2 hid + b2)
+__global__ void se_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
+                              const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ att,
+                              float* __restrict__ hid, int C, int R) {
+    extern __shared__ float sh[];   // [R]
+    const int n = blockIdx.x;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float s = b1[r];
+        for (int c = 0; c < C; ++c) s += w1[r * C + c] * mean[n * C + c];
+        s = fmaxf(s, 0.f);
+        sh[r] = s;
+        hid[n * R + r] = s;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = b2[c];
+        for (int r = 0; r < R; ++r) s += w2[c * R + r] * sh[r];
+        att[n * C + c] = sigmoidf_(s);
+    }
+}
+
+// out[n][p][c] = t[n][p][c] * att[n][c]  (+ add[n][c] if add != nullptr)
+template <class T>
+__global__ void scale_rows_kernel(const T* __restrict__ t, const float* __restrict__ att, const float* __restrict__ add,
+                                  T* __restrict__ out, long long nvec, long long vec_per_img, int C) {
+    constexpr int V = Vec16<T>::N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        long long n = i / vec_per_img;
+        int c0 = (int)((i * V) % C);
+        Vec16<T> v = ld16(t + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float r = v.get(j) * att[n * C + c0 + j];
+            if (add != nullptr) r += add[n * C + c0 + j];
+            o.set(j, r);
+        }
+        st16(out + i * V, o);
+    }
+}
+
+// single block: all the tiny per-image backward algebra + parameter gradients of the SE MLP.
+// in:  datt[n][c] = sum_hw dout*t ; out: dmean_scaled[n][c] = (W1^T dhid_pre)[c] / HW
+__global__ void se_mlp_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ att, const float* __restrict__ hid,
+                                  const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ w2,
+                                  float* __restrict__ dmean_scaled, float* __restrict__ dw1, float* __restrict__ db1,
+                                  float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R, float inv_hw) {
+    extern __shared__ float sh[];   // dpre[C] then dhid[R]
+    float* dpre = sh;
+    float* dhid = sh + C;
+    const int t = threadIdx.x;
+    for (int i = t; i < C * R; i += blockDim.x) { dw1[i] = 0.f; dw2[i] = 0.f; }
+    for (int i = t; i < C; i += blockDim.x) db2[i] = 0.f;
+    for (int i = t; i < R; i += blockDim.x) db1[i] = 0.f;
+    __syncthreads();
+    for (int n = 0; n < N; ++n) {
+        for (int c = t; c < C; c += blockDim.x) {
+            float a = att[n * C + c];
+            float d = datt[n * C + c] * a * (1.f - a);
+            dpre[c] = d;
+            db2[c] += d;
+            for (int r = 0; r < R; ++r) dw2[c * R + r] += d * hid[n * R + r];
+        }
+        __syncthreads();
+        for (int r = t; r < R; r += blockDim.x) {
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s += w2[c * R + r] * dpre[c];
+            s = hid[n * R + r] > 0.f ? s : 0.f;
+            dhid[r] = s;
+            db1[r] += s;
+        }
+        __syncthreads();
+        for (int c = t; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int r = 0; r < R; ++r) {
+                s += w1[r * C + c] * dhid[r];
+                dw1[r * C + c] += dhid[r] * mean[n * C + c];
+            }
+            dmean_scaled[n * C + c] = s * inv_hw;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] + wd * p[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+}  // namespace eel
+
+using namespace eel;
+
+#define EEL_VEC_CHECK(T, n, what) \
+    EEL_REQUIRE((n) % Vec16<T>::N == 0, what ": element count / channels must be a multiple of the 16-byte vector")
+
+extern "C" {
+
+size_t eel_reduce_workspace_bytes(int channels, int quantities) {
+    return sizeof(float) * (size_t)kRedMaxRowBlocks * (size_t)quantities * (size_t)channels;
+}
+
+int eel_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad argument");
+    long long HW = (long long)H * W, NHW = HW * N;
+    EEL_DISPATCH_DTYPE(dtype, {
+        nchw_to_nhwc_kernel<T><<<ew_grid(NHW, 256), 256, 0, (cudaStream_t)s>>>(x, (T*)y, NHW, C, HW);
+        return check_launch("nchw_to_nhwc");
+    });
+}
+
+int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0, int d1, int d2, int d3, int p0,
+                 int p1, int p2, int p3, eel_stream s) {
+    EEL_REQUIRE(in && out && d0 > 0 && d1 > 0 && d2 > 0 && d3 > 0, "permute4: bad argument");
+    int seen = (1 << p0) | (1 << p1) | (1 << p2) | (1 << p3);
+    EEL_REQUIRE(p0 >= 0 && p0 < 4 && p1 >= 0 && p1 < 4 && p2 >= 0 && p2 < 4 && p3 >= 0 && p3 < 4 && seen == 15,
+                "permute4: not a permutation");
+    long long total = (long long)d0 * d1 * d2 * d3;
+    int g = ew_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)s;
+    if (in_dtype == EEL_F32 && out_dtype == EEL_F32)
+        permute4_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, (float*)out, d0, d1, d2, d3, p0, p1, p2, p3);
+    else if (in_dtype == EEL_F32 && out_dtype == EEL_BF16)
+        permute4_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)in, (bf16*)out, d0, d1, d2, d3, p0, p1, p2, p3);
+    else if (in_dtype == EEL_BF16 && out_dtype == EEL_F32)
+        permute4_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)in, (float*)out, d0, d1, d2, d3, p0, p1, p2, p3);
+    else if (in_dtype == EEL_BF16 && out_dtype == EEL_BF16)
+        permute4_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)in, (bf16*)out, d0, d1, d2, d3, p0, p1, p2, p3);
+    else {
+        set_error("permute4: unsupported dtype");
+        return EEL_ERR_INVALID;
+    }
+    return check_launch("permute4");
+}
+
+int eel_colsum(const void* x, float* out, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && out && P > 0 && C > 0, "colsum: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        RedPlan pl;
+        SumF<T> f{(const T*)x, C};
+        if (int rc = run_colreduce<T, SumF<T>, 1>(f, P, C, 1, (float*)ws, ws_bytes, pl, (cudaStream_t)s, "colsum")) return rc;
+        return run_finalize((const float*)ws, pl.nrb, C, 1, out, 1.0f, (cudaStream_t)s, "colsum.finalize");
+    });
+}
+
+int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, float* running_mean, float* running_var,
+                 float momentum, float eps, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && mean && rstd && P > 0 && C > 0, "bn_stats: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        RedPlan pl;
+        MomentF<T> f{(const T*)z, C};
+        if (int rc = run_colreduce<T, MomentF<T>, 2>(f, P, C, 1, (float*)ws, ws_bytes, pl, (cudaStream_t)s, "bn_stats")) return rc;
+        bn_finalize_kernel<T><<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>((const float*)ws, pl.nrb, C, (const T*)z, (double)P, mean,
+                                                                      rstd, running_mean, running_var, momentum, eps);
+        return check_launch("bn_stats.finalize");
+    });
+}
+
+int eel_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd, int C,
+                      eel_stream s) {
+    EEL_REQUIRE(running_mean && running_var && mean && rstd && C > 0, "bn_eval_stats: bad argument");
+    bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>(running_mean, running_var, eps, mean, rstd, C);
+    return check_launch("bn_eval_stats");
+}
+
+int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   long long P, int C, int relu, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && y && mean && rstd && gamma && beta && P > 0 && C > 0, "bn_act_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "bn_act_fwd");
+        long long nvec = P * C / Vec16<T>::N;
+        bn_act_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)y, mean, rstd, gamma, beta, nvec, C, relu);
+        return check_launch("bn_act_fwd");
+    });
+}
+
+int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, void* dz, float* dgamma, float* dbeta, long long P, int C, int relu, int train,
+                   void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(dy && z && mean && rstd && gamma && beta && dz && dgamma && dbeta && P > 0 && C > 0, "bn_act_bwd: bad argument");
+    EEL_REQUIRE(ws_bytes >= sizeof(float) * 2 * (size_t)C, "bn_act_bwd: workspace too small");
+    EEL_DISPATCH_DTYPE(dtype, {
+        RedPlan pl;
+        // first 2*C floats of ws hold the finished sums {sum g, sum g*xhat}; partials follow
+        float* sums = (float*)ws;
+        float* partial = sums + 2 * C;
+        BnBwdF<T> f{(const T*)dy, (const T*)z, mean, rstd, gamma, beta, C, relu};
+        if (int rc = run_colreduce<T, BnBwdF<T>, 2>(f, P, C, 1, partial, ws_bytes - sizeof(float) * 2 * C, pl, (cudaStream_t)s,
+                                                   "bn_act_bwd.reduce")) return rc;
+        if (int rc = run_finalize(partial, pl.nrb, 2 * C, 1, sums, 1.0f, (cudaStream_t)s, "bn_act_bwd.finalize")) return rc;
+        cudaMemcpyAsync(dbeta, sums, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        cudaMemcpyAsync(dgamma, sums + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        long long nvec = P * C / Vec16<T>::N;
+        bn_act_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma,
+                                                                           beta, sums, 1.0f / (float)P, nvec, C, relu, train);
+        return check_launch("bn_act_bwd");
+    });
+}
+
+int eel_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad argument (H, W must be even)");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "maxpool2_fwd");
+        long long nvec = (long long)N * (H / 2) * (W / 2) * C / Vec16<T>::N;
+        maxpool2_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, nvec, H / 2, W / 2, C);
+        return check_launch("maxpool2_fwd");
+    });
+}
+
+int eel_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "maxpool2_bwd");
+        long long nvec = (long long)N * (H / 2) * (W / 2) * C / Vec16<T>::N;
+        maxpool2_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (T*)dx, nvec, H / 2, W / 2, C);
+        return check_launch("maxpool2_bwd");
+    });
+}
+
+int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* out, long long P, int C, int dtype,
+                           eel_stream s) {
+    EEL_REQUIRE(a && b && e && out && P > 0 && C > 0, "add_interleave_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "add_interleave_fwd");
+        long long nvec = P * C / Vec16<T>::N;
+        add_interleave_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (const T*)e, (T*)out, nvec);
+        return check_launch("add_interleave_fwd");
+    });
+}
+
+int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(dout && dab && de && P > 0 && C > 0, "add_interleave_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "add_interleave_bwd");
+        long long nvec = P * C / Vec16<T>::N;
+        add_interleave_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dout, (T*)dab, (T*)de, nvec);
+        return check_launch("add_interleave_bwd");
+    });
+}
+
+int eel_relu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && y && n > 0, "relu_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, n, "relu_fwd");
+        long long nvec = n / Vec16<T>::N;
+        relu_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, nvec);
+        return check_launch("relu_fwd");
+    });
+}
+
+int eel_relu_bwd(const void* y, const void* dy, void* dx, long long n, int dtype, eel_stream s) {
+    EEL_REQUIRE(y && dy && dx && n > 0, "relu_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, n, "relu_bwd");
+        long long nvec = n / Vec16<T>::N;
+        relu_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)y, (const T*)dy, (T*)dx, nvec);
+        return check_launch("relu_bwd");
+    });
+}
+
+int eel_gelu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && y && n > 0, "gelu_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, n, "gelu_fwd");
+        long long nvec = n / Vec16<T>::N;
+        gelu_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, nvec);
+        return check_launch("gelu_fwd");
+    });
+}
+
+int eel_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dx && n > 0, "gelu_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, n, "gelu_bwd");
+        long long nvec = n / Vec16<T>::N;
+        gelu_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (T*)dx, nvec);
+        return check_launch("gelu_bwd");
+    });
+}
+
+int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
+               float* mean, float* att, float* hid, int N, long long HW, int C, int R, void* ws, size_t ws_bytes,
+               int dtype, eel_stream s) {
+    EEL_REQUIRE(t && w1 && b1 && w2 && b2 && out && mean && att && hid && N > 0 && HW > 0 && C > 0 && R > 0, "se_fwd: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    EEL_DISPATCH_DTYPE(dtype, {
+        RedPlan pl;
+        SumF<T> f{(const T*)t, C};
+        if (int rc = run_colreduce<T, SumF<T>, 1>(f, HW, C, N, (float*)ws, ws_bytes, pl, st, "se_fwd.mean")) return rc;
+        if (int rc = run_finalize((const float*)ws, pl.nrb, C, N, mean, 1.0f / (float)HW, st, "se_fwd.finalize")) return rc;
+        se_mlp_kernel<<<N, 64, sizeof(float) * R, st>>>(mean, w1, b1, w2, b2, att, hid, C, R);
+        if (int rc = check_launch("se_fwd.mlp")) return rc;
+        long long nvec = (long long)N * HW * C / Vec16<T>::N;
+        scale_rows_kernel<T><<<ew_grid(nvec, 256), 256, 0, st>>>((const T*)t, att, nullptr, (T*)out, nvec, HW * C / Vec16<T>::N, C);
+        return check_launch("se_fwd.scale");
+    });
+}
+
+int eel_se_bwd(const void* t, const void* dout, const float* att, const float* hid, const float* mean, const float* w1,
+               const float* w2, void* dt, float* dw1, float* db1, float* dw2, float* db2, int N, long long HW, int C,
+               int R, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(t && dout && att && hid && mean && w1 && w2 && dt && dw1 && db1 && dw2 && db2 && N > 0 && HW > 0 && C > 0 && R > 0,
+                "se_bwd: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    size_t head = sizeof(float) * 2 * (size_t)N * C;   // datt[N][C], dmean_scaled[N][C]
+    EEL_REQUIRE(ws_bytes > head, "se_bwd: workspace too small");
+    EEL_DISPATCH_DTYPE(dtype, {
+        float* datt = (float*)ws;
+        float* dmean = datt + (size_t)N * C;
+        float* partial = dmean + (size_t)N * C;
+        RedPlan pl;
+        DotF<T> f{(const T*)dout, (const T*)t, C};
+        if (int rc = run_colreduce<T, DotF<T>, 1>(f, HW, C, N, partial, ws_bytes - head, pl, st, "se_bwd.dot")) return rc;
+        if (int rc = run_finalize(partial, pl.nrb, C, N, datt, 1.0f, st, "se_bwd.finalize")) return rc;
+        se_mlp_bwd_kernel<<<1, 64, sizeof(float) * (C + R), st>>>(datt, att, hid, mean, w1, w2, dmean, dw1, db1, dw2, db2, N, C, R,
+                                                               1.0f / (float)HW);
+        if (int rc = check_launch("se_bwd.mlp")) return rc;
+        long long nvec = (long long)N * HW * C / Vec16<T>::N;
+        scale_rows_kernel<T><<<ew_grid(nvec, 256), 256, 0, st>>>((const T*)dout, att, dmean, (T*)dt, nvec, HW * C / Vec16<T>::N, C);
+        return check_launch("se_bwd.scale");
+    });
+}
+
+int eel_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, eel_stream s) {
+    EEL_REQUIRE(p && g && m && v && n > 0 && step > 0, "adam_step: bad argument");
+    float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+    return check_launch("adam_step");
+}
+
+}  // extern "C"

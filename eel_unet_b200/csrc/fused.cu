@@ -1,0 +1,374 @@
+// Per-pixel fused ops: PredictionGuidedRefinement and the LayerNorm+1x1+sigmoid head, forward and
+// backward.  A group of G = min(32, C/vec) lanes owns one pixel; its channel reductions are warp
+// shuffles; parameter gradients are accumulated in registers, folded through shared memory and
+// written as one partial row per block (summed in fp64 by finalize_partials).
+#include "common.cuh"
+
+namespace eel {
+
+__device__ __forceinline__ float group_sum(float v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void finalize_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= width) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += (double)partial[(long long)r * width + j];
+    out[j] = (float)s;
+}
+
+constexpr int kPixThreads = 256;
+constexpr int kMaxIter = 8;   // C <= 1024
+
+// ------------------------------------------------------------------------------------ PGR
+template <class T>
+__global__ void __launch_bounds__(kPixThreads) pgr_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, T* __restrict__ y,
+                                                            float* __restrict__ sg, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    const int nv = C / V, iters = nv / G;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const float bias = b[0];
+    for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
+        long long p = p0 + g_in_block;
+        bool ok = p < P;
+        float dot = 0.f;
+        if (ok)
+            for (int k = 0; k < iters; ++k) {
+                int c0 = (gl + k * G) * V;
+                Vec16<T> v = ld16(x + p * C + c0);
+#pragma unroll
+                for (int j = 0; j < V; ++j) dot += v.get(j) * w[c0 + j];
+            }
+        dot = group_sum(dot, G);
+        float sv = sigmoidf_(dot + bias);
+        if (ok) {
+            if (gl == 0) sg[p] = sv;
+            for (int k = 0; k < iters; ++k) {
+                int c0 = (gl + k * G) * V;
+                Vec16<T> v = ld16(x + p * C + c0), o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o.set(j, v.get(j) * (1.f + sv));
+                st16(y + p * C + c0, o);
+            }
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel(const T* __restrict__ x, const float* __restrict__ sg,
+                                                            const float* __restrict__ w, const T* __restrict__ dy,
+                                                            const float* __restrict__ dsg, T* __restrict__ dx,
+                                                            float* __restrict__ partial, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float sh[];   // [C + 1]
+    const int nv = C / V, iters = nv / G;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    for (int i = threadIdx.x; i <= C; i += kPixThreads) sh[i] = 0.f;
+    __syncthreads();
+    float dwacc[kMaxIter][V];
+#pragma unroll
+    for (int k = 0; k < kMaxIter; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j) dwacc[k][j] = 0.f;
+    float dbacc = 0.f;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
+        long long p = p0 + g_in_block;
+        bool ok = p < P;
+        float dot = 0.f;
+        if (ok)
+#pragma unroll
+            for (int k = 0; k < kMaxIter; ++k) {
+                if (k < iters) {
+                    int c0 = (gl + k * G) * V;
+                    Vec16<T> vx = ld16(x + p * C + c0), vd = ld16(dy + p * C + c0);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) dot += vx.get(j) * vd.get(j);
+                }
+            }
+        dot = group_sum(dot, G);
+        if (ok) {
+            float sv = sg[p];
+            float dg = (dot + (dsg ? dsg[p] : 0.f)) * sv * (1.f - sv);
+            if (gl == 0) dbacc += dg;
+#pragma unroll
+            for (int k = 0; k < kMaxIter; ++k) {
+                if (k < iters) {
+                    int c0 = (gl + k * G) * V;
+                    Vec16<T> vx = ld16(x + p * C + c0), vd = ld16(dy + p * C + c0), o;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        o.set(j, vd.get(j) * (1.f + sv) + w[c0 + j] * dg);
+                        dwacc[k][j] += vx.get(j) * dg;
+                    }
+                    st16(dx + p * C + c0, o);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxIter; ++k) {
+        if (k < iters) {
+            int c0 = (gl + k * G) * V;
+#pragma unroll
+            for (int j = 0; j < V; ++j) atomicAdd(&sh[c0 + j], dwacc[k][j]);
+        }
+    }
+    if (gl == 0) atomicAdd(&sh[C], dbacc);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= C; i += kPixThreads) partial[(long long)blockIdx.x * (C + 1) + i] = sh[i];
+}
+
+// ------------------------------------------------------------------------------------ head (C = 64)
+constexpr int kHeadC = 64;
+constexpr int kHeadMaxO = 4;
+
+template <class T>
+__global__ void __launch_bounds__(kPixThreads) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                             const float* __restrict__ lnb, const float* __restrict__ w,
+                                                             const float* __restrict__ b, float* __restrict__ prob,
+                                                             long long P, long long HW, int O) {
+    constexpr int V = Vec16<T>::N, G = kHeadC / V;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const int c0 = gl * V;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
+        long long p = p0 + g_in_block;
+        bool ok = p < P;
+        float xv[V];
+        float s = 0.f;
+        if (ok) {
+            Vec16<T> v = ld16(x + p * kHeadC + c0);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { xv[j] = v.get(j); s += xv[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) xv[j] = 0.f;
+        }
+        float mu = group_sum(s, G) * (1.f / kHeadC);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) { float d = xv[j] - mu; q += d * d; }
+        float var = group_sum(q, G) * (1.f / kHeadC);
+        float r = 1.f / sqrtf(var + 1e-6f);
+        float nv[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) nv[j] = lnw[c0 + j] * ((xv[j] - mu) * r) + lnb[c0 + j];
+        for (int o = 0; o < O; ++o) {
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) d += w[o * kHeadC + c0 + j] * nv[j];
+            d = group_sum(d, G);
+            if (ok && gl == 0) {
+                long long n = p / HW, hw = p - n * HW;
+                prob[(n * O + o) * HW + hw] = sigmoidf_(d + b[o]);
+            }
+        }
+    }
+}
+
+// partial row layout: dlnw[64] dlnb[64] dw[O][64] db[O]
+template <class T>
+__global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                             const float* __restrict__ lnb, const float* __restrict__ w,
+                                                             const float* __restrict__ prob, const float* __restrict__ dprob,
+                                                             T* __restrict__ dx, float* __restrict__ partial, long long P,
+                                                             long long HW, int O) {
+    constexpr int V = Vec16<T>::N, G = kHeadC / V;
+    extern __shared__ float sh[];
+    const int width = (2 + O) * kHeadC + O;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const int c0 = gl * V;
+    for (int i = threadIdx.x; i < width; i += kPixThreads) sh[i] = 0.f;
+    __syncthreads();
+    float aw[V], ab[V], awo[kHeadMaxO][V], abo[kHeadMaxO];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { aw[j] = 0.f; ab[j] = 0.f; }
+#pragma unroll
+    for (int o = 0; o < kHeadMaxO; ++o) {
+        abo[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) awo[o][j] = 0.f;
+    }
+    for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
+        long long p = p0 + g_in_block;
+        bool ok = p < P;
+        float xv[V];
+        float s = 0.f;
+        if (ok) {
+            Vec16<T> v = ld16(x + p * kHeadC + c0);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { xv[j] = v.get(j); s += xv[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) xv[j] = 0.f;
+        }
+        float mu = group_sum(s, G) * (1.f / kHeadC);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) { float d = xv[j] - mu; q += d * d; }
+        float var = group_sum(q, G) * (1.f / kHeadC);
+        float r = 1.f / sqrtf(var + 1e-6f);
+        float xh[V], dn[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) { xh[j] = (xv[j] - mu) * r; dn[j] = 0.f; }
+        long long n = ok ? p / HW : 0, hw = ok ? p - n * HW : 0;
+#pragma unroll
+        for (int o = 0; o < kHeadMaxO; ++o) {
+            if (o < O) {
+                float dl = 0.f;
+                if (ok) {
+                    float pr = prob[(n * O + o) * HW + hw];
+                    dl = dprob[(n * O + o) * HW + hw] * pr * (1.f - pr);
+                }
+                if (gl == 0) abo[o] += dl;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    dn[j] += w[o * kHeadC + c0 + j] * dl;
+                    awo[o][j] += dl * (lnw[c0 + j] * xh[j] + lnb[c0 + j]);
+                }
+            }
+        }
+        float m1 = 0.f, m2 = 0.f;
+        float dxh[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            aw[j] += dn[j] * xh[j];
+            ab[j] += dn[j];
+            dxh[j] = dn[j] * lnw[c0 + j];
+            m1 += dxh[j];
+            m2 += dxh[j] * xh[j];
+        }
+        m1 = group_sum(m1, G) * (1.f / kHeadC);
+        m2 = group_sum(m2, G) * (1.f / kHeadC);
+        if (ok) {
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.set(j, r * (dxh[j] - m1 - xh[j] * m2));
+            st16(dx + p * kHeadC + c0, o);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        atomicAdd(&sh[c0 + j], aw[j]);
+        atomicAdd(&sh[kHeadC + c0 + j], ab[j]);
+    }
+#pragma unroll
+    for (int o = 0; o < kHeadMaxO; ++o) {
+        if (o < O) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) atomicAdd(&sh[(2 + o) * kHeadC + c0 + j], awo[o][j]);
+            if (gl == 0) atomicAdd(&sh[(2 + O) * kHeadC + o], abo[o]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += kPixThreads) partial[(long long)blockIdx.x * width + i] = sh[i];
+}
+
+static int pix_group(int C, int V) {
+    int nv = C / V;
+    return nv >= 32 ? 32 : nv;
+}
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace eel
+
+using namespace eel;
+
+extern "C" {
+
+int eel_pgr_fwd(const void* x, const float* w, const float* b, void* y, float* sgm, long long P, int C, int dtype,
+                eel_stream s) {
+    EEL_REQUIRE(x && w && b && y && sgm && P > 0 && C > 0, "pgr_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(C % V == 0 && pow2(C / V) && C / V <= 32 * kMaxIter, "pgr_fwd: C/vec must be a power of two <= 256");
+        int G = pix_group(C, V);
+        int gpb = kPixThreads / G;
+        long long blocks = (P + gpb - 1) / gpb;
+        int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+        pgr_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
+        return check_launch("pgr_fwd");
+    });
+}
+
+int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy, const float* dsgm, void* dx, float* dw,
+                float* db, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && sgm && w && dy && dx && dw && db && P > 0 && C > 0, "pgr_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(C % V == 0 && pow2(C / V) && C / V <= 32 * kMaxIter, "pgr_bwd: C/vec must be a power of two <= 256");
+        int G = pix_group(C, V);
+        int gpb = kPixThreads / G;
+        long long blocks = (P + gpb - 1) / gpb;
+        int grid = (int)(blocks < (long long)kNumSMs * 2 ? blocks : (long long)kNumSMs * 2);
+        size_t need = sizeof(float) * ((size_t)grid + 1) * (C + 1);
+        if (need > ws_bytes || !ws) { set_error("pgr_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
+        float* partial = (float*)ws;
+        float* fin = partial + (size_t)grid * (C + 1);
+        pgr_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * (C + 1), (cudaStream_t)s>>>((const T*)x, sgm, w, (const T*)dy, dsgm,
+                                                                                        (T*)dx, partial, P, C, G);
+        if (int rc = check_launch("pgr_bwd")) return rc;
+        finalize_rows_kernel<<<cdiv(C + 1, 128), 128, 0, (cudaStream_t)s>>>(partial, grid, C + 1, fin);
+        if (int rc = check_launch("pgr_bwd.finalize")) return rc;
+        cudaMemcpyAsync(dw, fin, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        cudaMemcpyAsync(db, fin + C, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        return EEL_OK;
+    });
+}
+
+int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float* w, const float* b, float* prob, int N,
+                 long long HW, int O, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && lnw && lnb && w && b && prob && N > 0 && HW > 0 && O > 0 && O <= kHeadMaxO, "head_fwd: bad argument (1 <= O <= 4)");
+    long long P = (long long)N * HW;
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int G = kHeadC / Vec16<T>::N;
+        int gpb = kPixThreads / G;
+        long long blocks = (P + gpb - 1) / gpb;
+        int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+        head_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P, HW, O);
+        return check_launch("head_fwd");
+    });
+}
+
+int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float* w, const float* b, const float* prob,
+                 const float* dprob, void* dx, float* dlnw, float* dlnb, float* dw, float* db, int N, long long HW,
+                 int O, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    (void)b;
+    EEL_REQUIRE(x && lnw && lnb && w && prob && dprob && dx && dlnw && dlnb && dw && db && N > 0 && HW > 0 && O > 0 && O <= kHeadMaxO,
+                "head_bwd: bad argument (1 <= O <= 4)");
+    long long P = (long long)N * HW;
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int G = kHeadC / Vec16<T>::N;
+        int gpb = kPixThreads / G;
+        long long blocks = (P + gpb - 1) / gpb;
+        int grid = (int)(blocks < (long long)kNumSMs * 2 ? blocks : (long long)kNumSMs * 2);
+        int width = (2 + O) * kHeadC + O;
+        size_t need = sizeof(float) * ((size_t)grid + 1) * width;
+        if (need > ws_bytes || !ws) { set_error("head_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
+        float* partial = (float*)ws;
+        float* fin = partial + (size_t)grid * width;
+        head_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx,
+                                                                                       partial, P, HW, O);
+        if (int rc = check_launch("head_bwd")) return rc;
+        finalize_rows_kernel<<<cdiv(width, 128), 128, 0, (cudaStream_t)s>>>(partial, grid, width, fin);
+        if (int rc = check_launch("head_bwd.finalize")) return rc;
+        cudaStream_t st = (cudaStream_t)s;
+        cudaMemcpyAsync(dlnw, fin, sizeof(float) * kHeadC, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dlnb, fin + kHeadC, sizeof(float) * kHeadC, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dw, fin + 2 * kHeadC, sizeof(float) * O * kHeadC, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(db, fin + (2 + O) * kHeadC, sizeof(float) * O, cudaMemcpyDeviceToDevice, st);
+        return EEL_OK;
+    });
+}
+
+}  // extern "C"

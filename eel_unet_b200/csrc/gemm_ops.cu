@@ -1,0 +1,373 @@
+// GEMM-class ops of the hot path on the exact SIMT engine (gemm_simt.cuh):
+// conv3x3 fprop/dgrad/wgrad, ConvTranspose2d(k2,s2) fprop/dgrad/wgrad, 1x1 conv / Linear (+ folded
+// ShiftedChannel).  All operands are 2-D views X(i, j) -- i a pixel-like index, j a channel-like
+// (memory-contiguous) index -- described by small accessor structs; a Problem wires two accessors
+// and an epilogue into the engine.
+#include "gemm_simt.cuh"
+
+namespace eel {
+
+// ------------------------------------------------------------------------------------ accessors
+// Dense row-major matrix X(i, j) = base[i * ld + j]
+template <class T> struct DenseAcc {
+    const T* base; long long I; int J; long long ld;
+    struct IH { const T* p; };
+    struct JH { int j; };
+    __device__ IH prepI(long long i) const { return IH{i < I ? base + i * ld : nullptr}; }
+    __device__ JH prepJ(int j) const { return JH{j < J ? j : -1}; }
+    __device__ float at(const IH& a, const JH& b) const {
+        return (a.p != nullptr && b.j >= 0) ? to_f32(a.p[b.j]) : 0.f;
+    }
+};
+
+// im2col view of an NHWC tensor for a 3x3 / pad 1 convolution: i = (n, y, x), j = (tap, c)
+template <class T> struct Conv3Acc {
+    const T* base; int N, H, W, C; int flip;
+    struct IH { const T* p; int y, x; };
+    struct JH { int off, dy, dx; };
+    __device__ IH prepI(long long i) const {
+        if (i >= (long long)N * H * W) return IH{nullptr, 0, 0};
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        return IH{base + i * C, y, x};
+    }
+    __device__ JH prepJ(int j) const {
+        if (j >= 9 * C) return JH{0, 100, 100};
+        int tap = j / C, c = j - tap * C;
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if (flip) { dy = -dy; dx = -dx; }
+        return JH{(dy * W + dx) * C + c, dy, dx};
+    }
+    __device__ float at(const IH& a, const JH& b) const {
+        int yy = a.y + b.dy, xx = a.x + b.dx;
+        if (a.p == nullptr || (unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) return 0.f;
+        return to_f32(a.p[b.off]);
+    }
+};
+
+// ShiftedChannel view (models/EELUnet.py:88-97) of an [N,H,W,C] tensor: i = pixel, j = channel.
+// quarter 0 reads row y-1, quarter 1 row y+1, quarter 2 column x-1 (all circular), rest unshifted.
+template <class T> struct ShiftAcc {
+    const T* base; long long P; int H, W, C;
+    struct IH { long long img; int y, x; };   // img = n*H*W, or -1
+    struct JH { int c, dy, dx; };
+    __device__ IH prepI(long long i) const {
+        if (i >= P) return IH{-1, 0, 0};
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        return IH{i - (long long)y * W - x, y, x};
+    }
+    __device__ JH prepJ(int j) const {
+        if (j >= C) return JH{-1, 0, 0};
+        int q = j / (C / 4);
+        return JH{j, q == 0 ? -1 : (q == 1 ? 1 : 0), q == 2 ? -1 : 0};
+    }
+    __device__ long long index(const IH& a, const JH& b) const {
+        int yy = a.y + b.dy, xx = a.x + b.dx;
+        yy = yy < 0 ? yy + H : (yy >= H ? yy - H : yy);
+        xx = xx < 0 ? xx + W : (xx >= W ? xx - W : xx);
+        return (a.img + (long long)yy * W + xx) * C + b.c;
+    }
+    __device__ float at(const IH& a, const JH& b) const {
+        return (a.img >= 0 && b.c >= 0) ? to_f32(base[index(a, b)]) : 0.f;
+    }
+};
+
+// View of the [N,2h,2w,Co] output-side tensor of a ConvTranspose2d(k2,s2) indexed by the INPUT pixel:
+// i = (n, y, x) over h x w, j = (dy, dx, co)
+template <class T> struct ConvTAcc {
+    const T* base; int N, h, w, Co;
+    struct IH { const T* p; };
+    struct JH { long long off; };
+    __device__ IH prepI(long long i) const {
+        if (i >= (long long)N * h * w) return IH{nullptr};
+        int x = (int)(i % w);
+        long long r = i / w;   // n*h + y
+        return IH{base + ((r * 2) * (2LL * w) + 2 * x) * Co};
+    }
+    __device__ JH prepJ(int j) const {
+        if (j >= 4 * Co) return JH{-1};
+        int dy = j / (2 * Co), rem = j - dy * 2 * Co;
+        return JH{(long long)dy * 2 * w * Co + rem};
+    }
+    __device__ float at(const IH& a, const JH& b) const {
+        return (a.p != nullptr && b.off >= 0) ? to_f32(a.p[b.off]) : 0.f;
+    }
+};
+
+// ------------------------------------------------------------------------------------ epilogues
+template <class T> struct StoreEpi {
+    T* out; long long M; int N; long long ld; const float* bias; int relu;
+    __device__ void operator()(int z, long long m, int n, const float (&acc)[kSimtTM][kSimtTN]) const {
+#pragma unroll
+        for (int i = 0; i < kSimtTM; ++i) {
+            if (m + i >= M) break;
+#pragma unroll
+            for (int j = 0; j < kSimtTN; ++j) {
+                if (n + j >= N) break;
+                float v = acc[i][j] + (bias ? bias[n + j] : 0.f);
+                if (relu) v = fmaxf(v, 0.f);
+                out[(m + i) * ld + n + j] = from_f32<T>(v);
+            }
+        }
+    }
+};
+
+struct AtomicEpi {
+    float* out; int M, N; long long ld;
+    __device__ void operator()(int z, long long m, int n, const float (&acc)[kSimtTM][kSimtTN]) const {
+#pragma unroll
+        for (int i = 0; i < kSimtTM; ++i) {
+            if (m + i >= M) break;
+#pragma unroll
+            for (int j = 0; j < kSimtTN; ++j) {
+                if (n + j >= N) break;
+                atomicAdd(out + (m + i) * ld + n + j, acc[i][j]);
+            }
+        }
+    }
+};
+
+// ConvTranspose scatter: row m = input pixel, col n = (dy, dx, co)
+template <class T> struct ConvTScatterEpi {
+    T* out; const float* bias; int N_, h, w, Co;
+    __device__ void operator()(int z, long long m, int n, const float (&acc)[kSimtTM][kSimtTN]) const {
+        ConvTAcc<T> v{out, N_, h, w, Co};
+#pragma unroll
+        for (int i = 0; i < kSimtTM; ++i) {
+            typename ConvTAcc<T>::IH ih = v.prepI(m + i);
+            if (ih.p == nullptr) break;
+#pragma unroll
+            for (int j = 0; j < kSimtTN; ++j) {
+                typename ConvTAcc<T>::JH jh = v.prepJ(n + j);
+                if (jh.off < 0) break;
+                int co = (n + j) % Co;
+                const_cast<T*>(ih.p)[jh.off] = from_f32<T>(acc[i][j] + (bias ? bias[co] : 0.f));
+            }
+        }
+    }
+};
+
+// adjoint of ShiftAcc: the gradient of shifted element (i, j) lands where the forward read it
+template <class T> struct ShiftScatterEpi {
+    T* out; long long P; int H, W, C;
+    __device__ void operator()(int z, long long m, int n, const float (&acc)[kSimtTM][kSimtTN]) const {
+        ShiftAcc<T> v{out, P, H, W, C};
+#pragma unroll
+        for (int i = 0; i < kSimtTM; ++i) {
+            typename ShiftAcc<T>::IH ih = v.prepI(m + i);
+            if (ih.img < 0) break;
+#pragma unroll
+            for (int j = 0; j < kSimtTN; ++j) {
+                typename ShiftAcc<T>::JH jh = v.prepJ(n + j);
+                if (jh.c < 0) break;
+                out[v.index(ih, jh)] = from_f32<T>(acc[i][j]);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------ problem
+// A(m,k) = XA(m,k) or XA(k,m) [TA]; B(k,n) = XB(k,n) or XB(n,k) [TB]; K split over gridZ slices.
+template <class XA, bool TA, class XB, bool TB, class Epi> struct Problem {
+    XA xa; XB xb; Epi epi;
+    int M, N; long long K; int splits; long long kchunk;
+    static constexpr bool A_KCONTIG = !TA;
+    static constexpr bool B_NCONTIG = !TB;
+    typedef typename std::conditional<TA, typename XA::JH, typename XA::IH>::type ARow;
+    typedef typename std::conditional<TA, typename XA::IH, typename XA::JH>::type AK;
+    typedef typename std::conditional<TB, typename XB::IH, typename XB::JH>::type BCol;
+    typedef typename std::conditional<TB, typename XB::JH, typename XB::IH>::type BK;
+    __host__ __device__ int gridZ() const { return splits; }
+    __device__ void krange(int z, int& kb, int& ke) const {
+        long long b = (long long)z * kchunk, e = b + kchunk;
+        kb = (int)b; ke = (int)(e < K ? e : K);
+    }
+    __device__ ARow prepA(int z, int m) const { if constexpr (TA) return xa.prepJ(m); else return xa.prepI(m); }
+    __device__ AK decA(int k) const { if constexpr (TA) return xa.prepI(k); else return xa.prepJ(k); }
+    __device__ float loadA(const ARow& r, const AK& k) const { if constexpr (TA) return xa.at(k, r); else return xa.at(r, k); }
+    __device__ BCol prepB(int z, int n) const { if constexpr (TB) return xb.prepI(n); else return xb.prepJ(n); }
+    __device__ BK decB(int k) const { if constexpr (TB) return xb.prepJ(k); else return xb.prepI(k); }
+    __device__ float loadB(const BCol& c, const BK& k) const { if constexpr (TB) return xb.at(c, k); else return xb.at(k, c); }
+    __device__ void epilogue(int z, int m, int n, const float (&acc)[kSimtTM][kSimtTN]) const { epi(z, m, n, acc); }
+};
+
+template <class XA, bool TA, class XB, bool TB, class Epi>
+static int run(const XA& xa, const XB& xb, const Epi& epi, long long M, long long N, long long K, int splits,
+               cudaStream_t st, const char* what) {
+    if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31)) {
+        set_error("%s: extent over 2^31", what);
+        return EEL_ERR_INVALID;
+    }
+    Problem<XA, TA, XB, TB, Epi> p{xa, xb, epi, (int)M, (int)N, K, 1, K};
+    if (splits > 1) {
+        long long chunk = (K + splits - 1) / splits;
+        chunk = (chunk + 15) / 16 * 16;
+        p.splits = (int)((K + chunk - 1) / chunk);
+        p.kchunk = chunk;
+    }
+    return launch_gemm_simt(p, st, what);
+}
+
+// split-K factor for weight gradients: enough blocks for ~3 waves, at least 256 reduction steps each
+static int pick_splits(long long M, long long N, long long K) {
+    long long tiles = (long long)cdiv(M, 128) * cdiv(N, 64);
+    long long want = (3LL * kNumSMs * 2 + tiles - 1) / tiles;
+    long long maxs = K / 256 > 0 ? K / 256 : 1;
+    long long s = want < maxs ? want : maxs;
+    return (int)(s < 1 ? 1 : (s > 4096 ? 4096 : s));
+}
+
+}  // namespace eel
+
+using namespace eel;
+
+extern "C" {
+
+int eel_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                    int Cout, int relu, int flip, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && wp && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_fwd: bad argument");
+    long long P = (long long)N * H * W;
+    EEL_DISPATCH_DTYPE(dtype, {
+        Conv3Acc<T> a{(const T*)x, N, H, W, Cin, flip};
+        DenseAcc<T> b{(const T*)wp, 9LL * Cin, Cout, Cout};
+        StoreEpi<T> e{(T*)y, P, Cout, Cout, bias, relu};
+        return (run<Conv3Acc<T>, false, DenseAcc<T>, false, StoreEpi<T>>(a, b, e, P, Cout, 9LL * Cin, 1,
+                                                                        (cudaStream_t)s, "conv3x3_fwd"));
+    });
+}
+
+int eel_conv3x3_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+                      int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dwp && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_wgrad: bad argument");
+    long long P = (long long)N * H * W;
+    if (cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * Cin * Cout, (cudaStream_t)s) != cudaSuccess) {
+        set_error("conv3x3_wgrad: memset failed");
+        return EEL_ERR_CUDA;
+    }
+    EEL_DISPATCH_DTYPE(dtype, {
+        Conv3Acc<T> a{(const T*)x, N, H, W, Cin, 0};
+        DenseAcc<T> b{(const T*)dy, P, Cout, Cout};
+        AtomicEpi e{dwp, 9 * Cin, Cout, Cout};
+        return (run<Conv3Acc<T>, true, DenseAcc<T>, false, AtomicEpi>(a, b, e, 9LL * Cin, Cout, P,
+                                                                     pick_splits(9LL * Cin, Cout, P),
+                                                                     (cudaStream_t)s, "conv3x3_wgrad"));
+    });
+}
+
+int eel_convt2x2_fwd(const void* x, const void* wp, const float* bias, void* y, int N, int h, int w, int Cin,
+                     int Cout, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && wp && y && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "convt2x2_fwd: bad argument");
+    long long P = (long long)N * h * w;
+    EEL_DISPATCH_DTYPE(dtype, {
+        DenseAcc<T> a{(const T*)x, P, Cin, Cin};
+        DenseAcc<T> b{(const T*)wp, Cin, 4 * Cout, 4LL * Cout};
+        ConvTScatterEpi<T> e{(T*)y, bias, N, h, w, Cout};
+        return (run<DenseAcc<T>, false, DenseAcc<T>, false, ConvTScatterEpi<T>>(a, b, e, P, 4LL * Cout, Cin, 1,
+                                                                               (cudaStream_t)s, "convt2x2_fwd"));
+    });
+}
+
+int eel_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h, int w, int Cin, int Cout,
+                       int dtype, eel_stream s) {
+    EEL_REQUIRE(dy && wp && dx && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "convt2x2_dgrad: bad argument");
+    long long P = (long long)N * h * w;
+    EEL_DISPATCH_DTYPE(dtype, {
+        ConvTAcc<T> a{(const T*)dy, N, h, w, Cout};
+        DenseAcc<T> b{(const T*)wp, Cin, 4 * Cout, 4LL * Cout};   // B(k, n) = wp[n][k]
+        StoreEpi<T> e{(T*)dx, P, Cin, Cin, nullptr, 0};
+        return (run<ConvTAcc<T>, false, DenseAcc<T>, true, StoreEpi<T>>(a, b, e, P, Cin, 4LL * Cout, 1,
+                                                                       (cudaStream_t)s, "convt2x2_dgrad"));
+    });
+}
+
+int eel_convt2x2_wgrad(const void* x, const void* dy, float* dwp, int N, int h, int w, int Cin, int Cout,
+                       int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dwp && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "convt2x2_wgrad: bad argument");
+    long long P = (long long)N * h * w;
+    if (cudaMemsetAsync(dwp, 0, sizeof(float) * 4 * Cin * Cout, (cudaStream_t)s) != cudaSuccess) {
+        set_error("convt2x2_wgrad: memset failed");
+        return EEL_ERR_CUDA;
+    }
+    EEL_DISPATCH_DTYPE(dtype, {
+        DenseAcc<T> a{(const T*)x, P, Cin, Cin};
+        ConvTAcc<T> b{(const T*)dy, N, h, w, Cout};
+        AtomicEpi e{dwp, Cin, 4 * Cout, 4LL * Cout};
+        return (run<DenseAcc<T>, true, ConvTAcc<T>, false, AtomicEpi>(a, b, e, Cin, 4LL * Cout, P,
+                                                                     pick_splits(Cin, 4LL * Cout, P),
+                                                                     (cudaStream_t)s, "convt2x2_wgrad"));
+    });
+}
+
+static int check_shift(long long P, int K, int shiftH, int shiftW, const char* what) {
+    if (shiftH < 0 || shiftW < 0 || (shiftH > 0) != (shiftW > 0)) {
+        set_error("%s: shiftH/shiftW must both be 0 or both positive", what);
+        return EEL_ERR_INVALID;
+    }
+    if (shiftH > 0 && (P % ((long long)shiftH * shiftW) != 0 || K % 4 != 0)) {
+        set_error("%s: rows must be whole %dx%d images and K a multiple of 4 for the folded shift", what, shiftH, shiftW);
+        return EEL_ERR_INVALID;
+    }
+    return EEL_OK;
+}
+
+int eel_linear_fwd(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
+                   int shiftH, int shiftW, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && w && y && P > 0 && K > 0 && Nout > 0, "linear_fwd: bad argument");
+    if (int rc = check_shift(P, K, shiftH, shiftW, "linear_fwd")) return rc;
+    EEL_DISPATCH_DTYPE(dtype, {
+        DenseAcc<T> b{(const T*)w, Nout, K, K};   // B(k, n) = w[n][k]
+        StoreEpi<T> e{(T*)y, P, Nout, Nout, bias, 0};
+        if (shiftH > 0) {
+            ShiftAcc<T> a{(const T*)x, P, shiftH, shiftW, K};
+            return (run<ShiftAcc<T>, false, DenseAcc<T>, true, StoreEpi<T>>(a, b, e, P, Nout, K, 1, (cudaStream_t)s,
+                                                                           "linear_fwd(shift)"));
+        }
+        DenseAcc<T> a{(const T*)x, P, K, K};
+        return (run<DenseAcc<T>, false, DenseAcc<T>, true, StoreEpi<T>>(a, b, e, P, Nout, K, 1, (cudaStream_t)s,
+                                                                       "linear_fwd"));
+    });
+}
+
+int eel_linear_dgrad(const void* dy, const void* w, void* dx, long long P, int K, int Nout, int shiftH,
+                     int shiftW, int dtype, eel_stream s) {
+    EEL_REQUIRE(dy && w && dx && P > 0 && K > 0 && Nout > 0, "linear_dgrad: bad argument");
+    if (int rc = check_shift(P, K, shiftH, shiftW, "linear_dgrad")) return rc;
+    EEL_DISPATCH_DTYPE(dtype, {
+        DenseAcc<T> a{(const T*)dy, P, Nout, Nout};
+        DenseAcc<T> b{(const T*)w, Nout, K, K};   // B(k = nout, n = kin) = w[k][n]
+        if (shiftH > 0) {
+            ShiftScatterEpi<T> e{(T*)dx, P, shiftH, shiftW, K};
+            return (run<DenseAcc<T>, false, DenseAcc<T>, false, ShiftScatterEpi<T>>(a, b, e, P, K, Nout, 1,
+                                                                                   (cudaStream_t)s, "linear_dgrad(shift)"));
+        }
+        StoreEpi<T> e{(T*)dx, P, K, K, nullptr, 0};
+        return (run<DenseAcc<T>, false, DenseAcc<T>, false, StoreEpi<T>>(a, b, e, P, K, Nout, 1, (cudaStream_t)s,
+                                                                        "linear_dgrad"));
+    });
+}
+
+int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int K, int Nout, int shiftH,
+                     int shiftW, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dw && P > 0 && K > 0 && Nout > 0, "linear_wgrad: bad argument");
+    if (int rc = check_shift(P, K, shiftH, shiftW, "linear_wgrad")) return rc;
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Nout * K, (cudaStream_t)s) != cudaSuccess) {
+        set_error("linear_wgrad: memset failed");
+        return EEL_ERR_CUDA;
+    }
+    EEL_DISPATCH_DTYPE(dtype, {
+        DenseAcc<T> a{(const T*)dy, P, Nout, Nout};   // A(m = nout, k = p) = dy[p][m]
+        AtomicEpi e{dw, Nout, K, K};
+        int splits = pick_splits(Nout, K, P);
+        if (shiftH > 0) {
+            ShiftAcc<T> b{(const T*)x, P, shiftH, shiftW, K};
+            return (run<DenseAcc<T>, true, ShiftAcc<T>, false, AtomicEpi>(a, b, e, Nout, K, P, splits, (cudaStream_t)s,
+                                                                         "linear_wgrad(shift)"));
+        }
+        DenseAcc<T> b{(const T*)x, P, K, K};
+        return (run<DenseAcc<T>, true, DenseAcc<T>, false, AtomicEpi>(a, b, e, Nout, K, P, splits, (cudaStream_t)s,
+                                                                     "linear_wgrad"));
+    });
+}
+
+}  // extern "C"

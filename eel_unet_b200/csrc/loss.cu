@@ -1,0 +1,150 @@
+// edge_BceDiceLoss (utils/Loss.py:92-113) forward and backward as single-pass block reductions.
+// Six prediction maps (seg + 5 side outputs) are reduced in ONE launch: grid.z = map, grid.y = sample;
+// the max-pooled targets (utils/Loss.py:102-106) are formed on the fly from the full-resolution target.
+#include "common.cuh"
+
+namespace eel {
+
+constexpr int kLossMaps = 6;
+__constant__ float kMapWeight[kLossMaps] = {1.0f, 0.1f, 0.2f, 0.3f, 0.4f, 0.5f};
+__constant__ int kMapStride[kLossMaps] = {1, 16, 8, 4, 2, 1};
+
+struct LossPtrs { const float* p[kLossMaps]; };
+struct LossGradPtrs { float* p[kLossMaps]; };
+
+__device__ __forceinline__ float pooled_target(const float* __restrict__ t, int W, int y, int x, int s) {
+    const float* base = t + (long long)(y * s) * W + x * s;
+    float m = base[0];
+    for (int dy = 0; dy < s; ++dy)
+        for (int dx = 0; dx < s; ++dx) m = fmaxf(m, base[dy * W + dx]);
+    return m;
+}
+
+// sums[map][n][4] += {sum p*t, sum p, sum t, sum bce}
+__global__ void __launch_bounds__(256) loss_partial_kernel(LossPtrs preds, const float* __restrict__ target, int H, int W,
+                                                         double* __restrict__ sums) {
+    const int map = blockIdx.z, n = blockIdx.y;
+    const int s = kMapStride[map];
+    const int h = H / s, w = W / s;
+    const long long M = (long long)h * w;
+    const float* p = preds.p[map] + (long long)n * M;
+    const float* t = target + (long long)n * H * W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        float tv = pooled_target(t, W, y, x, s);
+        float pv = p[i];
+        a0 += pv * tv;
+        a1 += pv;
+        a2 += tv;
+        a3 -= tv * fmaxf(logf(pv), -100.f) + (1.f - tv) * fmaxf(log1pf(-pv), -100.f);
+    }
+    __shared__ float red[4][8];
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][wid] = a0; red[1][wid] = a1; red[2][wid] = a2; red[3][wid] = a3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += (double)red[threadIdx.x][k];
+        if (v != 0.0) atomicAdd(&sums[((long long)map * gridDim.y + n) * 4 + threadIdx.x], v);
+    }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, int N, int H, int W, float wb, float wd,
+                                     float* __restrict__ loss) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double total = 0.0;
+    for (int map = 0; map < kLossMaps; ++map) {
+        int s = kMapStride[map];
+        double M = (double)(H / s) * (double)(W / s);
+        double dice = 0.0, bce = 0.0;
+        for (int n = 0; n < N; ++n) {
+            const double* q = sums + ((long long)map * N + n) * 4;
+            dice += (2.0 * q[0] + 1.0) / (q[1] + q[2] + 1.0);
+            bce += q[3];
+        }
+        total += (double)kMapWeight[map] * ((double)wd * (1.0 - dice / N) + (double)wb * bce / (N * M));
+    }
+    loss[0] = (float)total;
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(LossPtrs preds, const float* __restrict__ target,
+                                                     const double* __restrict__ sums, const float* __restrict__ dloss,
+                                                     LossGradPtrs grads, int N, int H, int W, float wb, float wd) {
+    const int map = blockIdx.z, n = blockIdx.y;
+    if (grads.p[map] == nullptr) return;
+    const int s = kMapStride[map];
+    const int h = H / s, w = W / s;
+    const long long M = (long long)h * w;
+    const float* p = preds.p[map] + (long long)n * M;
+    float* g = grads.p[map] + (long long)n * M;
+    const float* t = target + (long long)n * H * W;
+    const double* q = sums + ((long long)map * N + n) * 4;
+    const float D = (float)(q[1] + q[2] + 1.0);
+    const float num = (float)(2.0 * q[0] + 1.0);
+    const float up = dloss[0] * kMapWeight[map];
+    const float kb = wb / ((float)N * (float)M);
+    const float kd = wd / (float)N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        float tv = pooled_target(t, W, y, x, s);
+        float pv = p[i];
+        float bce = (pv - tv) / fmaxf(pv * (1.f - pv), 1e-12f);
+        float dice = (2.f * tv * D - num) / (D * D);
+        g[i] = up * (kb * bce - kd * dice);
+    }
+}
+
+}  // namespace eel
+
+using namespace eel;
+
+extern "C" {
+
+int eel_edge_loss_fwd(const float* const* preds_host, const float* target, int N, int H, int W, float wb, float wd,
+                      float* loss, double* sums, eel_stream s) {
+    EEL_REQUIRE(preds_host && target && loss && sums && N > 0 && H > 0 && W > 0, "edge_loss_fwd: bad argument");
+    EEL_REQUIRE(H % 16 == 0 && W % 16 == 0, "edge_loss_fwd: H and W must be multiples of 16");
+    LossPtrs lp;
+    for (int i = 0; i < kLossMaps; ++i) {
+        EEL_REQUIRE(preds_host[i] != nullptr, "edge_loss_fwd: null prediction map");
+        lp.p[i] = preds_host[i];
+    }
+    cudaStream_t st = (cudaStream_t)s;
+    if (cudaMemsetAsync(sums, 0, sizeof(double) * kLossMaps * N * 4, st) != cudaSuccess) {
+        set_error("edge_loss_fwd: memset failed");
+        return EEL_ERR_CUDA;
+    }
+    long long M = (long long)H * W;
+    int bx = (int)((M + 256 * 8 - 1) / (256 * 8));
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, N, kLossMaps);
+    loss_partial_kernel<<<grid, 256, 0, st>>>(lp, target, H, W, sums);
+    if (int rc = check_launch("edge_loss_fwd.partial")) return rc;
+    loss_finalize_kernel<<<1, 32, 0, st>>>(sums, N, H, W, wb, wd, loss);
+    return check_launch("edge_loss_fwd.finalize");
+}
+
+int eel_edge_loss_bwd(const float* const* preds_host, const float* target, const double* sums, const float* dloss,
+                      float* const* dpreds_host, int N, int H, int W, float wb, float wd, eel_stream s) {
+    EEL_REQUIRE(preds_host && target && sums && dloss && dpreds_host && N > 0 && H > 0 && W > 0, "edge_loss_bwd: bad argument");
+    EEL_REQUIRE(H % 16 == 0 && W % 16 == 0, "edge_loss_bwd: H and W must be multiples of 16");
+    LossPtrs lp;
+    LossGradPtrs gp;
+    for (int i = 0; i < kLossMaps; ++i) {
+        EEL_REQUIRE(preds_host[i] != nullptr, "edge_loss_bwd: null prediction map");
+        lp.p[i] = preds_host[i];
+        gp.p[i] = dpreds_host[i];
+    }
+    long long M = (long long)H * W;
+    int bx = (int)((M + 256 * 8 - 1) / (256 * 8));
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, N, kLossMaps);
+    loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(lp, target, sums, dloss, gp, N, H, W, wb, wd);
+    return check_launch("edge_loss_bwd");
+}
+
+}  // extern "C"

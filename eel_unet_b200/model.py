@@ -1,0 +1,227 @@
+"""Drop-in ``EELUnet`` for the reference's ``models/EELUnet.py``.
+
+Same constructor ``EELUnet(in_channels, out_channels)``, same ``.name == "eelunet"`` dispatch key
+(reference train.py:63, evaluate.py:84, test.py:109), same 365 ``state_dict`` keys / shapes / default
+initialisation order (so a reference checkpoint loads with ``strict=True`` and the same seed gives the
+same weights), same return value ``(seg_prob, [edge_5, ..., edge_1])`` (reference
+models/EELUnet.py:471).  The module tree below only *holds parameters*; ``forward`` never calls the
+sub-modules -- it drives the sm_100a kernels of libeel.so through ``ops`` on NHWC activations.
+
+There is no CPU path: a CPU tensor raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import EelError
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter containers (mirror the reference's module tree; reference models/EELUnet.py:8-225)
+class ChannelAttention(nn.Module):
+    def __init__(self, in_channels, reduction=16):
+        super().__init__()
+        self.in_channels, self.reduction = in_channels, reduction
+        self.global_avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc1 = nn.Conv2d(in_channels, in_channels // reduction, kernel_size=1, bias=True)
+        self.fc2 = nn.Conv2d(in_channels // reduction, in_channels, kernel_size=1, bias=True)
+        self.relu = nn.ReLU(inplace=True)
+        self.sigmoid = nn.Sigmoid()
+
+
+class ShiftedChannel(nn.Module):
+    def __init__(self, shift_ratio=0.25):
+        super().__init__()
+        self.shift_ratio = shift_ratio
+
+
+class ChannelAwarePatchedMLP(nn.Module):
+    def __init__(self, in_channels, out_channels, token_dim=64):
+        super().__init__()
+        self.shift = ShiftedChannel()
+        self.to_patch = nn.Conv2d(in_channels, token_dim, kernel_size=1)
+        self.channel_attention = ChannelAttention(token_dim)
+        self.mlp = nn.Sequential(nn.Linear(token_dim, token_dim * 4), nn.GELU(), nn.Linear(token_dim * 4, out_channels))
+        self.to_space = nn.Conv2d(out_channels, out_channels, kernel_size=1)
+
+
+class FeatureInterleaveBridge(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+
+
+class HighFourierTransform(nn.Module):
+    def __init__(self, mask_range=20):
+        super().__init__()
+        self.mask_range = mask_range
+
+
+class PredictionGuidedRefinement(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.in_channels = in_channels
+        self.conv = nn.Conv2d(in_channels, 1, kernel_size=1, stride=1)
+
+
+class LayerNorm(nn.Module):
+    def __init__(self, normalized_shape, eps=1e-6, data_format="channels_last"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+        self.data_format = data_format
+        if data_format not in ("channels_last", "channels_first"):
+            raise NotImplementedError
+        self.normalized_shape = (normalized_shape,)
+
+
+def _conv_block(cin, cout):
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+        nn.Conv2d(cout, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+def _mlp_conv_block(cin, cout):
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+        ChannelAwarePatchedMLP(cout, cout), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+def _upconv_block(cin, cout):
+    return nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2), nn.BatchNorm2d(cout))
+
+
+def _mlp_upconv_block(cin, cout):
+    return nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2), ChannelAwarePatchedMLP(cout, cout),
+                         nn.BatchNorm2d(cout))
+
+
+_PRECISIONS = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}
+
+
+class EELUnet(nn.Module):
+    """B200-native EEL-UNet (reference models/EELUnet.py:228-471)."""
+
+    def __init__(self, in_channels, out_channels, precision="fp32"):
+        super().__init__()
+        self.name = "eelunet"
+        # construction order = the reference's, so that default init consumes the RNG identically
+        self.enc1 = nn.Sequential(_conv_block(in_channels, 64))
+        self.enc2 = nn.Sequential(_conv_block(64, 128))
+        self.enc3 = nn.Sequential(_mlp_conv_block(128, 256))
+        self.enc4 = nn.Sequential(_mlp_conv_block(256, 512))
+        self.bottleneck = nn.Sequential(
+            nn.BatchNorm2d(512), nn.Conv2d(512, 1024, kernel_size=3, padding=1), nn.ReLU(inplace=True),
+            ChannelAwarePatchedMLP(1024, 1024), nn.ReLU(inplace=True))
+        self.upconv4 = _mlp_upconv_block(1024, 512)
+        self.dec4 = _mlp_conv_block(1024, 512)
+        self.upconv3 = _mlp_upconv_block(512, 256)
+        self.dec3 = _mlp_conv_block(512, 256)
+        self.upconv2 = _upconv_block(256, 128)
+        self.dec2 = _conv_block(256, 128)
+        self.upconv1 = _upconv_block(128, 64)
+        self.dec1 = _conv_block(128, 64)
+        self.pred5 = PredictionGuidedRefinement(1024)
+        self.pred4 = PredictionGuidedRefinement(512)
+        self.pred3 = PredictionGuidedRefinement(256)
+        self.pred2 = PredictionGuidedRefinement(128)
+        self.pred1 = PredictionGuidedRefinement(64)
+        self.channel_interleave_bridge4 = FeatureInterleaveBridge(1024)
+        self.channel_interleave_bridge3 = FeatureInterleaveBridge(512)
+        self.channel_interleave_bridge2 = FeatureInterleaveBridge(256)
+        self.channel_interleave_bridge1 = FeatureInterleaveBridge(128)
+        self.edge_upconv_4 = nn.Sequential(_mlp_upconv_block(1024, 512), _mlp_conv_block(512, 512))
+        self.edge_upconv_3 = nn.Sequential(_mlp_upconv_block(512, 256), _mlp_conv_block(256, 256))
+        self.edge_upconv_2 = nn.Sequential(_upconv_block(256, 128), HighFourierTransform(), _conv_block(128, 128))
+        self.edge_upconv_1 = nn.Sequential(_upconv_block(128, 64), HighFourierTransform(), _conv_block(64, 64))
+        self.final = nn.Sequential(LayerNorm(normalized_shape=64, data_format="channels_first"), nn.Conv2d(64, out_channels, 1))
+        self.set_precision(precision)
+
+    # ------------------------------------------------------------------------------------------
+    def set_precision(self, precision):
+        """'fp32': fp32 storage + exact FFMA GEMMs; 'bf16': bf16 activations, fp32 accumulation/statistics."""
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        self.compute_dtype = _PRECISIONS[precision]
+        return self
+
+    # ---- fused stages ------------------------------------------------------------------------
+    @staticmethod
+    def _bn(bn, z, relu):
+        training = bn.training or bn.running_mean is None
+        if training and bn.track_running_stats:
+            if bn.momentum is None:
+                raise EelError("BatchNorm momentum=None (cumulative average) is not used by the reference and not supported")
+            bn.num_batches_tracked += 1
+        return ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu,
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+
+    @staticmethod
+    def _capmlp(m, x):
+        """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch."""
+        t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
+        ca = m.channel_attention
+        t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias)
+        t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
+        t = ops.Gelu.apply(t)
+        t = ops.Linear.apply(t, m.mlp[2].weight, m.mlp[2].bias, False)
+        return ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+
+    def _conv_block(self, blk, x):
+        x = self._bn(blk[1], ops.Conv3x3.apply(x, blk[0].weight, blk[0].bias, False), True)
+        return self._bn(blk[4], ops.Conv3x3.apply(x, blk[3].weight, blk[3].bias, False), True)
+
+    def _mlp_conv_block(self, blk, x):
+        x = self._bn(blk[1], ops.Conv3x3.apply(x, blk[0].weight, blk[0].bias, False), True)
+        return self._bn(blk[4], self._capmlp(blk[3], x), True)
+
+    def _upconv(self, blk, x):
+        return self._bn(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), False)
+
+    def _mlp_upconv(self, blk, x):
+        return self._bn(blk[2], self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias)), False)
+
+    @staticmethod
+    def _pgr(m, x):
+        return ops.PGR.apply(x, m.conv.weight, m.conv.bias)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x):
+        if not x.is_cuda:
+            raise EelError("eel_unet_b200.EELUnet runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
+            raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+        a = ops.nchw_to_nhwc(x, self.compute_dtype)
+
+        enc1 = self._conv_block(self.enc1[0], a)
+        enc2 = self._conv_block(self.enc2[0], ops.MaxPool2.apply(enc1))
+        enc3 = self._mlp_conv_block(self.enc3[0], ops.MaxPool2.apply(enc2))
+        enc4 = self._mlp_conv_block(self.enc4[0], ops.MaxPool2.apply(enc3))
+
+        bt = self.bottleneck
+        b = self._bn(bt[0], ops.MaxPool2.apply(enc4), False)
+        b = ops.Conv3x3.apply(b, bt[1].weight, bt[1].bias, True)
+        b = ops.Relu.apply(self._capmlp(bt[3], b))
+        b, edge_5 = self._pgr(self.pred5, b)
+
+        # edge branch (reference models/EELUnet.py:300-328, 415-418)
+        e4 = self._mlp_conv_block(self.edge_upconv_4[1], self._mlp_upconv(self.edge_upconv_4[0], b))
+        e3 = self._mlp_conv_block(self.edge_upconv_3[1], self._mlp_upconv(self.edge_upconv_3[0], e4))
+        e2 = ops.HFT.apply(self._upconv(self.edge_upconv_2[0], e3), self.edge_upconv_2[1].mask_range)
+        e2 = self._conv_block(self.edge_upconv_2[2], e2)
+        e1 = ops.HFT.apply(self._upconv(self.edge_upconv_1[0], e2), self.edge_upconv_1[1].mask_range)
+        e1 = self._conv_block(self.edge_upconv_1[2], e1)
+
+        # decoder (reference models/EELUnet.py:421-465)
+        d = self._mlp_conv_block(self.dec4, ops.AddInterleave.apply(self._mlp_upconv(self.upconv4, b), e4, enc4))
+        d, edge_4 = self._pgr(self.pred4, d)
+        d = self._mlp_conv_block(self.dec3, ops.AddInterleave.apply(self._mlp_upconv(self.upconv3, d), e3, enc3))
+        d, edge_3 = self._pgr(self.pred3, d)
+        d = self._conv_block(self.dec2, ops.AddInterleave.apply(self._upconv(self.upconv2, d), e2, enc2))
+        d, edge_2 = self._pgr(self.pred2, d)
+        d = self._conv_block(self.dec1, ops.AddInterleave.apply(self._upconv(self.upconv1, d), e1, enc1))
+        d, edge_1 = self._pgr(self.pred1, d)
+
+        seg = ops.Head.apply(d, self.final[0].weight, self.final[0].bias, self.final[1].weight, self.final[1].bias)
+        return seg, [edge_5, edge_4, edge_3, edge_2, edge_1]

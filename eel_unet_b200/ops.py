@@ -1,0 +1,470 @@
+"""torch.autograd bindings of the libeel.so kernels (host-side mirror of the ATen ops the reference's
+hot path dispatches).  Activations are NHWC tensors [N, H, W, C] in fp32 or bf16; parameters are the
+module's own fp32 nn.Parameters in the reference's layout.  Every op here ends in a C-ABI call --
+there is no PyTorch / CPU fallback.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import call, dtype_code, ptr, stream, workspace
+
+F32 = torch.float32
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _pack(w4, perm, dtype):
+    """permute + cast a 4-D fp32 parameter into the operand layout a kernel wants."""
+    w4 = _c(w4.detach())
+    d = list(w4.shape)
+    out = torch.empty([d[p] for p in perm], dtype=dtype, device=w4.device)
+    call("eel_permute4", ptr(w4), dtype_code(w4), ptr(out), dtype_code(out), d[0], d[1], d[2], d[3],
+         perm[0], perm[1], perm[2], perm[3], stream())
+    return out
+
+
+def _as_dtype2d(w2, dtype):
+    """[A, B] fp32 parameter -> same layout in the activation dtype (no copy for fp32)."""
+    w2 = _c(w2.detach())
+    if w2.dtype == dtype:
+        return w2
+    return _pack(w2.view(1, 1, w2.shape[0], w2.shape[1]), (0, 1, 2, 3), dtype).view(w2.shape)
+
+
+def _reduce_ws(device, channels, quantities, extra=0):
+    n = _lib.lib.eel_reduce_workspace_bytes(int(channels), int(quantities)) + extra
+    return workspace(n, device), n
+
+
+def _colsum(x2d, C):
+    out = torch.empty(C, dtype=F32, device=x2d.device)
+    ws, n = _reduce_ws(x2d.device, C, 1)
+    call("eel_colsum", ptr(x2d), ptr(out), x2d.numel() // C, C, ptr(ws), n, dtype_code(x2d), stream())
+    return out
+
+
+def nchw_to_nhwc(x, dtype):
+    """fp32 NCHW model input -> NHWC activations (no gradient: the image is a leaf input)."""
+    x = _c(x.detach().to(F32))
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=dtype, device=x.device)
+    call("eel_nchw_to_nhwc", ptr(x), ptr(y), N, C, H, W, dtype_code(y), stream())
+    return y
+
+
+# --------------------------------------------------------------------------------------- conv 3x3
+class Conv3x3(Function):
+    """nn.Conv2d(k=3, pad=1) (reference models/EELUnet.py:338,341,351,257), optional fused ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = _c(x)
+        N, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
+        y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+        call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
+             dtype_code(x), stream())
+        ctx.relu = relu
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        st = stream()
+        if ctx.relu:
+            dz = torch.empty_like(dy)
+            call("eel_relu_bwd", ptr(y), ptr(dy), ptr(dz), dy.numel(), dtype_code(dy), st)
+            dy = dz
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
+            dx = torch.empty_like(x)
+            call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
+        dwp = torch.empty((3, 3, Cin, Cout), dtype=F32, device=x.device)
+        call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
+        dw = _pack(dwp, (3, 2, 0, 1), F32)
+        db = _colsum(dy, Cout)
+        return dx, dw, db, None
+
+
+# --------------------------------------------------------------------------------------- conv transpose
+class ConvT2x2(Function):
+    """nn.ConvTranspose2d(k=2, s=2) (reference models/EELUnet.py:364,371)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        N, h, w, Cin = x.shape
+        Cout = weight.shape[1]
+        wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
+        y = torch.empty((N, 2 * h, 2 * w, Cout), dtype=x.dtype, device=x.device)
+        call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        N, h, w, Cin = x.shape
+        Cout = weight.shape[1]
+        st = stream()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wp = _pack(weight, (0, 2, 3, 1), x.dtype)
+            dx = torch.empty_like(x)
+            call("eel_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, dtype_code(x), st)
+        dwp = torch.empty((Cin, 2, 2, Cout), dtype=F32, device=x.device)
+        call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
+        dw = _pack(dwp, (0, 3, 1, 2), F32)
+        db = _colsum(dy, Cout)
+        return dx, dw, db
+
+
+# --------------------------------------------------------------------------------------- 1x1 conv / Linear
+class Linear(Function):
+    """nn.Linear / nn.Conv2d(k=1) on the channel axis (reference models/EELUnet.py:105-112).
+
+    ``shift=True`` folds ShiftedChannel (reference :88-97) into the operand addressing.
+    weight is [Nout, K] or [Nout, K, 1, 1].
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, shift):
+        x = _c(x)
+        N, H, W, K = x.shape
+        Nout = weight.shape[0]
+        w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
+        y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
+        sh, sw = (H, W) if shift else (0, 0)
+        call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
+        ctx.shift = shift
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, K = x.shape
+        Nout = weight.shape[0]
+        P = N * H * W
+        sh, sw = (H, W) if ctx.shift else (0, 0)
+        st = stream()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
+            dx = torch.empty_like(x)
+            call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
+        dw = torch.empty((Nout, K), dtype=F32, device=x.device)
+        call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
+        db = _colsum(dy, Nout)
+        return dx, dw.view(weight.shape), db, None
+
+
+# --------------------------------------------------------------------------------------- BatchNorm (+ReLU)
+class BNAct(Function):
+    """nn.BatchNorm2d [+ nn.ReLU] (reference models/EELUnet.py:339-344,352-357,365,373,256)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps):
+        z = _c(z)
+        C = z.shape[-1]
+        P = z.numel() // C
+        dev = z.device
+        mean = torch.empty(C, dtype=F32, device=dev)
+        rstd = torch.empty(C, dtype=F32, device=dev)
+        st = stream()
+        if training:
+            ws, n = _reduce_ws(dev, C, 2)
+            call("eel_bn_stats", ptr(z), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
+                 float(momentum), float(eps), ptr(ws), n, dtype_code(z), st)
+        else:
+            call("eel_bn_eval_stats", ptr(running_mean), ptr(running_var), float(eps), ptr(mean), ptr(rstd), C, st)
+        y = torch.empty_like(z)
+        g, b = gamma.detach(), beta.detach()
+        call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
+        ctx.relu, ctx.training = relu, training
+        ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma, beta = ctx.saved_tensors
+        dy = _c(dy)
+        C = z.shape[-1]
+        P = z.numel() // C
+        dz = torch.empty_like(z)
+        dgamma = torch.empty(C, dtype=F32, device=z.device)
+        dbeta = torch.empty(C, dtype=F32, device=z.device)
+        ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+        call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
+             ptr(dgamma), ptr(dbeta), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
+        return dz, dgamma, dbeta, None, None, None, None, None, None
+
+
+class Relu(Function):
+    """standalone nn.ReLU (reference models/EELUnet.py:260)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("eel_relu_fwd", ptr(x), ptr(y), x.numel(), dtype_code(x), stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        call("eel_relu_bwd", ptr(y), ptr(dy), ptr(dx), dy.numel(), dtype_code(dy), stream())
+        return dx
+
+
+class Gelu(Function):
+    """nn.GELU() (erf form; reference models/EELUnet.py:109)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("eel_gelu_fwd", ptr(x), ptr(y), x.numel(), dtype_code(x), stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("eel_gelu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x), stream())
+        return dx
+
+
+class MaxPool2(Function):
+    """nn.MaxPool2d(2) (reference models/EELUnet.py:391,396,401,406)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        call("eel_maxpool2_fwd", ptr(x), ptr(y), N, H, W, C, dtype_code(x), stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        call("eel_maxpool2_bwd", ptr(x), ptr(dy), ptr(dx), N, H, W, C, dtype_code(x), stream())
+        return dx
+
+
+class AddInterleave(Function):
+    """torch.add + FeatureInterleaveBridge (reference models/EELUnet.py:422-426,132-141)."""
+
+    @staticmethod
+    def forward(ctx, a, b, e):
+        a, b, e = _c(a), _c(b), _c(e)
+        N, H, W, C = a.shape
+        out = torch.empty((N, H, W, 2 * C), dtype=a.dtype, device=a.device)
+        call("eel_add_interleave_fwd", ptr(a), ptr(b), ptr(e), ptr(out), N * H * W, C, dtype_code(a), stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout)
+        N, H, W, C2 = dout.shape
+        C = C2 // 2
+        dab = torch.empty((N, H, W, C), dtype=dout.dtype, device=dout.device)
+        de = torch.empty_like(dab)
+        call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), N * H * W, C, dtype_code(dout), stream())
+        return dab, dab, de
+
+
+class PGR(Function):
+    """PredictionGuidedRefinement (reference models/EELUnet.py:200-203).  Returns (x*(1+s), s[N,1,H,W] fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty_like(x)
+        s = torch.empty((N, 1, H, W), dtype=F32, device=x.device)
+        call("eel_pgr_fwd", ptr(x), ptr(_c(weight.detach())), ptr(bias.detach()), ptr(y), ptr(s), N * H * W, C,
+             dtype_code(x), stream())
+        ctx.save_for_backward(x, s, weight)
+        return y, s
+
+    @staticmethod
+    def backward(ctx, dy, ds):
+        x, s, weight = ctx.saved_tensors
+        N, H, W, C = x.shape
+        dy = _c(dy)
+        ds = _c(ds.to(F32)) if ds is not None else None
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=F32, device=x.device)
+        db = torch.empty(1, dtype=F32, device=x.device)
+        n = 4 * (2 * _lib_sms() + 1) * (C + 1)
+        ws = workspace(n, x.device)
+        call("eel_pgr_bwd", ptr(x), ptr(s), ptr(_c(weight.detach())), ptr(dy), ptr(ds), ptr(dx), ptr(dw), ptr(db),
+             N * H * W, C, ptr(ws), n, dtype_code(x), stream())
+        return dx, dw.view(weight.shape), db
+
+
+def _lib_sms():
+    return 148
+
+
+class Head(Function):
+    """final = LayerNorm(channels_first) + conv1x1, then sigmoid (reference models/EELUnet.py:217-225,330-333,467-469)."""
+
+    @staticmethod
+    def forward(ctx, x, lnw, lnb, weight, bias):
+        x = _c(x)
+        N, H, W, C = x.shape
+        if C != 64:
+            raise _lib.EelError("head kernel is specialised for the reference's 64-channel final stage")
+        O = weight.shape[0]
+        prob = torch.empty((N, O, H, W), dtype=F32, device=x.device)
+        call("eel_head_fwd", ptr(x), ptr(lnw.detach()), ptr(lnb.detach()), ptr(_c(weight.detach())), ptr(bias.detach()),
+             ptr(prob), N, H * W, O, dtype_code(x), stream())
+        ctx.save_for_backward(x, lnw, lnb, weight, bias, prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        x, lnw, lnb, weight, bias, prob = ctx.saved_tensors
+        N, H, W, C = x.shape
+        O = weight.shape[0]
+        dprob = _c(dprob.to(F32))
+        dev = x.device
+        dx = torch.empty_like(x)
+        dlnw = torch.empty(64, dtype=F32, device=dev)
+        dlnb = torch.empty(64, dtype=F32, device=dev)
+        dw = torch.empty((O, 64), dtype=F32, device=dev)
+        db = torch.empty(O, dtype=F32, device=dev)
+        n = 4 * (2 * _lib_sms() + 1) * ((2 + O) * 64 + O)
+        ws = workspace(n, dev)
+        call("eel_head_bwd", ptr(x), ptr(lnw.detach()), ptr(lnb.detach()), ptr(_c(weight.detach())), ptr(bias.detach()),
+             ptr(prob), ptr(dprob), ptr(dx), ptr(dlnw), ptr(dlnb), ptr(dw), ptr(db), N, H * W, O, ptr(ws), n,
+             dtype_code(x), stream())
+        return dx, dlnw, dlnb, dw.view(weight.shape), db
+
+
+class SE(Function):
+    """ChannelAttention (reference models/EELUnet.py:57-80) on NHWC tokens t:[N,H,W,C]."""
+
+    @staticmethod
+    def forward(ctx, t, w1, b1, w2, b2):
+        t = _c(t)
+        N, H, W, C = t.shape
+        R = w1.shape[0]
+        dev = t.device
+        out = torch.empty_like(t)
+        mean = torch.empty((N, C), dtype=F32, device=dev)
+        att = torch.empty((N, C), dtype=F32, device=dev)
+        hid = torch.empty((N, R), dtype=F32, device=dev)
+        ws, n = _reduce_ws(dev, C, 1)
+        call("eel_se_fwd", ptr(t), ptr(_c(w1.detach())), ptr(b1.detach()), ptr(_c(w2.detach())), ptr(b2.detach()), ptr(out),
+             ptr(mean), ptr(att), ptr(hid), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
+        ctx.save_for_backward(t, mean, att, hid, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        t, mean, att, hid, w1, w2 = ctx.saved_tensors
+        dout = _c(dout)
+        N, H, W, C = t.shape
+        R = w1.shape[0]
+        dev = t.device
+        dt = torch.empty_like(t)
+        dw1 = torch.empty((R, C), dtype=F32, device=dev)
+        db1 = torch.empty(R, dtype=F32, device=dev)
+        dw2 = torch.empty((C, R), dtype=F32, device=dev)
+        db2 = torch.empty(C, dtype=F32, device=dev)
+        ws, n = _reduce_ws(dev, C, 1, extra=8 * N * C)
+        call("eel_se_bwd", ptr(t), ptr(dout), ptr(att), ptr(hid), ptr(mean), ptr(_c(w1.detach())), ptr(_c(w2.detach())),
+             ptr(dt), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
+        return dt, dw1.view(w1.shape), db1, dw2.view(w2.shape), db2
+
+
+class HFT(Function):
+    """HighFourierTransform (reference models/EELUnet.py:153-191) as an exact low-rank projection."""
+
+    @staticmethod
+    def forward(ctx, x, mask_range):
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty_like(x)
+        phase = torch.empty((N, H, W, 2, C), dtype=x.dtype, device=x.device)
+        n = _lib.lib.eel_hft_workspace_bytes(N, H, W, C, int(mask_range))
+        ws = workspace(n, x.device, slot=1)
+        call("eel_hft_fwd", ptr(x), ptr(y), ptr(phase), N, H, W, C, int(mask_range), ptr(ws), n, dtype_code(x), stream())
+        ctx.mask_range = int(mask_range)
+        ctx.save_for_backward(phase)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (phase,) = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, C = dy.shape
+        dx = torch.empty_like(dy)
+        n = _lib.lib.eel_hft_workspace_bytes(N, H, W, C, ctx.mask_range)
+        ws = workspace(n, dy.device, slot=1)
+        call("eel_hft_bwd", ptr(dy), ptr(phase), ptr(dx), N, H, W, C, ctx.mask_range, ptr(ws), n, dtype_code(dy), stream())
+        return dx, None
+
+
+# --------------------------------------------------------------------------------------- loss
+import ctypes as _ct
+
+
+def _ptr_array(tensors):
+    arr = (_ct.c_void_p * 6)()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t) if t is not None else None
+    return arr
+
+
+class EdgeBceDice(Function):
+    """edge_BceDiceLoss.forward (reference utils/Loss.py:97-113) over (seg, edge_5..edge_1, target)."""
+
+    @staticmethod
+    def forward(ctx, seg, e5, e4, e3, e2, e1, target, wb, wd):
+        preds = [_c(t.to(F32)) for t in (seg, e5, e4, e3, e2, e1)]
+        target = _c(target.to(F32))
+        N, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+        if seg.numel() != target.numel():
+            raise _lib.EelError("edge_BceDiceLoss: seg and target must have the same number of elements (1 class)")
+        dev = target.device
+        loss = torch.empty((), dtype=F32, device=dev)
+        sums = torch.empty((6, N, 4), dtype=torch.float64, device=dev)
+        call("eel_edge_loss_fwd", _ptr_array(preds), ptr(target), N, H, W, float(wb), float(wd), ptr(loss), ptr(sums), stream())
+        ctx.wb, ctx.wd = float(wb), float(wd)
+        ctx.save_for_backward(target, sums, *preds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        target, sums, *preds = ctx.saved_tensors
+        N, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+        dloss = _c(dloss.to(F32))
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[i] else None for i, p in enumerate(preds)]
+        call("eel_edge_loss_bwd", _ptr_array(preds), ptr(target), ptr(sums), ptr(dloss), _ptr_array(grads), N, H, W,
+             ctx.wb, ctx.wd, stream())
+        return (*grads, None, None, None)

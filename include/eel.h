@@ -1,0 +1,177 @@
+/* eel.h -- C ABI of libeel.so: the B200 (sm_100a) kernels behind the EEL-Unet hot path.
+ *
+ * The reference (DiWu17/EEL-Unet) is pure Python/PyTorch and has no FFI; the boundary a maintainer
+ * would bind is therefore the set of torch ops its hot path dispatches.  Every
+ * entry point below names the reference lines (paths relative to the reference root) whose ATen /
+ * OpenCV work it replaces.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host
+ *   - activations are NHWC ("pixels x channels", P = N*H*W rows), storage dtype EEL_F32 or EEL_BF16;
+ *     parameters, statistics, probabilities and all gradients of parameters are fp32
+ *   - the library never allocates or frees: scratch comes in as (ws, ws_bytes); sizes from the
+ *     *_workspace_bytes queries
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     returns EEL_OK or a negative code; eel_last_error() holds the message (thread-local)
+ */
+#ifndef EEL_H_
+#define EEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEL_OK 0
+#define EEL_ERR_INVALID (-1)
+#define EEL_ERR_CUDA (-2)
+#define EEL_ERR_WORKSPACE (-3)
+
+#define EEL_F32 0
+#define EEL_BF16 1
+
+typedef void* eel_stream; /* cudaStream_t */
+
+const char* eel_last_error(void);
+int eel_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long eel_launch_count(void);
+
+/* ------------------------------------------------------------------ layout / parameter packing */
+/* x: fp32 NCHW (what train.py:38 hands the model) -> y: dtype NHWC */
+int eel_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int dtype, eel_stream s);
+/* generic 4-D permute + cast: out[i_p0][i_p1][i_p2][i_p3] = in[i0][i1][i2][i3]; used to pack weights */
+int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0, int d1, int d2, int d3,
+                 int p0, int p1, int p2, int p3, eel_stream s);
+
+/* ------------------------------------------------------------------ GEMM-class ops
+ * nn.Conv2d 3x3 pad 1 (models/EELUnet.py:338,341,351,257).  x:[N,H,W,Cin], wp:[9][Cin][Cout] (dtype),
+ * y:[N,H,W,Cout].  flip != 0 mirrors the tap offsets: the data gradient of the convolution is this same
+ * call on dy with wp = [tap][Cout][Cin], flip = 1 and bias = NULL. */
+int eel_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                    int Cout, int relu, int flip, int dtype, eel_stream s);
+/* dwp:[9][Cin][Cout] fp32 (overwritten) */
+int eel_conv3x3_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+                      int dtype, eel_stream s);
+/* nn.ConvTranspose2d k2 s2 (models/EELUnet.py:364,371).  x:[N,h,w,Cin], wp:[Cin][2][2][Cout], y:[N,2h,2w,Cout] */
+int eel_convt2x2_fwd(const void* x, const void* wp, const float* bias, void* y, int N, int h, int w, int Cin,
+                     int Cout, int dtype, eel_stream s);
+int eel_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h, int w, int Cin, int Cout,
+                       int dtype, eel_stream s);
+int eel_convt2x2_wgrad(const void* x, const void* dy, float* dwp, int N, int h, int w, int Cin, int Cout,
+                       int dtype, eel_stream s);
+/* 1x1 conv / nn.Linear (models/EELUnet.py:105-112): y[P,Nout] = x[P,K] . w[Nout,K]^T + bias.
+ * shiftH/shiftW > 0 folds ShiftedChannel (models/EELUnet.py:88-97) into the operand addressing:
+ * rows are pixels of an [*,shiftH,shiftW,K] tensor and channel quarter q of x is read circularly
+ * shifted (q0: +1 along H, q1: -1 along H, q2: +1 along W, rest: none). */
+int eel_linear_fwd(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
+                   int shiftH, int shiftW, int dtype, eel_stream s);
+int eel_linear_dgrad(const void* dy, const void* w, void* dx, long long P, int K, int Nout, int shiftH,
+                     int shiftW, int dtype, eel_stream s);
+/* dw:[Nout][K] fp32 (overwritten) */
+int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int K, int Nout, int shiftH,
+                     int shiftW, int dtype, eel_stream s);
+
+/* ------------------------------------------------------------------ reductions / normalisation */
+size_t eel_reduce_workspace_bytes(int channels, int quantities);
+/* out[c] = sum_p x[p][c]   (bias gradients) */
+int eel_colsum(const void* x, float* out, long long P, int C, void* ws, size_t ws_bytes, int dtype,
+               eel_stream s);
+/* nn.BatchNorm2d train-mode statistics (eps inside rsqrt, biased variance for normalisation, unbiased
+ * for running_var, momentum update in place; running_* may be NULL). */
+int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, float* running_mean,
+                 float* running_var, float momentum, float eps, void* ws, size_t ws_bytes, int dtype,
+                 eel_stream s);
+int eel_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean,
+                      float* rstd, int C, eel_stream s);
+/* y = [relu](gamma * (z - mean) * rstd + beta) */
+int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, long long P, int C, int relu, int dtype, eel_stream s);
+/* train != 0: batch-statistics backward; train == 0: frozen statistics */
+int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, void* dz, float* dgamma, float* dbeta, long long P, int C, int relu,
+                   int train, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+
+/* ------------------------------------------------------------------ fused bandwidth-bound ops */
+/* nn.MaxPool2d(2) (models/EELUnet.py:391,396,401,406); x:[N,H,W,C] -> y:[N,H/2,W/2,C] */
+int eel_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, eel_stream s);
+int eel_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                     eel_stream s);
+/* torch.add + FeatureInterleaveBridge (models/EELUnet.py:422-426,132-141):
+ * out[p][2c] = a[p][c] + b[p][c], out[p][2c+1] = e[p][c] */
+int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* out, long long P, int C,
+                           int dtype, eel_stream s);
+int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, int C, int dtype,
+                           eel_stream s);
+/* PredictionGuidedRefinement (models/EELUnet.py:200-203): s = sigmoid(w.x + b), y = x (1 + s) */
+int eel_pgr_fwd(const void* x, const float* w, const float* b, void* y, float* sgm, long long P, int C,
+                int dtype, eel_stream s);
+int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy, const float* dsgm, void* dx,
+                float* dw, float* db, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+/* LayerNorm(channels_first, eps 1e-6) + conv1x1 64->O + sigmoid (models/EELUnet.py:217-225,330-333,469).
+ * x:[N*HW][64] NHWC, prob: fp32 NCHW [N][O][HW] */
+int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float* w, const float* b,
+                 float* prob, int N, long long HW, int O, int dtype, eel_stream s);
+int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float* w, const float* b,
+                 const float* prob, const float* dprob, void* dx, float* dlnw, float* dlnb, float* dw,
+                 float* db, int N, long long HW, int O, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+/* ChannelAttention (models/EELUnet.py:57-80) on t:[N][HW][C]; w1:[R][C], w2:[C][R] */
+int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
+               float* mean, float* att, float* hid, int N, long long HW, int C, int R, void* ws,
+               size_t ws_bytes, int dtype, eel_stream s);
+int eel_se_bwd(const void* t, const void* dout, const float* att, const float* hid, const float* mean,
+               const float* w1, const float* w2, void* dt, float* dw1, float* db1, float* dw2, float* db2,
+               int N, long long HW, int C, int R, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+/* standalone nn.ReLU (models/EELUnet.py:258,260); backward masks with the OUTPUT y */
+int eel_relu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s);
+int eel_relu_bwd(const void* y, const void* dy, void* dx, long long n, int dtype, eel_stream s);
+/* exact (erf) GELU (models/EELUnet.py:109) */
+int eel_gelu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s);
+int eel_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, eel_stream s);
+
+/* HighFourierTransform (models/EELUnet.py:153-191) as an exact low-rank projection:
+ * y = | x - U_H (U_H^H x conj(U_W)) U_W^T |, frequencies -r..r-1, r = min(mask_range, H/2, W/2).
+ * phase:[N][H][W][2][C] (dtype) keeps z/|z| for the backward. */
+size_t eel_hft_workspace_bytes(int N, int H, int W, int C, int mask_range);
+int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C, int mask_range, void* ws,
+                size_t ws_bytes, int dtype, eel_stream s);
+int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W, int C, int mask_range,
+                void* ws, size_t ws_bytes, int dtype, eel_stream s);
+
+/* ------------------------------------------------------------------ loss
+ * edge_BceDiceLoss (utils/Loss.py:92-113) with BceDiceLoss/DiceLoss/BCELoss (utils/Loss.py:28-73).
+ * preds[6] = {seg, edge_5, edge_4, edge_3, edge_2, edge_1} fp32 probabilities, spatial strides
+ * {1,16,8,4,2,1} of the H x W target; sums: fp64 [6][N][4] scratch kept for the backward. */
+int eel_edge_loss_fwd(const float* const* preds_host, const float* target, int N, int H, int W, float wb,
+                      float wd, float* loss, double* sums, eel_stream s);
+int eel_edge_loss_bwd(const float* const* preds_host, const float* target, const double* sums,
+                      const float* dloss, float* const* dpreds_host, int N, int H, int W, float wb, float wd,
+                      eel_stream s);
+
+/* ------------------------------------------------------------------ integer edge maps (OpenCV semantics)
+ * cv2.cvtColor(RGB2GRAY) + cv2.Canny(gray, low, high) (augmentation/AddCannyEdge.py:25-27,
+ * augmentation/CannyEnhance.py:32-35, utils/tools.py:145).  rgb:[N][H][W][3] u8, edges:[N][H][W] u8 */
+size_t eel_canny_workspace_bytes(int N, int H, int W);
+int eel_gray_u8(const uint8_t* rgb, uint8_t* gray, int N, int H, int W, eel_stream s);
+int eel_canny_rgb(const uint8_t* rgb, uint8_t* edges, int N, int H, int W, int low, int high, void* ws,
+                  size_t ws_bytes, eel_stream s);
+int eel_canny_gray(const uint8_t* gray, uint8_t* edges, int N, int H, int W, int low, int high, void* ws,
+                   size_t ws_bytes, eel_stream s);
+/* augmentation/Sobel.py:9-14 and :17-18 */
+int eel_sobel_map(const uint8_t* gray, uint8_t* out, int N, int H, int W, eel_stream s);
+int eel_laplacian_map(const uint8_t* gray, uint8_t* out, int N, int H, int W, eel_stream s);
+/* augmentation/CannyEnhance.py:38-43 */
+int eel_canny_enhance(const uint8_t* rgb, const uint8_t* edges, uint8_t* out, int N, int H, int W, int cr,
+                      int cg, int cb, float alpha, eel_stream s);
+
+/* ------------------------------------------------------------------ optimizer
+ * optim.Adam(lr, weight_decay) with L2-coupled decay (train.py:312) over one flat fp32 buffer */
+int eel_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, eel_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEL_H_ */

@@ -1,0 +1,378 @@
+"""Per-kernel parity (GPU): every autograd op of eel_unet_b200.ops, forward and backward, against the
+plain PyTorch fp32 formulation of the reference op it replaces (computed in fp64 on the same inputs).
+
+Tolerances (relative L2 per tensor): fp32 storage 2e-5 forward / 1e-4 gradients; bf16 storage 2e-2
+(the north_star's stated bf16 tolerance), with the checker fed the bf16-rounded inputs.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def tol(dtype, fwd=True):
+    if dtype == torch.bfloat16:
+        return 2e-2
+    return 2e-5 if fwd else 1e-4
+
+
+def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1.0):
+    """inputs: list of NCHW fp32 tensors (activations); params: list of fp32 parameter tensors.
+
+    fn_mine(nhwc activations (dtype, requires_grad), params) -> NHWC output (or tuple)
+    fn_ref(nchw fp64 activations, fp64 params) -> NCHW output (or tuple)
+    """
+    from eel_unet_b200 import ops  # noqa: F401
+
+    torch.manual_seed(0)
+    acts = [nhwc(x).to(dtype).requires_grad_(True) for x in inputs]
+    ps = [p.clone().requires_grad_(True) for p in params]
+    outs = fn_mine(acts, ps)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    racts = [nchw(a.detach().double()).requires_grad_(True) for a in acts]
+    rps = [p.detach().double().requires_grad_(True) for p in params]
+    routs = fn_ref(racts, rps)
+    routs = routs if isinstance(routs, tuple) else (routs,)
+    gs = []
+    for o, r in zip(outs, routs):
+        o_cmp = nchw(o.float()) if (o.dim() == 4 and out_nhwc and o.dtype == dtype and o.shape != r.shape) else o.float()
+        e = rel(o_cmp, r)
+        assert e < tol(dtype) * atol_scale, "forward mismatch %g" % e
+        g = torch.randn_like(r)
+        gs.append(g)
+    # backward
+    mine_g = []
+    for o, g, r in zip(outs, gs, routs):
+        if o.dim() == 4 and o.shape != r.shape:
+            mine_g.append(nhwc(g).to(o.dtype))
+        else:
+            mine_g.append(g.to(o.dtype))
+    torch.autograd.backward(outs, mine_g)
+    # the checker sees the same (possibly bf16-rounded) upstream gradients
+    rg = []
+    for o, g, r in zip(outs, mine_g, routs):
+        gg = g.double()
+        rg.append(nchw(gg) if gg.shape != r.shape else gg)
+    torch.autograd.backward(routs, rg)
+    for a, ra in zip(acts, racts):
+        e = rel(nchw(a.grad.float()), ra.grad)
+        assert e < tol(dtype, False) * atol_scale, "input-grad mismatch %g" % e
+    for p, rp in zip(ps, rps):
+        e = rel(p.grad, rp.grad)
+        assert e < tol(dtype, False) * atol_scale, "param-grad mismatch %g (shape %s)" % (e, tuple(p.shape))
+
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 8, 12, 20, 16), (1, 64, 16, 16, 72), (3, 16, 9, 7, 8)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv3x3(dtype, shape, relu):
+    from eel_unet_b200 import ops
+
+    n, cin, h, w, cout = shape
+    x = torch.randn(n, cin, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(9 * cin)
+    b = torch.randn(cout, device=DEV)
+
+    def mine(a, p):
+        return ops.Conv3x3.apply(a[0], p[0], p[1], relu)
+
+    def ref(a, p):
+        y = F.conv2d(a[0], p[0], p[1], padding=1)
+        return F.relu(y) if relu else y
+
+    run_case(mine, ref, [x], [wt, b], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv3x3_first_layer_three_channels(dtype):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    wt = torch.randn(64, 3, 3, 3, device=DEV) / math.sqrt(27)
+    b = torch.randn(64, device=DEV)
+    a = ops.nchw_to_nhwc(x, dtype)
+    y = ops.Conv3x3.apply(a, wt.requires_grad_(True), b.requires_grad_(True), False)
+    r = F.conv2d(nchw(a.double()), wt.double(), b.double(), padding=1)
+    assert rel(nchw(y.float()), r) < tol(dtype)
+    y.backward(torch.ones_like(y))   # leaf input: only wgrad/bias paths run
+    assert wt.grad is not None and torch.isfinite(wt.grad).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 6, 10, 8), (1, 64, 8, 8, 32)])
+def test_convt2x2(dtype, shape):
+    from eel_unet_b200 import ops
+
+    n, cin, h, w, cout = shape
+    x = torch.randn(n, cin, h, w, device=DEV)
+    wt = torch.randn(cin, cout, 2, 2, device=DEV) / math.sqrt(cin)
+    b = torch.randn(cout, device=DEV)
+    run_case(lambda a, p: ops.ConvT2x2.apply(a[0], p[0], p[1]),
+             lambda a, p: F.conv_transpose2d(a[0], p[0], p[1], stride=2), [x], [wt, b], dtype)
+
+
+def ref_shift(x):
+    s = int(x.shape[1] * 0.25)
+    return torch.cat([x[:, :s].roll(1, 2), x[:, s:2 * s].roll(-1, 2), x[:, 2 * s:3 * s].roll(1, 3), x[:, 3 * s:]], 1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shift", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 8, 12, 24), (1, 256, 16, 16, 64)])
+def test_linear(dtype, shift, shape):
+    from eel_unet_b200 import ops
+
+    n, k, h, w, nout = shape
+    x = torch.randn(n, k, h, w, device=DEV)
+    wt = torch.randn(nout, k, 1, 1, device=DEV) / math.sqrt(k)
+    b = torch.randn(nout, device=DEV)
+    run_case(lambda a, p: ops.Linear.apply(a[0], p[0], p[1], shift),
+             lambda a, p: F.conv2d(ref_shift(a[0]) if shift else a[0], p[0], p[1]), [x], [wt, b], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act(dtype, relu, training):
+    from eel_unet_b200 import ops
+
+    n, c, h, w = 3, 32, 10, 6
+    x = torch.randn(n, c, h, w, device=DEV) * 2 + 3.0   # mean >> 0 exercises the shifted-moment statistics
+    g = torch.rand(c, device=DEV) + 0.5
+    b = torch.randn(c, device=DEV)
+    rm0 = torch.randn(c, device=DEV) * 0.1
+    rv0 = torch.rand(c, device=DEV) + 0.5
+    rm, rv = rm0.clone(), rv0.clone()
+    rrm, rrv = rm0.double(), rv0.double()
+
+    def mine(a, p):
+        return ops.BNAct.apply(a[0], p[0], p[1], rm, rv, training, relu, 0.1, 1e-5)
+
+    def ref(a, p):
+        y = F.batch_norm(a[0], rrm, rrv, p[0], p[1], training, 0.1, 1e-5)
+        return F.relu(y) if relu else y
+
+    run_case(mine, ref, [x], [g, b], dtype)
+    if training:
+        t = 1e-5 if dtype == torch.float32 else 1e-2
+        assert rel(rm, rrm) < t and rel(rv, rrv) < t
+    else:
+        assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_relu_gelu(dtype):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(2, 16, 8, 12, device=DEV)
+    run_case(lambda a, p: ops.MaxPool2.apply(a[0]), lambda a, p: F.max_pool2d(a[0], 2), [x], [], dtype)
+    run_case(lambda a, p: ops.Relu.apply(a[0]), lambda a, p: F.relu(a[0]), [x], [], dtype)
+    run_case(lambda a, p: ops.Gelu.apply(a[0]), lambda a, p: F.gelu(a[0]), [x], [], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_ties_go_to_first_max(dtype):
+    from eel_unet_b200 import ops
+
+    x = torch.zeros(1, 8, 4, 4, device=DEV)   # all ties (post-ReLU zeros)
+    a = nhwc(x).to(dtype).requires_grad_(True)
+    y = ops.MaxPool2.apply(a)
+    y.backward(torch.ones_like(y))
+    r = x.clone().requires_grad_(True)
+    F.max_pool2d(r, 2).backward(torch.ones(1, 8, 2, 2, device=DEV))
+    assert torch.equal(nchw(a.grad.float()), r.grad)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_add_interleave(dtype):
+    from eel_unet_b200 import ops
+
+    xs = [torch.randn(2, 16, 6, 6, device=DEV) for _ in range(3)]
+
+    def ref(a, p):
+        s = a[0] + a[1]
+        n, c, h, w = s.shape
+        return torch.stack([s, a[2]], dim=2).reshape(n, 2 * c, h, w)
+
+    run_case(lambda a, p: ops.AddInterleave.apply(a[0], a[1], a[2]), ref, xs, [], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c", [64, 128, 1024])
+def test_pgr(dtype, c):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(2, c, 6, 10, device=DEV)
+    wt = torch.randn(1, c, 1, 1, device=DEV) / math.sqrt(c)
+    b = torch.randn(1, device=DEV)
+
+    def ref(a, p):
+        s = torch.sigmoid(F.conv2d(a[0], p[0], p[1]))
+        return a[0] + a[0] * s, s
+
+    run_case(lambda a, p: ops.PGR.apply(a[0], p[0], p[1]), ref, [x], [wt, b], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("o", [1, 3])
+def test_head(dtype, o):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(2, 64, 10, 6, device=DEV) * 1.5 + 0.3
+    lw = torch.rand(64, device=DEV) + 0.5
+    lb = torch.randn(64, device=DEV) * 0.1
+    wt = torch.randn(o, 64, 1, 1, device=DEV) / 8
+    b = torch.randn(o, device=DEV)
+
+    def ref(a, p):
+        u = a[0].mean(1, keepdim=True)
+        s = (a[0] - u).pow(2).mean(1, keepdim=True)
+        y = (a[0] - u) / torch.sqrt(s + 1e-6)
+        y = p[0][None, :, None, None] * y + p[1][None, :, None, None]
+        return torch.sigmoid(F.conv2d(y, p[2], p[3]))
+
+    run_case(lambda a, p: ops.Head.apply(a[0], p[0], p[1], p[2], p[3]), ref, [x], [lw, lb, wt, b], dtype, out_nhwc=False)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_se(dtype):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(3, 64, 6, 10, device=DEV)
+    w1 = torch.randn(4, 64, 1, 1, device=DEV) / 8
+    b1 = torch.randn(4, device=DEV) * 0.5
+    w2 = torch.randn(64, 4, 1, 1, device=DEV) / 2
+    b2 = torch.randn(64, device=DEV) * 0.5
+
+    def ref(a, p):
+        g = a[0].mean(dim=(2, 3), keepdim=True)
+        g = torch.sigmoid(F.conv2d(F.relu(F.conv2d(g, p[0], p[1])), p[2], p[3]))
+        return a[0] * g
+
+    run_case(lambda a, p: ops.SE.apply(a[0], p[0], p[1], p[2], p[3]), ref, [x], [w1, b1, w2, b2], dtype)
+
+
+def ref_hft(x, mask_range=20):
+    h, w = x.shape[-2:]
+    crow, ccol = h // 2, w // 2
+    r = min(mask_range, crow, ccol)
+    mask = torch.ones(h, w, dtype=x.dtype, device=x.device)
+    mask[crow - r:crow + r, ccol - r:ccol + r] = 0
+    d = torch.fft.fftshift(torch.fft.fft2(x), dim=(-2, -1)) * mask
+    return torch.abs(torch.fft.ifft2(torch.fft.ifftshift(d, dim=(-2, -1))))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 8, 64, 64), (1, 16, 48, 80), (1, 8, 16, 16)])
+def test_hft(dtype, shape):
+    from eel_unet_b200 import ops
+
+    x = torch.randn(*shape, device=DEV)
+    if shape[-1] == 16:
+        # fully masked spectrum (r = H/2): output is exactly the rounding residue of x - Px; compare absolutely
+        a = nhwc(x).to(dtype)
+        y = ops.HFT.apply(a, 20)
+        assert y.float().abs().max().item() < (1e-4 if dtype == torch.float32 else 5e-2)
+        return
+    run_case(lambda a, p: ops.HFT.apply(a[0], 20), lambda a, p: ref_hft(a[0]), [x], [], dtype,
+             atol_scale=5.0 if dtype == torch.float32 else 1.5)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_edge_loss(soft):
+    from eel_unet_b200 import edge_BceDiceLoss
+
+    torch.manual_seed(3)
+    n, h, w = 3, 64, 96
+    t = (torch.rand(n, 1, h, w, device=DEV) > 0.7).float()
+    if soft:
+        t = F.avg_pool2d(t, 3, 1, 1)
+    preds = [torch.rand(n, 1, h // s, w // s, device=DEV).clamp(1e-4, 1 - 1e-4).requires_grad_(True) for s in (1, 16, 8, 4, 2, 1)]
+    loss = edge_BceDiceLoss(1, 1)(preds[1:], preds[0], t)
+
+    def bd(p, tt):
+        p, tt = p.double(), tt.double()
+        nn_ = p.shape[0]
+        p_, t_ = p.reshape(nn_, -1), tt.reshape(nn_, -1)
+        bce = F.binary_cross_entropy(p_, t_)
+        dice = 1 - ((2 * (p_ * t_).sum(1) + 1) / (p_.sum(1) + t_.sum(1) + 1)).sum() / nn_
+        return bce + dice
+
+    rp = [p.detach().double().requires_grad_(True) for p in preds]
+    rl = bd(rp[0], t)
+    for k, (s, wk) in enumerate(zip((16, 8, 4, 2, 1), (0.1, 0.2, 0.3, 0.4, 0.5))):
+        tt = F.max_pool2d(t, s, s) if s > 1 else t
+        rl = rl + wk * bd(rp[k + 1], tt)
+    assert abs(loss.item() - rl.item()) < 1e-5 * abs(rl.item())
+    (loss * 1.7).backward()
+    (rl * 1.7).backward()
+    for p, r in zip(preds, rp):
+        assert rel(p.grad, r.grad) < 1e-5
+
+
+def test_edge_loss_saturated_probabilities():
+    """p exactly 0/1: log clamps at -100 (nn.BCELoss) and the gradient divides by max(p(1-p), 1e-12)."""
+    from eel_unet_b200 import edge_BceDiceLoss
+
+    n, h, w = 1, 16, 16
+    t = torch.zeros(n, 1, h, w, device=DEV)
+    t[..., :8] = 1
+    preds = [torch.full((n, 1, h // s, w // s), 0.5, device=DEV) for s in (1, 16, 8, 4, 2, 1)]
+    preds[0] = torch.where(torch.rand(n, 1, h, w, device=DEV) > 0.5, torch.ones(()).to(DEV), torch.zeros(()).to(DEV))
+    preds = [p.requires_grad_(True) for p in preds]
+    loss = edge_BceDiceLoss(1, 1)(preds[1:], preds[0], t)
+    rp = [p.detach().clone().requires_grad_(True) for p in preds]
+    crit_b = torch.nn.BCELoss()
+
+    def bd(p, tt):
+        nn_ = p.shape[0]
+        p_, t_ = p.view(nn_, -1), tt.view(nn_, -1)
+        return crit_b(p_, t_) + 1 - ((2 * (p_ * t_).sum(1) + 1) / (p_.sum(1) + t_.sum(1) + 1)).sum() / nn_
+
+    rl = bd(rp[0], t)
+    for k, (s, wk) in enumerate(zip((16, 8, 4, 2, 1), (0.1, 0.2, 0.3, 0.4, 0.5))):
+        rl = rl + wk * bd(rp[k + 1], F.max_pool2d(t, s, s) if s > 1 else t)
+    assert abs(loss.item() - rl.item()) < 1e-4 * abs(rl.item())
+    loss.backward()
+    rl.backward()
+    assert rel(preds[0].grad, rp[0].grad) < 1e-5
+
+
+def test_adam_matches_torch():
+    from eel_unet_b200 import _lib
+
+    torch.manual_seed(0)
+    n = 10007
+    p = torch.randn(n, device=DEV)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3, weight_decay=1e-5)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        g = torch.randn(n, device=DEV)
+        ref_p.grad = g.clone()
+        opt.step()
+        _lib.call("eel_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-5,
+                  step, _lib.stream())
+    assert rel(p, ref_p.detach()) < 1e-6
