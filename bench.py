@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- EEL-Unet training throughput (BASELINE.json metric: train images/s at 256^2, % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision bf16|fp32] [--size 256] [--batch 64] [--no-cpu-baseline]
+
+One step = one pass of the hot path over one batch of synthetic tooth-like images: EELUnet forward,
+edge_BceDiceLoss, backward, (N > 1: bucketed NCCL gradient all-reduce overlapped with backward) and the
+fused Adam update.  Workload at every N: BASELINE config 3 per GPU (bf16 training, batch 64 at 3x256x256),
+i.e. weak scaling.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the CPU oracle port of the same step (oracle/eelunet_torch.py -- the reference is
+Python and cannot travel to the GPU box) on all host threads, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], d["bf16_tflops"], "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_step_rate(batch, size, iters, warmup, seed=0):
+    """images/s of the CPU oracle port (fp32, fwd + loss + bwd + Adam) on all host threads."""
+    import torch
+
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    torch.manual_seed(0)
+    from eel_unet_b200.model import EELUnet as Tree  # parameter container only (never run on CPU)
+
+    sd = {k: v for k, v in Tree(3, 1).state_dict().items()}
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running_" not in k) for k, v in sd.items()}
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=1e-5)
+    xs, ys, _ = synth.batch(batch, size, size, seed)
+    x, y = torch.from_numpy(xs), torch.from_numpy(ys)
+    times = []
+    for it in range(warmup + iters):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        seg, edges = O.forward(params, x, True, {})
+        loss = O.edge_bce_dice_loss(edges, seg, y)
+        loss.backward()
+        opt.step()
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    # bounded sample: keep (K + W) CPU steps inside ~150 s at ~0.05 img/s/core
+    per_step = 150.0 / max(1, args.steps + args.warmup)
+    b = int(max(1, min(8, per_step * 0.055 * cores)))
+    rate, sec = cpu_step_rate(b, args.size, args.steps, args.warmup)
+    line = {
+        "metric": "EELUnet train images/sec @%d^2" % args.size, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "EELUnet fp32 fwd+loss+bwd+Adam on host CPU, 3x%dx%d" % (args.size, args.size),
+                   "sample": "batch %d per step (bounded sample of the batch-%d workload)" % (b, args.batch)},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "oracle/eelunet_torch.py, batch %d at %d^2, %d timed steps" % (b, args.size, args.steps)},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from eel_unet_b200 import EELUnet, _lib, edge_BceDiceLoss, profiling
+    from eel_unet_b200.parallel import DataParallel, FusedAdam
+    from oracle import synth  # synthetic-input generator only
+
+    hbm, tens_sus, tens_burst, peak_src = _peaks()
+    B, S = args.batch, args.size
+    torch.manual_seed(0)
+    model = EELUnet(3, 1, precision=args.precision).to(dev).train()
+    dp = DataParallel(model, bucket_mb=25.0)
+    opt = FusedAdam(dp.buckets, lr=1e-4, weight_decay=1e-5)
+    crit = edge_BceDiceLoss(1, 1)
+
+    # synthetic data (seeded per rank): a few distinct images tiled to the batch keeps host prep short
+    base = min(B, 16)
+    xs, ys, _ = synth.batch(base, S, S, seed=rank)
+    reps = (B + base - 1) // base
+    x_host = torch.from_numpy(xs).repeat(reps, 1, 1, 1)[:B].contiguous().pin_memory()
+    y_host = torch.from_numpy(ys).repeat(reps, 1, 1, 1)[:B].contiguous().pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(x, y):
+        dp.zero_grad()
+        seg, edges = dp(x)
+        loss = crit(edges, seg, y)
+        loss.backward()
+        dp.finish_backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM --------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- end to end: pinned host buffers in, loss scalar out, copies inside the timed region -----
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        float(step(xd, yd).item())
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / (float(t.item()) / 1e3)
+
+    # ---- per-kernel CUDA-event profile of one more step (rank 0): roofline of the dominant kernel ----
+    roof, breakdown = None, None
+    if rank == 0:
+        rec = []
+        _lib.set_profiler(rec)
+        step(x_dev, y_dev)
+        _lib.set_profiler(None)
+        torch.cuda.synchronize()
+        fam = profiling.summarize(rec)
+        rows = profiling.table(fam, hbm, tens_sus)
+        breakdown = [{"kernel": r[0], "calls": r[1], "ms": round(r[2], 3), "share": round(r[3], 2), "tflops": round(r[4], 2),
+                      "gbs": round(r[6], 1)} for r in rows[:12]]
+        top = rows[0]
+        d = fam[top[0]]
+        if top[0] in profiling.GEMM_CLASS:
+            ach = d["flops"] / d["ms"] / 1e9
+            roof = {"bound": "tensor", "kernel": top[0], "achieved": ach, "peak": tens_sus, "unit": "TFLOP/s", "frac": ach / tens_sus,
+                    "traffic": None, "peak_source": peak_src + " (sustained cuBLAS bf16)", "share_of_step": top[3] / 100.0}
+        else:
+            ach = d["bytes"] / d["ms"] / 1e6
+            roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": None, "peak_source": peak_src + " (copy)", "share_of_step": top[3] / 100.0}
+        # the best bandwidth-bound kernel family, for the north_star's ">= 70 % of HBM roofline" target
+        ew = [r for r in rows if r[0] not in profiling.GEMM_CLASS and fam[r[0]]["bytes"] > 1e8]
+        if ew:
+            tot_b = sum(fam[r[0]]["bytes"] for r in ew)
+            tot_ms = sum(fam[r[0]]["ms"] for r in ew)
+            roof["elementwise_hbm_frac"] = tot_b / tot_ms / 1e6 / hbm
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                f.write("kernel,calls,ms,share_pct,tflops,pct_tensor_peak,gbs,pct_hbm_peak\n")
+                for r in rows:
+                    f.write("%s,%d,%.3f,%.2f,%.2f,%.2f,%.1f,%.2f\n" % r)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        b = 4 if cores >= 8 else 2
+        rate, sec = cpu_step_rate(b, S, 1, 1)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "oracle/eelunet_torch.py fp32 fwd+loss+bwd+Adam, batch %d at %d^2, 1 warm-up + 1 timed step" % (b, S)}
+
+    if rank == 0:
+        line = {
+            "metric": "EELUnet train images/sec @%d^2" % S, "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "EELUnet %s training (fwd + edge_BceDiceLoss + bwd + Adam%s), batch %d per GPU at 3x%dx%d"
+                                   % (args.precision, " + NCCL allreduce" if world > 1 else "", B, S, S),
+                       "global_batch": world * B, "parallelism": "dp%d" % world,
+                       "l2": "no flush needed: per-step activation working set is GBs >> 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
+            "loss": float(loss.item()),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,8 +75,25 @@ def check(rc, what=""):
         raise EelError("%s failed (%d): %s" % (what or "eel call", rc, lib.eel_last_error().decode()))
 
 
+_profile = None
+
+
+def set_profiler(records):
+    """records: a list that receives (name, args, start_event, end_event) per C-ABI call, or None to stop.
+    Used by bench.py to time each kernel family with CUDA events on the launching stream."""
+    global _profile
+    _profile = records
+
+
 def call(name, *args):
+    if _profile is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     check(getattr(lib, name)(*args), name)
+    e.record()
+    _profile.append((name, args, s, e))
 
 
 def dtype_code(t):

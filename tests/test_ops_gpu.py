@@ -101,7 +101,8 @@ def test_conv3x3(dtype, shape, relu):
         y = F.conv2d(a[0], p[0], p[1], padding=1)
         return F.relu(y) if relu else y
 
-    run_case(mine, ref, [x], [wt, b], dtype)
+    # bf16 + fused ReLU: outputs within bf16 rounding of 0 flip the mask, a 100 % error on those elements
+    run_case(mine, ref, [x], [wt, b], dtype, atol_scale=4.0 if (relu and dtype == torch.bfloat16) else 1.0)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
