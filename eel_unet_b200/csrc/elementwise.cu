@@ -340,6 +340,29 @@ __global__ void add_interleave_bwd_kernel(const T* __restrict__ dout, T* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------ ShiftedChannel
+// y[n,h,w,c] = x[n,(h+dh)%H,(w+dw)%W,c]; quarter 0: dh=-1, quarter 1: dh=+1, quarter 2: dw=-1 (signs flip for the adjoint)
+template <class T>
+__global__ void shift_channels_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, int H, int W, int C, int inverse) {
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * V;
+        long long pix = i / cv;
+        int w = (int)(pix % W);
+        long long r = pix / W;
+        int h = (int)(r % H);
+        long long n = r / H;
+        int q = c / (C / 4);
+        int dh = q == 0 ? -1 : (q == 1 ? 1 : 0), dw = q == 2 ? -1 : 0;
+        if (inverse) { dh = -dh; dw = -dw; }
+        int hh = h + dh, ww = w + dw;
+        hh = hh < 0 ? hh + H : (hh >= H ? hh - H : hh);
+        ww = ww < 0 ? ww + W : (ww >= W ? ww - W : ww);
+        st16(y + i * V, ld16(x + ((n * H + hh) * W + ww) * C + c));
+    }
+}
+
 // ------------------------------------------------------------------------------------ ReLU
 template <class T>
 __global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec) {
@@ -639,6 +662,16 @@ int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, i
         long long nvec = P * C / Vec16<T>::N;
         add_interleave_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dout, (T*)dab, (T*)de, nvec);
         return check_launch("add_interleave_bwd");
+    });
+}
+
+int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int inverse, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "shift_channels: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_REQUIRE(C % (4 * Vec16<T>::N) == 0, "shift_channels: C/4 must be a multiple of the 16-byte vector");
+        long long nvec = (long long)N * H * W * C / Vec16<T>::N;
+        shift_channels_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, nvec, H, W, C, inverse);
+        return check_launch("shift_channels");
     });
 }
 

@@ -46,6 +46,21 @@ def _colsum(x2d, C):
     return out
 
 
+BF16 = torch.bfloat16
+
+
+def _tc_ok(x, *chans):
+    """bf16 storage and every channel count a multiple of 64 -> tcgen05 tensor-core kernels (gemm_tc.cu)."""
+    return x.dtype == BF16 and all(c % 64 == 0 for c in chans)
+
+
+def _shift(x, inverse):
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    call("eel_shift_channels", ptr(x), ptr(y), N, H, W, C, int(inverse), dtype_code(x), stream())
+    return y
+
+
 def nchw_to_nhwc(x, dtype):
     """fp32 NCHW model input -> NHWC activations (no gradient: the image is a leaf input)."""
     x = _c(x.detach().to(F32))
@@ -64,10 +79,14 @@ class Conv3x3(Function):
         x = _c(x)
         N, H, W, Cin = x.shape
         Cout = weight.shape[0]
-        wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
         y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
-        call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
-             dtype_code(x), stream())
+        if _tc_ok(x, Cin, Cout):
+            wk = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]  (K-major B operand)
+            call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0, stream())
+        else:
+            wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
+            call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
+                 dtype_code(x), stream())
         ctx.relu = relu
         ctx.save_for_backward(x, weight, y if relu else None)
         return y
@@ -85,9 +104,13 @@ class Conv3x3(Function):
             dy = dz
         dx = None
         if ctx.needs_input_grad[0]:
-            wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
             dx = torch.empty_like(x)
-            call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
+            if _tc_ok(x, Cin, Cout):
+                wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
+                call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, st)
+            else:
+                wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
+                call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
         dwp = torch.empty((3, 3, Cin, Cout), dtype=F32, device=x.device)
         call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
         dw = _pack(dwp, (3, 2, 0, 1), F32)
@@ -104,9 +127,13 @@ class ConvT2x2(Function):
         x = _c(x)
         N, h, w, Cin = x.shape
         Cout = weight.shape[1]
-        wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
         y = torch.empty((N, 2 * h, 2 * w, Cout), dtype=x.dtype, device=x.device)
-        call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())
+        if _tc_ok(x, Cin, Cout):
+            wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
+            call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, stream())
+        else:
+            wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
+            call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())
         ctx.save_for_backward(x, weight)
         return y
 
@@ -121,7 +148,11 @@ class ConvT2x2(Function):
         if ctx.needs_input_grad[0]:
             wp = _pack(weight, (0, 2, 3, 1), x.dtype)
             dx = torch.empty_like(x)
-            call("eel_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, dtype_code(x), st)
+            gw = min(w, 128)
+            if _tc_ok(x, Cin, Cout) and 128 % gw == 0 and w % gw == 0:
+                call("eel_tc_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, st)
+            else:
+                call("eel_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, dtype_code(x), st)
         dwp = torch.empty((Cin, 2, 2, Cout), dtype=F32, device=x.device)
         call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
         dw = _pack(dwp, (0, 3, 1, 2), F32)
@@ -144,8 +175,14 @@ class Linear(Function):
         Nout = weight.shape[0]
         w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
         y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
-        sh, sw = (H, W) if shift else (0, 0)
-        call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
+        ctx.tc = _tc_ok(x, K, Nout)
+        if ctx.tc:
+            if shift:
+                x = _shift(x, False)           # saved shifted: wgrad then needs no gather
+            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, stream())
+        else:
+            sh, sw = (H, W) if shift else (0, 0)
+            call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
         ctx.shift = shift
         ctx.save_for_backward(x, weight)
         return y
@@ -157,13 +194,19 @@ class Linear(Function):
         N, H, W, K = x.shape
         Nout = weight.shape[0]
         P = N * H * W
-        sh, sw = (H, W) if ctx.shift else (0, 0)
+        sh, sw = (H, W) if (ctx.shift and not ctx.tc) else (0, 0)
         st = stream()
         dx = None
         if ctx.needs_input_grad[0]:
-            w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
             dx = torch.empty_like(x)
-            call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
+            if ctx.tc:
+                wt = _pack(weight.detach().view(1, 1, Nout, K), (0, 1, 3, 2), x.dtype)   # [K][Nout]
+                call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, st)
+                if ctx.shift:
+                    dx = _shift(dx, True)
+            else:
+                w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
+                call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
         dw = torch.empty((Nout, K), dtype=F32, device=x.device)
         call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
         db = _colsum(dy, Nout)

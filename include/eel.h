@@ -74,6 +74,21 @@ int eel_linear_dgrad(const void* dy, const void* w, void* dx, long long P, int K
 int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int K, int Nout, int shiftH,
                      int shiftW, int dtype, eel_stream s);
 
+/* ---- bf16 tensor-core (tcgen05 + TMEM + TMA) versions of the heavy GEMM-class ops; bf16 storage only,
+ * channel counts multiples of 64.  wk layouts are K-major: conv3x3 wk:[9][Cout][Cin] (flip != 0: the data
+ * gradient, wk:[9][Cin_of_layer][Cout_of_layer] with mirrored taps); linear w:[Nout][K]; convt wk:[2][2][Cout][Cin]. */
+int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin,
+                   int Cout, int relu, int flip, eel_stream s);
+int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
+                  int relu, eel_stream s);
+int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin,
+                        int Cout, eel_stream s);
+/* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */
+int eel_tc_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h, int w, int Cin, int Cout,
+                          eel_stream s);
+/* ShiftedChannel (models/EELUnet.py:88-97) as a standalone gather; inverse != 0 applies the adjoint shifts */
+int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int inverse, int dtype, eel_stream s);
+
 /* ------------------------------------------------------------------ reductions / normalisation */
 size_t eel_reduce_workspace_bytes(int channels, int quantities);
 /* out[c] = sum_p x[p][c]   (bias gradients) */

@@ -84,7 +84,9 @@ DTYPES = [torch.float32, torch.bfloat16]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 8, 12, 20, 16), (1, 64, 16, 16, 72), (3, 16, 9, 7, 8)])
+@pytest.mark.parametrize("shape", [(2, 8, 12, 20, 16), (1, 64, 16, 16, 72), (3, 16, 9, 7, 8),
+                                   (2, 64, 24, 20, 64), (1, 128, 16, 16, 256), (2, 256, 8, 8, 128), (1, 64, 32, 40, 512),
+                                   (3, 192, 5, 9, 64)])
 @pytest.mark.parametrize("relu", [False, True])
 def test_conv3x3(dtype, shape, relu):
     from eel_unet_b200 import ops
@@ -121,7 +123,8 @@ def test_conv3x3_first_layer_three_channels(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 16, 6, 10, 8), (1, 64, 8, 8, 32)])
+@pytest.mark.parametrize("shape", [(2, 16, 6, 10, 8), (1, 64, 8, 8, 32), (2, 128, 8, 16, 64), (1, 64, 3, 5, 128),
+                                   (1, 256, 16, 16, 128)])
 def test_convt2x2(dtype, shape):
     from eel_unet_b200 import ops
 
@@ -140,7 +143,8 @@ def ref_shift(x):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shift", [False, True])
-@pytest.mark.parametrize("shape", [(2, 32, 8, 12, 24), (1, 256, 16, 16, 64)])
+@pytest.mark.parametrize("shape", [(2, 32, 8, 12, 24), (1, 256, 16, 16, 64), (2, 64, 12, 20, 256), (1, 256, 5, 7, 512),
+                                   (3, 512, 4, 4, 64)])
 def test_linear(dtype, shift, shape):
     from eel_unet_b200 import ops
 
