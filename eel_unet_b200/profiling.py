@@ -18,6 +18,31 @@ def cost(name, a):
         N, H, W, ci, co, dt = a[4], a[5], a[6], a[7], a[8], a[11]
         P = N * H * W
         return 2.0 * P * 9 * ci * co, P * (ci + co) * _esz(dt) + 9 * ci * co * _esz(dt)
+    if n == "tc_conv3x3":
+        N, H, W, ci, co = a[4], a[5], a[6], a[7], a[8]
+        P = N * H * W
+        return 2.0 * P * 9 * ci * co, P * (ci + co) * 2 + 9 * ci * co * 2
+    if n == "tc_linear":
+        P, K, No = a[4], a[5], a[6]
+        return 2.0 * P * K * No, P * (K + No) * 2 + K * No * 2
+    if n == "tc_convt2x2_fwd":
+        N, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
+        P = N * h * w
+        return 2.0 * P * ci * 4 * co, P * (ci + 4 * co) * 2 + 4 * ci * co * 2
+    if n == "tc_convt2x2_dgrad":
+        N, h, w, ci, co = a[3], a[4], a[5], a[6], a[7]
+        P = N * h * w
+        return 2.0 * P * ci * 4 * co, P * (ci + 4 * co) * 2 + 4 * ci * co * 2
+    if n in ("tc_conv3x3_wgrad",):
+        N, H, W, ci, co = a[3], a[4], a[5], a[6], a[7]
+        P = N * H * W
+        return 2.0 * P * 9 * ci * co, P * (ci + co) * 2 + 9 * ci * co * 4
+    if n == "tc_wgrad":
+        P, Ma, Nb = a[3], a[4], a[5]
+        return 2.0 * P * Ma * Nb, P * (Ma + Nb) * 2 + Ma * Nb * 4
+    if n == "shift_channels":
+        tot = a[2] * a[3] * a[4] * a[5]
+        return 0.0, 2 * tot * _esz(a[7])
     if n == "conv3x3_wgrad":
         N, H, W, ci, co, dt = a[3], a[4], a[5], a[6], a[7], a[8]
         P = N * H * W
@@ -113,7 +138,7 @@ def cost(name, a):
     return 0.0, 0.0
 
 
-GEMM_CLASS = {"conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
+GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}
 
 

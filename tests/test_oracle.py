@@ -1,0 +1,150 @@
+"""CPU: pin the oracle (oracle/) to the fixtures the real reference produced (tests/golden/, made by
+tests/golden/make_golden.py) and -- when /root/reference is present (build container) -- to the live reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def _weights():
+    """Seed-0 default-init weights via the drop-in's parameter tree (same construction order as the reference)."""
+    from eel_unet_b200.model import EELUnet
+
+    torch.manual_seed(0)
+    return {k: v.clone() for k, v in EELUnet(3, 1).state_dict().items()}
+
+
+def test_seed0_weights_match_reference_checksums():
+    g = np.load(os.path.join(GOLD, "eelunet_train_2x128.npz"))
+    sd = _weights()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    chk = np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in sd.values()])
+    assert np.allclose(chk, g["state_checksums"], rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_train_step_matches_reference_golden():
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    g = np.load(os.path.join(GOLD, "eelunet_train_2x128.npz"))
+    sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in _weights().items()}
+    xs, ys, _ = synth.batch(2, 128, 128, 0)
+    loss, seg, edges, grads, ns = O.train_step(sd, torch.from_numpy(xs).double(), torch.from_numpy(ys).double())
+    assert abs(loss.item() - float(g["loss"])) < 1e-12
+    assert rel(seg, g["seg"]) < 1e-6                      # fixture stored as fp32
+    for k, e in enumerate(edges):
+        assert rel(e, g["edge%d" % (5 - k)]) < 1e-6
+    names = [str(n) for n in g["grad_names"]]
+    for n, gn, gs in zip(names, g["grad_norm"], g["grad_sum"]):
+        assert abs(grads[n].norm().item() - gn) <= 1e-9 * max(gn, 1e-12) + 1e-14, n
+        assert abs(grads[n].sum().item() - gs) <= 1e-8 * max(gn, 1e-12) * grads[n].numel() ** 0.5 + 1e-14, n
+    for key in g.files:
+        if key.startswith("grad:"):
+            assert rel(grads[key[5:]], g[key]) < 1e-9 or np.linalg.norm(g[key]) < 1e-12, key
+        if key.startswith("stat:"):
+            assert rel(ns[key[5:]], g[key]) < 1e-12, key
+
+
+def test_oracle_eval_forward_matches_reference_golden():
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    g = np.load(os.path.join(GOLD, "eelunet_eval_2x128.npz"))
+    sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in _weights().items()}
+    xs, _, _ = synth.batch(2, 128, 128, 0)
+    with torch.no_grad():
+        seg, edges = O.forward(sd, torch.from_numpy(xs).double(), False)
+    assert rel(seg, g["seg"]) < 1e-6
+    for k, e in enumerate(edges):
+        assert rel(e, g["edge%d" % (5 - k)]) < 1e-6
+
+
+def test_oracle_loss_matches_reference_golden():
+    from oracle import eelunet_torch as O
+
+    g = np.load(os.path.join(GOLD, "loss_cases.npz"))
+    preds = [torch.from_numpy(g["pred%d" % i]).requires_grad_(True) for i in range(6)]
+    loss = O.edge_bce_dice_loss(preds[1:], preds[0], torch.from_numpy(g["target"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-12
+    for i, p in enumerate(preds):
+        assert rel(p.grad, g["grad%d" % i]) < 1e-12
+
+
+def test_hft_restatement_equals_fft_definition():
+    """oracle.hft (mask built in unshifted order) == the reference's shift / mask / unshift formulation."""
+    from oracle import eelunet_torch as O
+
+    torch.manual_seed(0)
+    for h, w in [(64, 64), (48, 80), (16, 16), (33, 47)]:
+        x = torch.randn(2, 3, h, w, dtype=torch.float64)
+        crow, ccol = h // 2, w // 2
+        r = min(20, crow, ccol)
+        mask = torch.ones(h, w, dtype=torch.float64)
+        mask[crow - r:crow + r, ccol - r:ccol + r] = 0
+        ref = torch.abs(torch.fft.ifft2(torch.fft.ifftshift(torch.fft.fftshift(torch.fft.fft2(x)) * mask)))
+        assert (O.hft(x) - ref).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["edges_2x96x128.npz", "edges_2x37x53.npz", "edges_1x256x256.npz"])
+def test_edge_oracle_matches_cv2_golden(name):
+    from oracle import edge_np, synth
+
+    g = np.load(os.path.join(GOLD, name))
+    n, h, w = g["gray"].shape
+    imgs, masks = synth.tooth_images(n, h, w, seed=int(g["seed"]))
+    gray = edge_np.gray_u8(imgs)
+    assert np.array_equal(gray, g["gray"])
+    assert np.array_equal(edge_np.canny(gray), g["canny"])
+    assert np.array_equal(edge_np.sobel_map(gray), g["sobel"])
+    assert np.array_equal(edge_np.laplacian_map(gray), g["laplacian"])
+    assert np.array_equal(edge_np.canny_enhance(imgs, g["canny"], (255, 255, 255), 0.2), g["enhance"])
+    assert np.array_equal((edge_np.edge_label(masks[:, 0]) * 255).astype(np.uint8), g["label"])
+
+
+def test_edge_oracle_matches_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import edge_np, synth
+
+    rng = np.random.default_rng(3)
+    for (h, w) in [(64, 80), (1, 1), (2, 7), (31, 33)]:
+        imgs, _ = synth.tooth_images(2, h, w, seed=h + w)
+        for img in list(imgs) + [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)]:
+            g = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY).reshape(h, w)
+            assert np.array_equal(edge_np.gray_u8(img), g)
+            assert np.array_equal(edge_np.canny(g), cv2.Canny(g, 100, 200).reshape(h, w))
+
+
+def test_oracle_matches_live_reference():
+    from oracle import ref_import
+
+    if not ref_import.available():
+        pytest.skip("reference only exists in the build container")
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    EELUnet, EdgeLoss, _ = ref_import.load()
+    torch.manual_seed(0)
+    m = EELUnet(3, 1).double().train()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    xs, ys, _ = synth.batch(1, 128, 128, 3)
+    x, y = torch.from_numpy(xs).double(), torch.from_numpy(synth.soften(ys)).double()
+    seg, edges = m(x)
+    loss = EdgeLoss(1, 1)(edges, seg, y)
+    loss.backward()
+    l2, seg2, e2, grads, ns = O.train_step(sd, x, y)
+    assert abs(loss.item() - l2.item()) < 1e-12 and rel(seg2, seg.detach()) < 1e-12
+    for n, p in m.named_parameters():
+        if p.grad.norm().item() > 1e-9:
+            assert rel(grads[n], p.grad) < 1e-9, n
+    after = m.state_dict()
+    for k, v in ns.items():
+        assert rel(v, after[k]) < 1e-12, k
