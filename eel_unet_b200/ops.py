@@ -112,7 +112,10 @@ class Conv3x3(Function):
                 wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
                 call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
         dwp = torch.empty((3, 3, Cin, Cout), dtype=F32, device=x.device)
-        call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
+        if _tc_ok(x, Cin, Cout) and (Cin == 64 or Cin % 128 == 0):
+            call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, st)
+        else:
+            call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
         dw = _pack(dwp, (3, 2, 0, 1), F32)
         db = _colsum(dy, Cout)
         return dx, dw, db, None
@@ -154,7 +157,11 @@ class ConvT2x2(Function):
             else:
                 call("eel_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, dtype_code(x), st)
         dwp = torch.empty((Cin, 2, 2, Cout), dtype=F32, device=x.device)
-        call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
+        gw = min(w, 64)
+        if _tc_ok(x, Cin, Cout) and Cin % 128 == 0 and 64 % gw == 0 and w % gw == 0:
+            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwp), N * h * w, Cin, 4 * Cout, 4 * Cout, 1, dwp.numel(), w, st)
+        else:
+            call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
         dw = _pack(dwp, (0, 3, 1, 2), F32)
         db = _colsum(dy, Cout)
         return dx, dw, db
@@ -208,7 +215,12 @@ class Linear(Function):
                 w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
                 call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
         dw = torch.empty((Nout, K), dtype=F32, device=x.device)
-        call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
+        if ctx.tc and Nout % 128 == 0:
+            call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dw), P, Nout, K, K, 1, dw.numel(), 0, st)      # D[m=nout][n=k]
+        elif ctx.tc and K % 128 == 0:
+            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, 1, K, dw.numel(), 0, st)      # D[m=k][n=nout] -> dw[n][m]
+        else:
+            call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
         db = _colsum(dy, Nout)
         return dx, dw.view(weight.shape), db, None
 

@@ -86,6 +86,15 @@ int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* 
 /* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */
 int eel_tc_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h, int w, int Cin, int Cout,
                           eel_stream s);
+/* weight gradients on the tensor cores (reduction over pixels, fp32 accumulation in TMEM, split-K + fp32 atomics).
+ * conv: dwp:[3][3][Cin][Cout] fp32 (overwritten); Cin == 64 or Cin % 128 == 0; Cout % 64 == 0. */
+int eel_tc_conv3x3_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+                         eel_stream s);
+/* out[m*ldm + n*ldn] = sum_p a[p][m] * b[p][n]; a:[P][Ma], b:[P][Nb] bf16; Ma % 128 == 0, Nb % 64 == 0; the first
+ * out_elems floats of out are zeroed first.  gather_w > 0: b is a ConvTranspose2d(k2,s2) output-side tensor
+ * [N,2h,2w,Co] read through its input pixel p with columns (dy,dx,co), Nb = 4*Co, gather_w = w. */
+int eel_tc_wgrad(const void* a, const void* b, float* out, long long P, int Ma, int Nb, long long ldm,
+                 long long ldn, long long out_elems, int gather_w, eel_stream s);
 /* ShiftedChannel (models/EELUnet.py:88-97) as a standalone gather; inverse != 0 applies the adjoint shifts */
 int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int inverse, int dtype, eel_stream s);
 

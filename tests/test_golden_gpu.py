@@ -78,7 +78,9 @@ def test_loss_vs_reference_golden():
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) <= 2e-6 * float(g["loss"])
     for i, p in enumerate(preds):
-        assert rel(p.grad, g["grad%d" % i]) <= 1e-5
+        # fixture probabilities are fp64 and reach 1 - 1e-4: casting them to fp32 perturbs 1 - p by 6e-4 relative,
+        # which the BCE gradient 1 / (p (1 - p)) passes straight through
+        assert rel(p.grad, g["grad%d" % i]) <= 2e-4
 
 
 @pytest.mark.parametrize("name", ["edges_2x96x128.npz", "edges_2x37x53.npz", "edges_1x256x256.npz"])
