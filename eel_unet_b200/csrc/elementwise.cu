@@ -65,10 +65,25 @@ template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) 
     return p;
 }
 
+// same thread layout for pure streaming kernels: more row blocks (no partial buffer to bound them)
+template <class T> static RedPlan plan_stream(long long rows, int C) {
+    RedPlan p = plan_reduce<T>(rows, C, 1);
+    long long want = (8LL * kNumSMs) / p.ncb;
+    if (want < 1) want = 1;
+    long long maxrb = cdiv(rows, p.TY * 4);
+    if (maxrb < 1) maxrb = 1;
+    long long nrb = want < maxrb ? want : maxrb;
+    if (nrb > 65535) nrb = 65535;
+    p.nrb = (int)nrb;
+    p.rows_per_rb = (rows + nrb - 1) / nrb;
+    return p;
+}
+
 template <class T, class F, int Q>
 __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(const F f, long long rows, int C, int TX,
                                                               long long rows_per_rb, float* __restrict__ partial) {
     constexpr int V = Vec16<T>::N;
+    constexpr int U = 4;   // independent 16-byte loads in flight per thread and input tensor
     __shared__ float sm[kRedThreads][Q * V + 1];
     const int TY = kRedThreads / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
@@ -81,9 +96,18 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(const F f, long 
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[q][v] = 0.f;
     if (c0 < C) {
+        typename F::State stt = f.init(c0);
         long long r0 = rb * rows_per_rb, r1 = r0 + rows_per_rb;
         if (r1 > rows) r1 = rows;
-        for (long long r = r0 + ty; r < r1; r += TY) f.template accum<V>(b * rows + r, c0, acc);
+        for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
+            Vec16<T> in[U][F::NIN];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + (long long)u * TY < r1) f.load(b * rows + r + (long long)u * TY, c0, in[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + (long long)u * TY < r1) f.template accum<V>(stt, in[u], acc);
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q)
@@ -137,49 +161,74 @@ static int run_finalize(const float* partial, int nrb, int width, int batch, flo
     return check_launch(what);
 }
 
+struct NoState {};
+
 template <class T> struct SumF {
     const T* x; int C;
-    template <int V> __device__ void accum(long long r, int c0, float (&acc)[1][V]) const {
-        Vec16<T> v = ld16(x + r * C + c0);
+    static constexpr int NIN = 1;
+    typedef NoState State;
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(long long r, int c0, Vec16<T> (&in)[1]) const { in[0] = ld16(x + r * C + c0); }
+    template <int V> __device__ void accum(const State&, const Vec16<T> (&in)[1], float (&acc)[1][V]) const {
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[0][i] += v.get(i);
+        for (int i = 0; i < V; ++i) acc[0][i] += in[0].get(i);
     }
 };
 
 // sum of a*b (squeeze-excite backward: d att = sum_hw dout * t)
 template <class T> struct DotF {
     const T* a; const T* b; int C;
-    template <int V> __device__ void accum(long long r, int c0, float (&acc)[1][V]) const {
-        Vec16<T> va = ld16(a + r * C + c0), vb = ld16(b + r * C + c0);
+    static constexpr int NIN = 2;
+    typedef NoState State;
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(long long r, int c0, Vec16<T> (&in)[2]) const { in[0] = ld16(a + r * C + c0); in[1] = ld16(b + r * C + c0); }
+    template <int V> __device__ void accum(const State&, const Vec16<T> (&in)[2], float (&acc)[1][V]) const {
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[0][i] += va.get(i) * vb.get(i);
+        for (int i = 0; i < V; ++i) acc[0][i] += in[0].get(i) * in[1].get(i);
     }
 };
 
 // shifted moments for BatchNorm: d = z - z[0][c]  ->  sum d, sum d^2 (no catastrophic cancellation)
 template <class T> struct MomentF {
     const T* z; int C;
-    template <int V> __device__ void accum(long long r, int c0, float (&acc)[2][V]) const {
-        Vec16<T> v = ld16(z + r * C + c0), p = ld16(z + c0);
+    static constexpr int NIN = 1;
+    struct State { float pivot[Vec16<T>::N]; };
+    __device__ State init(int c0) const {
+        State s;
+        Vec16<T> p = ld16(z + c0);
+#pragma unroll
+        for (int i = 0; i < Vec16<T>::N; ++i) s.pivot[i] = p.get(i);
+        return s;
+    }
+    __device__ void load(long long r, int c0, Vec16<T> (&in)[1]) const { in[0] = ld16(z + r * C + c0); }
+    template <int V> __device__ void accum(const State& s, const Vec16<T> (&in)[1], float (&acc)[2][V]) const {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            float d = v.get(i) - p.get(i);
+            float d = in[0].get(i) - s.pivot[i];
             acc[0][i] += d;
             acc[1][i] += d * d;
         }
     }
 };
 
-// BatchNorm backward sums: g = dy * relu_mask;  sum g, sum g * xhat
+// BatchNorm backward sums: g = dy * relu_mask;  sum g, sum g * xhat.  Per-channel constants live in registers.
 template <class T> struct BnBwdF {
     const T* dy; const T* z; const float* mean; const float* rstd; const float* gamma; const float* beta; int C; int relu;
-    template <int V> __device__ void accum(long long r, int c0, float (&acc)[2][V]) const {
-        Vec16<T> vd = ld16(dy + r * C + c0), vz = ld16(z + r * C + c0);
+    static constexpr int NIN = 2;
+    struct State { float m[Vec16<T>::N], r[Vec16<T>::N], g[Vec16<T>::N], b[Vec16<T>::N]; };
+    __device__ State init(int c0) const {
+        State s;
+#pragma unroll
+        for (int i = 0; i < Vec16<T>::N; ++i) { s.m[i] = mean[c0 + i]; s.r[i] = rstd[c0 + i]; s.g[i] = gamma[c0 + i]; s.b[i] = beta[c0 + i]; }
+        return s;
+    }
+    __device__ void load(long long r, int c0, Vec16<T> (&in)[2]) const { in[0] = ld16(dy + r * C + c0); in[1] = ld16(z + r * C + c0); }
+    template <int V> __device__ void accum(const State& s, const Vec16<T> (&in)[2], float (&acc)[2][V]) const {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            float xh = (vz.get(i) - mean[c0 + i]) * rstd[c0 + i];
-            float g = vd.get(i);
-            if (relu && !(gamma[c0 + i] * xh + beta[c0 + i] > 0.f)) g = 0.f;
+            float xh = (in[1].get(i) - s.m[i]) * s.r[i];
+            float g = in[0].get(i);
+            if (relu && !(s.g[i] * xh + s.b[i] > 0.f)) g = 0.f;
             acc[0][i] += g;
             acc[1][i] += g * xh;
         }
@@ -217,45 +266,90 @@ __global__ void bn_eval_stats_kernel(const float* rmean, const float* rvar, floa
     rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
 }
 
+// Row-streaming layout shared by the BatchNorm apply kernels: a thread owns one 16-byte channel vector (its
+// per-channel constants stay in registers) and walks down the rows with 4 independent loads in flight.
+// grid = (channel-vector blocks, row blocks); block = TX x TY threads.
 template <class T>
-__global__ void bn_act_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, long long nvec, int C, int relu) {
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, long long rows, int C, int TX,
+                                                       long long rows_per_rb, int relu) {
     constexpr int V = Vec16<T>::N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        int c0 = (int)((i * V) % C);
-        Vec16<T> v = ld16(z + i * V), o;
+    constexpr int U = 4;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    if (c0 >= C) return;
+    float sc[V], sh[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float sc = gamma[c0 + j] * rstd[c0 + j];
-            float r = (v.get(j) - mean[c0 + j]) * sc + beta[c0 + j];
-            o.set(j, relu ? fmaxf(r, 0.f) : r);
-        }
-        st16(y + i * V, o);
+    for (int j = 0; j < V; ++j) {
+        sc[j] = gamma[c0 + j] * rstd[c0 + j];
+        sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    }
+    long long r0 = blockIdx.y * rows_per_rb, r1 = r0 + rows_per_rb;
+    if (r1 > rows) r1 = rows;
+    for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
+        Vec16<T> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + (long long)u * TY < r1) v[u] = ld16(z + (r + (long long)u * TY) * C + c0);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + (long long)u * TY < r1) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float t = fmaf(v[u].get(j), sc[j], sh[j]);
+                    o.set(j, relu ? fmaxf(t, 0.f) : t);
+                }
+                st16(y + (r + (long long)u * TY) * C + c0, o);
+            }
     }
 }
 
 // dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n)  (train)   or   gamma*rstd*g  (frozen statistics)
 template <class T>
-__global__ void bn_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
-                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ sums /* [2][C]: dbeta, dgamma */, float inv_count,
-                                  long long nvec, int C, int relu, int train) {
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ sums /* [2][C]: dbeta, dgamma */, float inv_count,
+                                                       long long rows, int C, int TX, long long rows_per_rb, int relu, int train) {
     constexpr int V = Vec16<T>::N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        int c0 = (int)((i * V) % C);
-        Vec16<T> vd = ld16(dy + i * V), vz = ld16(z + i * V), o;
+    constexpr int U = 4;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    if (c0 >= C) return;
+    float m[V], rs[V], gm[V], bt[V], k1[V], k2[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            int c = c0 + j;
-            float xh = (vz.get(j) - mean[c]) * rstd[c];
-            float g = vd.get(j);
-            if (relu && !(gamma[c] * xh + beta[c] > 0.f)) g = 0.f;
-            float r = train ? (g - sums[c] * inv_count - xh * sums[C + c] * inv_count) : g;
-            o.set(j, gamma[c] * rstd[c] * r);
-        }
-        st16(dz + i * V, o);
+    for (int j = 0; j < V; ++j) {
+        m[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; gm[j] = gamma[c0 + j]; bt[j] = beta[c0 + j];
+        k1[j] = train ? sums[c0 + j] * inv_count : 0.f;
+        k2[j] = train ? sums[C + c0 + j] * inv_count : 0.f;
+    }
+    long long r0 = blockIdx.y * rows_per_rb, r1 = r0 + rows_per_rb;
+    if (r1 > rows) r1 = rows;
+    for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
+        Vec16<T> vd[U], vz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + (long long)u * TY < r1) {
+                vd[u] = ld16(dy + (r + (long long)u * TY) * C + c0);
+                vz[u] = ld16(z + (r + (long long)u * TY) * C + c0);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + (long long)u * TY < r1) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float xh = (vz[u].get(j) - m[j]) * rs[j];
+                    float g = vd[u].get(j);
+                    if (relu && !(gm[j] * xh + bt[j] > 0.f)) g = 0.f;
+                    o.set(j, gm[j] * rs[j] * (g - k1[j] - xh * k2[j]));
+                }
+                st16(dz + (r + (long long)u * TY) * C + c0, o);
+            }
     }
 }
 
@@ -595,8 +689,9 @@ int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd,
     EEL_REQUIRE(z && y && mean && rstd && gamma && beta && P > 0 && C > 0, "bn_act_fwd: bad argument");
     EEL_DISPATCH_DTYPE(dtype, {
         EEL_VEC_CHECK(T, C, "bn_act_fwd");
-        long long nvec = P * C / Vec16<T>::N;
-        bn_act_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)y, mean, rstd, gamma, beta, nvec, C, relu);
+        RedPlan pl = plan_stream<T>(P, C);
+        dim3 grid(pl.ncb, pl.nrb);
+        bn_act_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)y, mean, rstd, gamma, beta, P, C, pl.TX, pl.rows_per_rb, relu);
         return check_launch("bn_act_fwd");
     });
 }
@@ -617,9 +712,10 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
         if (int rc = run_finalize(partial, pl.nrb, 2 * C, 1, sums, 1.0f, (cudaStream_t)s, "bn_act_bwd.finalize")) return rc;
         cudaMemcpyAsync(dbeta, sums, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
         cudaMemcpyAsync(dgamma, sums + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-        long long nvec = P * C / Vec16<T>::N;
-        bn_act_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma,
-                                                                           beta, sums, 1.0f / (float)P, nvec, C, relu, train);
+        RedPlan ps = plan_stream<T>(P, C);
+        dim3 grid(ps.ncb, ps.nrb);
+        bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
+                                                            1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train);
         return check_launch("bn_act_bwd");
     });
 }

@@ -95,7 +95,7 @@ def test_train_step_matches_oracle(precision):
         t = g64[name]
         if t.norm().item() < 1e-6 * gnorm:
             # analytically-zero gradients (conv bias in front of a train-mode BatchNorm): pure rounding noise
-            assert p.grad.norm().item() <= (1e-3 if precision == "fp32" else 2e-2) * gnorm, name
+            assert p.grad.norm().item() <= (1e-3 if precision == "fp32" else 1e-1) * gnorm, name
             continue
         mine, floor = rel(p.grad, t), rel(g32[name], t)
         ratios.append(mine / max(floor, 1e-7))
