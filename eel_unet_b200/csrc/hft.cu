@@ -110,6 +110,33 @@ struct BufEpi {
         }
     }
 };
+// same addressing, bf16 output (feeds the tensor-core step 4 of hft_tc.cu)
+struct BufEpiB {
+    bf16* out; long long zstride; int M, N; int rdiv; long long s0, s1;
+    __device__ void operator()(int z, int m, int n, const float (&acc)[kSimtTM][kSimtTN]) const {
+#pragma unroll
+        for (int i = 0; i < kSimtTM; ++i) {
+            if (m + i >= M) break;
+            bf16* row = out + (long long)z * zstride + (long long)((m + i) % rdiv) * s0 + (long long)((m + i) / rdiv) * s1;
+#pragma unroll
+            for (int j = 0; j < kSimtTN; ++j)
+                if (n + j < N) row[n + j] = __float2bfloat16_rn(acc[i][j]);
+        }
+    }
+};
+// out[i] = dy[pixel] * phase[pixel][re/im]  (complex upstream gradient as (re, im) row pairs)
+__global__ void hft_grad_pairs_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ph, bf16* __restrict__ g, long long nvec, int C) {
+    constexpr int V = 8;
+    const int cv = C / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        long long pix2 = i / cv;          // pixel * 2 + ri
+        int c = (int)(i - pix2 * cv) * V;
+        Vec16<bf16> a = ld16(dy + (pix2 >> 1) * C + c), b = ld16(ph + i * V), o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.set(j, a.get(j) * b.get(j));
+        st16(g + i * V, o);
+    }
+}
 // forward step 4: rows m = 2w + {re, im} of low;  y = |x - low|, phase = (x - low)/|x - low|
 template <class T> struct AbsEpi {
     const T* x; T* y; T* ph; int W, C;
@@ -180,7 +207,15 @@ static int hft_run(const SmallA& a, const BL& b, const Epi& e, int M, int N, int
     return launch_gemm_simt(p, st, what);
 }
 
-struct HftWs { float *Cw, *Sw, *Ch, *Sh, *T1, *T2; };
+namespace tc {
+bool hft_tc_supported(int H, int W, int C, int r);
+size_t hft_tc_matrix_elems(int W);
+int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, int N, int H, int W, int C, int r, cudaStream_t st);
+int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf16* y_or_dx, bf16* phase, int N, int H, int W, int C,
+                 int r, cudaStream_t st);
+}  // namespace tc
+
+struct HftWs { float *Cw, *Sw, *Ch, *Sh, *T1, *T2; bf16 *T3b, *G, *M1, *M4; };
 
 static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base) {
     int F = 2 * r;
@@ -188,10 +223,14 @@ static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base
     auto take = [&](size_t n) { size_t o = off; off += (n * sizeof(float) + 255) / 256 * 256; return o; };
     size_t oCw = take((size_t)F * W), oSw = take((size_t)F * W), oCh = take((size_t)F * H), oSh = take((size_t)F * H);
     size_t oT1 = take((size_t)N * H * 2 * F * C), oT2 = take((size_t)N * 2 * F * F * C);
+    // tensor-core path (bf16): T3 in bf16, the (re, im) gradient pairs, the two resident DFT matrices
+    size_t oT3b = take(((size_t)N * H * 2 * F * C + 1) / 2), oG = take((size_t)N * H * W * C);
+    size_t oM1 = take(((size_t)80 * 2 * W + 1) / 2), oM4 = take(((size_t)2 * W * 128 + 1) / 2);
     if (ws && base) {
         char* b = (char*)base;
         ws->Cw = (float*)(b + oCw); ws->Sw = (float*)(b + oSw); ws->Ch = (float*)(b + oCh); ws->Sh = (float*)(b + oSh);
         ws->T1 = (float*)(b + oT1); ws->T2 = (float*)(b + oT2);
+        ws->T3b = (bf16*)(b + oT3b); ws->G = (bf16*)(b + oG); ws->M1 = (bf16*)(b + oM1); ws->M4 = (bf16*)(b + oM4);
     }
     return off;
 }
@@ -204,7 +243,7 @@ static int hft_radius(int H, int W, int mask_range) {
 }
 
 // steps 2 and 3 are shared by forward and backward
-static int hft_middle(const HftWs& w, int N, int H, int C, int F, cudaStream_t st) {
+static int hft_middle(const HftWs& w, int N, int H, int C, int F, cudaStream_t st, bool t3_bf16 = false) {
     long long FC = (long long)F * C;
     {   // T2[n][(ro,g)][(f,c)] = sum_(ri,h) A2 * T1[n][h][ri*F+f][c]
         SmallA a{w.Ch, w.Sh, F, H, IDX_R_F, IDX_R_X, 1, 0, 2 * F, 2 * H};
@@ -215,6 +254,11 @@ static int hft_middle(const HftWs& w, int N, int H, int C, int F, cudaStream_t s
     {   // T3[n][h][ro*F+f][c] = sum_(ri,g) A3 * T2[n][(ri,g)][(f,c)]   (T3 aliases T1)
         SmallA a{w.Ch, w.Sh, F, H, IDX_R_X, IDX_R_F, 0, 1, 2 * H, 2 * F};
         BufB b{w.T2, 2 * F * FC, 2 * F, (int)FC, 2 * F, FC, 0};
+        if (t3_bf16) {
+            BufEpiB e{w.T3b, (long long)H * 2 * FC, 2 * H, (int)FC, H, 2 * FC, FC};
+            if (int rc = hft_run<BufB, BufEpiB, false>(a, b, e, 2 * H, (int)FC, 2 * F, N, st, "hft.step3(bf16)")) return rc;
+            return EEL_OK;
+        }
         BufEpi e{w.T1, (long long)H * 2 * FC, 2 * H, (int)FC, H, 2 * FC, FC};
         if (int rc = hft_run<BufB, BufEpi, false>(a, b, e, 2 * H, (int)FC, 2 * F, N, st, "hft.step3")) return rc;
     }
@@ -253,6 +297,12 @@ int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C,
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
     if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
+    if (dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, F / 2)) {
+        // bf16 mode: the two large projections run on the tensor cores (hft_tc.cu); the small H-axis steps stay SIMT fp32
+        if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, w.T1, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = hft_middle(w, N, H, C, F, st, true)) return rc;
+        return tc::hft_tc_step4(w.T3b, w.M4, true, (const bf16*)x, (bf16*)y, (bf16*)phase, N, H, W, C, F / 2, st);
+    }
     EEL_DISPATCH_DTYPE(dtype, {
         {   // T1[(n,h)][(ro,f)][c] = sum_w A1 * x[n,h,w,c],  A1 = [C; -S]
             SmallA a{w.Cw, w.Sw, F, W, IDX_R_F, IDX_X, 1, 0, 2 * F, W};
@@ -276,6 +326,16 @@ int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
     if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
+    if (dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, F / 2)) {
+        const long long nvec = (long long)N * H * W * 2 * C / 8;
+        long long blocks = (nvec + 255) / 256;
+        if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+        hft_grad_pairs_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)phase, w.G, nvec, C);
+        if (int rc = check_launch("hft_bwd.pairs")) return rc;
+        if (int rc = tc::hft_tc_step1(w.G, 2 * W, w.M1, 1, w.T1, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = hft_middle(w, N, H, C, F, st, true)) return rc;
+        return tc::hft_tc_step4(w.T3b, w.M4, false, w.G, (bf16*)dx, nullptr, N, H, W, C, F / 2, st);
+    }
     EEL_DISPATCH_DTYPE(dtype, {
         {   // complex input g = dy * phase, k = 2w + ri, A = [[C, S], [-S, C]]
             SmallA a{w.Cw, w.Sw, F, W, IDX_R_F, IDX_X_R, 1, 0, 2 * F, 2 * W};

@@ -1,0 +1,302 @@
+// HighFourierTransform on the tensor cores (bf16 mode): the two large projections of hft.cu -- step 1
+// (along W: [2F x W] . x[n,h]) and step 4 (back along W: [2W x 2F] . T3[n,h], fused with |x - low| or with the
+// gradient subtraction) -- as tcgen05 GEMMs whose M dimension is the CHANNEL axis of the NHWC tensor:
+//
+//     D[(row j, c)][col] = sum_k A[n, h0 + j, k, c] * Bmat[col][k]
+//
+// A (MN-major: channels contiguous, K = pixel / frequency rows) streams through a TMA ring; the small DFT matrix
+// Bmat (K-major, bf16) is loaded ONCE per CTA and stays resident in shared memory; the accumulators live in TMEM.
+// With C = 64 two image rows share one M = 128 tile, with C = 128 one row does.  Both steps are HBM-bound: x is
+// read once per step and y / phase are written once.
+#include "tc_common.cuh"
+
+namespace eel {
+namespace tc {
+
+enum { HEPI_T = 0, HEPI_ABS = 1, HEPI_SUB = 2 };
+
+struct HftTcParams {
+    int items;          // N * H / rows_per_item
+    int H, C, W;
+    int rows_per_item;  // 128 / C
+    int kchunks;        // ceil(K / 64)
+    int k16_last;       // MMAs (K = 16) in the last chunk
+    int nblocks;        // column blocks of NB
+    int n_stages;
+    int ncols;          // valid output columns (T step: 2F)
+    float* T;           // HEPI_T: fp32 [N][H][ncols][C]
+    const bf16* x;      // HEPI_ABS: input x [N,H,W,C];  HEPI_SUB: g [N,H,W,2,C]
+    bf16* y;            // HEPI_ABS: |z| ; HEPI_SUB: dx
+    bf16* phase;        // HEPI_ABS: z/|z| [N,H,W,2,C]
+};
+
+constexpr int kHThreads = 192;
+constexpr int kAStage = 16384;   // 2 atoms x 64 rows x 128 B
+
+template <int NB, int EPI>
+__global__ void __launch_bounds__(kHThreads, 1)
+hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HftTcParams p) {
+    constexpr int BT = NB * 128;   // bytes of one resident B tile (NB rows x 128 B)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.kchunks * p.nblocks * BT;
+    uint8_t* sB = smem;
+    uint8_t* sA = smem + ((b_bytes + 1023) & ~1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.n_stages * kAStage);
+    uint64_t* empty = full + p.n_stages;
+    uint64_t* bFull = empty + p.n_stages;
+    uint64_t* accFull = bFull + 1;     // [2]
+    uint64_t* accEmpty = accFull + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accEmpty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int acc_cols = p.nblocks * (NB == 80 ? 128 : NB);   // column pitch 128 for the 80-wide tiles
+    const int nacc = 2 * acc_cols <= 512 ? 2 : 1;
+    const uint32_t tmem_cols = nacc * acc_cols <= 128 ? 128 : (nacc * acc_cols <= 256 ? 256 : 512);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(bFull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        mbar_expect_tx(bFull, b_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int nb = 0; nb < p.nblocks; ++nb) tma_load_2d(sB + (kc * p.nblocks + nb) * BT, &tmB, bFull, kc * 64, nb * NB);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int hb = p.H / p.rows_per_item;
+            const int n = item / hb, h0 = (item - n * hb) * p.rows_per_item;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], kAStage);
+                uint8_t* a = sA + st * kAStage;
+                if (p.rows_per_item == 2) {
+                    tma_load_4d(a, &tmA, &full[st], 0, kc * 64, h0, n);
+                    tma_load_4d(a + 8192, &tmA, &full[st], 0, kc * 64, h0 + 1, n);
+                } else {
+                    tma_load_4d(a, &tmA, &full[st], 0, kc * 64, h0, n);
+                    tma_load_4d(a + 8192, &tmA, &full[st], 64, kc * 64, h0, n);
+                }
+                if (++st == p.n_stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================================== MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(128, NB, 1, 0);   // A: MN-major, B: K-major
+        mbar_wait(bFull, 0);
+        int st = 0, it = 0;
+        uint32_t ph = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            const int acc = nacc == 2 ? (it & 1) : 0;
+            const uint32_t par = nacc == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&accEmpty[acc], par ^ 1);
+            tc_fence_after();
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t a = smem_u32(sA + st * kAStage);
+                const int nk = kc == p.kchunks - 1 ? p.k16_last : 4;
+                for (int nb = 0; nb < p.nblocks; ++nb) {
+                    const uint32_t b = smem_u32(sB + (kc * p.nblocks + nb) * BT);
+                    const uint32_t d = tmem_base + acc * acc_cols + nb * (NB == 80 ? 128 : NB);
+                    for (int ks = 0; ks < nk; ++ks)
+                        umma_bf16(d, make_smem_desc(a + ks * 2048, 8192, 1024, false), make_smem_desc(b + ks * 32, 16, 1024, false),
+                                  idesc, (kc | ks) != 0);
+                }
+                umma_commit(&empty[st]);
+                if (++st == p.n_stages) { st = 0; ph ^= 1; }
+            }
+            umma_commit(&accFull[acc]);
+        }
+    } else if (warp >= 2) {
+        // ===================================================================== epilogue
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int j = p.rows_per_item == 2 ? (r >> 6) : 0;
+        const int c = p.rows_per_item == 2 ? (r & 63) : r;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            const int acc = nacc == 2 ? (it & 1) : 0;
+            const uint32_t par = nacc == 2 ? ((it >> 1) & 1) : (it & 1);
+            const int hb = p.H / p.rows_per_item;
+            const int n = item / hb, h = (item - n * hb) * p.rows_per_item + j;
+            const long long row = (long long)n * p.H + h;
+            mbar_wait(&accFull[acc], par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+            if (EPI == HEPI_T) {
+                float* dst = p.T + row * p.ncols * p.C + c;
+#pragma unroll 1
+                for (int cc = 0; cc < p.ncols; cc += 16) {
+                    float v[32];
+                    tmem_ld32(taddr + cc, v);    // reads 32 columns; only the first 16 are consumed per step (80 = 5 x 16)
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) dst[(long long)(cc + t) * p.C] = v[t];
+                }
+            } else {
+                const int total = p.nblocks * NB;
+#pragma unroll 1
+                for (int cc = 0; cc < total; cc += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + cc, v);
+                    if (EPI == HEPI_ABS) {
+                        // columns (w, re/im): 16 pixels per chunk
+                        const int w0 = cc >> 1;
+                        const long long base = (row * p.W + w0) * p.C + c;
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const long long e = base + (long long)t * p.C;
+                            float zr = __bfloat162float(p.x[e]) - v[2 * t];
+                            float zi = -v[2 * t + 1];
+                            float mag = sqrtf(zr * zr + zi * zi);
+                            float inv = mag > 0.f ? 1.0f / mag : 0.f;
+                            p.y[e] = __float2bfloat16_rn(mag);
+                            const long long pe = (e - c) * 2 + c;
+                            p.phase[pe] = __float2bfloat16_rn(zr * inv);
+                            p.phase[pe + p.C] = __float2bfloat16_rn(zi * inv);
+                        }
+                    } else {
+                        const long long base = (row * p.W + cc) * p.C + c;
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const long long e = base + (long long)t * p.C;
+                            float g = __bfloat162float(p.x[(e - c) * 2 + c]);   // real part of the (re, im) pair
+                            p.y[e] = __float2bfloat16_rn(g - v[t]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accEmpty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// real-expanded DFT matrices in bf16 (rows = output index, K contiguous, K padded to Kp)
+//   kind 0 (step 1 fwd):  rows (ro, f), cols w            [[C], [-S]]
+//   kind 1 (step 1 bwd):  rows (ro, f), cols 2w + ri      [[C, S], [-S, C]]
+//   kind 2 (step 4 fwd):  rows 2w + ro, cols ri*F + f     [[C, -S], [S, C]]
+//   kind 3 (step 4 bwd):  rows w,       cols ri*F + f     [C, -S]
+__global__ void hft_tc_matrix_kernel(bf16* __restrict__ out, int kind, int rows, int Kp, int F, int r, int W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * Kp) return;
+    const int row = i / Kp, k = i - row * Kp;
+    int f = -1, w = 0, ro = 0, ri = 0;
+    if (kind == 0) { ro = row / F; f = row % F; if (k < W) w = k; else f = -1; }
+    else if (kind == 1) { ro = row / F; f = row % F; if (k < 2 * W) { w = k >> 1; ri = k & 1; } else f = -1; }
+    else if (kind == 2) { w = row >> 1; ro = row & 1; if (k < 2 * F) { ri = k / F; f = k % F; } }
+    else { w = row; ro = 0; if (k < 2 * F) { ri = k / F; f = k % F; } }
+    float v = 0.f;
+    if (f >= 0) {
+        long long kk = f - r;
+        long long ph = ((kk * w) % W + W) % W;
+        double s, c;
+        sincospi(2.0 * (double)ph / (double)W, &s, &c);
+        const double sc = 1.0 / sqrt((double)W);
+        const bool useS = ro != ri;
+        const bool table1 = kind >= 2;
+        double val = useS ? s : c;
+        if (useS && (table1 ? (ro == 0) : (ro == 1))) val = -val;
+        v = (float)(val * sc);
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+template <int NB, int EPI>
+static int launch_hft(const CUtensorMap& a, const CUtensorMap& b, HftTcParams& p, cudaStream_t st, const char* what) {
+    static bool configured = false;
+    const int kMax = 227 * 1024;
+    if (!configured) {
+        if (cudaFuncSetAttribute(hft_tc_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory", what);
+            return EEL_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int b_bytes = ((p.kchunks * p.nblocks * NB * 128) + 1023) & ~1023;
+    int ns = (kMax - 2048 - 1024 - b_bytes) / kAStage;
+    if (ns > 8) ns = 8;
+    if (ns < 2) { set_error("%s: resident matrix leaves no room for the operand ring", what); return EEL_ERR_INVALID; }
+    p.n_stages = ns;
+    const int smem = b_bytes + ns * kAStage + 2048 + 1024;
+    const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+    hft_tc_kernel<NB, EPI><<<grid, kHThreads, smem, st>>>(a, b, p);
+    return check_launch(what);
+}
+
+static int make_a_map(CUtensorMap* m, const void* base, int C, int R, int H, int N, const char* what) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)R, (uint64_t)H, (uint64_t)N};
+    uint64_t str[4] = {1, (uint64_t)C, (uint64_t)R * C, (uint64_t)H * R * C};
+    uint32_t box[4] = {64, 64, 1, 1};
+    return make_tmap_bf16(m, base, 4, dims, str, box, what);
+}
+static int make_b_map(CUtensorMap* m, const void* base, int Kp, int rows, int nb, const char* what) {
+    uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)rows};
+    uint64_t str[2] = {1, (uint64_t)Kp};
+    uint32_t box[2] = {64, (uint32_t)nb};
+    return make_tmap_bf16(m, base, 2, dims, str, box, what);
+}
+
+bool hft_tc_supported(int H, int W, int C, int r) {
+    return (C == 64 || C == 128) && r == 20 && W % 64 == 0 && W <= 256 && W >= 128 && H % 2 == 0;
+}
+
+size_t hft_tc_matrix_elems(int W) { return (size_t)80 * 2 * W + (size_t)2 * W * 128; }
+
+// step 1: T[n][h][2F][c] (fp32) = Bmat . rows, rows = x (R = W, kind 0) or g pairs (R = 2W, kind 1)
+int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, int N, int H, int W, int C, int r, cudaStream_t st) {
+    const int F = 2 * r;
+    const int Kp = (R + 63) / 64 * 64;
+    hft_tc_matrix_kernel<<<cdiv(2 * F * Kp, 256), 256, 0, st>>>(mat_ws, kind, 2 * F, Kp, F, r, W);
+    if (int rc = check_launch("hft_tc.matrix1")) return rc;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_a_map(&tmA, rows_in, C, R, H, N, "hft_tc.step1(A)")) return rc;
+    if (int rc = make_b_map(&tmB, mat_ws, Kp, 2 * F, 2 * F, "hft_tc.step1(B)")) return rc;
+    HftTcParams p{};
+    p.rows_per_item = 128 / C;
+    p.items = N * H / p.rows_per_item;
+    p.H = H; p.C = C; p.W = W;
+    p.kchunks = Kp / 64; p.k16_last = 4;
+    p.nblocks = 1; p.ncols = 2 * F; p.T = T;
+    return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step1");
+}
+
+// step 4: low = Bmat . T3b[n,h] (K = 2F);  fwd: y = |x - low|, phase;  bwd: dx = g_re - Re(low)
+int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf16* y_or_dx, bf16* phase, int N, int H, int W, int C,
+                 int r, cudaStream_t st) {
+    const int F = 2 * r;
+    const int rows = fwd ? 2 * W : W;
+    hft_tc_matrix_kernel<<<cdiv(rows * 128, 256), 256, 0, st>>>(mat_ws, fwd ? 2 : 3, rows, 128, F, r, W);
+    if (int rc = check_launch("hft_tc.matrix4")) return rc;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_a_map(&tmA, T3b, C, 2 * F, H, N, "hft_tc.step4(A)")) return rc;
+    if (int rc = make_b_map(&tmB, mat_ws, 128, rows, 128, "hft_tc.step4(B)")) return rc;
+    HftTcParams p{};
+    p.rows_per_item = 128 / C;
+    p.items = N * H / p.rows_per_item;
+    p.H = H; p.C = C; p.W = W;
+    p.kchunks = 2; p.k16_last = (2 * F - 64) / 16;
+    p.nblocks = rows / 128;
+    p.x = x_or_g; p.y = y_or_dx; p.phase = phase;
+    if (fwd) return launch_hft<128, HEPI_ABS>(tmA, tmB, p, st, "hft_tc.step4_fwd");
+    return launch_hft<128, HEPI_SUB>(tmA, tmB, p, st, "hft_tc.step4_bwd");
+}
+
+}  // namespace tc
+}  // namespace eel
