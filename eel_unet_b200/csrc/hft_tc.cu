@@ -145,38 +145,6 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                     for (int t = 0; t < 16; ++t) dst[(long long)(cc + t) * p.C] = v[t];
                 }
-            } else {
-                const int total = p.nblocks * NB;
-#pragma unroll 1
-                for (int cc = 0; cc < total; cc += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + cc, v);
-                    if (EPI == HEPI_ABS) {
-                        // columns (w, re/im): 16 pixels per chunk
-                        const int w0 = cc >> 1;
-                        const long long base = (row * p.W + w0) * p.C + c;
-#pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const long long e = base + (long long)t * p.C;
-                            float zr = __bfloat162float(p.x[e]) - v[2 * t];
-                            float zi = -v[2 * t + 1];
-                            float mag = sqrtf(zr * zr + zi * zi);
-                            float inv = mag > 0.f ? 1.0f / mag : 0.f;
-                            p.y[e] = __float2bfloat16_rn(mag);
-                            const long long pe = (e - c) * 2 + c;
-                            p.phase[pe] = __float2bfloat16_rn(zr * inv);
-                            p.phase[pe + p.C] = __float2bfloat16_rn(zi * inv);
-                        }
-                    } else {
-                        const long long base = (row * p.W + cc) * p.C + c;
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const long long e = base + (long long)t * p.C;
-                            float g = __bfloat162float(p.x[(e - c) * 2 + c]);   // real part of the (re, im) pair
-                            p.y[e] = __float2bfloat16_rn(g - v[t]);
-                        }
-                    }
-                }
             }
             tc_fence_before();
             __syncwarp();
@@ -186,6 +154,196 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- step 4 with the PIXEL axis as M -------------------------------------------------------------------------
+// D[(w, re/im)][c] = sum_k Bmat[(w, re/im)][k] * T3b[n, h, k, c].  The DFT matrix (K-major, rows = output pixels) is
+// the resident A operand, T3b[n,h] (MN-major, N = C) streams.  A thread of the epilogue owns one (pixel, re/im) row and
+// 32 consecutive channels, so x / y / phase move as 64-byte vectors; re and im of a pixel sit in adjacent lanes and
+// meet through one shuffle.
+struct Hft4Params {
+    int items;        // N * H
+    int H, W, C;
+    int mtiles;       // rows / 128
+    int stage_bytes;  // 2 k-chunks x (C/64) atoms x 8192
+    int n_stages;
+    int nacc;         // accumulator slots of C columns
+    const bf16* x;    // fwd: x [N,H,W,C];  bwd: g [N,H,W,2,C]
+    bf16* y;          // fwd: |z|;  bwd: dx
+    bf16* phase;      // fwd: z/|z| [N,H,W,2,C]
+};
+
+template <int C, bool FWD>
+__global__ void __launch_bounds__(kHThreads, 1)
+hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmT, const Hft4Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int m_bytes = p.mtiles * 2 * 16384;
+    uint8_t* sM = smem;                 // [mtile][kchunk][128 rows x 128 B]
+    uint8_t* sT = smem + m_bytes;       // ring of T3b[n,h]: [kchunk][atom][64 rows x 128 B]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sT + p.n_stages * p.stage_bytes);
+    uint64_t* empty = full + p.n_stages;
+    uint64_t* mFull = empty + p.n_stages;
+    uint64_t* accFull = mFull + 1;      // [8]
+    uint64_t* accEmpty = accFull + 8;   // [8]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accEmpty + 8);
+    constexpr int ATOMS = C / 64;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmM);
+        tma_prefetch_desc(&tmT);
+        for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(mFull, 1);
+        for (int i = 0; i < 8; ++i) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        mbar_expect_tx(mFull, m_bytes);
+        for (int mt = 0; mt < p.mtiles; ++mt)
+            for (int kc = 0; kc < 2; ++kc) tma_load_2d(sM + (mt * 2 + kc) * 16384, &tmM, mFull, kc * 64, mt * 128);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int n = item / p.H, h = item - n * p.H;
+            mbar_wait(&empty[st], ph ^ 1);
+            mbar_expect_tx(&full[st], p.stage_bytes);
+            uint8_t* t = sT + st * p.stage_bytes;
+            for (int kc = 0; kc < 2; ++kc)
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(t + (kc * ATOMS + a) * 8192, &tmT, &full[st], a * 64, kc * 64, h, n);
+            if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A: K-major (matrix), B: MN-major (T3b)
+        mbar_wait(mFull, 0);
+        int st = 0;
+        uint32_t ph = 0;
+        long long tile_no = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            const uint32_t t = smem_u32(sT + st * p.stage_bytes);
+            for (int mt = 0; mt < p.mtiles; ++mt, ++tile_no) {
+                const int slot = (int)(tile_no % p.nacc);
+                const uint32_t par = (uint32_t)((tile_no / p.nacc) & 1);
+                mbar_wait(&accEmpty[slot], par ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + slot * C;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {      // K = 80 = 5 x 16: chunk 0 holds k-steps 0..3, chunk 1 k-step 4
+                    const int kc = k >> 2, ks = k & 3;
+                    const uint32_t a = smem_u32(sM + (mt * 2 + kc) * 16384) + ks * 32;
+                    const uint32_t b = t + kc * ATOMS * 8192 + ks * 2048;
+                    umma_bf16(d, make_smem_desc(a, 16, 1024, false), make_smem_desc(b, 8192, 1024, false), idesc, k != 0);
+                }
+                umma_commit(&accFull[slot]);
+            }
+            umma_commit(&empty[st]);
+            if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        long long tile_no = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int n = item / p.H, h = item - n * p.H;
+            const long long rowbase = ((long long)n * p.H + h) * p.W;
+            for (int mt = 0; mt < p.mtiles; ++mt, ++tile_no) {
+                const int slot = (int)(tile_no % p.nacc);
+                const uint32_t par = (uint32_t)((tile_no / p.nacc) & 1);
+                mbar_wait(&accFull[slot], par);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * C;
+                const int m = mt * 128 + r;
+#pragma unroll 1
+                for (int cc = 0; cc < C; cc += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + cc, v);
+                    if (FWD) {
+                        const int w = m >> 1, ro = m & 1;
+                        const long long e = (rowbase + w) * C + cc;
+                        float mine[32];
+                        if (ro == 0) {
+                            const uint4* xp = reinterpret_cast<const uint4*>(p.x + e);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                Vec16<bf16> xv; xv.raw = xp[i];
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) mine[i * 8 + jj] = xv.get(jj) - v[i * 8 + jj];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) mine[i] = -v[i];
+                        }
+                        Vec16<bf16> om[4], op[4];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float other = __shfl_xor_sync(0xffffffffu, mine[i], 1);
+                            const float mag = sqrtf(mine[i] * mine[i] + other * other);
+                            const float inv = mag > 0.f ? 1.0f / mag : 0.f;
+                            om[i >> 3].set(i & 7, mag);
+                            op[i >> 3].set(i & 7, mine[i] * inv);
+                        }
+                        uint4* pp = reinterpret_cast<uint4*>(p.phase + ((rowbase + w) * 2 + ro) * C + cc);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) pp[i] = op[i].raw;
+                        if (ro == 0) {
+                            uint4* yp = reinterpret_cast<uint4*>(p.y + e);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) yp[i] = om[i].raw;
+                        }
+                    } else {
+                        const long long e = (rowbase + m) * C + cc;
+                        const uint4* gp = reinterpret_cast<const uint4*>(p.x + ((rowbase + m) * 2) * C + cc);   // real half of the pair
+                        uint4* dp = reinterpret_cast<uint4*>(p.y + e);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            Vec16<bf16> gv, o; gv.raw = gp[i];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) o.set(jj, gv.get(jj) - v[i * 8 + jj]);
+                            dp[i] = o.raw;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accEmpty[slot]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int C, bool FWD>
+static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p, cudaStream_t st, const char* what) {
+    static bool configured = false;
+    const int kMax = 227 * 1024;
+    if (!configured) {
+        if (cudaFuncSetAttribute(hft_tc4_kernel<C, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory", what);
+            return EEL_ERR_CUDA;
+        }
+        configured = true;
+    }
+    p.stage_bytes = 2 * (C / 64) * 8192;
+    p.nacc = 512 / C;
+    const int m_bytes = p.mtiles * 2 * 16384;
+    int ns = (kMax - 3072 - m_bytes) / p.stage_bytes;
+    if (ns > 6) ns = 6;
+    if (ns < 2) { set_error("%s: resident matrix leaves no room for the operand ring", what); return EEL_ERR_INVALID; }
+    p.n_stages = ns;
+    const int smem = m_bytes + ns * p.stage_bytes + 3072;
+    const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+    hft_tc4_kernel<C, FWD><<<grid, kHThreads, smem, st>>>(m, t, p);
+    return check_launch(what);
 }
 
 // real-expanded DFT matrices in bf16 (rows = output index, K contiguous, K padded to Kp)
@@ -254,7 +412,7 @@ static int make_b_map(CUtensorMap* m, const void* base, int Kp, int rows, int nb
 }
 
 bool hft_tc_supported(int H, int W, int C, int r) {
-    return (C == 64 || C == 128) && r == 20 && W % 64 == 0 && W <= 256 && W >= 128 && H % 2 == 0;
+    return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256) && H % 2 == 0;
 }
 
 size_t hft_tc_matrix_elems(int W) { return (size_t)80 * 2 * W + (size_t)2 * W * 128; }
@@ -284,18 +442,16 @@ int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf
     const int rows = fwd ? 2 * W : W;
     hft_tc_matrix_kernel<<<cdiv(rows * 128, 256), 256, 0, st>>>(mat_ws, fwd ? 2 : 3, rows, 128, F, r, W);
     if (int rc = check_launch("hft_tc.matrix4")) return rc;
-    CUtensorMap tmA, tmB;
-    if (int rc = make_a_map(&tmA, T3b, C, 2 * F, H, N, "hft_tc.step4(A)")) return rc;
-    if (int rc = make_b_map(&tmB, mat_ws, 128, rows, 128, "hft_tc.step4(B)")) return rc;
-    HftTcParams p{};
-    p.rows_per_item = 128 / C;
-    p.items = N * H / p.rows_per_item;
-    p.H = H; p.C = C; p.W = W;
-    p.kchunks = 2; p.k16_last = (2 * F - 64) / 16;
-    p.nblocks = rows / 128;
+    CUtensorMap tmM, tmT;
+    if (int rc = make_b_map(&tmM, mat_ws, 128, rows, 128, "hft_tc.step4(M)")) return rc;
+    if (int rc = make_a_map(&tmT, T3b, C, 2 * F, H, N, "hft_tc.step4(T)")) return rc;
+    Hft4Params p{};
+    p.items = N * H;
+    p.H = H; p.W = W; p.C = C;
+    p.mtiles = rows / 128;
     p.x = x_or_g; p.y = y_or_dx; p.phase = phase;
-    if (fwd) return launch_hft<128, HEPI_ABS>(tmA, tmB, p, st, "hft_tc.step4_fwd");
-    return launch_hft<128, HEPI_SUB>(tmA, tmB, p, st, "hft_tc.step4_bwd");
+    if (C == 64) return fwd ? launch_hft4<64, true>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<64, false>(tmM, tmT, p, st, "hft_tc.step4_bwd");
+    return fwd ? launch_hft4<128, true>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<128, false>(tmM, tmT, p, st, "hft_tc.step4_bwd");
 }
 
 }  // namespace tc
