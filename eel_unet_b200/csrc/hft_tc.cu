@@ -173,8 +173,10 @@ struct Hft4Params {
     bf16* phase;      // fwd: z/|z| [N,H,W,2,C]
 };
 
+constexpr int kH4Threads = 320;   // TMA warp, MMA warp, two epilogue warpgroups of 4 warps that alternate tiles
+
 template <int C, bool FWD>
-__global__ void __launch_bounds__(kHThreads, 1)
+__global__ void __launch_bounds__(kH4Threads, 1)
 hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmT, const Hft4Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -249,19 +251,30 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         }
     } else if (warp >= 2) {
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;     // epilogue warpgroup 0 / 1
         const int r = q * 32 + lane;
         long long tile_no = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const int n = item / p.H, h = item - n * p.H;
             const long long rowbase = ((long long)n * p.H + h) * p.W;
             for (int mt = 0; mt < p.mtiles; ++mt, ++tile_no) {
+                if ((int)(tile_no & 1) != grp) continue;
                 const int slot = (int)(tile_no % p.nacc);
                 const uint32_t par = (uint32_t)((tile_no / p.nacc) & 1);
+                const int m = mt * 128 + r;
+                // the global operand of the epilogue (x, or the real half of g) is fetched BEFORE waiting for the MMAs
+                uint4 pre[C / 8];
+                {
+                    const bf16* src = FWD ? p.x + (rowbase + (m >> 1)) * C : p.x + ((rowbase + m) * 2) * C;
+                    if (!FWD || (m & 1) == 0) {
+#pragma unroll
+                        for (int i = 0; i < C / 8; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
+                    }
+                }
                 mbar_wait(&accFull[slot], par);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * C;
-                const int m = mt * 128 + r;
-#pragma unroll 1
+#pragma unroll
                 for (int cc = 0; cc < C; cc += 32) {
                     float v[32];
                     tmem_ld32(taddr + cc, v);
@@ -270,10 +283,9 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                         const long long e = (rowbase + w) * C + cc;
                         float mine[32];
                         if (ro == 0) {
-                            const uint4* xp = reinterpret_cast<const uint4*>(p.x + e);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                Vec16<bf16> xv; xv.raw = xp[i];
+                                Vec16<bf16> xv; xv.raw = pre[cc / 8 + i];
 #pragma unroll
                                 for (int jj = 0; jj < 8; ++jj) mine[i * 8 + jj] = xv.get(jj) - v[i * 8 + jj];
                             }
@@ -300,11 +312,10 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                         }
                     } else {
                         const long long e = (rowbase + m) * C + cc;
-                        const uint4* gp = reinterpret_cast<const uint4*>(p.x + ((rowbase + m) * 2) * C + cc);   // real half of the pair
                         uint4* dp = reinterpret_cast<uint4*>(p.y + e);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            Vec16<bf16> gv, o; gv.raw = gp[i];
+                            Vec16<bf16> gv, o; gv.raw = pre[cc / 8 + i];   // real half of the (re, im) pair
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) o.set(jj, gv.get(jj) - v[i * 8 + jj]);
                             dp[i] = o.raw;
@@ -342,7 +353,7 @@ static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p
     p.n_stages = ns;
     const int smem = m_bytes + ns * p.stage_bytes + 3072;
     const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-    hft_tc4_kernel<C, FWD><<<grid, kHThreads, smem, st>>>(m, t, p);
+    hft_tc4_kernel<C, FWD><<<grid, kH4Threads, smem, st>>>(m, t, p);
     return check_launch(what);
 }
 
