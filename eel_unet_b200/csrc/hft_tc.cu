@@ -297,8 +297,9 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float other = __shfl_xor_sync(0xffffffffu, mine[i], 1);
-                            const float mag = sqrtf(mine[i] * mine[i] + other * other);
-                            const float inv = mag > 0.f ? 1.0f / mag : 0.f;
+                            const float sq = mine[i] * mine[i] + other * other;
+                            const float inv = sq > 0.f ? rsqrtf(sq) : 0.f;
+                            const float mag = sq * inv;
                             om[i >> 3].set(i & 7, mag);
                             op[i >> 3].set(i & 7, mine[i] * inv);
                         }
