@@ -145,7 +145,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from eel_unet_b200 import EELUnet, _lib, edge_BceDiceLoss, profiling
     from eel_unet_b200.parallel import DataParallel, FusedAdam
@@ -222,12 +223,13 @@ def run_ours(args):
 
     # ---- per-kernel CUDA-event profile of one more step (rank 0): roofline of the dominant kernel ----
     roof, breakdown = None, None
+    rec = []
     if rank == 0:
-        rec = []
         _lib.set_profiler(rec)
-        step(x_dev, y_dev)
-        _lib.set_profiler(None)
-        torch.cuda.synchronize()
+    step(x_dev, y_dev)            # every rank runs it: the step contains collectives
+    _lib.set_profiler(None)
+    barrier()
+    if rank == 0:
         fam = profiling.summarize(rec)
         rows = profiling.table(fam, hbm, tens_sus)
         breakdown = [{"kernel": r[0], "calls": r[1], "ms": round(r[2], 3), "share": round(r[3], 2), "tflops": round(r[4], 2),
