@@ -313,22 +313,27 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ d
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ sums /* [2][C]: dbeta, dgamma */, float inv_count,
-                                                       long long rows, int C, int TX, long long rows_per_rb, int relu, int train) {
+                                                       long long rows, int C, int TX, long long rows_per_rb, int relu, int train,
+                                                       float* __restrict__ dzsum /* [C] or null: += column sums of dz */) {
     constexpr int V = Vec16<T>::N;
     constexpr int U = 4;
+    __shared__ float red[256][V + 1];
     const int TY = 256 / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c0 = (blockIdx.x * TX + tx) * V;
-    if (c0 >= C) return;
-    float m[V], rs[V], gm[V], bt[V], k1[V], k2[V];
+    const bool live = c0 < C;
+    float m[V], rs[V], gm[V], bt[V], k1[V], k2[V], cs[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        m[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; gm[j] = gamma[c0 + j]; bt[j] = beta[c0 + j];
-        k1[j] = train ? sums[c0 + j] * inv_count : 0.f;
-        k2[j] = train ? sums[C + c0 + j] * inv_count : 0.f;
+        const int c = live ? c0 + j : 0;
+        m[j] = mean[c]; rs[j] = rstd[c]; gm[j] = gamma[c]; bt[j] = beta[c];
+        k1[j] = train ? sums[c] * inv_count : 0.f;
+        k2[j] = train ? sums[C + c] * inv_count : 0.f;
+        cs[j] = 0.f;
     }
     long long r0 = blockIdx.y * rows_per_rb, r1 = r0 + rows_per_rb;
     if (r1 > rows) r1 = rows;
+    if (!live) r1 = r0;
     for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
         Vec16<T> vd[U], vz[U];
 #pragma unroll
@@ -346,10 +351,25 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ d
                     float xh = (vz[u].get(j) - m[j]) * rs[j];
                     float g = vd[u].get(j);
                     if (relu && !(gm[j] * xh + bt[j] > 0.f)) g = 0.f;
-                    o.set(j, gm[j] * rs[j] * (g - k1[j] - xh * k2[j]));
+                    const float dzv = gm[j] * rs[j] * (g - k1[j] - xh * k2[j]);
+                    cs[j] += dzv;
+                    o.set(j, dzv);
                 }
                 st16(dz + (r + (long long)u * TY) * C + c0, o);
             }
+    }
+    if (dzsum != nullptr) {   // bias gradient of the producing conv / linear, for free
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[threadIdx.x][j] = cs[j];
+        __syncthreads();
+        if (ty == 0 && live) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float t = 0.f;
+                for (int y = 0; y < TY; ++y) t += red[y * TX + tx][j];
+                atomicAdd(dzsum + c0 + j, t);
+            }
+        }
     }
 }
 
@@ -697,8 +717,8 @@ int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd,
 }
 
 int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
-                   const float* beta, void* dz, float* dgamma, float* dbeta, long long P, int C, int relu, int train,
-                   void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+                   const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, long long P, int C, int relu,
+                   int train, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
     EEL_REQUIRE(dy && z && mean && rstd && gamma && beta && dz && dgamma && dbeta && P > 0 && C > 0, "bn_act_bwd: bad argument");
     EEL_REQUIRE(ws_bytes >= sizeof(float) * 2 * (size_t)C, "bn_act_bwd: workspace too small");
     EEL_DISPATCH_DTYPE(dtype, {
@@ -714,8 +734,9 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
         cudaMemcpyAsync(dgamma, sums + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
         RedPlan ps = plan_stream<T>(P, C);
         dim3 grid(ps.ncb, ps.nrb);
+        if (dz_colsum != nullptr) cudaMemsetAsync(dz_colsum, 0, sizeof(float) * C, (cudaStream_t)s);
         bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
-                                                            1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train);
+                                                            1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train, dz_colsum);
         return check_launch("bn_act_bwd");
     });
 }

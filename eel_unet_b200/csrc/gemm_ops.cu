@@ -218,6 +218,77 @@ static int pick_splits(long long M, long long N, long long K) {
     return (int)(s < 1 ? 1 : (s > 4096 ? 4096 : s));
 }
 
+// ------------------------------------------------------------------------------------ stem weight gradient
+// conv3x3 wgrad for the 3(4)-channel input layer (K = 27: far too thin for a GEMM tile): one block walks image rows,
+// the three input rows live in shared memory, a thread owns 4 output channels x all 9*CIN taps in registers.
+template <class T, int CIN>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwp,
+                                                        int N, int H, int W, int Cout) {
+    extern __shared__ float sh[];
+    float* xs = sh;                               // [3][W + 2][CIN]
+    float* sdw = sh + 3 * (W + 2) * CIN;          // [9 * CIN][64]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int cb = 0; cb < Cout; cb += 64) {
+        float acc[9 * CIN][4];
+#pragma unroll
+        for (int k = 0; k < 9 * CIN; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+        for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+            const int n = row / H, h = row - n * H;
+            __syncthreads();
+            for (int i = threadIdx.x; i < 3 * (W + 2) * CIN; i += 256) {
+                int c = i % CIN, r = i / CIN;
+                int ww = r % (W + 2) - 1, hh = h + r / (W + 2) - 1;
+                float v = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = to_f32(x[(((long long)n * H + hh) * W + ww) * CIN + c]);
+                xs[i] = v;
+            }
+            __syncthreads();
+            const T* drow = dy + ((long long)row * W) * Cout + cb + tx * 4;
+            for (int w = ty; w < W; w += 16) {
+                float d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = to_f32(drow[(long long)w * Cout + j]);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float* xp = xs + ((t / 3) * (W + 2) + w + (t % 3)) * CIN;
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float xv = xp[c];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[t * CIN + c][j] = fmaf(xv, d[j], acc[t * CIN + c][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * CIN * 64; i += 256) sdw[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 9 * CIN; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(&sdw[k * 64 + tx * 4 + j], acc[k][j]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * CIN * 64; i += 256) atomicAdd(dwp + (long long)(i / 64) * Cout + cb + (i % 64), sdw[i]);
+    }
+}
+
+template <class T, int CIN>
+static int launch_stem_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cout, cudaStream_t st) {
+    size_t smem = sizeof(float) * (3 * (size_t)(W + 2) * CIN + 9 * CIN * 64);
+    if (smem > 200 * 1024) return 1;   // caller falls back to the generic engine
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(stem_wgrad_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    int rows = N * H;
+    int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
+    stem_wgrad_kernel<T, CIN><<<grid, 256, smem, st>>>((const T*)x, (const T*)dy, dwp, N, H, W, Cout);
+    return check_launch("conv3x3_wgrad(stem)");
+}
+
 }  // namespace eel
 
 using namespace eel;
@@ -244,6 +315,14 @@ int eel_conv3x3_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
     if (cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * Cin * Cout, (cudaStream_t)s) != cudaSuccess) {
         set_error("conv3x3_wgrad: memset failed");
         return EEL_ERR_CUDA;
+    }
+    if ((Cin == 3 || Cin == 4) && Cout % 64 == 0) {
+        int rc = 1;
+        if (dtype == EEL_F32) rc = Cin == 3 ? launch_stem_wgrad<float, 3>(x, dy, dwp, N, H, W, Cout, (cudaStream_t)s)
+                                            : launch_stem_wgrad<float, 4>(x, dy, dwp, N, H, W, Cout, (cudaStream_t)s);
+        else if (dtype == EEL_BF16) rc = Cin == 3 ? launch_stem_wgrad<bf16, 3>(x, dy, dwp, N, H, W, Cout, (cudaStream_t)s)
+                                                  : launch_stem_wgrad<bf16, 4>(x, dy, dwp, N, H, W, Cout, (cudaStream_t)s);
+        if (rc <= 0) return rc;
     }
     EEL_DISPATCH_DTYPE(dtype, {
         Conv3Acc<T> a{(const T*)x, N, H, W, Cin, 0};

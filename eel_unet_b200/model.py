@@ -148,14 +148,16 @@ class EELUnet(nn.Module):
 
     # ---- fused stages ------------------------------------------------------------------------
     @staticmethod
-    def _bn(bn, z, relu):
+    def _bn(bn, z, relu, producer_bias=True):
         training = bn.training or bn.running_mean is None
         if training and bn.track_running_stats:
             if bn.momentum is None:
                 raise EelError("BatchNorm momentum=None (cumulative average) is not used by the reference and not supported")
             bn.num_batches_tracked += 1
+        # producer_bias: z comes straight from a biased conv / linear, whose bias gradient (= column sums of dz) the
+        # BatchNorm backward then delivers for free
         return ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu,
-                               bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias)
 
     @staticmethod
     def _capmlp(m, x):
@@ -200,7 +202,7 @@ class EELUnet(nn.Module):
         enc4 = self._mlp_conv_block(self.enc4[0], ops.MaxPool2.apply(enc3))
 
         bt = self.bottleneck
-        b = self._bn(bt[0], ops.MaxPool2.apply(enc4), False)
+        b = self._bn(bt[0], ops.MaxPool2.apply(enc4), False, producer_bias=False)
         b = ops.Conv3x3.apply(b, bt[1].weight, bt[1].bias, True)
         b = ops.Relu.apply(self._capmlp(bt[3], b))
         b, edge_5 = self._pgr(self.pred5, b)

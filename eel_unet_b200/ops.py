@@ -39,7 +39,15 @@ def _reduce_ws(device, channels, quantities, extra=0):
     return workspace(n, device), n
 
 
+# bias gradients that a BatchNorm backward already produced (column sums of dz), keyed by the dz buffer address.
+# An entry is written only when the BN's producer is a biased conv / linear whose backward runs next and pops it.
+_DZ_COLSUM = {}
+
+
 def _colsum(x2d, C):
+    hit = _DZ_COLSUM.pop(x2d.data_ptr(), None)
+    if hit is not None and hit.numel() == C:
+        return hit
     out = torch.empty(C, dtype=F32, device=x2d.device)
     ws, n = _reduce_ws(x2d.device, C, 1)
     call("eel_colsum", ptr(x2d), ptr(out), x2d.numel() // C, C, ptr(ws), n, dtype_code(x2d), stream())
@@ -230,7 +238,7 @@ class BNAct(Function):
     """nn.BatchNorm2d [+ nn.ReLU] (reference models/EELUnet.py:339-344,352-357,365,373,256)."""
 
     @staticmethod
-    def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps):
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps, producer_bias=False):
         z = _c(z)
         C = z.shape[-1]
         P = z.numel() // C
@@ -247,7 +255,7 @@ class BNAct(Function):
         y = torch.empty_like(z)
         g, b = gamma.detach(), beta.detach()
         call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
-        ctx.relu, ctx.training = relu, training
+        ctx.relu, ctx.training, ctx.producer_bias = relu, training, producer_bias
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
         return y
 
@@ -261,9 +269,13 @@ class BNAct(Function):
         dgamma = torch.empty(C, dtype=F32, device=z.device)
         dbeta = torch.empty(C, dtype=F32, device=z.device)
         ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+        dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
         call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
-             ptr(dgamma), ptr(dbeta), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
-        return dz, dgamma, dbeta, None, None, None, None, None, None
+             ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
+        if dzsum is not None:
+            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
+            _DZ_COLSUM[dz.data_ptr()] = dzsum
+        return dz, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class Relu(Function):

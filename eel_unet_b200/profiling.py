@@ -68,7 +68,7 @@ def cost(name, a):
         P, C, dt = a[6], a[7], a[9]
         return 4.0 * P * C, 2 * P * C * _esz(dt)
     if n == "bn_act_bwd":
-        P, C, dt = a[9], a[10], a[15]
+        P, C, dt = a[10], a[11], a[16]
         return 12.0 * P * C, 3 * P * C * _esz(dt)
     if n in ("maxpool2_fwd", "maxpool2_bwd"):
         if n == "maxpool2_fwd":

@@ -113,10 +113,11 @@ int eel_bn_eval_stats(const float* running_mean, const float* running_var, float
 /* y = [relu](gamma * (z - mean) * rstd + beta) */
 int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, long long P, int C, int relu, int dtype, eel_stream s);
-/* train != 0: batch-statistics backward; train == 0: frozen statistics */
+/* train != 0: batch-statistics backward; train == 0: frozen statistics.
+ * dz_colsum (nullable, [C]): receives sum_p dz[p][c] = the bias gradient of the conv / linear that produced z. */
 int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
-                   const float* beta, void* dz, float* dgamma, float* dbeta, long long P, int C, int relu,
-                   int train, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+                   const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, long long P, int C,
+                   int relu, int train, void* ws, size_t ws_bytes, int dtype, eel_stream s);
 
 /* ------------------------------------------------------------------ fused bandwidth-bound ops */
 /* nn.MaxPool2d(2) (models/EELUnet.py:391,396,401,406); x:[N,H,W,C] -> y:[N,H/2,W/2,C] */

@@ -172,7 +172,7 @@ def test_bn_act(dtype, relu, training):
     rrm, rrv = rm0.double(), rv0.double()
 
     def mine(a, p):
-        return ops.BNAct.apply(a[0], p[0], p[1], rm, rv, training, relu, 0.1, 1e-5)
+        return ops.BNAct.apply(a[0], p[0], p[1], rm, rv, training, relu, 0.1, 1e-5, False)
 
     def ref(a, p):
         y = F.batch_norm(a[0], rrm, rrv, p[0], p[1], training, 0.1, 1e-5)
