@@ -54,7 +54,7 @@ template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) 
     p.TX = cv >= 32 ? 32 : (cv >= 16 ? 16 : (cv >= 8 ? 8 : (cv >= 4 ? 4 : (cv >= 2 ? 2 : 1))));
     p.TY = kRedThreads / p.TX;
     p.ncb = cdiv(cv, p.TX);
-    long long want = (4LL * kNumSMs) / ((long long)p.ncb * batch);
+    long long want = (8LL * kNumSMs) / ((long long)p.ncb * batch);
     if (want < 1) want = 1;
     long long maxrb = cdiv(rows, p.TY * 4);
     if (maxrb < 1) maxrb = 1;

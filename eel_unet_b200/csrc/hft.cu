@@ -210,12 +210,14 @@ static int hft_run(const SmallA& a, const BL& b, const Epi& e, int M, int N, int
 namespace tc {
 bool hft_tc_supported(int H, int W, int C, int r);
 size_t hft_tc_matrix_elems(int W);
-int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, int N, int H, int W, int C, int r, cudaStream_t st);
+int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, bf16* Tb, int N, int H, int W, int C, int r, cudaStream_t st);
+int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, int N, int H, int C, int r, cudaStream_t st);
+int hft_tc_step3(const bf16* T2b, bf16* mat_ws, bf16* T3b, int N, int H, int C, int r, cudaStream_t st);
 int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf16* y_or_dx, bf16* phase, int N, int H, int W, int C,
                  int r, cudaStream_t st);
 }  // namespace tc
 
-struct HftWs { float *Cw, *Sw, *Ch, *Sh, *T1, *T2; bf16 *T3b, *G, *M1, *M4; };
+struct HftWs { float *Cw, *Sw, *Ch, *Sh, *T1, *T2; bf16 *T3b, *G, *M1, *M4, *M2, *M3; };
 
 static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base) {
     int F = 2 * r;
@@ -226,11 +228,12 @@ static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base
     // tensor-core path (bf16): T3 in bf16, the (re, im) gradient pairs, the two resident DFT matrices
     size_t oT3b = take(((size_t)N * H * 2 * F * C + 1) / 2), oG = take((size_t)N * H * W * C);
     size_t oM1 = take(((size_t)80 * 2 * W + 1) / 2), oM4 = take(((size_t)2 * W * 128 + 1) / 2);
+    size_t oM2 = take(((size_t)80 * 2 * H + 1) / 2), oM3 = take(((size_t)2 * H * 128 + 1) / 2);
     if (ws && base) {
         char* b = (char*)base;
         ws->Cw = (float*)(b + oCw); ws->Sw = (float*)(b + oSw); ws->Ch = (float*)(b + oCh); ws->Sh = (float*)(b + oSh);
         ws->T1 = (float*)(b + oT1); ws->T2 = (float*)(b + oT2);
-        ws->T3b = (bf16*)(b + oT3b); ws->G = (bf16*)(b + oG); ws->M1 = (bf16*)(b + oM1); ws->M4 = (bf16*)(b + oM4);
+        ws->T3b = (bf16*)(b + oT3b); ws->G = (bf16*)(b + oG); ws->M1 = (bf16*)(b + oM1); ws->M4 = (bf16*)(b + oM4); ws->M2 = (bf16*)(b + oM2); ws->M3 = (bf16*)(b + oM3);
     }
     return off;
 }
@@ -299,8 +302,10 @@ int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C,
     if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
     if (dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, F / 2)) {
         // bf16 mode: the two large projections run on the tensor cores (hft_tc.cu); the small H-axis steps stay SIMT fp32
-        if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, w.T1, N, H, W, C, F / 2, st)) return rc;
-        if (int rc = hft_middle(w, N, H, C, F, st, true)) return rc;
+        // every step on the tensor cores; T1 / T2 / T3 live in bf16 (the fp32 regions T1, T2 are reused as storage)
+        if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, nullptr, (bf16*)w.T1, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, N, H, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step3((const bf16*)w.T2, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
         return tc::hft_tc_step4(w.T3b, w.M4, true, (const bf16*)x, (bf16*)y, (bf16*)phase, N, H, W, C, F / 2, st);
     }
     EEL_DISPATCH_DTYPE(dtype, {
@@ -332,8 +337,9 @@ int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W
         if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
         hft_grad_pairs_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)phase, w.G, nvec, C);
         if (int rc = check_launch("hft_bwd.pairs")) return rc;
-        if (int rc = tc::hft_tc_step1(w.G, 2 * W, w.M1, 1, w.T1, N, H, W, C, F / 2, st)) return rc;
-        if (int rc = hft_middle(w, N, H, C, F, st, true)) return rc;
+        if (int rc = tc::hft_tc_step1(w.G, 2 * W, w.M1, 1, nullptr, (bf16*)w.T1, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, N, H, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step3((const bf16*)w.T2, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
         return tc::hft_tc_step4(w.T3b, w.M4, false, w.G, (bf16*)dx, nullptr, N, H, W, C, F / 2, st);
     }
     EEL_DISPATCH_DTYPE(dtype, {

@@ -24,7 +24,12 @@ struct HftTcParams {
     int nblocks;        // column blocks of NB
     int n_stages;
     int ncols;          // valid output columns (T step: 2F)
-    float* T;           // HEPI_T: fp32 [N][H][ncols][C]
+    int mode;           // 0: step 1 (rows of x / g);  1: step 2 (T1b[n] with K = (re/im, h), M = 128-blocks of (f, c))
+    int mtiles;         // mode 1: 128-blocks of the F*C axis
+    int hc;             // mode 1: 64-row chunks per re/im half (H / 64)
+    long long Cst;      // output channel extent (C, or F*C in mode 1)
+    float* T;           // fp32 output [rows][ncols][Cst] (or null)
+    bf16* Tb;           // bf16 output, same layout (or null)
     const bf16* x;      // HEPI_ABS: input x [N,H,W,C];  HEPI_SUB: g [N,H,W,2,C]
     bf16* y;            // HEPI_ABS: |z| ; HEPI_SUB: dx
     bf16* phase;        // HEPI_ABS: z/|z| [N,H,W,2,C]
@@ -76,13 +81,17 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const int hb = p.H / p.rows_per_item;
+            const int hb = p.mode == 0 ? p.H / p.rows_per_item : p.mtiles;
             const int n = item / hb, h0 = (item - n * hb) * p.rows_per_item;
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 mbar_wait(&empty[st], ph ^ 1);
                 mbar_expect_tx(&full[st], kAStage);
                 uint8_t* a = sA + st * kAStage;
-                if (p.rows_per_item == 2) {
+                if (p.mode == 1) {
+                    const int mt = item - n * hb;
+                    tma_load_4d(a, &tmA, &full[st], mt * 128, (kc % p.hc) * 64, kc / p.hc, n);
+                    tma_load_4d(a + 8192, &tmA, &full[st], mt * 128 + 64, (kc % p.hc) * 64, kc / p.hc, n);
+                } else if (p.rows_per_item == 2) {
                     tma_load_4d(a, &tmA, &full[st], 0, kc * 64, h0, n);
                     tma_load_4d(a + 8192, &tmA, &full[st], 0, kc * 64, h0 + 1, n);
                 } else {
@@ -130,20 +139,27 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             const int acc = nacc == 2 ? (it & 1) : 0;
             const uint32_t par = nacc == 2 ? ((it >> 1) & 1) : (it & 1);
-            const int hb = p.H / p.rows_per_item;
-            const int n = item / hb, h = (item - n * hb) * p.rows_per_item + j;
-            const long long row = (long long)n * p.H + h;
+            const int hb = p.mode == 0 ? p.H / p.rows_per_item : p.mtiles;
+            const int n = item / hb;
+            long long row, ch;
+            if (p.mode == 0) { row = (long long)n * p.H + (item - n * hb) * p.rows_per_item + j; ch = c; }
+            else { row = n; ch = (long long)(item - n * hb) * 128 + r; }
             mbar_wait(&accFull[acc], par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
             if (EPI == HEPI_T) {
-                float* dst = p.T + row * p.ncols * p.C + c;
+                const long long off = row * p.ncols * p.Cst + ch;
 #pragma unroll 1
                 for (int cc = 0; cc < p.ncols; cc += 16) {
                     float v[32];
                     tmem_ld32(taddr + cc, v);    // reads 32 columns; only the first 16 are consumed per step (80 = 5 x 16)
+                    if (p.Tb != nullptr) {
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) dst[(long long)(cc + t) * p.C] = v[t];
+                        for (int t = 0; t < 16; ++t) p.Tb[off + (long long)(cc + t) * p.Cst] = __float2bfloat16_rn(v[t]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) p.T[off + (long long)(cc + t) * p.Cst] = v[t];
+                    }
                 }
             }
             tc_fence_before();
@@ -169,13 +185,17 @@ struct Hft4Params {
     int n_stages;
     int nacc;         // accumulator slots of C columns
     const bf16* x;    // fwd: x [N,H,W,C];  bwd: g [N,H,W,2,C]
-    bf16* y;          // fwd: |z|;  bwd: dx
+    bf16* y;          // fwd: |z|;  bwd: dx;  step 3: T3b [N][H][2F][Cc]
     bf16* phase;      // fwd: z/|z| [N,H,W,2,C]
+    int ntiles;       // step 3: 128-blocks of the F*Cc axis (items = N * ntiles)
+    int F, Cc;        // step 3: frequencies, channels
 };
+
+enum { H4_FWD = 0, H4_BWD = 1, H4_T3 = 2 };
 
 constexpr int kH4Threads = 320;   // TMA warp, MMA warp, two epilogue warpgroups of 4 warps that alternate tiles
 
-template <int C, bool FWD>
+template <int C, int EPI>
 __global__ void __launch_bounds__(kH4Threads, 1)
 hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmT, const Hft4Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -190,6 +210,8 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     uint64_t* accEmpty = accFull + 8;   // [8]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accEmpty + 8);
     constexpr int ATOMS = C / 64;
+    constexpr bool FWD = EPI == H4_FWD;
+    const int idiv = EPI == H4_T3 ? p.ntiles : p.H;   // items = N * idiv
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -213,12 +235,15 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const int n = item / p.H, h = item - n * p.H;
+            const int n = item / idiv, h = item - n * idiv;
             mbar_wait(&empty[st], ph ^ 1);
             mbar_expect_tx(&full[st], p.stage_bytes);
             uint8_t* t = sT + st * p.stage_bytes;
             for (int kc = 0; kc < 2; ++kc)
-                for (int a = 0; a < ATOMS; ++a) tma_load_4d(t + (kc * ATOMS + a) * 8192, &tmT, &full[st], a * 64, kc * 64, h, n);
+                for (int a = 0; a < ATOMS; ++a) {
+                    if (EPI == H4_T3) tma_load_4d(t + (kc * ATOMS + a) * 8192, &tmT, &full[st], h * 128 + a * 64, kc * 64, 0, n);
+                    else tma_load_4d(t + (kc * ATOMS + a) * 8192, &tmT, &full[st], a * 64, kc * 64, h, n);
+                }
             if (++st == p.n_stages) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
@@ -255,13 +280,38 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int r = q * 32 + lane;
         long long tile_no = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const int n = item / p.H, h = item - n * p.H;
+            const int n = item / idiv, h = item - n * idiv;
             const long long rowbase = ((long long)n * p.H + h) * p.W;
             for (int mt = 0; mt < p.mtiles; ++mt, ++tile_no) {
                 if ((int)(tile_no & 1) != grp) continue;
                 const int slot = (int)(tile_no % p.nacc);
                 const uint32_t par = (uint32_t)((tile_no / p.nacc) & 1);
                 const int m = mt * 128 + r;
+                if (EPI == H4_T3) {
+                    // rows m = (re/im, h'), columns = 128 of the (f, c) axis: T3b[n][h'][ro*F + f][c]
+                    mbar_wait(&accFull[slot], par);
+                    tc_fence_after();
+                    const uint32_t taddr3 = tmem_base + ((uint32_t)(q * 32) << 16) + slot * C;
+                    const int ro = m / p.H, hh = m - ro * p.H;
+                    bf16* dst = p.y + (((long long)n * p.H + hh) * 2 * p.F + (long long)ro * p.F) * p.Cc + (long long)h * 128;
+#pragma unroll
+                    for (int cc = 0; cc < C; cc += 32) {
+                        float v[32];
+                        tmem_ld32(taddr3 + cc, v);
+                        uint4* dp = reinterpret_cast<uint4*>(dst + cc);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            Vec16<bf16> o;
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) o.set(jj, v[i * 8 + jj]);
+                            dp[i] = o.raw;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[slot]);
+                    continue;
+                }
                 // the global operand of the epilogue (x, or the real half of g) is fetched BEFORE waiting for the MMAs
                 uint4 pre[C / 8];
                 {
@@ -334,12 +384,12 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int C, bool FWD>
+template <int C, int EPI>
 static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p, cudaStream_t st, const char* what) {
     static bool configured = false;
     const int kMax = 227 * 1024;
     if (!configured) {
-        if (cudaFuncSetAttribute(hft_tc4_kernel<C, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
+        if (cudaFuncSetAttribute(hft_tc4_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
             set_error("%s: cannot raise dynamic shared memory", what);
             return EEL_ERR_CUDA;
         }
@@ -354,7 +404,7 @@ static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p
     p.n_stages = ns;
     const int smem = m_bytes + ns * p.stage_bytes + 3072;
     const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-    hft_tc4_kernel<C, FWD><<<grid, kH4Threads, smem, st>>>(m, t, p);
+    hft_tc4_kernel<C, EPI><<<grid, kH4Threads, smem, st>>>(m, t, p);
     return check_launch(what);
 }
 
@@ -371,7 +421,9 @@ __global__ void hft_tc_matrix_kernel(bf16* __restrict__ out, int kind, int rows,
     if (kind == 0) { ro = row / F; f = row % F; if (k < W) w = k; else f = -1; }
     else if (kind == 1) { ro = row / F; f = row % F; if (k < 2 * W) { w = k >> 1; ri = k & 1; } else f = -1; }
     else if (kind == 2) { w = row >> 1; ro = row & 1; if (k < 2 * F) { ri = k / F; f = k % F; } }
-    else { w = row; ro = 0; if (k < 2 * F) { ri = k / F; f = k % F; } }
+    else if (kind == 3) { w = row; ro = 0; if (k < 2 * F) { ri = k / F; f = k % F; } }
+    else if (kind == 4) { ro = row / W; w = row % W; if (k < 2 * F) { ri = k / F; f = k % F; } }
+    else { ro = row / F; f = row % F; if (k < 2 * W) { ri = k / W; w = k % W; } else f = -1; }
     float v = 0.f;
     if (f >= 0) {
         long long kk = f - r;
@@ -380,7 +432,7 @@ __global__ void hft_tc_matrix_kernel(bf16* __restrict__ out, int kind, int rows,
         sincospi(2.0 * (double)ph / (double)W, &s, &c);
         const double sc = 1.0 / sqrt((double)W);
         const bool useS = ro != ri;
-        const bool table1 = kind >= 2;
+        const bool table1 = kind >= 2 && kind <= 4;
         double val = useS ? s : c;
         if (useS && (table1 ? (ro == 0) : (ro == 1))) val = -val;
         v = (float)(val * sc);
@@ -424,13 +476,13 @@ static int make_b_map(CUtensorMap* m, const void* base, int Kp, int rows, int nb
 }
 
 bool hft_tc_supported(int H, int W, int C, int r) {
-    return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256) && H % 2 == 0;
+    return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256) && (H == 128 || H == 256);
 }
 
 size_t hft_tc_matrix_elems(int W) { return (size_t)80 * 2 * W + (size_t)2 * W * 128; }
 
 // step 1: T[n][h][2F][c] (fp32) = Bmat . rows, rows = x (R = W, kind 0) or g pairs (R = 2W, kind 1)
-int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, int N, int H, int W, int C, int r, cudaStream_t st) {
+int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, bf16* Tb, int N, int H, int W, int C, int r, cudaStream_t st) {
     const int F = 2 * r;
     const int Kp = (R + 63) / 64 * 64;
     hft_tc_matrix_kernel<<<cdiv(2 * F * Kp, 256), 256, 0, st>>>(mat_ws, kind, 2 * F, Kp, F, r, W);
@@ -443,8 +495,55 @@ int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, i
     p.items = N * H / p.rows_per_item;
     p.H = H; p.C = C; p.W = W;
     p.kchunks = Kp / 64; p.k16_last = 4;
-    p.nblocks = 1; p.ncols = 2 * F; p.T = T;
+    p.nblocks = 1; p.ncols = 2 * F; p.T = T; p.Tb = Tb; p.Cst = C; p.mode = 0;
     return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step1");
+}
+
+// step 2: T2b[n][(ro,g)][(f,c)] = sum_(ri,h) A2[(ro,g)][(ri,h)] * T1b[n][h][ri*F + f][c]      (bf16 in, bf16 out)
+int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, int N, int H, int C, int r, cudaStream_t st) {
+    const int F = 2 * r;
+    const long long FC = (long long)F * C;
+    hft_tc_matrix_kernel<<<cdiv(2 * F * 2 * H, 256), 256, 0, st>>>(mat_ws, 5, 2 * F, 2 * H, F, r, H);
+    if (int rc = check_launch("hft_tc.matrix2")) return rc;
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {(uint64_t)FC, (uint64_t)H, 2, (uint64_t)N};
+        uint64_t str[4] = {1, (uint64_t)(2 * FC), (uint64_t)FC, (uint64_t)H * 2 * FC};
+        uint32_t box[4] = {64, 64, 1, 1};
+        if (int rc = make_tmap_bf16(&tmA, T1b, 4, dims, str, box, "hft_tc.step2(A)")) return rc;
+    }
+    if (int rc = make_b_map(&tmB, mat_ws, 2 * H, 2 * F, 2 * F, "hft_tc.step2(B)")) return rc;
+    HftTcParams p{};
+    p.rows_per_item = 1;
+    p.mode = 1; p.mtiles = (int)(FC / 128); p.hc = H / 64;
+    p.items = N * p.mtiles;
+    p.H = H; p.C = C;
+    p.kchunks = 2 * H / 64; p.k16_last = 4;
+    p.nblocks = 1; p.ncols = 2 * F; p.Tb = T2b; p.Cst = FC;
+    return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step2");
+}
+
+// step 3: T3b[n][h][ro*F + f][c] = sum_(ri,g) A3[(ro,h)][(ri,g)] * T2b[n][(ri,g)][(f,c)]
+int hft_tc_step3(const bf16* T2b, bf16* mat_ws, bf16* T3b, int N, int H, int C, int r, cudaStream_t st) {
+    const int F = 2 * r;
+    const long long FC = (long long)F * C;
+    hft_tc_matrix_kernel<<<cdiv(2 * H * 128, 256), 256, 0, st>>>(mat_ws, 4, 2 * H, 128, F, r, H);
+    if (int rc = check_launch("hft_tc.matrix3")) return rc;
+    CUtensorMap tmM, tmT;
+    if (int rc = make_b_map(&tmM, mat_ws, 128, 2 * H, 128, "hft_tc.step3(M)")) return rc;
+    {
+        uint64_t dims[4] = {(uint64_t)FC, (uint64_t)(2 * F), 1, (uint64_t)N};
+        uint64_t str[4] = {1, (uint64_t)FC, (uint64_t)(2 * F) * FC, (uint64_t)(2 * F) * FC};
+        uint32_t box[4] = {64, 64, 1, 1};
+        if (int rc = make_tmap_bf16(&tmT, T2b, 4, dims, str, box, "hft_tc.step3(T)")) return rc;
+    }
+    Hft4Params p{};
+    p.ntiles = (int)(FC / 128);
+    p.items = N * p.ntiles;
+    p.H = H; p.W = 0; p.C = 128;
+    p.mtiles = 2 * H / 128;
+    p.y = T3b; p.F = F; p.Cc = C;
+    return launch_hft4<128, H4_T3>(tmM, tmT, p, st, "hft_tc.step3");
 }
 
 // step 4: low = Bmat . T3b[n,h] (K = 2F);  fwd: y = |x - low|, phase;  bwd: dx = g_re - Re(low)
@@ -462,8 +561,8 @@ int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf
     p.H = H; p.W = W; p.C = C;
     p.mtiles = rows / 128;
     p.x = x_or_g; p.y = y_or_dx; p.phase = phase;
-    if (C == 64) return fwd ? launch_hft4<64, true>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<64, false>(tmM, tmT, p, st, "hft_tc.step4_bwd");
-    return fwd ? launch_hft4<128, true>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<128, false>(tmM, tmT, p, st, "hft_tc.step4_bwd");
+    if (C == 64) return fwd ? launch_hft4<64, H4_FWD>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<64, H4_BWD>(tmM, tmT, p, st, "hft_tc.step4_bwd");
+    return fwd ? launch_hft4<128, H4_FWD>(tmM, tmT, p, st, "hft_tc.step4_fwd") : launch_hft4<128, H4_BWD>(tmM, tmT, p, st, "hft_tc.step4_bwd");
 }
 
 }  // namespace tc
