@@ -44,7 +44,7 @@ __global__ void permute4_kernel(const TI* __restrict__ in, TO* __restrict__ out,
 // partial[b][rb][q][c] = sum over the rows of row-block rb (of image-batch b) of f.q-th quantity.
 // Threads: TX lanes across channel vectors, TY = 256/TX across rows.
 constexpr int kRedThreads = 256;
-constexpr int kRedMaxRowBlocks = 1024;
+constexpr int kRedMaxRowBlocks = 4096;
 
 struct RedPlan { int TX, TY, ncb, nrb; long long rows_per_rb; };
 
@@ -59,7 +59,7 @@ template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) 
     long long maxrb = cdiv(rows, p.TY * 4);
     if (maxrb < 1) maxrb = 1;
     long long nrb = want < maxrb ? want : maxrb;
-    if (nrb > kRedMaxRowBlocks) nrb = kRedMaxRowBlocks;
+    if (nrb * batch > kRedMaxRowBlocks) nrb = kRedMaxRowBlocks / batch > 0 ? kRedMaxRowBlocks / batch : 1;
     p.nrb = (int)nrb;
     p.rows_per_rb = (rows + nrb - 1) / nrb;
     return p;
