@@ -125,15 +125,25 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(const F f, long 
     }
 }
 
-// out[b][j] = scale * sum_rb partial[b][rb][j]   (fp64 accumulation)
-__global__ void finalize_partials_kernel(const float* __restrict__ partial, int nrb, int width, float* __restrict__ out,
-                                         float scale) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int b = blockIdx.y;
-    if (j >= width) return;
+// out[b][j] = scale * sum_rb partial[b][rb][j]   (fp64 accumulation).  Block = 32 columns x 32 row-slices: the sum over
+// row blocks is itself parallel (a serial loop over ~1000 partials per column was a ~100 us latency chain per call).
+__global__ void __launch_bounds__(1024) finalize_partials_kernel(const float* __restrict__ partial, int nrb, int width,
+                                                               float* __restrict__ out, float scale) {
+    __shared__ double sm[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    const int b = blockIdx.y;
     double s = 0.0;
-    for (int r = 0; r < nrb; ++r) s += (double)partial[((long long)b * nrb + r) * width + j];
-    out[(long long)b * width + j] = (float)(s * scale);
+    if (j < width)
+        for (int r = ty; r < nrb; r += 32) s += (double)partial[((long long)b * nrb + r) * width + j];
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sm[y][tx];
+        out[(long long)b * width + j] = (float)(t * scale);
+    }
 }
 
 template <class T, class F, int Q>
@@ -156,8 +166,8 @@ static int run_colreduce(const F& f, long long rows, int C, int batch, float* pa
 
 static int run_finalize(const float* partial, int nrb, int width, int batch, float* out, float scale, cudaStream_t st,
                         const char* what) {
-    dim3 grid(cdiv(width, 128), batch);
-    finalize_partials_kernel<<<grid, 128, 0, st>>>(partial, nrb, width, out, scale);
+    dim3 grid(cdiv(width, 32), batch);
+    finalize_partials_kernel<<<grid, 1024, 0, st>>>(partial, nrb, width, out, scale);
     return check_launch(what);
 }
 
@@ -236,15 +246,25 @@ template <class T> struct BnBwdF {
 };
 
 template <class T>
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nrb, int C, const T* __restrict__ z, double count,
-                                   float* mean, float* rstd, float* rmean, float* rvar, float momentum, float eps) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nrb, int C, const T* __restrict__ z,
+                                                         double count, float* mean, float* rstd, float* rmean, float* rvar,
+                                                         float momentum, float eps) {
+    __shared__ double sm1[32][33], sm2[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < nrb; ++r) {
-        s1 += (double)partial[((long long)r * 2 + 0) * C + c];
-        s2 += (double)partial[((long long)r * 2 + 1) * C + c];
-    }
+    if (c < C)
+        for (int r = ty; r < nrb; r += 32) {
+            s1 += (double)partial[((long long)r * 2 + 0) * C + c];
+            s2 += (double)partial[((long long)r * 2 + 1) * C + c];
+        }
+    sm1[ty][tx] = s1;
+    sm2[ty][tx] = s2;
+    __syncthreads();
+    if (ty != 0 || c >= C) return;
+    s1 = 0.0; s2 = 0.0;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) { s1 += sm1[y][tx]; s2 += sm2[y][tx]; }
     double pivot = (double)to_f32(z[c]);
     double md = s1 / count;
     double var = s2 / count - md * md;
@@ -691,7 +711,7 @@ int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, fl
         RedPlan pl;
         MomentF<T> f{(const T*)z, C};
         if (int rc = run_colreduce<T, MomentF<T>, 2>(f, P, C, 1, (float*)ws, ws_bytes, pl, (cudaStream_t)s, "bn_stats")) return rc;
-        bn_finalize_kernel<T><<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>((const float*)ws, pl.nrb, C, (const T*)z, (double)P, mean,
+        bn_finalize_kernel<T><<<cdiv(C, 32), 1024, 0, (cudaStream_t)s>>>((const float*)ws, pl.nrb, C, (const T*)z, (double)P, mean,
                                                                       rstd, running_mean, running_var, momentum, eps);
         return check_launch("bn_stats.finalize");
     });

@@ -11,12 +11,22 @@ __device__ __forceinline__ float group_sum(float v, int G) {
     return v;
 }
 
-__global__ void finalize_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= width) return;
+// block = 32 columns x 32 row-slices (parallel over the per-block partial rows)
+__global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+    __shared__ double sm[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
     double s = 0.0;
-    for (int r = 0; r < nrows; ++r) s += (double)partial[(long long)r * width + j];
-    out[j] = (float)s;
+    if (j < width)
+        for (int r = ty; r < nrows; r += 32) s += (double)partial[(long long)r * width + j];
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sm[y][tx];
+        out[j] = (float)t;
+    }
 }
 
 constexpr int kPixThreads = 256;
@@ -318,7 +328,7 @@ int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy,
         pgr_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * (C + 1), (cudaStream_t)s>>>((const T*)x, sgm, w, (const T*)dy, dsgm,
                                                                                         (T*)dx, partial, P, C, G);
         if (int rc = check_launch("pgr_bwd")) return rc;
-        finalize_rows_kernel<<<cdiv(C + 1, 128), 128, 0, (cudaStream_t)s>>>(partial, grid, C + 1, fin);
+        finalize_rows_kernel<<<cdiv(C + 1, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, C + 1, fin);
         if (int rc = check_launch("pgr_bwd.finalize")) return rc;
         cudaMemcpyAsync(dw, fin, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
         cudaMemcpyAsync(db, fin + C, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s);
@@ -360,7 +370,7 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         head_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx,
                                                                                        partial, P, HW, O);
         if (int rc = check_launch("head_bwd")) return rc;
-        finalize_rows_kernel<<<cdiv(width, 128), 128, 0, (cudaStream_t)s>>>(partial, grid, width, fin);
+        finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, width, fin);
         if (int rc = check_launch("head_bwd.finalize")) return rc;
         cudaStream_t st = (cudaStream_t)s;
         cudaMemcpyAsync(dlnw, fin, sizeof(float) * kHeadC, cudaMemcpyDeviceToDevice, st);
