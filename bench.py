@@ -276,7 +276,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
-            "loss": float(loss.item()),
+            "loss": float(loss.item()), "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
         }
         print(json.dumps(line))
     if world > 1:
