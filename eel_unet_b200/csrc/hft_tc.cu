@@ -180,7 +180,8 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 struct Hft4Params {
     int items;        // N * H
     int H, W, C;
-    int mtiles;       // rows / 128
+    int mtiles;       // 128-row tiles handled by this launch
+    int m_begin;      // first tile (the resident matrix holds tiles m_begin .. m_begin + mtiles)
     int stage_bytes;  // 2 k-chunks x (C/64) atoms x 8192
     int n_stages;
     int nacc;         // accumulator slots of C columns
@@ -231,7 +232,7 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         mbar_expect_tx(mFull, m_bytes);
         for (int mt = 0; mt < p.mtiles; ++mt)
-            for (int kc = 0; kc < 2; ++kc) tma_load_2d(sM + (mt * 2 + kc) * 16384, &tmM, mFull, kc * 64, mt * 128);
+            for (int kc = 0; kc < 2; ++kc) tma_load_2d(sM + (mt * 2 + kc) * 16384, &tmM, mFull, kc * 64, (p.m_begin + mt) * 128);
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -286,7 +287,7 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                 if ((int)(tile_no & 1) != grp) continue;
                 const int slot = (int)(tile_no % p.nacc);
                 const uint32_t par = (uint32_t)((tile_no / p.nacc) & 1);
-                const int m = mt * 128 + r;
+                const int m = (p.m_begin + mt) * 128 + r;
                 if (EPI == H4_T3) {
                     // rows m = (re/im, h'), columns = 128 of the (f, c) axis: T3b[n][h'][ro*F + f][c]
                     mbar_wait(&accFull[slot], par);
@@ -397,15 +398,21 @@ static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p
     }
     p.stage_bytes = 2 * (C / 64) * 8192;
     p.nacc = 512 / C;
-    const int m_bytes = p.mtiles * 2 * 16384;
-    int ns = (kMax - 3072 - m_bytes) / p.stage_bytes;
-    if (ns > 6) ns = 6;
-    if (ns < 2) { set_error("%s: resident matrix leaves no room for the operand ring", what); return EEL_ERR_INVALID; }
-    p.n_stages = ns;
-    const int smem = m_bytes + ns * p.stage_bytes + 3072;
-    const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-    hft_tc4_kernel<C, EPI><<<grid, kH4Threads, smem, st>>>(m, t, p);
-    return check_launch(what);
+    const int total_tiles = p.mtiles;
+    for (int mb = 0; mb < total_tiles; mb += 4) {      // at most 4 resident tiles (128 KB) per pass
+        p.m_begin = mb;
+        p.mtiles = total_tiles - mb < 4 ? total_tiles - mb : 4;
+        const int m_bytes = p.mtiles * 2 * 16384;
+        int ns = (kMax - 3072 - m_bytes) / p.stage_bytes;
+        if (ns > 6) ns = 6;
+        if (ns < 2) { set_error("%s: resident matrix leaves no room for the operand ring", what); return EEL_ERR_INVALID; }
+        p.n_stages = ns;
+        const int smem = m_bytes + ns * p.stage_bytes + 3072;
+        const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+        hft_tc4_kernel<C, EPI><<<grid, kH4Threads, smem, st>>>(m, t, p);
+        if (int rc = check_launch(what)) return rc;
+    }
+    return EEL_OK;
 }
 
 // real-expanded DFT matrices in bf16 (rows = output index, K contiguous, K padded to Kp)
@@ -476,7 +483,7 @@ static int make_b_map(CUtensorMap* m, const void* base, int Kp, int rows, int nb
 }
 
 bool hft_tc_supported(int H, int W, int C, int r) {
-    return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256) && (H == 128 || H == 256);
+    return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256 || W == 512) && (H == 128 || H == 256 || H == 512);
 }
 
 size_t hft_tc_matrix_elems(int W) { return (size_t)80 * 2 * W + (size_t)2 * W * 128; }
