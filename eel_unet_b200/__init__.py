@@ -9,5 +9,6 @@ from . import _lib  # noqa: F401  (fails loudly when libeel.so is missing)
 from . import edges  # noqa: F401
 from .loss import edge_BceDiceLoss  # noqa: F401
 from .model import EELUnet  # noqa: F401
+from .unet import Unet  # noqa: F401
 
-__all__ = ["EELUnet", "edge_BceDiceLoss", "edges"]
+__all__ = ["EELUnet", "Unet", "edge_BceDiceLoss", "edges"]

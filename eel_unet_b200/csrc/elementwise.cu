@@ -474,6 +474,19 @@ __global__ void add_interleave_bwd_kernel(const T* __restrict__ dout, T* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------ column-block copy (torch.concat on C)
+template <class T>
+__global__ void copy_cols_kernel(const T* __restrict__ src, long long src_ld, int src_c0, T* __restrict__ dst, long long dst_ld,
+                                 int dst_c0, long long nvec, int ncols) {
+    constexpr int V = Vec16<T>::N;
+    const int cv = ncols / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / cv;
+        int c = (int)(i - p * cv) * V;
+        st16(dst + p * dst_ld + dst_c0 + c, ld16(src + p * src_ld + src_c0 + c));
+    }
+}
+
 // ------------------------------------------------------------------------------------ ShiftedChannel
 // y[n,h,w,c] = x[n,(h+dh)%H,(w+dw)%W,c]; quarter 0: dh=-1, quarter 1: dh=+1, quarter 2: dw=-1 (signs flip for the adjoint)
 template <class T>
@@ -799,6 +812,19 @@ int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, i
         long long nvec = P * C / Vec16<T>::N;
         add_interleave_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dout, (T*)dab, (T*)de, nvec);
         return check_launch("add_interleave_bwd");
+    });
+}
+
+int eel_copy_cols(const void* src, long long src_ld, int src_c0, void* dst, long long dst_ld, int dst_c0, long long P, int ncols,
+                  int dtype, eel_stream s) {
+    EEL_REQUIRE(src && dst && P > 0 && ncols > 0 && src_c0 >= 0 && dst_c0 >= 0, "copy_cols: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(ncols % V == 0 && src_c0 % V == 0 && dst_c0 % V == 0 && src_ld % V == 0 && dst_ld % V == 0,
+                    "copy_cols: columns and strides must be multiples of the 16-byte vector");
+        long long nvec = P * (ncols / V);
+        copy_cols_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)src, src_ld, src_c0, (T*)dst, dst_ld, dst_c0, nvec, ncols);
+        return check_launch("copy_cols");
     });
 }
 

@@ -362,6 +362,55 @@ class AddInterleave(Function):
         return dab, dab, de
 
 
+class Concat(Function):
+    """torch.concat((a, b), dim=1) of the reference (models/Unet.py:78,83,88,93) on NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        N, H, W, Ca = a.shape
+        Cb = b.shape[-1]
+        out = torch.empty((N, H, W, Ca + Cb), dtype=a.dtype, device=a.device)
+        P, st = N * H * W, stream()
+        call("eel_copy_cols", ptr(a), Ca, 0, ptr(out), Ca + Cb, 0, P, Ca, dtype_code(a), st)
+        call("eel_copy_cols", ptr(b), Cb, 0, ptr(out), Ca + Cb, Ca, P, Cb, dtype_code(a), st)
+        ctx.split = (Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout)
+        Ca, Cb = ctx.split
+        N, H, W, _ = dout.shape
+        da = torch.empty((N, H, W, Ca), dtype=dout.dtype, device=dout.device)
+        db = torch.empty((N, H, W, Cb), dtype=dout.dtype, device=dout.device)
+        P, st = N * H * W, stream()
+        call("eel_copy_cols", ptr(dout), Ca + Cb, 0, ptr(da), Ca, 0, P, Ca, dtype_code(dout), st)
+        call("eel_copy_cols", ptr(dout), Ca + Cb, Ca, ptr(db), Cb, 0, P, Cb, dtype_code(dout), st)
+        return da, db
+
+
+class ToNCHW(Function):
+    """NHWC activations -> fp32 NCHW (the layout / dtype the reference's callers receive)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, C, H, W), dtype=F32, device=x.device)
+        call("eel_permute4", ptr(x), dtype_code(x), ptr(y), dtype_code(y), N, H, W, C, 0, 3, 1, 2, stream())
+        ctx.dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy.to(F32))
+        N, C, H, W = dy.shape
+        dx = torch.empty((N, H, W, C), dtype=ctx.dtype, device=dy.device)
+        call("eel_permute4", ptr(dy), dtype_code(dy), ptr(dx), dtype_code(dx), N, C, H, W, 0, 2, 3, 1, stream())
+        return dx
+
+
 class PGR(Function):
     """PredictionGuidedRefinement (reference models/EELUnet.py:200-203).  Returns (x*(1+s), s[N,1,H,W] fp32)."""
 

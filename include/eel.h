@@ -95,6 +95,10 @@ int eel_tc_conv3x3_wgrad(const void* x, const void* dy, float* dwp, int N, int H
  * [N,2h,2w,Co] read through its input pixel p with columns (dy,dx,co), Nb = 4*Co, gather_w = w. */
 int eel_tc_wgrad(const void* a, const void* b, float* out, long long P, int Ma, int Nb, long long ldm,
                  long long ldn, long long out_elems, int gather_w, eel_stream s);
+/* dst[p][dst_c0 .. dst_c0+ncols) = src[p][src_c0 .. src_c0+ncols): torch.concat along channels and its backward
+ * (models/Unet.py:78,83,88,93) */
+int eel_copy_cols(const void* src, long long src_ld, int src_c0, void* dst, long long dst_ld, int dst_c0,
+                  long long P, int ncols, int dtype, eel_stream s);
 /* ShiftedChannel (models/EELUnet.py:88-97) as a standalone gather; inverse != 0 applies the adjoint shifts */
 int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int inverse, int dtype, eel_stream s);
 

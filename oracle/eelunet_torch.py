@@ -208,5 +208,22 @@ def train_step(sd, x, target, train=True):
     return loss.detach(), seg.detach(), [e.detach() for e in edges], grads, ns
 
 
+def unet_forward(sd, x):
+    """Unet.forward, models/Unet.py:58-98 (no BatchNorm; logits out; skip = concat((dec, enc), dim=1))."""
+    def blk(p, t):
+        t = F.relu(F.conv2d(t, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=1))
+        return F.relu(F.conv2d(t, sd[p + ".2.weight"], sd[p + ".2.bias"], padding=1))
+
+    e1 = blk("enc1", x)
+    e2 = blk("enc2", F.max_pool2d(e1, 2))
+    e3 = blk("enc3", F.max_pool2d(e2, 2))
+    e4 = blk("enc4", F.max_pool2d(e3, 2))
+    d = blk("bottleneck", F.max_pool2d(e4, 2))
+    for k, skip in ((4, e4), (3, e3), (2, e2), (1, e1)):
+        d = F.conv_transpose2d(d, sd["upconv%d.0.weight" % k], sd["upconv%d.0.bias" % k], stride=2)
+        d = blk("conv%d" % k, torch.cat((d, skip), dim=1))
+    return F.conv2d(d, sd["final_conv.weight"], sd["final_conv.bias"])
+
+
 def gelu_exact(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
