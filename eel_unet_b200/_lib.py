@@ -42,6 +42,8 @@ def parse_header(path=HEADER):
                 a = a.strip()
                 if "*" in a:
                     argtypes.append(ctypes.c_void_p)
+                elif "unsigned long long" in a:
+                    argtypes.append(ctypes.c_ulonglong)
                 else:
                     ty = re.sub(r"\s+\w+$", "", a).replace("const ", "").strip()
                     argtypes.append(_CTYPES[ty])

@@ -195,6 +195,15 @@ int eel_laplacian_map(const uint8_t* gray, uint8_t* out, int N, int H, int W, ee
 int eel_canny_enhance(const uint8_t* rgb, const uint8_t* edges, uint8_t* out, int N, int H, int W, int cr,
                       int cg, int cb, float alpha, eel_stream s);
 
+/* ------------------------------------------------------------------ evaluate() metrics
+ * evaluate.py:91-100: counts[4] += {TP, TN, FP, FN} of (seg > 0.5) against labels == 1 / == 0 */
+int eel_confusion_counts(const float* seg, const float* labels, long long n, unsigned long long* counts,
+                         eel_stream s);
+/* evaluate.py:25-60: per_sample[n][3] += {|pred_b & gt_b|, |pred_b|, |gt_b|}, boundary = mask - erode(mask, 3x3, iterations) */
+size_t eel_boundary_workspace_bytes(int N, int H, int W);
+int eel_boundary_counts(const float* seg, const float* labels, int N, int H, int W, int iterations,
+                        unsigned long long* per_sample, void* ws, size_t ws_bytes, eel_stream s);
+
 /* ------------------------------------------------------------------ optimizer
  * optim.Adam(lr, weight_decay) with L2-coupled decay (train.py:312) over one flat fp32 buffer */
 int eel_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
