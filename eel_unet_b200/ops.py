@@ -48,6 +48,17 @@ def _colsum(x2d, C):
     hit = _DZ_COLSUM.pop(x2d.data_ptr(), None)
     if hit is not None and hit.numel() == C:
         return hit
+    vec = 8 if x2d.dtype == BF16 else 4
+    if C % vec != 0:
+        # thin outputs (e.g. the 1-channel logits of Unet.final_conv): fold rows so a row is lcm(C, vec) wide
+        import math
+        L = C * vec // math.gcd(C, vec)
+        if x2d.numel() % L != 0:
+            raise _lib.EelError("colsum: %d elements do not fold into rows of %d" % (x2d.numel(), L))
+        wide = torch.empty(L, dtype=F32, device=x2d.device)
+        ws, n = _reduce_ws(x2d.device, L, 1)
+        call("eel_colsum", ptr(x2d), ptr(wide), x2d.numel() // L, L, ptr(ws), n, dtype_code(x2d), stream())
+        return wide.view(L // C, C).sum(0)
     out = torch.empty(C, dtype=F32, device=x2d.device)
     ws, n = _reduce_ws(x2d.device, C, 1)
     call("eel_colsum", ptr(x2d), ptr(out), x2d.numel() // C, C, ptr(ws), n, dtype_code(x2d), stream())
