@@ -255,6 +255,11 @@ def run_ours(args):
                 f.write("kernel,calls,ms,share_pct,tflops,pct_tensor_peak,gbs,pct_hbm_peak\n")
                 for r in rows:
                     f.write("%s,%d,%.3f,%.2f,%.2f,%.2f,%.1f,%.2f\n" % r)
+        if args.profile_shapes:
+            with open(args.profile_shapes, "w") as f:
+                f.write("kernel,int_args,calls,ms,tflops,gbs\n")
+                for r in profiling.shape_table(rec):
+                    f.write("%s,%s,%d,%.3f,%.2f,%.1f\n" % r)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -294,6 +299,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
+    ap.add_argument("--profile-shapes", default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

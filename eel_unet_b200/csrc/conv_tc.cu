@@ -1,0 +1,345 @@
+// bf16 implicit-GEMM 3x3 convolution (fprop + data gradient) for sm_100a, second generation.
+//
+// Measured on B200 (tools/umma_probe.cu): a tcgen05 K-major SWIZZLE_128B operand is addressed through the ABSOLUTE
+// shared-memory address bits, so the 8-row groups of an operand view need not sit on 1024-byte boundaries.  That
+// lets ONE dense halo block per 64-channel K chunk serve all nine taps:
+//
+//     smem A stage = [TH+2 image rows][10 columns][64 ch] = (TH+2) * 1280 B   (one 4-D TMA box, OOB = zero padding)
+//     tap (dy, dx), accumulator j:  start = stage + ((16 j + 1 + dy) * 10 + 1 + dx) * 128,  SBO = 1280 B
+//
+// i.e. activations cross L2 -> SM 1.3-1.4x instead of 3.4x (three column-shifted copies in generation one).
+// An output tile is TH x 8 pixels, TH = 16 * MT: MT accumulators of 128 rows share every weight tile, which
+// divides the weight traffic per pixel by MT.  When the whole [9][Cin][BN] weight block fits (<= 144 KB:
+// 64->64, 128->64, 64->128 -- the full-resolution layers that hold most of the FLOPs) it is loaded ONCE per CTA and
+// stays resident (RES), so the steady state only streams activations.
+//
+//   warp 0  TMA producer   warp 1  MMA issuer (one thread)   warps 2-5  epilogue (TMEM -> +bias/ReLU -> bf16 -> global)
+// Two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent, one CTA per SM.
+#include "tc_common.cuh"
+
+namespace eel {
+namespace tc {
+
+struct ConvParams {
+    int kchunks;            // 64-wide input-channel chunks
+    int m_tiles, n_tiles;
+    int N, H, W;
+    int tiles_h, tiles_w;
+    int Ntot;               // output channels
+    int flip;               // mirror the tap offsets (data gradient)
+    int relu;
+    int na;                 // A stages in shared memory
+    const float* bias;
+    bf16* out;
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+template <int BN, int MT, bool RES> struct ConvCfg {
+    static constexpr int TH = 16 * MT;
+    static constexpr int A_TX = (TH + 2) * 10 * 128;
+    static constexpr int A_BYTES = (A_TX + 1023) & ~1023;
+    static constexpr int B_TILE = BN * 128;                                   // one (chunk, tap) weight tile
+    static constexpr int NB = RES ? 0 : (BN == 256 ? 3 : (BN == 128 ? 5 : 8));
+    static constexpr int TMEM_COLS = 2 * MT * BN;
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "accumulators must fill a power of two of TMEM");
+};
+
+constexpr int kSmemLimit = 232448 - 1024;   // 227 KB per CTA minus alignment slack
+constexpr int kStageBytes = 4 * 2048;       // epilogue transposition buffers (2 KB per warp)
+
+template <int BN, int MT, bool RES>
+__device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, uint8_t* sB, uint64_t* fullA, uint64_t* emptyA,
+                                              uint64_t* fullB, uint64_t* emptyB, uint64_t* tmemFull, uint64_t* tmemEmpty,
+                                              const uint32_t tmem_base, const int total_tiles) {
+    typedef ConvCfg<BN, MT, RES> Cfg;
+    {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        // The issuing thread must sustain one MMA per 32-128 cycles: descriptors are built ONCE (stage 0) and every
+        // operand view is that descriptor plus a 16-byte-unit offset in its start-address field (no carry: < 256 KB).
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 16, 1280, false);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, false);
+        uint32_t tap_off[9];                       // (view start - stage start) / 16 per tap
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            int dy = t / 3 - 1, dx = t % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+            tap_off[t] = (uint32_t)(((1 + dy) * 10 + 1 + dx) * 128) >> 4;
+        }
+        if (RES) {
+            mbar_wait(&fullB[0], 0);
+            tc_fence_after();
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_par = (it >> 1) & 1;
+            mbar_wait(&tmemEmpty[acc], acc_par ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * (MT * BN);
+            for (int c = 0; c < p.kchunks; ++c) {
+                mbar_wait(&fullA[sa], pa);
+                tc_fence_after();
+                const uint64_t a_stage = a_desc0 + (uint32_t)((sa * Cfg::A_BYTES) >> 4);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    uint64_t b_tile;
+                    if (RES) b_tile = b_desc0 + (uint32_t)(((c * 9 + t) * Cfg::B_TILE) >> 4);
+                    else {
+                        mbar_wait(&fullB[sb], pb);
+                        tc_fence_after();
+                        b_tile = b_desc0 + (uint32_t)((sb * Cfg::B_TILE) >> 4);
+                    }
+                    const uint64_t a_tap = a_stage + tap_off[t];
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_d + j * BN, a_tap + (uint32_t)((j * 16 * 1280 + k * 32) >> 4), b_tile + (uint32_t)(k * 2), idesc,
+                                      (t | k) != 0 ? 1u : (uint32_t)(c != 0));
+                    }
+                    if (!RES) {
+                        umma_commit(&emptyB[sb]);
+                        if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
+                    }
+                }
+                umma_commit(&emptyA[sa]);
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
+            }
+            umma_commit(&tmemFull[acc]);
+        }
+    }
+}
+
+
+template <int BN, int MT, bool RES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    typedef ConvCfg<BN, MT, RES> Cfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + p.na * Cfg::A_BYTES;
+    const int b_tiles = RES ? 9 * p.kchunks : Cfg::NB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_tiles * Cfg::B_TILE);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + kMaxStages;
+    uint64_t* fullB = emptyA + kMaxStages;      // RES: fullB[0] = "weights resident"
+    uint64_t* emptyB = fullB + kMaxStages;
+    uint64_t* tmemFull = emptyB + kMaxStages;
+    uint64_t* tmemEmpty = tmemFull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmemEmpty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1);
+            mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        if (RES) {
+            mbar_expect_tx(&fullB[0], (uint32_t)(b_tiles * Cfg::B_TILE));
+            for (int c = 0; c < p.kchunks; ++c)
+                for (int t = 0; t < 9; ++t)
+                    tma_load_3d(sB + (c * 9 + t) * Cfg::B_TILE, &tmB, &fullB[0], c * 64, 0, t);
+        }
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int n0 = nt * BN;
+            const int tw = mt % p.tiles_w, r = mt / p.tiles_w;
+            const int th = r % p.tiles_h, c_n = r / p.tiles_h;
+            const int c_h = th * Cfg::TH - 1, c_w = tw * 8 - 1;
+            for (int c = 0; c < p.kchunks; ++c) {
+                mbar_wait(&emptyA[sa], pa ^ 1);
+                mbar_expect_tx(&fullA[sa], Cfg::A_TX);
+                tma_load_4d(sA + sa * Cfg::A_BYTES, &tmA, &fullA[sa], c * 64, c_w, c_h, c_n);
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
+                if (!RES) {
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(&emptyB[sb], pb ^ 1);
+                        mbar_expect_tx(&fullB[sb], Cfg::B_TILE);
+                        tma_load_3d(sB + sb * Cfg::B_TILE, &tmB, &fullB[sb], c * 64, n0, t);
+                        if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && elect_one()) {
+        // ===================================================================== MMA issuer
+        // The first allocation of a CTA that owns its SM starts at TMEM column 0; with the base a literal the
+        // accumulator addresses are immediates and an MMA costs ~4 issue slots instead of ~9 (N = 64 MMAs last 32 cycles).
+        if (tmem_base == 0) conv_mma_loop<BN, MT, RES>(p, sA, sB, fullA, emptyA, fullB, emptyB, tmemFull, tmemEmpty, 0u, total_tiles);
+        else conv_mma_loop<BN, MT, RES>(p, sA, sB, fullA, emptyA, fullB, emptyB, tmemFull, tmemEmpty, tmem_base, total_tiles);
+    } else if (warp >= 2) {
+        // ===================================================================== epilogue
+        // Thread = accumulator row = pixel; a pixel's 32 channels are 64 contiguous bytes, so storing straight from
+        // the TMEM layout would hit 32 different lines with 16 bytes each per instruction.  The chunk is transposed
+        // through a 2 KB per-warp buffer (16-byte slots XOR-swizzled, conflict free both ways): afterwards four lanes
+        // write one pixel's 64 bytes and a warp-wide store covers full 32-byte sectors only.
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        uint8_t* stg = reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + q * 2048;
+        const uint32_t wr_base = smem_u32(stg) + lane * 64;
+        const uint32_t wr_sw = (lane >> 1) & 3;
+        const int px_lo = lane >> 2, ch = lane & 3;           // after the transposition: pixel (px_lo + 8 i), 16-byte slot ch
+        const uint32_t rd_base = smem_u32(stg) + px_lo * 64 + ((ch ^ ((lane >> 3) & 3)) << 4);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_par = (it >> 1) & 1;
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int n0 = nt * BN;
+            const int tw = mt % p.tiles_w, rr = mt / p.tiles_w;
+            const int th = rr % p.tiles_h, n = rr / p.tiles_h;
+            const int w = tw * 8 + px_lo;
+            mbar_wait(&tmemFull[acc], acc_par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int j = 0; j < MT; ++j) {
+                const int h0 = th * Cfg::TH + j * 16 + q * 4;          // image row of this warp's pixels 0-7
+                bf16* row = p.out + (((long long)n * p.H + h0) * p.W + w) * p.Ntot + n0 + ch * 8;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + j * BN;
+#pragma unroll 1
+                for (int cc = 0; cc < BN; cc += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + cc, v);
+                    if (p.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + cc);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b4 = __ldg(bp + i);
+                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_base + ((c ^ wr_sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+                                     "r"(pk[2]), "r"(pk[3]) : "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(rd_base + i * 512) : "memory");
+                        if (h0 + i < p.H && w < p.W) *reinterpret_cast<uint4*>(row + (long long)i * p.W * p.Ntot + cc) = o;
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int MT, bool RES>
+static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int Cout, cudaStream_t st, const char* what) {
+    typedef ConvCfg<BN, MT, RES> Cfg;
+    const int b_bytes = (RES ? 9 * p.kchunks : Cfg::NB) * Cfg::B_TILE;
+    int na = (kSmemLimit - 1024 - kStageBytes - b_bytes) / Cfg::A_BYTES;
+    if (na > kMaxStages) na = kMaxStages;
+    if (na > 6) na = 6;
+    if (na < 2) {
+        set_error("%s: weights (%d B) leave no room for two activation stages", what, b_bytes);
+        return EEL_ERR_INVALID;
+    }
+    p.na = na;
+    const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + kStageBytes + 1024 /* alignment slack */;
+    static int configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
+            return EEL_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+        uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)p.W * Cin, (uint64_t)p.H * p.W * Cin};
+        uint32_t box[4] = {64, 10, (uint32_t)(Cfg::TH + 2), 1};
+        if (int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, what)) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+        uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cin * Cout};
+        uint32_t box[3] = {64, (uint32_t)BN, 1};
+        if (int rc = make_tmap_bf16(&tmB, wk, 3, dims, str, box, what)) return rc;
+    }
+    p.tiles_h = cdiv(p.H, Cfg::TH);
+    p.tiles_w = cdiv(p.W, 8);
+    p.m_tiles = p.N * p.tiles_h * p.tiles_w;
+    p.n_tiles = Cout / BN;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    tc_conv_kernel<BN, MT, RES><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+    return check_launch(what);
+}
+
+}  // namespace tc
+}  // namespace eel
+
+using namespace eel;
+using namespace eel::tc;
+
+extern "C" {
+
+int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                   int relu, int flip, eel_stream s) {
+    EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
+    EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
+    ConvParams p{};
+    p.kchunks = Cin / 64;
+    p.Ntot = Cout;
+    p.N = N; p.H = H; p.W = W;
+    p.flip = flip; p.relu = relu;
+    p.bias = bias; p.out = (bf16*)y;
+    cudaStream_t st = (cudaStream_t)s;
+    const bool tall = H > 16;                  // a 32-row tile would be half empty on 16-row maps
+    if (Cin == 64 && Cout == 64)
+        return tall ? launch_conv<64, 2, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)")
+                    : launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)");
+    if (Cin == 128 && Cout == 64) return launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 128x64)");
+    if (Cin == 64 && Cout == 128) return launch_conv<128, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x128)");
+    // N = 256 MMAs read the least shared memory per FLOP (A 4 KB + B 8 KB per 128 cycles): preferred when Cout allows
+    if (Cout % 256 == 0) return launch_conv<256, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(256x1)");
+    if (Cout % 128 == 0)
+        return tall ? launch_conv<128, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x2)")
+                    : launch_conv<128, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x1)");
+    return tall ? launch_conv<64, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x2)")
+                : launch_conv<64, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x1)");
+}
+
+}  // extern "C"

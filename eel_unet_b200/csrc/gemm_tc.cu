@@ -167,7 +167,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         // ===================================================================== MMA issuer
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
         int sa = 0, sb = 0;
@@ -314,8 +314,8 @@ using namespace eel::tc;
 
 extern "C" {
 
-int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                   int relu, int flip, eel_stream s) {
+int eel_tc_conv3x3_v1(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                      int relu, int flip, eel_stream s) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     const int bn = pick_bn(Cout);

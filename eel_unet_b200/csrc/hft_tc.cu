@@ -101,7 +101,7 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (++st == p.n_stages) { st = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         // ===================================================================== MMA issuer
         constexpr uint32_t idesc = make_idesc_bf16(128, NB, 1, 0);   // A: MN-major, B: K-major
         mbar_wait(bFull, 0);
@@ -247,7 +247,7 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                 }
             if (++st == p.n_stages) { st = 0; ph ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         constexpr uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A: K-major (matrix), B: MN-major (T3b)
         mbar_wait(mFull, 0);
         int st = 0;

@@ -126,7 +126,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (++st == Cfg::NS) { st = 0; ph ^= 1; }
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1 && elect_one()) {
             // ================================================================= MMA issuer
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
             int st = 0;

@@ -165,3 +165,21 @@ def table(fam, hbm_gbs, tensor_tflops):
         gb = d["bytes"] / ms / 1e6
         rows.append((k, d["calls"], d["ms"], 100.0 * d["ms"] / total, tf, 100.0 * tf / tensor_tflops, gb, 100.0 * gb / hbm_gbs))
     return rows
+
+
+def shape_table(records):
+    """per (kernel, integer arguments) rows: calls, ms, TFLOP/s, GB/s -- finds the slow SHAPES inside a family."""
+    acc = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    for name, args, s, e in records:
+        dims = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 28))
+        f, b = cost(name, args)
+        d = acc[(name[4:], dims)]
+        d[0] += 1
+        d[1] += s.elapsed_time(e)
+        d[2] += f
+        d[3] += b
+    rows = []
+    for (k, dims), (calls, ms, f, b) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
+        ms = ms or 1e-9
+        rows.append((k, "x".join(str(v) for v in dims), calls, ms, f / ms / 1e9, b / ms / 1e6))
+    return rows

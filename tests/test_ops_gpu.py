@@ -86,7 +86,7 @@ DTYPES = [torch.float32, torch.bfloat16]
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 8, 12, 20, 16), (1, 64, 16, 16, 72), (3, 16, 9, 7, 8),
                                    (2, 64, 24, 20, 64), (1, 128, 16, 16, 256), (2, 256, 8, 8, 128), (1, 64, 32, 40, 512),
-                                   (3, 192, 5, 9, 64)])
+                                   (3, 192, 5, 9, 64), (2, 128, 40, 24, 64), (1, 64, 16, 16, 64), (1, 128, 70, 36, 128)])
 @pytest.mark.parametrize("relu", [False, True])
 def test_conv3x3(dtype, shape, relu):
     from eel_unet_b200 import ops

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Micro-benchmark of single C-ABI kernels at the model's shapes (batch 64 at 256^2 by default).
+
+    python tools/op_bench.py [--batch 64] [--iters 5] [--only conv,wgrad,bn,...] [--once]
+
+Each case is timed with CUDA events on the launching stream after warm-up; between iterations the inputs are
+larger than L2 or a 256 MB buffer is rewritten (L2 flush).  `--once` launches every case exactly once (for ncu).
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+
+from eel_unet_b200 import _lib, profiling
+from eel_unet_b200._lib import call, ptr
+
+BF16, F32 = torch.bfloat16, torch.float32
+DEV = torch.device("cuda", 0)
+
+
+def rnd(*shape, dtype=BF16):
+    return torch.randn(*shape, device=DEV, dtype=torch.float32).to(dtype)
+
+
+def cases(B, S, only):
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    out = []
+
+    def add(group, name, args_fn):
+        if only and not any(group.startswith(o) or name.startswith(o) for o in only):
+            return
+        out.append((group, name, args_fn))
+
+    conv_shapes = [(S, 64, 64), (S, 128, 64), (S // 2, 128, 128), (S // 2, 256, 128), (S // 2, 64, 128), (S // 4, 256, 256),
+                   (S // 4, 512, 256), (S // 8, 512, 512), (S // 8, 1024, 512), (S // 16, 512, 1024)]
+    for (s, ci, co) in conv_shapes:
+        def mk(s=s, ci=ci, co=co):
+            x, w, b, y = rnd(B, s, s, ci), rnd(3, 3, co, ci), rnd(co, dtype=F32), torch.empty(B, s, s, co, device=DEV, dtype=BF16)
+            return "eel_tc_conv3x3", (ptr(x), ptr(w), ptr(b), ptr(y), B, s, s, ci, co, int(os.environ.get("EEL_RELU", "0")), 0, st()), (x, w, b, y)
+        add("conv", "conv3x3 %dx%d %d->%d" % (s, s, ci, co), mk)
+    for (s, ci, co) in conv_shapes:
+        def mk(s=s, ci=ci, co=co):
+            x, dy, dw = rnd(B, s, s, ci), rnd(B, s, s, co), torch.empty(3, 3, ci, co, device=DEV, dtype=F32)
+            return "eel_tc_conv3x3_wgrad", (ptr(x), ptr(dy), ptr(dw), B, s, s, ci, co, st()), (x, dy, dw)
+        add("wgrad", "wgrad3x3 %dx%d %d->%d" % (s, s, ci, co), mk)
+    for (s, c) in [(S, 64), (S // 2, 128), (S // 4, 256), (S // 8, 512)]:
+        P = B * s * s
+
+        def mk_stats(P=P, c=c):
+            z, mean, rstd = rnd(P, c), torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+            rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+            n = _lib.lib.eel_reduce_workspace_bytes(c, 2)
+            ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+            return "eel_bn_stats", (ptr(z), P, c, ptr(mean), ptr(rstd), ptr(rm), ptr(rv), 0.1, 1e-5, ptr(ws), n, 1, st()), (z, mean, rstd, rm, rv, ws)
+        add("bn", "bn_stats P=%d C=%d" % (P, c), mk_stats)
+
+        def mk_bwd(P=P, c=c):
+            z, dy, dz = rnd(P, c), rnd(P, c), torch.empty(P, c, device=DEV, dtype=BF16)
+            mean, rstd, g, b = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+            dg, db, dzs = torch.empty(c, device=DEV), torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+            n = _lib.lib.eel_reduce_workspace_bytes(c, 2) + 8 * c
+            ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+            return "eel_bn_act_bwd", (ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dz), ptr(dg), ptr(db), ptr(dzs), P, c, 1, 1,
+                                      ptr(ws), n, 1, st()), (z, dy, dz, mean, rstd, g, b, dg, db, dzs, ws)
+        add("bn", "bn_act_bwd P=%d C=%d" % (P, c), mk_bwd)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--once", action="store_true")
+    a = ap.parse_args()
+    only = [o for o in a.only.split(",") if o]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    print("%-34s %9s %9s %9s" % ("case", "us", "TFLOP/s", "GB/s"))
+    for group, name, mk in cases(a.batch, a.size, only):
+        fn, args, keep = mk()
+        if a.once:
+            call(fn, *args)
+            torch.cuda.synchronize()
+            continue
+        call(fn, *args)
+        call(fn, *args)
+        ts = []
+        for _ in range(a.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call(fn, *args)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        f, b = profiling.cost(fn, args)
+        print("%-34s %9.1f %9.1f %9.1f" % (name, ms * 1e3, f / ms / 1e9, b / ms / 1e6))
+        del keep
+
+
+if __name__ == "__main__":
+    main()
