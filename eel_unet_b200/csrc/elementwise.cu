@@ -605,46 +605,60 @@ __global__ void scale_rows_kernel(const T* __restrict__ t, const float* __restri
     }
 }
 
-// single block: all the tiny per-image backward algebra + parameter gradients of the SE MLP.
-// in:  datt[n][c] = sum_hw dout*t ; out: dmean_scaled[n][c] = (W1^T dhid_pre)[c] / HW
+// Squeeze-excite backward, phase A: one block per image does that image's tiny backward algebra.
+// in:  datt[n][c] = sum_hw dout*t ; out: dmean_scaled[n][c] = (W1^T dhid_pre)[c] / HW, dpre[n][c], dhid[n][r]
 __global__ void se_mlp_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ att, const float* __restrict__ hid,
-                                  const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ w2,
-                                  float* __restrict__ dmean_scaled, float* __restrict__ dw1, float* __restrict__ db1,
-                                  float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R, float inv_hw) {
+                                  const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ dmean_scaled,
+                                  float* __restrict__ dpre_out, float* __restrict__ dhid_out, int C, int R, float inv_hw) {
     extern __shared__ float sh[];   // dpre[C] then dhid[R]
     float* dpre = sh;
     float* dhid = sh + C;
-    const int t = threadIdx.x;
-    for (int i = t; i < C * R; i += blockDim.x) { dw1[i] = 0.f; dw2[i] = 0.f; }
-    for (int i = t; i < C; i += blockDim.x) db2[i] = 0.f;
-    for (int i = t; i < R; i += blockDim.x) db1[i] = 0.f;
+    const int t = threadIdx.x, n = blockIdx.x;
+    for (int c = t; c < C; c += blockDim.x) {
+        float a = att[n * C + c];
+        float d = datt[n * C + c] * a * (1.f - a);
+        dpre[c] = d;
+        dpre_out[n * C + c] = d;
+    }
     __syncthreads();
-    for (int n = 0; n < N; ++n) {
-        for (int c = t; c < C; c += blockDim.x) {
-            float a = att[n * C + c];
-            float d = datt[n * C + c] * a * (1.f - a);
-            dpre[c] = d;
-            db2[c] += d;
-            for (int r = 0; r < R; ++r) dw2[c * R + r] += d * hid[n * R + r];
-        }
-        __syncthreads();
-        for (int r = t; r < R; r += blockDim.x) {
-            float s = 0.f;
-            for (int c = 0; c < C; ++c) s += w2[c * R + r] * dpre[c];
-            s = hid[n * R + r] > 0.f ? s : 0.f;
-            dhid[r] = s;
-            db1[r] += s;
-        }
-        __syncthreads();
-        for (int c = t; c < C; c += blockDim.x) {
-            float s = 0.f;
-            for (int r = 0; r < R; ++r) {
-                s += w1[r * C + c] * dhid[r];
-                dw1[r * C + c] += dhid[r] * mean[n * C + c];
-            }
-            dmean_scaled[n * C + c] = s * inv_hw;
-        }
-        __syncthreads();
+    for (int r = t; r < R; r += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += w2[c * R + r] * dpre[c];
+        s = hid[n * R + r] > 0.f ? s : 0.f;
+        dhid[r] = s;
+        dhid_out[n * R + r] = s;
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += w1[r * C + c] * dhid[r];
+        dmean_scaled[n * C + c] = s * inv_hw;
+    }
+}
+
+// phase B: one thread per parameter-gradient element sums its contributions over the images (deterministic order).
+__global__ void se_param_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ dhid, const float* __restrict__ hid,
+                                     const float* __restrict__ mean, float* __restrict__ dw1, float* __restrict__ db1,
+                                     float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int CR = C * R;
+    float s = 0.f;
+    if (i < CR) {                       // dw2[c][r] = sum_n dpre[n][c] * hid[n][r]
+        const int c = i / R, r = i % R;
+        for (int n = 0; n < N; ++n) s += dpre[n * C + c] * hid[n * R + r];
+        dw2[i] = s;
+    } else if (i < 2 * CR) {            // dw1[r][c] = sum_n dhid[n][r] * mean[n][c]
+        const int j = i - CR, r = j / C, c = j % C;
+        for (int n = 0; n < N; ++n) s += dhid[n * R + r] * mean[n * C + c];
+        dw1[j] = s;
+    } else if (i < 2 * CR + C) {        // db2[c]
+        const int c = i - 2 * CR;
+        for (int n = 0; n < N; ++n) s += dpre[n * C + c];
+        db2[c] = s;
+    } else if (i < 2 * CR + C + R) {    // db1[r]
+        const int r = i - 2 * CR - C;
+        for (int n = 0; n < N; ++n) s += dhid[n * R + r];
+        db1[r] = s;
     }
 }
 
@@ -902,19 +916,23 @@ int eel_se_bwd(const void* t, const void* dout, const float* att, const float* h
     EEL_REQUIRE(t && dout && att && hid && mean && w1 && w2 && dt && dw1 && db1 && dw2 && db2 && N > 0 && HW > 0 && C > 0 && R > 0,
                 "se_bwd: bad argument");
     cudaStream_t st = (cudaStream_t)s;
-    size_t head = sizeof(float) * 2 * (size_t)N * C;   // datt[N][C], dmean_scaled[N][C]
-    EEL_REQUIRE(ws_bytes > head, "se_bwd: workspace too small");
+    size_t head = sizeof(float) * 4 * (size_t)N * C;   // datt[N][C], dmean_scaled[N][C], dpre[N][C], dhid[N][R] (R <= C)
+    EEL_REQUIRE(ws_bytes > head && R <= C, "se_bwd: workspace too small");
     EEL_DISPATCH_DTYPE(dtype, {
         float* datt = (float*)ws;
         float* dmean = datt + (size_t)N * C;
-        float* partial = dmean + (size_t)N * C;
+        float* dpre = dmean + (size_t)N * C;
+        float* dhid = dpre + (size_t)N * C;
+        float* partial = dhid + (size_t)N * C;
         RedPlan pl;
         DotF<T> f{(const T*)dout, (const T*)t, C};
         if (int rc = run_colreduce<T, DotF<T>, 1>(f, HW, C, N, partial, ws_bytes - head, pl, st, "se_bwd.dot")) return rc;
         if (int rc = run_finalize(partial, pl.nrb, C, N, datt, 1.0f, st, "se_bwd.finalize")) return rc;
-        se_mlp_bwd_kernel<<<1, 64, sizeof(float) * (C + R), st>>>(datt, att, hid, mean, w1, w2, dmean, dw1, db1, dw2, db2, N, C, R,
-                                                               1.0f / (float)HW);
+        se_mlp_bwd_kernel<<<N, 64, sizeof(float) * (C + R), st>>>(datt, att, hid, w1, w2, dmean, dpre, dhid, C, R, 1.0f / (float)HW);
         if (int rc = check_launch("se_bwd.mlp")) return rc;
+        const int nout = 2 * C * R + C + R;
+        se_param_grad_kernel<<<cdiv(nout, 128), 128, 0, st>>>(dpre, dhid, hid, mean, dw1, db1, dw2, db2, N, C, R);
+        if (int rc = check_launch("se_bwd.param_grad")) return rc;
         long long nvec = (long long)N * HW * C / Vec16<T>::N;
         scale_rows_kernel<T><<<ew_grid(nvec, 256), 256, 0, st>>>((const T*)dout, att, dmean, (T*)dt, nvec, HW * C / Vec16<T>::N, C);
         return check_launch("se_bwd.scale");

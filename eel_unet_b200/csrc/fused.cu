@@ -135,6 +135,90 @@ __global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel(const T* __restric
     for (int i = threadIdx.x; i <= C; i += kPixThreads) partial[(long long)blockIdx.x * (C + 1) + i] = sh[i];
 }
 
+// Same op with ITERS (vectors per lane and pixel) a compile-time constant and U pixels per group in flight:
+// every x / dy vector is loaded ONCE into registers (2*U*ITERS independent 16-byte loads per thread) before any
+// arithmetic, which is what it takes to keep HBM busy at two blocks per SM.
+template <class T, int ITERS, int U>
+__global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel2(const T* __restrict__ x, const float* __restrict__ sg,
+                                                             const float* __restrict__ w, const T* __restrict__ dy,
+                                                             const float* __restrict__ dsg, T* __restrict__ dx,
+                                                             float* __restrict__ partial, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float sh[];   // [C + 1]
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    for (int i = threadIdx.x; i <= C; i += kPixThreads) sh[i] = 0.f;
+    __syncthreads();
+    float dwacc[ITERS][V], wreg[ITERS][V];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j) { dwacc[k][j] = 0.f; wreg[k][j] = w[(gl + k * G) * V + j]; }
+    float dbacc = 0.f;
+    const long long stride = (long long)gridDim.x * groups_per_block * U;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block * U; p0 < P; p0 += stride) {
+        Vec16<T> vx[U][ITERS], vd[U][ITERS];
+        float sv[U], ds[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            ok[u] = p < P;
+            sv[u] = 0.f; ds[u] = 0.f;
+            if (ok[u]) {
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k) {
+                    const int c0 = (gl + k * G) * V;
+                    vx[u][k] = ld16(x + p * C + c0);
+                    vd[u][k] = ld16(dy + p * C + c0);
+                }
+                sv[u] = sg[p];
+                if (dsg) ds[u] = dsg[p];
+            }
+        }
+        float dot[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            dot[u] = 0.f;
+            if (ok[u])
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) dot[u] += vx[u][k].get(j) * vd[u][k].get(j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] = group_sum(dot[u], G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            const float dg = (dot[u] + ds[u]) * sv[u] * (1.f - sv[u]);
+            if (gl == 0) dbacc += dg;
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k) {
+                const int c0 = (gl + k * G) * V;
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    o.set(j, vd[u][k].get(j) * (1.f + sv[u]) + wreg[k][j] * dg);
+                    dwacc[k][j] += vx[u][k].get(j) * dg;
+                }
+                st16(dx + p * C + c0, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+        const int c0 = (gl + k * G) * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) atomicAdd(&sh[c0 + j], dwacc[k][j]);
+    }
+    if (gl == 0) atomicAdd(&sh[C], dbacc);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= C; i += kPixThreads) partial[(long long)blockIdx.x * (C + 1) + i] = sh[i];
+}
+
 // ------------------------------------------------------------------------------------ head (C = 64)
 constexpr int kHeadC = 64;
 constexpr int kHeadMaxO = 4;
@@ -149,6 +233,7 @@ __global__ void __launch_bounds__(kPixThreads) head_fwd_kernel(const T* __restri
     const int groups_per_block = kPixThreads / G;
     const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
     const int c0 = gl * V;
+#pragma unroll 4
     for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
         long long p = p0 + g_in_block;
         bool ok = p < P;
@@ -209,6 +294,7 @@ __global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restri
 #pragma unroll
         for (int j = 0; j < V; ++j) awo[o][j] = 0.f;
     }
+#pragma unroll 2
     for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
         long long p = p0 + g_in_block;
         bool ok = p < P;
@@ -325,8 +411,13 @@ int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy,
         if (need > ws_bytes || !ws) { set_error("pgr_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
         float* partial = (float*)ws;
         float* fin = partial + (size_t)grid * (C + 1);
-        pgr_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * (C + 1), (cudaStream_t)s>>>((const T*)x, sgm, w, (const T*)dy, dsgm,
-                                                                                        (T*)dx, partial, P, C, G);
+        const int iters = C / V / G;
+        const size_t shb = sizeof(float) * (C + 1);
+        cudaStream_t st2 = (cudaStream_t)s;
+        if (iters == 1) pgr_bwd_kernel2<T, 1, 4><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
+        else if (iters == 2) pgr_bwd_kernel2<T, 2, 2><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
+        else if (iters == 4) pgr_bwd_kernel2<T, 4, 1><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
+        else pgr_bwd_kernel<T><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
         if (int rc = check_launch("pgr_bwd")) return rc;
         finalize_rows_kernel<<<cdiv(C + 1, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, C + 1, fin);
         if (int rc = check_launch("pgr_bwd.finalize")) return rc;
@@ -361,7 +452,7 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         constexpr int G = kHeadC / Vec16<T>::N;
         int gpb = kPixThreads / G;
         long long blocks = (P + gpb - 1) / gpb;
-        int grid = (int)(blocks < (long long)kNumSMs * 2 ? blocks : (long long)kNumSMs * 2);
+        int grid = (int)(blocks < (long long)kNumSMs * 4 ? blocks : (long long)kNumSMs * 4);
         int width = (2 + O) * kHeadC + O;
         size_t need = sizeof(float) * ((size_t)grid + 1) * width;
         if (need > ws_bytes || !ws) { set_error("head_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }

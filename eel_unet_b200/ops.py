@@ -484,7 +484,7 @@ class Head(Function):
         dlnb = torch.empty(64, dtype=F32, device=dev)
         dw = torch.empty((O, 64), dtype=F32, device=dev)
         db = torch.empty(O, dtype=F32, device=dev)
-        n = 4 * (2 * _lib_sms() + 1) * ((2 + O) * 64 + O)
+        n = 4 * (4 * _lib_sms() + 1) * ((2 + O) * 64 + O)
         ws = workspace(n, dev)
         call("eel_head_bwd", ptr(x), ptr(lnw.detach()), ptr(lnb.detach()), ptr(_c(weight.detach())), ptr(bias.detach()),
              ptr(prob), ptr(dprob), ptr(dx), ptr(dlnw), ptr(dlnb), ptr(dw), ptr(db), N, H * W, O, ptr(ws), n,
@@ -523,7 +523,7 @@ class SE(Function):
         db1 = torch.empty(R, dtype=F32, device=dev)
         dw2 = torch.empty((C, R), dtype=F32, device=dev)
         db2 = torch.empty(C, dtype=F32, device=dev)
-        ws, n = _reduce_ws(dev, C, 1, extra=8 * N * C)
+        ws, n = _reduce_ws(dev, C, 1, extra=16 * N * C)
         call("eel_se_bwd", ptr(t), ptr(dout), ptr(att), ptr(hid), ptr(mean), ptr(_c(w1.detach())), ptr(_c(w2.detach())),
              ptr(dt), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
         return dt, dw1.view(w1.shape), db1, dw2.view(w2.shape), db2
