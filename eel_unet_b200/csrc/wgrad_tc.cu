@@ -131,35 +131,38 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
             int st = 0;
             uint32_t ph = 0;
+            // descriptors are built once for stage 0; every operand view is one of them plus a 16-byte-unit offset in
+            // the start-address field, so an MMA costs a few issue slots (N = 64 MMAs last only 32 cycles)
+            const uint32_t s0 = smem_u32(smem);
+            const uint64_t dB = make_smem_desc(s0 + Cfg::A_BYTES, MODE == WG_PLAIN ? 8192 : kTile, 1024, false);
+            const uint64_t dA0 = make_smem_desc(s0, MODE == WG_PLAIN ? 8192 : (MODE == WG_CONV_B ? kCopy : 1024), 1024, false);
+            const uint64_t dA3 = make_smem_desc(s0, kCopy, 1024, false);   // CONV_A group 3: second atom = next column copy
+            const uint64_t dA4 = make_smem_desc(s0, 0, 1024, false);       // CONV_A group 4: second atom = first (unused half)
             for (int s = 0; s < nstages; ++s) {
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
-                const uint32_t a = smem_u32(smem + st * Cfg::STAGE);
-                const uint32_t b = a + Cfg::A_BYTES;
+                const uint32_t so = (uint32_t)(st * Cfg::STAGE) >> 4;
                 if (MODE == WG_PLAIN) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem_base, make_smem_desc(a + ks * 2048, 8192, 1024, false),
-                                  make_smem_desc(b + ks * 2048, 8192, 1024, false), idesc, (s | ks) != 0);
+                        umma_bf16(tmem_base, dA0 + (so + ks * 128), dB + (so + ks * 128), idesc, (s | ks) != 0);
                 } else if (MODE == WG_CONV_B) {
 #pragma unroll
                     for (int t = 0; t < 3; ++t)
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            umma_bf16(tmem_base + t * BN, make_smem_desc(a + t * 1024 + ks * 2048, kCopy, 1024, false),
-                                      make_smem_desc(b + ks * 2048, kTile, 1024, false), idesc, (s | ks) != 0);
+                            umma_bf16(tmem_base + t * BN, dA0 + (so + t * 64 + ks * 128), dB + (so + ks * 128), idesc, (s | ks) != 0);
                 } else {
                     // accumulator g: rows 0-63 = tap t1, rows 64-127 = tap t2 (second atom = first + LBO)
                     //   g0..g2: copy g, dy = -1 and 0 (LBO = one image row);  g3: (dy=+1, dx=-1) and (dy=+1, dx=0);
                     //   g4: (dy=+1, dx=+1) twice (upper half unused)
 #pragma unroll
                     for (int g = 0; g < 5; ++g) {
-                        const uint32_t off = g < 3 ? g * kCopy : (g == 3 ? 2 * 1024 : 2 * kCopy + 2 * 1024);
-                        const uint32_t lbo = g < 3 ? 1024 : (g == 3 ? kCopy : 0);
+                        const uint32_t off = (g < 3 ? g * kCopy : (g == 3 ? 2 * 1024 : 2 * kCopy + 2 * 1024)) >> 4;
+                        const uint64_t dA = g < 3 ? dA0 : (g == 3 ? dA3 : dA4);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            umma_bf16(tmem_base + g * BN, make_smem_desc(a + off + ks * 2048, lbo, 1024, false),
-                                      make_smem_desc(b + ks * 2048, kTile, 1024, false), idesc, (s | ks) != 0);
+                            umma_bf16(tmem_base + g * BN, dA + (so + off + ks * 128), dB + (so + ks * 128), idesc, (s | ks) != 0);
                     }
                 }
                 umma_commit(&empty[st]);
@@ -179,19 +182,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int ncols_valid = BN;
                 if (MODE == WG_PLAIN) {
                     const int m = mb * 128 + r;
-                    if (m < p.Ma) row = p.out + m * p.ldm + (long long)(nb * BN) * p.ldn;
+                    if (m < p.Ma && p.out) row = p.out + m * p.ldm + (long long)(nb * BN) * p.ldn;
                     cstride = p.ldn;
                     ncols_valid = min(BN, p.Nb - nb * BN);
                 } else if (MODE == WG_CONV_B) {
                     const int tap = g * 3 + grp;   // (dy = g - 1, dx = grp - 1)
-                    row = p.out + ((long long)tap * p.Cin + mb * 128 + r) * p.Cout + nb * BN;
+                    if (p.out) row = p.out + ((long long)tap * p.Cin + mb * 128 + r) * p.Cout + nb * BN;
                 } else {
                     const int half = r >> 6, ci = r & 63;
                     int tap;
                     if (g < 3) tap = half * 3 + g;              // dy = -1 / 0, dx = g - 1
                     else if (g == 3) tap = 6 + half;            // dy = +1, dx = -1 / 0
                     else tap = half == 0 ? 8 : -1;              // dy = +1, dx = +1
-                    if (tap >= 0) row = p.out + ((long long)tap * p.Cin + ci) * p.Cout + nb * BN;
+                    if (tap >= 0 && p.out) row = p.out + ((long long)tap * p.Cin + ci) * p.Cout + nb * BN;
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN;
 #pragma unroll 1
@@ -199,9 +202,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     float v[32];
                     tmem_ld32(taddr + cc, v);
                     if (row != nullptr) {
+                        if (cstride == 1 && cc + 32 <= ncols_valid) {
+                            // contiguous columns: 16-byte vector reductions (4x fewer L2 atomic operations)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (cc + j < ncols_valid) atomicAdd(row + (long long)(cc + j) * cstride, v[j]);
+                            for (int j = 0; j < 32; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + cc + j), "f"(v[j]), "f"(v[j + 1]),
+                                             "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (cc + j < ncols_valid) atomicAdd(row + (long long)(cc + j) * cstride, v[j]);
+                        }
                     }
                 }
             }
@@ -226,7 +237,7 @@ static int launch_wg(const CUtensorMap& a, const CUtensorMap& b, WgParams& p, in
     // split-K factor: minimise waves x stages-per-CTA
     long long best = -1;
     int bestS = 1;
-    const int maxS = p.stages_total < 64 ? p.stages_total : 64;
+    const int maxS = p.stages_total < kNumSMs ? p.stages_total : kNumSMs;
     for (int S = 1; S <= maxS; ++S) {
         long long waves = ((long long)units * S + kNumSMs - 1) / kNumSMs;
         long long cost = waves * ((p.stages_total + S - 1) / S + 6);   // +6: fixed prologue / epilogue per CTA
