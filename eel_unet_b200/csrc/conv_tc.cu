@@ -13,7 +13,7 @@
 // 64->64, 128->64, 64->128 -- the full-resolution layers that hold most of the FLOPs) it is loaded ONCE per CTA and
 // stays resident (RES), so the steady state only streams activations.
 //
-//   warp 0  TMA producer   warp 1  MMA issuer (one thread)   warps 2-5  epilogue (TMEM -> +bias/ReLU -> bf16 -> global)
+//   warp 0  TMA producer   warp 1  MMA issuer (one thread)   warps 2-5 / 2-9  epilogue (TMEM -> +bias/ReLU -> bf16 -> smem transposition -> global)
 // Two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent, one CTA per SM.
 #include "tc_common.cuh"
 
@@ -33,7 +33,6 @@ struct ConvParams {
     bf16* out;
 };
 
-constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 
 template <int BN, int MT, bool RES> struct ConvCfg {
@@ -47,7 +46,6 @@ template <int BN, int MT, bool RES> struct ConvCfg {
 };
 
 constexpr int kSmemLimit = 232448 - 1024;   // 227 KB per CTA minus alignment slack
-constexpr int kStageBytes = 4 * 2048;       // epilogue transposition buffers (2 KB per warp)
 
 template <int BN, int MT, bool RES>
 __device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, uint8_t* sB, uint64_t* fullA, uint64_t* emptyA,
@@ -115,8 +113,8 @@ __device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, 
 }
 
 
-template <int BN, int MT, bool RES>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int MT, bool RES, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     typedef ConvCfg<BN, MT, RES> Cfg;
     extern __shared__ uint8_t smem_raw[];
@@ -143,7 +141,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1);
             mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], EW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -190,17 +188,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (tmem_base == 0) conv_mma_loop<BN, MT, RES>(p, sA, sB, fullA, emptyA, fullB, emptyB, tmemFull, tmemEmpty, 0u, total_tiles);
         else conv_mma_loop<BN, MT, RES>(p, sA, sB, fullA, emptyA, fullB, emptyB, tmemFull, tmemEmpty, tmem_base, total_tiles);
     } else if (warp >= 2) {
-        // ===================================================================== epilogue
-        // Thread = accumulator row = pixel; a pixel's 32 channels are 64 contiguous bytes, so storing straight from
-        // the TMEM layout would hit 32 different lines with 16 bytes each per instruction.  The chunk is transposed
-        // through a 2 KB per-warp buffer (16-byte slots XOR-swizzled, conflict free both ways): afterwards four lanes
-        // write one pixel's 64 bytes and a warp-wide store covers full 32-byte sectors only.
+        // ===================================================================== epilogue (EW = 4 or 8 warps)
+        // With 8 warps two warps share each TMEM lane quarter and split the tile's MT * BN / 32 column chunks.  The TMEM
+        // read of chunk i+1 is in flight while chunk i is converted, transposed (epi_store_chunk) and stored.
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        uint8_t* stg = reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + q * 2048;
-        const uint32_t wr_base = smem_u32(stg) + lane * 64;
-        const uint32_t wr_sw = (lane >> 1) & 3;
-        const int px_lo = lane >> 2, ch = lane & 3;           // after the transposition: pixel (px_lo + 8 i), 16-byte slot ch
-        const uint32_t rd_base = smem_u32(stg) + px_lo * 64 + ((ch ^ ((lane >> 3) & 3)) << 4);
+        const int half = (warp - 2) >> 2;       // 0 when EW == 4
+        const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
+        constexpr int NCH_ALL = MT * BN / 32;
+        constexpr int NCH = NCH_ALL / (EW / 4);   // chunks per warp and tile
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -209,50 +204,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n0 = nt * BN;
             const int tw = mt % p.tiles_w, rr = mt / p.tiles_w;
             const int th = rr % p.tiles_h, n = rr / p.tiles_h;
-            const int w = tw * 8 + px_lo;
+            const int w = tw * 8 + L.row_lo;
+            // rows (row_lo + 8 i) of this warp's quarter are image rows h0 + i of accumulator j (+ 16 j)
+            const int h0 = th * Cfg::TH + q * 4;
+            bf16* const pix = p.out + (((long long)n * p.H + h0) * p.W + w) * p.Ntot + n0 + L.slot * 8;
             mbar_wait(&tmemFull[acc], acc_par);
             tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < MT; ++j) {
-                const int h0 = th * Cfg::TH + j * 16 + q * 4;          // image row of this warp's pixels 0-7
-                bf16* row = p.out + (((long long)n * p.H + h0) * p.W + w) * p.Ntot + n0 + ch * 8;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + j * BN;
-#pragma unroll 1
-                for (int cc = 0; cc < BN; cc += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + cc, v);
-                    if (p.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + cc);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + half * NCH * 32;
+            uint32_t buf[2][32];
+            tmem_ld32_async(taddr, buf[0]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 b4 = __ldg(bp + i);
-                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-                        }
-                    }
-                    if (p.relu) {
+            for (int ci = 0; ci < NCH; ++ci) {
+                tmem_ld_wait();
+                if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[(ci + 1) & 1]);
+                const int col = (half * NCH + ci) * 32;       // column within the MT * BN accumulator block
+                const int j = col / BN, cc = col - j * BN;
+                bf16* dst[4];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
-                            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_base + ((c ^ wr_sw) << 4)), "r"(pk[0]), "r"(pk[1]),
-                                     "r"(pk[2]), "r"(pk[3]) : "memory");
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 o;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(rd_base + i * 512) : "memory");
-                        if (h0 + i < p.H && w < p.W) *reinterpret_cast<uint4*>(row + (long long)i * p.W * p.Ntot + cc) = o;
-                    }
-                    __syncwarp();
+                for (int i = 0; i < 4; ++i) {
+                    const int h = h0 + j * 16 + i;
+                    dst[i] = (h < p.H && w < p.W) ? pix + (long long)(j * 16 + i) * p.W * p.Ntot + cc : nullptr;
                 }
+                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst);
             }
             tc_fence_before();
             __syncwarp();
@@ -268,22 +241,29 @@ template <int BN, int MT, bool RES>
 static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int Cout, cudaStream_t st, const char* what) {
     typedef ConvCfg<BN, MT, RES> Cfg;
     const int b_bytes = (RES ? 9 * p.kchunks : Cfg::NB) * Cfg::B_TILE;
-    int na = (kSmemLimit - 1024 - kStageBytes - b_bytes) / Cfg::A_BYTES;
-    if (na > kMaxStages) na = kMaxStages;
+    // 8 epilogue warps (16 KB of transposition buffers) unless that would leave fewer than three activation stages
+    int ew = 8;
+    int na = (kSmemLimit - 1024 - ew * 2048 - b_bytes) / Cfg::A_BYTES;
+    if (na < 3) {
+        ew = 4;
+        na = (kSmemLimit - 1024 - ew * 2048 - b_bytes) / Cfg::A_BYTES;
+    }
     if (na > 6) na = 6;
     if (na < 2) {
         set_error("%s: weights (%d B) leave no room for two activation stages", what, b_bytes);
         return EEL_ERR_INVALID;
     }
     p.na = na;
-    const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + kStageBytes + 1024 /* alignment slack */;
-    static int configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + ew * 2048 + 1024 /* alignment slack */;
+    static int configured[2] = {0, 0};
+    if (configured[ew == 8] < smem) {
+        cudaError_t e = ew == 8 ? cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
             set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
             return EEL_ERR_CUDA;
         }
-        configured = smem;
+        configured[ew == 8] = smem;
     }
     CUtensorMap tmA, tmB;
     {
@@ -304,7 +284,8 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     p.n_tiles = Cout / BN;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    tc_conv_kernel<BN, MT, RES><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+    if (ew == 8) tc_conv_kernel<BN, MT, RES, 8><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
+    else tc_conv_kernel<BN, MT, RES, 4><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
     return check_launch(what);
 }
 

@@ -1,19 +1,16 @@
-// bf16 tensor-core GEMM-class kernels for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma with
-// fp32 accumulators in TMEM -> tcgen05.ld epilogue.  One persistent, warp-specialised kernel template:
+// bf16 tensor-core GEMM kernels for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma with fp32
+// accumulators in TMEM -> tcgen05.ld epilogue.  One persistent, warp-specialised kernel template:
 //
-//   warp 0   TMA producer (one elected thread)          warp 1   TMEM allocator + MMA issuer (one thread)
-//   warps 2-5  epilogue: TMEM -> registers -> (+bias, ReLU) -> bf16 -> global
+//   warp 0   TMA producer (one elected thread)          warp 1   TMEM allocator + MMA issuer (one elected thread)
+//   warps 2-9  epilogue: TMEM -> registers -> (+bias, ReLU) -> bf16 -> transposed through smem -> global
 //
-// TAPS = 1 : plain GEMM   C[M, N] = A[M, K] . B[N, K]^T          (1x1 conv / Linear / ConvTranspose2d as GEMM)
-// TAPS = 9 : implicit-GEMM 3x3 convolution over NHWC.  An output tile is 16 x 8 pixels (= 128 GEMM rows).  Per
-//            64-channel K chunk THREE 18 x 8 row-halo tiles of the input (column offsets -1, 0, +1) are brought
-//            into shared memory by 4-D TMA box loads (out-of-bounds = zero = the conv padding) and the nine taps
-//            are nine *views*: tap (dy, dx) is copy dx+1 with the A descriptor's start address advanced by
-//            (1+dy) image rows = (1+dy) * 1024 B, so every view starts on a swizzle-pattern boundary.
-//            Activations cross L2 -> SM 3.4x instead of 9x.  Weights stream per (chunk, tap) through their own
-//            ring: B tile = [BN output channels][64 input channels] of tap t, K-major.
-// Two rings (A, B) with full/empty mbarriers; two TMEM accumulator stages so the epilogue of tile i overlaps
-// the MMAs of tile i+1.
+//   C[M, N] = A[M, K] . B[N, K]^T     (1x1 conv / Linear; ConvTranspose2d(k2,s2) forward with a scatter epilogue and
+//                                      its data gradient with a gathered A operand)
+// A streams through a ring of 128 x 64 tiles.  B (the weights) either streams through its own ring or -- when the whole
+// [N][K] block of the single N tile fits beside the A ring (<= 128 KB: every CAPMLP layer of the 256-channel stages) --
+// is loaded ONCE per CTA and stays resident, so the steady state moves activations only.
+// Two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1.
+// (The 3x3 convolution lives in conv_tc.cu.)
 #include "tc_common.cuh"
 
 #include <dlfcn.h>
@@ -62,51 +59,42 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-enum { EPI_DENSE = 0, EPI_CONV = 1, EPI_CONVT = 2 };
+enum { EPI_DENSE = 0, EPI_CONVT = 2 };
 
 struct TcParams {
-    int kchunks;            // 64-wide K chunks (per tap)
+    int kchunks;            // 64-wide K chunks
     int m_tiles, n_tiles;
-    long long M;            // GEMM rows (dense / convT)
+    long long M;            // GEMM rows
     int Ntot;               // total output columns
-    int N, H, W;            // conv: image batch / height / width; convT: input w in W
-    int tiles_h, tiles_w;
-    int flip;               // conv: mirror the tap offsets (data gradient)
+    int W;                  // convT: input width
     int relu;
     int Co;                 // convT: output channels
+    int na, nb;             // ring depths (nb unused when res)
+    int res;                // weights resident (n_tiles == 1)
     const float* bias;
     bf16* out;
 };
 
-constexpr int kThreads = 192;
-constexpr int kHaloH = 18;                       // 16 + 2 rows, 8 columns per copy
-constexpr int kCopyBytes = 8 * kHaloH * 128;      // 18432 per column-shifted copy
-constexpr int kHaloBytes = 3 * kCopyBytes;        // 55296
+constexpr int kThreads = 320;                     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 16384;                    // 128 rows x 64 bf16
+constexpr int kSmemBudget = 232448 - 1024 /* alignment */ - 1024 /* barriers */ - 16384 /* epilogue staging */;
 
-template <int BN, int TAPS> struct TcCfg {
-    static constexpr int A_BYTES = TAPS == 9 ? kHaloBytes : 16384;   // 1024-aligned stage sizes
-    static constexpr int A_TX = TAPS == 9 ? kHaloBytes : 16384;
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int NA = TAPS == 9 ? 2 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-    static constexpr int NB = TAPS == 9 ? (BN == 256 ? 3 : (BN == 128 ? 6 : 8)) : NA;
-    static constexpr int SMEM = NA * A_BYTES + NB * B_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512: powers of two
-};
-
-template <int BN, int TAPS, int EPI, int AGATHER>
+template <int BN, int EPI, int AGATHER>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    typedef TcCfg<BN, TAPS> Cfg;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int TMEM_COLS = 2 * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + Cfg::NA * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::NB * Cfg::B_BYTES);
+    uint8_t* sB = smem + p.na * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (p.res ? p.kchunks : p.nb) * B_BYTES);
     uint64_t* fullA = bars;
-    uint64_t* emptyA = fullA + Cfg::NA;
-    uint64_t* fullB = emptyA + Cfg::NA;
-    uint64_t* emptyB = fullB + Cfg::NB;
-    uint64_t* tmemFull = emptyB + Cfg::NB;
+    uint64_t* emptyA = fullA + kMaxStages;
+    uint64_t* fullB = emptyA + kMaxStages;      // res: fullB[0] = "weights resident"
+    uint64_t* emptyB = fullB + kMaxStages;
+    uint64_t* tmemFull = emptyB + kMaxStages;
     uint64_t* tmemEmpty = tmemFull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmemEmpty + 2);
 
@@ -116,12 +104,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < Cfg::NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-        for (int i = 0; i < Cfg::NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], 4); }
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1);
+            mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -129,41 +119,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer
+        if (p.res) {
+            mbar_expect_tx(&fullB[0], (uint32_t)(p.kchunks * B_BYTES));
+            for (int c = 0; c < p.kchunks; ++c) tma_load_2d(sB + c * B_BYTES, &tmB, &fullB[0], c * 64, 0);
+        }
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int n0 = nt * BN;
-            int c_w = 0, c_h = 0, c_n = 0;
-            if (TAPS == 9) {
-                const int tw = mt % p.tiles_w, r = mt / p.tiles_w;
-                const int th = r % p.tiles_h;
-                c_n = r / p.tiles_h;
-                c_h = th * 16 - 1;
-                c_w = tw * 8;
-            }
             for (int c = 0; c < p.kchunks; ++c) {
                 mbar_wait(&emptyA[sa], pa ^ 1);
-                mbar_expect_tx(&fullA[sa], Cfg::A_TX);
-                if (TAPS == 9) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        tma_load_4d(sA + sa * Cfg::A_BYTES + j * kCopyBytes, &tmA, &fullA[sa], c * 64, c_w + j - 1, c_h, c_n);
-                } else if (AGATHER) {
+                mbar_expect_tx(&fullA[sa], kABytes);
+                if (AGATHER) {
                     // ConvTranspose data gradient: A(m, k) = g[n, 2y+dy, 2x+dx, co], k = (dy, dx, co); the tensor map
-                    // views g as {2*Co, w, 2 (dy), N*h}; a tile is p.gw columns x 128/p.gw (n,y) rows
+                    // views g as {2*Co, w, 2 (dy), N*h}; a tile is gw columns x 128/gw (n,y) rows
                     const int per_dy = p.kchunks >> 1;
                     const int dy = c / per_dy, kc = (c - dy * per_dy) * 64;
                     const long long m0 = (long long)mt * 128;
-                    tma_load_4d(sA + sa * Cfg::A_BYTES, &tmA, &fullA[sa], kc, (int)(m0 % p.W), dy, (int)(m0 / p.W));
-                } else tma_load_2d(sA + sa * Cfg::A_BYTES, &tmA, &fullA[sa], c * 64, mt * 128);
-                if (++sa == Cfg::NA) { sa = 0; pa ^= 1; }
-                for (int t = 0; t < TAPS; ++t) {
+                    tma_load_4d(sA + sa * kABytes, &tmA, &fullA[sa], kc, (int)(m0 % p.W), dy, (int)(m0 / p.W));
+                } else tma_load_2d(sA + sa * kABytes, &tmA, &fullA[sa], c * 64, mt * 128);
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
+                if (!p.res) {
                     mbar_wait(&emptyB[sb], pb ^ 1);
-                    mbar_expect_tx(&fullB[sb], Cfg::B_BYTES);
-                    if (TAPS == 9) tma_load_3d(sB + sb * Cfg::B_BYTES, &tmB, &fullB[sb], c * 64, n0, t);
-                    else tma_load_2d(sB + sb * Cfg::B_BYTES, &tmB, &fullB[sb], c * 64, n0);
-                    if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
+                    mbar_expect_tx(&fullB[sb], B_BYTES);
+                    tma_load_2d(sB + sb * B_BYTES, &tmB, &fullB[sb], c * 64, n0);
+                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
                 }
             }
         }
@@ -173,102 +154,91 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         int it = 0;
+        // descriptors built once; a view = descriptor + (byte offset >> 4) in the start-address field
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 16, 1024, false);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, false);
+        if (p.res) {
+            mbar_wait(&fullB[0], 0);
+            tc_fence_after();
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_par = (it >> 1) & 1;
             mbar_wait(&tmemEmpty[acc], acc_par ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
-            uint32_t accum = 0;
             for (int c = 0; c < p.kchunks; ++c) {
                 mbar_wait(&fullA[sa], pa);
-                const uint32_t a_base = smem_u32(sA + sa * Cfg::A_BYTES);
-                for (int t = 0; t < TAPS; ++t) {
+                uint64_t b_view;
+                if (p.res) b_view = b_desc0 + (uint32_t)((c * B_BYTES) >> 4);
+                else {
                     mbar_wait(&fullB[sb], pb);
-                    tc_fence_after();
-                    uint32_t a_view = a_base;
-                    if (TAPS == 9) {
-                        int dy = t / 3 - 1, dx = t % 3 - 1;
-                        if (p.flip) { dy = -dy; dx = -dx; }
-                        a_view += (dx + 1) * kCopyBytes + (1 + dy) * 1024;
-                    }
-                    const uint32_t b_base = smem_u32(sB + sb * Cfg::B_BYTES);
+                    b_view = b_desc0 + (uint32_t)((sb * B_BYTES) >> 4);
+                }
+                tc_fence_after();
+                const uint64_t a_view = a_desc0 + (uint32_t)((sa * kABytes) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = make_smem_desc(a_view + k * 32, 16, 1024, false);
-                        const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024, false);
-                        umma_bf16(tmem_d, da, db, idesc, accum);
-                        accum = 1;
-                    }
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_d, a_view + (uint32_t)(k * 2), b_view + (uint32_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                if (!p.res) {
                     umma_commit(&emptyB[sb]);
-                    if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
+                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
                 }
                 umma_commit(&emptyA[sa]);
-                if (++sa == Cfg::NA) { sa = 0; pa ^= 1; }
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
             }
             umma_commit(&tmemFull[acc]);
         }
     } else if (warp >= 2) {
-        // ===================================================================== epilogue
+        // ===================================================================== epilogue (8 warps)
+        // Two warps share each TMEM lane quarter and split the tile's columns; the TMEM read of chunk i+1 is in flight
+        // while chunk i is converted, transposed (epi_store_chunk) and stored.
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int r = q * 32 + lane;            // accumulator row = GEMM row within the tile
+        const int half = (warp - 2) >> 2;       // which half of the columns
+        const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
+        constexpr int NCH = BN / 64;            // 32-column chunks per warp and tile
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_par = (it >> 1) & 1;
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-            const int n0 = nt * BN;
-            bool valid;
-            long long row_off = 0;       // element offset of this row's output (dense / conv)
-            long long ct_base = 0;       // convT: offset of (2*ny, 2*x, 0)
-            if (EPI == EPI_CONV) {
-                const int tw = mt % p.tiles_w, rr = mt / p.tiles_w;
-                const int th = rr % p.tiles_h, n = rr / p.tiles_h;
-                const int h = th * 16 + (r >> 3), w = tw * 8 + (r & 7);
-                valid = h < p.H && w < p.W;
-                row_off = (((long long)n * p.H + h) * p.W + w) * p.Ntot;
-            } else {
-                const long long m = (long long)mt * 128 + r;
-                valid = m < p.M;
-                if (EPI == EPI_DENSE) row_off = m * p.Ntot;
+            const int n0 = nt * BN + half * (BN / 2);
+            long long roff[4];           // element offset of output row (row_lo + 8 i); -1 = out of range
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long m = (long long)mt * 128 + q * 32 + L.row_lo + 8 * i;
+                if (m >= p.M) roff[i] = -1;
+                else if (EPI == EPI_DENSE) roff[i] = m * p.Ntot;
                 else {
                     const long long ny = m / p.W;
                     const int x = (int)(m - ny * p.W);
-                    ct_base = ((ny * 2) * (2LL * p.W) + 2 * x) * p.Co;
+                    roff[i] = ((ny * 2) * (2LL * p.W) + 2 * x) * p.Co;   // (2*ny, 2*x, 0)
                 }
             }
             mbar_wait(&tmemFull[acc], acc_par);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int cc = 0; cc < BN; cc += 32) {
-                float v[32];
-                tmem_ld32(taddr + cc, v);
-                if (valid) {
-                    const int gcol = n0 + cc;
-                    bf16* dst;
-                    const float* bp = nullptr;
-                    if (EPI == EPI_CONVT) {
-                        const int dy = gcol / (2 * p.Co), rem = gcol - dy * 2 * p.Co;
-                        dst = p.out + ct_base + (long long)dy * (2LL * p.W) * p.Co + rem;
-                        if (p.bias) bp = p.bias + (rem % p.Co);
-                    } else {
-                        dst = p.out + row_off + gcol;
-                        if (p.bias) bp = p.bias + gcol;
-                    }
-                    uint32_t pk[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+            uint32_t buf[2][32];
+            tmem_ld32_async(taddr, buf[0]);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a = v[j] + (bp ? __ldg(bp + j) : 0.f);
-                        float b = v[j + 1] + (bp ? __ldg(bp + j + 1) : 0.f);
-                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-                    }
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            for (int ci = 0; ci < NCH; ++ci) {
+                tmem_ld_wait();
+                if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[(ci + 1) & 1]);
+                const int gcol = n0 + ci * 32;
+                long long coff;              // column part of the destination offset (same for every row)
+                const float* bp = nullptr;
+                if (EPI == EPI_CONVT) {
+                    const int dy = gcol / (2 * p.Co), rem = gcol - dy * 2 * p.Co;
+                    coff = (long long)dy * (2LL * p.W) * p.Co + rem;
+                    if (p.bias) bp = p.bias + (rem % p.Co);
+                } else {
+                    coff = gcol;
+                    if (p.bias) bp = p.bias + gcol;
                 }
+                bf16* dst[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = roff[i] >= 0 ? p.out + roff[i] + coff + L.slot * 8 : nullptr;
+                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst);
             }
             tc_fence_before();
             __syncwarp();
@@ -277,31 +247,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int TAPS, int EPI, int AGATHER>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st, const char* what) {
-    typedef TcCfg<BN, TAPS> Cfg;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, TAPS, EPI, AGATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory to %d", what, Cfg::SMEM);
+template <int BN, int EPI, int AGATHER>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t st, const char* what) {
+    constexpr int B_BYTES = BN * 128;
+    // resident weights: single N tile whose whole K extent fits beside >= 4 A stages
+    p.res = (p.n_tiles == 1 && p.kchunks * B_BYTES + 4 * kABytes <= kSmemBudget) ? 1 : 0;
+    int b_bytes;
+    if (p.res) {
+        b_bytes = p.kchunks * B_BYTES;
+        p.na = (kSmemBudget - b_bytes) / kABytes;
+        if (p.na > kMaxStages) p.na = kMaxStages;
+        p.nb = 0;
+    } else {
+        p.na = p.nb = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+        b_bytes = p.nb * B_BYTES;
+    }
+    const int smem = p.na * kABytes + b_bytes + 1024 + 16384 + 1024;
+    static int configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, AGATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
             return EEL_ERR_CUDA;
         }
-        configured = true;
+        configured = smem;
     }
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    tc_gemm_kernel<BN, TAPS, EPI, AGATHER><<<grid, kThreads, Cfg::SMEM, st>>>(tmA, tmB, p);
+    tc_gemm_kernel<BN, EPI, AGATHER><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
     return check_launch(what);
 }
 
-template <int TAPS, int EPI, int AGATHER = 0>
+template <int EPI, int AGATHER = 0>
 static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, cudaStream_t st, const char* what) {
-    if (bn == 256) return launch_tc<256, TAPS, EPI, AGATHER>(a, b, p, st, what);
-    if (bn == 128) return launch_tc<128, TAPS, EPI, AGATHER>(a, b, p, st, what);
-    return launch_tc<64, TAPS, EPI, AGATHER>(a, b, p, st, what);
+    if (bn == 256) return launch_tc<256, EPI, AGATHER>(a, b, p, st, what);
+    if (bn == 128) return launch_tc<128, EPI, AGATHER>(a, b, p, st, what);
+    return launch_tc<64, EPI, AGATHER>(a, b, p, st, what);
 }
 
 static int pick_bn(int ncols) { return ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64); }
@@ -313,37 +296,6 @@ using namespace eel;
 using namespace eel::tc;
 
 extern "C" {
-
-int eel_tc_conv3x3_v1(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                      int relu, int flip, eel_stream s) {
-    EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
-    EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
-    const int bn = pick_bn(Cout);
-    CUtensorMap tmA, tmB;
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
-        uint32_t box[4] = {64, 8, (uint32_t)kHaloH, 1};
-        if (int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, "tc_conv3x3(A)")) return rc;
-    }
-    {
-        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
-        uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cin * Cout};
-        uint32_t box[3] = {64, (uint32_t)bn, 1};
-        if (int rc = make_tmap_bf16(&tmB, wk, 3, dims, str, box, "tc_conv3x3(B)")) return rc;
-    }
-    TcParams p{};
-    p.kchunks = Cin / 64;
-    p.tiles_h = cdiv(H, 16);
-    p.tiles_w = cdiv(W, 8);
-    p.m_tiles = N * p.tiles_h * p.tiles_w;
-    p.n_tiles = Cout / bn;
-    p.Ntot = Cout;
-    p.N = N; p.H = H; p.W = W;
-    p.flip = flip; p.relu = relu;
-    p.bias = bias; p.out = (bf16*)y;
-    return dispatch_bn<9, EPI_CONV>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_conv3x3");
-}
 
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout, int relu,
                   eel_stream s) {
@@ -369,7 +321,7 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
     p.n_tiles = Nout / bn;
     p.M = P; p.Ntot = Nout;
     p.relu = relu; p.bias = bias; p.out = (bf16*)y;
-    return dispatch_bn<1, EPI_DENSE>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_linear");
+    return dispatch_bn<EPI_DENSE>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_linear");
 }
 
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin, int Cout,
@@ -398,7 +350,7 @@ int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* 
     p.n_tiles = ncols / bn;
     p.M = P; p.Ntot = ncols; p.W = w; p.Co = Cout;
     p.bias = bias; p.out = (bf16*)y;
-    return dispatch_bn<1, EPI_CONVT>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_convt2x2_fwd");
+    return dispatch_bn<EPI_CONVT>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_convt2x2_fwd");
 }
 
 
@@ -428,7 +380,7 @@ int eel_tc_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h
     p.n_tiles = Cin / bn;
     p.M = P; p.Ntot = Cin; p.W = w;
     p.out = (bf16*)dx;
-    return dispatch_bn<1, EPI_DENSE, 1>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_convt2x2_dgrad");
+    return dispatch_bn<EPI_DENSE, 1>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_convt2x2_dgrad");
 }
 
 }  // extern "C"

@@ -128,6 +128,80 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// same load without the wait: lets the next chunk's TMEM read overlap the processing of the current one
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- epilogue: 32 rows x 32 fp32 columns (thread = row) -> bf16 -> coalesced global stores -----------------------
+// A row's 32 channels are 64 contiguous output bytes, so storing straight from the TMEM layout would touch 32 lines
+// with 16 bytes each per instruction.  The chunk is transposed through a 2 KB per-warp buffer (16-byte slots
+// XOR-swizzled, conflict free both ways): afterwards four lanes write one row's 64 bytes and a warp-wide store covers
+// full 32-byte sectors only.  After the transposition lane l holds slot (l & 3) of rows (l >> 2) + 8 i, i = 0..3.
+struct EpiLane {
+    uint32_t wr_base, wr_sw, rd_base;
+    int row_lo, slot;
+};
+__device__ __forceinline__ EpiLane epi_lane(uint8_t* staging_2k, int lane) {
+    EpiLane L;
+    L.wr_base = smem_u32(staging_2k) + lane * 64;
+    L.wr_sw = (lane >> 1) & 3;
+    L.row_lo = lane >> 2;
+    L.slot = lane & 3;
+    L.rd_base = smem_u32(staging_2k) + L.row_lo * 64 + ((L.slot ^ ((lane >> 3) & 3)) << 4);
+    return L;
+}
+// r: the 32 accumulator columns of this thread's row; bias32: 32 floats (16-byte aligned) or null;
+// dst[i]: where row (row_lo + 8 i) keeps these 32 columns (already offset by slot * 8 elements), null = skip
+__device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t (&r)[32], const float* bias32, int relu,
+                                                __nv_bfloat16* const (&dst)[4]) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (bias32) {
+        const float4* b4p = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(b4p + i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+        }
+    }
+    if (relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(L.wr_base + ((c ^ L.wr_sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(L.rd_base + i * 512) : "memory");
+        if (dst[i] != nullptr) *reinterpret_cast<uint4*>(dst[i]) = o;
+    }
+    __syncwarp();
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory operand descriptor, 128-byte swizzle.  lbo/sbo in bytes.
 //   K-major  : rows of 128 B (64 bf16 of K); 8-row groups `sbo` apart; lbo unused.

@@ -45,6 +45,24 @@ def cases(B, S, only):
             x, dy, dw = rnd(B, s, s, ci), rnd(B, s, s, co), torch.empty(3, 3, ci, co, device=DEV, dtype=F32)
             return "eel_tc_conv3x3_wgrad", (ptr(x), ptr(dy), ptr(dw), B, s, s, ci, co, st()), (x, dy, dw)
         add("wgrad", "wgrad3x3 %dx%d %d->%d" % (s, s, ci, co), mk)
+    for (P, K, No) in [(B * (S // 4) ** 2, 256, 256), (B * (S // 4) ** 2, 256, 64), (B * (S // 4) ** 2, 64, 256), (B * (S // 8) ** 2, 512, 512),
+                       (B * (S // 8) ** 2, 256, 512), (B * (S // 16) ** 2, 1024, 1024)]:
+        def mk(P=P, K=K, No=No):
+            x, w, b, y = rnd(P, K), rnd(No, K), rnd(No, dtype=F32), torch.empty(P, No, device=DEV, dtype=BF16)
+            return "eel_tc_linear", (ptr(x), ptr(w), ptr(b), ptr(y), P, K, No, int(os.environ.get("EEL_RELU", "0")), st()), (x, w, b, y)
+        add("linear", "linear P=%d %d->%d" % (P, K, No), mk)
+
+        def mkw(P=P, K=K, No=No):
+            x, dy, dw = rnd(P, K), rnd(P, No), torch.empty(No, K, device=DEV, dtype=F32)
+            if No % 128 == 0:
+                return "eel_tc_wgrad", (ptr(dy), ptr(x), ptr(dw), P, No, K, K, 1, dw.numel(), 0, st()), (x, dy, dw)
+            return "eel_tc_wgrad", (ptr(x), ptr(dy), ptr(dw), P, K, No, 1, K, dw.numel(), 0, st()), (x, dy, dw)
+        add("lwgrad", "lin-wgrad P=%d %d->%d" % (P, K, No), mkw)
+    for (s, ci, co) in [(S // 2, 128, 64), (S // 4, 256, 128), (S // 8, 512, 256), (S // 16, 1024, 512)]:
+        def mk(s=s, ci=ci, co=co):
+            x, w, b, y = rnd(B, s, s, ci), rnd(2, 2, co, ci), rnd(co, dtype=F32), torch.empty(B, 2 * s, 2 * s, co, device=DEV, dtype=BF16)
+            return "eel_tc_convt2x2_fwd", (ptr(x), ptr(w), ptr(b), ptr(y), B, s, s, ci, co, st()), (x, w, b, y)
+        add("convt", "convT %dx%d %d->%d" % (s, s, ci, co), mk)
     for (s, c) in [(S, 64), (S // 2, 128), (S // 4, 256), (S // 8, 512)]:
         P = B * s * s
 
