@@ -135,7 +135,13 @@ __global__ void __launch_bounds__(1024) finalize_partials_kernel(const float* __
     const int b = blockIdx.y;
     double s = 0.0;
     if (j < width)
-        for (int r = ty; r < nrb; r += 32) s += (double)partial[((long long)b * nrb + r) * width + j];
+        for (int r = ty; r < nrb; r += 32 * 8) {      // 8 independent loads in flight (the partials sit in L2: ~1 us each)
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = r + 32 * u < nrb ? partial[((long long)b * nrb + r + 32 * u) * width + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
     sm[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && j < width) {
@@ -143,6 +149,38 @@ __global__ void __launch_bounds__(1024) finalize_partials_kernel(const float* __
 #pragma unroll
         for (int y = 0; y < 32; ++y) t += sm[y][tx];
         out[(long long)b * width + j] = (float)(t * scale);
+    }
+}
+
+
+// BatchNorm backward: sums[j] = sum_rb partial[rb][j] for j in [0, 2C) = {sum g | sum g*xhat}; also written straight to
+// dbeta / dgamma (no device-to-device copies) and the optional dz column-sum accumulator is cleared for the apply pass.
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nrb, int C, float* __restrict__ sums,
+                                                             float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                             float* __restrict__ dz_colsum) {
+    __shared__ double sm[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    const int width = 2 * C;
+    double s = 0.0;
+    if (j < width)
+        for (int r = ty; r < nrb; r += 32 * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = r + 32 * u < nrb ? partial[(long long)(r + 32 * u) * width + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sm[y][tx];
+        const float f = (float)t;
+        sums[j] = f;
+        if (j < C) { dbeta[j] = f; if (dz_colsum != nullptr) dz_colsum[j] = 0.f; }
+        else dgamma[j - C] = f;
     }
 }
 
@@ -254,9 +292,16 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     const int c = blockIdx.x * 32 + tx;
     double s1 = 0.0, s2 = 0.0;
     if (c < C)
-        for (int r = ty; r < nrb; r += 32) {
-            s1 += (double)partial[((long long)r * 2 + 0) * C + c];
-            s2 += (double)partial[((long long)r * 2 + 1) * C + c];
+        for (int r = ty; r < nrb; r += 32 * 4) {      // 8 independent loads in flight
+            float v1[4], v2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = r + 32 * u < nrb;
+                v1[u] = ok ? partial[((long long)(r + 32 * u) * 2 + 0) * C + c] : 0.f;
+                v2[u] = ok ? partial[((long long)(r + 32 * u) * 2 + 1) * C + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s1 += (double)v1[u]; s2 += (double)v2[u]; }
         }
     sm1[ty][tx] = s1;
     sm2[ty][tx] = s2;
@@ -351,7 +396,9 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ d
         k2[j] = train ? sums[C + c] * inv_count : 0.f;
         cs[j] = 0.f;
     }
-    long long r0 = blockIdx.y * rows_per_rb, r1 = r0 + rows_per_rb;
+    // row blocks are walked from the END of the tensor: the reduction pass that ran just before finished there, so the
+    // last ~100 MB of dy / z it read are still in the 126 MB L2 when this pass starts
+    long long r0 = (long long)(gridDim.y - 1 - blockIdx.y) * rows_per_rb, r1 = r0 + rows_per_rb;
     if (r1 > rows) r1 = rows;
     if (!live) r1 = r0;
     for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
@@ -776,12 +823,10 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
         BnBwdF<T> f{(const T*)dy, (const T*)z, mean, rstd, gamma, beta, C, relu};
         if (int rc = run_colreduce<T, BnBwdF<T>, 2>(f, P, C, 1, partial, ws_bytes - sizeof(float) * 2 * C, pl, (cudaStream_t)s,
                                                    "bn_act_bwd.reduce")) return rc;
-        if (int rc = run_finalize(partial, pl.nrb, 2 * C, 1, sums, 1.0f, (cudaStream_t)s, "bn_act_bwd.finalize")) return rc;
-        cudaMemcpyAsync(dbeta, sums, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-        cudaMemcpyAsync(dgamma, sums + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        bn_bwd_finalize_kernel<<<cdiv(2 * C, 32), 1024, 0, (cudaStream_t)s>>>(partial, pl.nrb, C, sums, dbeta, dgamma, dz_colsum);
+        if (int rc = check_launch("bn_act_bwd.finalize")) return rc;
         RedPlan ps = plan_stream<T>(P, C);
         dim3 grid(ps.ncb, ps.nrb);
-        if (dz_colsum != nullptr) cudaMemsetAsync(dz_colsum, 0, sizeof(float) * C, (cudaStream_t)s);
         bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
                                                             1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train, dz_colsum);
         return check_launch("bn_act_bwd");

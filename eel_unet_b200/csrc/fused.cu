@@ -11,21 +11,31 @@ __device__ __forceinline__ float group_sum(float v, int G) {
     return v;
 }
 
-// block = 32 columns x 32 row-slices (parallel over the per-block partial rows)
-__global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+// block = 32 columns x 32 row-slices (parallel over the per-block partial rows).  Column j of the finished row goes to the
+// output segment that contains it (the parameter gradients are separate tensors: no device-to-device copies afterwards).
+struct RowSegs { float* p[4]; int end[4]; };   // segment k holds columns [end[k-1], end[k])
+__global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __restrict__ partial, int nrows, int width, RowSegs segs) {
     __shared__ double sm[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
     double s = 0.0;
     if (j < width)
-        for (int r = ty; r < nrows; r += 32) s += (double)partial[(long long)r * width + j];
+        for (int r = ty; r < nrows; r += 32 * 8) {    // 8 independent loads in flight
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = r + 32 * u < nrows ? partial[(long long)(r + 32 * u) * width + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
     sm[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && j < width) {
         double t = 0.0;
 #pragma unroll
         for (int y = 0; y < 32; ++y) t += sm[y][tx];
-        out[j] = (float)t;
+        int k = 0, start = 0;
+        while (k < 3 && j >= segs.end[k]) { start = segs.end[k]; ++k; }
+        segs.p[k][j - start] = (float)t;
     }
 }
 
@@ -410,7 +420,6 @@ int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy,
         size_t need = sizeof(float) * ((size_t)grid + 1) * (C + 1);
         if (need > ws_bytes || !ws) { set_error("pgr_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
         float* partial = (float*)ws;
-        float* fin = partial + (size_t)grid * (C + 1);
         const int iters = C / V / G;
         const size_t shb = sizeof(float) * (C + 1);
         cudaStream_t st2 = (cudaStream_t)s;
@@ -419,11 +428,9 @@ int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy,
         else if (iters == 4) pgr_bwd_kernel2<T, 4, 1><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
         else pgr_bwd_kernel<T><<<grid, kPixThreads, shb, st2>>>((const T*)x, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
         if (int rc = check_launch("pgr_bwd")) return rc;
-        finalize_rows_kernel<<<cdiv(C + 1, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, C + 1, fin);
-        if (int rc = check_launch("pgr_bwd.finalize")) return rc;
-        cudaMemcpyAsync(dw, fin, sizeof(float) * C, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-        cudaMemcpyAsync(db, fin + C, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-        return EEL_OK;
+        RowSegs segs{{dw, db, db, db}, {C, C + 1, C + 1, C + 1}};
+        finalize_rows_kernel<<<cdiv(C + 1, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, C + 1, segs);
+        return check_launch("pgr_bwd.finalize");
     });
 }
 
@@ -457,18 +464,12 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         size_t need = sizeof(float) * ((size_t)grid + 1) * width;
         if (need > ws_bytes || !ws) { set_error("head_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
         float* partial = (float*)ws;
-        float* fin = partial + (size_t)grid * width;
         head_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx,
                                                                                        partial, P, HW, O);
         if (int rc = check_launch("head_bwd")) return rc;
-        finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, width, fin);
-        if (int rc = check_launch("head_bwd.finalize")) return rc;
-        cudaStream_t st = (cudaStream_t)s;
-        cudaMemcpyAsync(dlnw, fin, sizeof(float) * kHeadC, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(dlnb, fin + kHeadC, sizeof(float) * kHeadC, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(dw, fin + 2 * kHeadC, sizeof(float) * O * kHeadC, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(db, fin + (2 + O) * kHeadC, sizeof(float) * O, cudaMemcpyDeviceToDevice, st);
-        return EEL_OK;
+        RowSegs segs{{dlnw, dlnb, dw, db}, {kHeadC, 2 * kHeadC, (2 + O) * kHeadC, (2 + O) * kHeadC + O}};
+        finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, width, segs);
+        return check_launch("head_bwd.finalize");
     });
 }
 
