@@ -40,6 +40,30 @@ __global__ void permute4_kernel(const TI* __restrict__ in, TO* __restrict__ out,
     }
 }
 
+
+// One launch packs a whole table of weights (fp32, reference layout) into their bf16 operand layouts: blockIdx.y = job.
+struct PackJob {           // mirrors eel_pack_job in eel.h (64 bytes)
+    const float* src;
+    bf16* dst;
+    int d[4];
+    int p[4];
+    long long pad[2];
+};
+__global__ void pack_batch_kernel(const PackJob* __restrict__ jobs) {
+    const PackJob j = jobs[blockIdx.y];
+    const int od1 = j.d[j.p[1]], od2 = j.d[j.p[2]], od3 = j.d[j.p[3]];
+    const long long istr[4] = {(long long)j.d[1] * j.d[2] * j.d[3], (long long)j.d[2] * j.d[3], j.d[3], 1};
+    const long long s0 = istr[j.p[0]], s1 = istr[j.p[1]], s2 = istr[j.p[2]], s3 = istr[j.p[3]];
+    const long long total = (long long)j.d[0] * j.d[1] * j.d[2] * j.d[3];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int o3 = (int)(r % od3); r /= od3;
+        const int o2 = (int)(r % od2); r /= od2;
+        const int o1 = (int)(r % od1); r /= od1;
+        j.dst[i] = __float2bfloat16_rn(j.src[r * s0 + o1 * s1 + o2 * s2 + o3 * s3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------ column reductions
 // partial[b][rb][q][c] = sum over the rows of row-block rb (of image-batch b) of f.q-th quantity.
 // Threads: TX lanes across channel vectors, TY = 256/TX across rows.
@@ -742,6 +766,14 @@ int eel_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int dt
         nchw_to_nhwc_kernel<T><<<ew_grid(NHW, 256), 256, 0, (cudaStream_t)s>>>(x, (T*)y, NHW, C, HW);
         return check_launch("nchw_to_nhwc");
     });
+}
+
+int eel_pack_batch(const void* jobs_device, int njobs, int blocks_per_job, eel_stream s) {
+    EEL_REQUIRE(jobs_device && njobs > 0 && blocks_per_job > 0 && njobs <= 65535, "pack_batch: bad argument");
+    static_assert(sizeof(PackJob) == 64, "PackJob must match eel_pack_job");
+    dim3 grid(blocks_per_job, njobs);
+    pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const PackJob*)jobs_device);
+    return check_launch("pack_batch");
 }
 
 int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0, int d1, int d2, int d3, int p0,

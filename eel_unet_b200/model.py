@@ -144,7 +144,13 @@ class EELUnet(nn.Module):
         if precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.compute_dtype = _PRECISIONS[precision]
+        self._packer = None
         return self
+
+    def _weight_packer(self):
+        if self._packer is None:
+            self._packer = ops.build_packer(self)
+        return self._packer
 
     # ---- fused stages ------------------------------------------------------------------------
     @staticmethod
@@ -194,6 +200,12 @@ class EELUnet(nn.Module):
             raise EelError("eel_unet_b200.EELUnet runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
             raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+        if self.compute_dtype == torch.bfloat16:
+            pk = self._weight_packer()
+            pk.refresh(x.device)
+            ops.set_packer(pk)
+        else:
+            ops.set_packer(None)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
         enc1 = self._conv_block(self.enc1[0], a)

@@ -68,6 +68,110 @@ def _colsum(x2d, C):
 BF16 = torch.bfloat16
 
 
+
+# --------------------------------------------------------------------------------------- batched weight packing
+class WeightPacker:
+    """Packs every tensor-core layer's fp32 weight into its two bf16 operand layouts (forward, data gradient)
+    with ONE kernel launch per step (eel_pack_batch) instead of two small permute launches per layer.
+
+    ``get(weight)`` -> (fwd_operand, dgrad_operand) or None when the parameter is not in the table (SIMT / fp32 layers
+    pack on their own).  The table is rebuilt when a parameter moves (e.g. re-homed into the flat optimizer buffer)."""
+
+    def __init__(self):
+        self.entries = []      # (param, dims, perm_fwd, perm_dgrad)
+        self.by_param = {}
+        self.table = None
+        self.ptrs = None
+        self.versions = None
+
+    def add(self, param, dims, perm_fwd, perm_dgrad):
+        self.entries.append((param, tuple(int(d) for d in dims), perm_fwd, perm_dgrad))
+
+    def _build(self, device):
+        import numpy as np
+        rec = np.zeros((2 * len(self.entries), 8), dtype=np.int64)   # 64-byte records (eel_pack_job)
+        self.by_param = {}
+        keep = []
+        for k, (w, dims, pf, pd) in enumerate(self.entries):
+            outs = []
+            for u, perm in enumerate((pf, pd)):
+                dst = torch.empty([dims[i] for i in perm], dtype=BF16, device=device)
+                r = rec[2 * k + u]
+                r[0], r[1] = w.data_ptr(), dst.data_ptr()
+                d32 = np.array(list(dims) + list(perm), dtype=np.int32)
+                r[2:6] = d32.view(np.int64)
+                outs.append(dst)
+            self.by_param[id(w)] = tuple(outs)
+            keep.append(w)
+        self.table = torch.from_numpy(rec.reshape(-1).view(np.uint8).copy()).to(device)
+        self.ptrs = [w.data_ptr() for w in keep]
+        self.versions = None
+
+    def refresh(self, device):
+        """(re)pack if any weight changed since the last call; call at the start of every forward."""
+        if not self.entries:
+            return
+        if self.table is None or self.table.device != device or self.ptrs != [e[0].data_ptr() for e in self.entries]:
+            self._build(device)
+        # torch-side in-place updates bump ``_version``; kernels that write parameters through raw pointers
+        # (FusedAdam) announce themselves with ``weights_changed()``
+        ver = [_WEIGHT_EPOCH] + [e[0]._version for e in self.entries]
+        if ver == self.versions:
+            return
+        call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream())
+        self.versions = ver
+
+    def get(self, w):
+        return self.by_param.get(id(w))
+
+
+_PACKER = None
+_WEIGHT_EPOCH = 0
+
+
+def weights_changed():
+    """to be called by anything that rewrites parameters behind torch's back (the fused Adam kernel)"""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+def build_packer(module):
+    """table of every tensor-core layer's weight of ``module`` -> (forward, data-gradient) bf16 operand layouts"""
+    import torch.nn as nn
+
+    pk = WeightPacker()
+    for m in module.modules():
+        w = getattr(m, "weight", None)
+        if not isinstance(w, nn.Parameter):
+            continue
+        if isinstance(m, nn.ConvTranspose2d):
+            ci, co = w.shape[0], w.shape[1]
+            if ci % 64 == 0 and co % 64 == 0 and m.kernel_size == (2, 2):
+                pk.add(w, w.shape, (2, 3, 1, 0), (0, 2, 3, 1))
+        elif isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3):
+            co, ci = w.shape[0], w.shape[1]
+            if ci % 64 == 0 and co % 64 == 0:
+                pk.add(w, w.shape, (2, 3, 0, 1), (2, 3, 1, 0))
+        elif isinstance(m, nn.Linear) or (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1)):
+            no, k = w.shape[0], w.shape[1]
+            if no % 64 == 0 and k % 64 == 0:
+                pk.add(w, (1, 1, no, k), (0, 1, 2, 3), (0, 1, 3, 2))
+    return pk
+
+
+def set_packer(p):
+    """the model installs its packer for the duration of a forward/backward; ops look their weights up in it"""
+    global _PACKER
+    _PACKER = p
+
+
+def _packed(weight, which):
+    if _PACKER is None:
+        return None
+    hit = _PACKER.get(weight)
+    return None if hit is None else hit[which]
+
+
 def _tc_ok(x, *chans):
     """bf16 storage and every channel count a multiple of 64 -> tcgen05 tensor-core kernels (gemm_tc.cu)."""
     return x.dtype == BF16 and all(c % 64 == 0 for c in chans)
@@ -100,7 +204,9 @@ class Conv3x3(Function):
         Cout = weight.shape[0]
         y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
         if _tc_ok(x, Cin, Cout):
-            wk = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]  (K-major B operand)
+            wk = _packed(weight, 0)
+            if wk is None:
+                wk = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]  (K-major B operand)
             call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0, stream())
         else:
             wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
@@ -125,7 +231,9 @@ class Conv3x3(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if _tc_ok(x, Cin, Cout):
-                wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
+                wk = _packed(weight, 1)
+                if wk is None:
+                    wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
                 call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, st)
             else:
                 wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
@@ -151,7 +259,9 @@ class ConvT2x2(Function):
         Cout = weight.shape[1]
         y = torch.empty((N, 2 * h, 2 * w, Cout), dtype=x.dtype, device=x.device)
         if _tc_ok(x, Cin, Cout):
-            wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
+            wk = _packed(weight, 0)
+            if wk is None:
+                wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
             call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, stream())
         else:
             wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
@@ -168,7 +278,9 @@ class ConvT2x2(Function):
         st = stream()
         dx = None
         if ctx.needs_input_grad[0]:
-            wp = _pack(weight, (0, 2, 3, 1), x.dtype)
+            wp = _packed(weight, 1)
+            if wp is None:
+                wp = _pack(weight, (0, 2, 3, 1), x.dtype)
             dx = torch.empty_like(x)
             gw = min(w, 128)
             if _tc_ok(x, Cin, Cout) and 128 % gw == 0 and w % gw == 0:
@@ -199,9 +311,12 @@ class Linear(Function):
         x = _c(x)
         N, H, W, K = x.shape
         Nout = weight.shape[0]
-        w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
-        y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
         ctx.tc = _tc_ok(x, K, Nout)
+        w2 = _packed(weight, 0) if ctx.tc else None
+        if w2 is None:
+            w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
+        w2 = w2.view(Nout, K)
+        y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
         if ctx.tc:
             if shift:
                 x = _shift(x, False)           # saved shifted: wgrad then needs no gather
@@ -226,7 +341,9 @@ class Linear(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if ctx.tc:
-                wt = _pack(weight.detach().view(1, 1, Nout, K), (0, 1, 3, 2), x.dtype)   # [K][Nout]
+                wt = _packed(weight, 1)
+                if wt is None:
+                    wt = _pack(weight.detach().view(1, 1, Nout, K), (0, 1, 3, 2), x.dtype)   # [K][Nout]
                 call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, st)
                 if ctx.shift:
                     dx = _shift(dx, True)

@@ -159,6 +159,8 @@ class FusedAdam:
         self._lib.call("eel_adam_step", b.flat_param.data_ptr(), b.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                        b.flat_param.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                        float(self.wd), int(self.t), self._lib.stream())
+        from . import ops
+        ops.weights_changed()      # the kernel rewrote the parameters through raw pointers: packed copies are stale
 
     def zero_grad(self, set_to_none=True):
         self.b.zero_grad()

@@ -1,6 +1,7 @@
 """Drop-in ``Unet`` for the reference's ``models/Unet.py`` (BASELINE config 5 comparator): same constructor, same
 ``.name == "unet"`` (train.py:67), same state_dict keys, logits out.  It reuses the conv3x3 / ConvTranspose /
 max-pool kernels of the EELUnet path; conv + ReLU is one fused kernel (no BatchNorm in this model)."""
+import torch
 import torch.nn as nn
 
 from . import ops
@@ -34,6 +35,7 @@ class Unet(nn.Module):
         if precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.compute_dtype = _PRECISIONS[precision]
+        self._packer = None
         return self
 
     @staticmethod
@@ -46,6 +48,13 @@ class Unet(nn.Module):
             raise EelError("eel_unet_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
             raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+        if self.compute_dtype == torch.bfloat16:
+            if self._packer is None:
+                self._packer = ops.build_packer(self)
+            self._packer.refresh(x.device)
+            ops.set_packer(self._packer)
+        else:
+            ops.set_packer(None)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
         e1 = self._b(self.enc1, a)
         e2 = self._b(self.enc2, ops.MaxPool2.apply(e1))

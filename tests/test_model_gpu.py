@@ -156,3 +156,35 @@ def test_state_dict_roundtrip_and_hooks():
         a(torch.zeros(1, 3, 32, 32, device="cuda"))   # leaf hooks (torchsummary, train.py:291) must not break forward
     for h in hooks:
         h.remove()
+
+
+def test_packed_weights_follow_every_kind_of_update():
+    """bf16 mode packs all tensor-core weights once per step (ops.WeightPacker).  The packed copies must follow
+    (a) the fused Adam kernel, which rewrites parameters through raw pointers, (b) torch-side in-place updates
+    (load_state_dict) and (c) parameters that move (re-homed into the flat optimizer buffer)."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+    from eel_unet_b200.parallel import DataParallel, FusedAdam
+
+    torch.manual_seed(0)
+    x, y = torch.randn(2, 3, 32, 32, device="cuda"), (torch.rand(2, 1, 32, 32, device="cuda") > 0.5).float()
+    model = EELUnet(3, 1, precision="bf16").cuda().train()
+    crit = edge_BceDiceLoss(1, 1)
+    model(x)                                    # table built on the original parameter storage
+    dp = DataParallel(model)                    # (c) parameters move into the flat buffer
+    opt = FusedAdam(dp.buckets, lr=1e-2)
+    seg, edges = dp(x)
+    crit(edges, seg, y).backward()
+    dp.finish_backward()
+    opt.step()                                  # (a) raw-pointer update
+    model.eval()
+    with torch.no_grad():
+        seg_after, _ = model(x)
+        fresh = EELUnet(3, 1, precision="bf16").cuda().eval()
+        fresh.load_state_dict(model.state_dict())
+        seg_fresh, _ = fresh(x)
+        assert torch.equal(seg_after, seg_fresh), "packed weights went stale after the fused Adam step"
+        sd = {k: (v * 0.5 if v.dtype.is_floating_point and v.dim() == 4 else v) for k, v in model.state_dict().items()}
+        model.load_state_dict(sd)               # (b) torch in-place update
+        fresh2 = EELUnet(3, 1, precision="bf16").cuda().eval()
+        fresh2.load_state_dict(sd)
+        assert torch.equal(model(x)[0], fresh2(x)[0]), "packed weights went stale after load_state_dict"
