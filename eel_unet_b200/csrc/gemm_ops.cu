@@ -218,15 +218,126 @@ static int pick_splits(long long M, long long N, long long K) {
     return (int)(s < 1 ? 1 : (s > 4096 ? 4096 : s));
 }
 
+// ------------------------------------------------------------------------------------ stem forward
+// conv3x3 forward for the 3(4)-channel input layer (K = 27): HBM-bound on its 64-channel output.  One block walks image
+// rows; the three input rows live in shared memory (fp32); a thread owns 4 output channels with all 9*CIN weights in
+// registers and strides over the row's pixels; 16 threads write one pixel's 64 channels as one contiguous line.
+// smem row pitch in floats: a 4-pixel window (6 columns x CIN floats starting at pixel w, w % 4 == 0) is 16-byte aligned
+// 128-thread blocks: ~150-220 registers per thread still leave 2-3 blocks per SM, so one block's row load and store
+// phases overlap another's FMA phase
+constexpr int kStemThreads = 128;
+__host__ __device__ constexpr int stem_pitch(int W, int CIN) { return ((W + 2) * CIN + 3) / 4 * 4 + 4; }
+
+template <class T, int CIN>
+__device__ __forceinline__ void stem_load_rows(float* sh, const T* __restrict__ x, int n, int h, int H, int W) {
+    const int RP = stem_pitch(W, CIN);
+    for (int i = threadIdx.x; i < 3 * (W + 2) * CIN; i += kStemThreads) {
+        const int c = i % CIN, r = i / CIN;
+        const int col = r % (W + 2), dy = r / (W + 2);
+        const int ww = col - 1, hh = h + dy - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = to_f32(x[(((long long)n * H + hh) * W + ww) * CIN + c]);
+        sh[dy * RP + col * CIN + c] = v;
+    }
+}
+
+// window of pixels w .. w+3 (columns w-1 .. w+4) of the three rows -> xw[3][6 * CIN] by 16-byte loads
+template <int CIN>
+__device__ __forceinline__ void stem_window(const float* sh, int RP, int w, float (&xw)[3][6 * CIN + 2]) {
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const float4* p4 = reinterpret_cast<const float4*>(sh + dy * RP + w * CIN);
+#pragma unroll
+        for (int k = 0; k < (6 * CIN + 3) / 4; ++k) {
+            const float4 v = p4[k];
+            xw[dy][4 * k] = v.x; xw[dy][4 * k + 1] = v.y;
+            if (4 * k + 2 < 6 * CIN + 2) { xw[dy][4 * k + 2] = v.z; xw[dy][4 * k + 3] = v.w; }
+        }
+    }
+}
+
+template <class T, int CIN>
+__global__ void __launch_bounds__(kStemThreads) stem_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
+                                                      T* __restrict__ y, int N, int H, int W, int Cout, int relu) {
+    extern __shared__ __align__(16) float sh[];   // [3][pitch]
+    const int RP = stem_pitch(W, CIN);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int cb = 0; cb < Cout; cb += 64) {
+        float wr[9 * CIN][4], b4[4];
+#pragma unroll
+        for (int k = 0; k < 9 * CIN; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wr[k][j] = to_f32(wp[(long long)k * Cout + cb + tx * 4 + j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b4[j] = bias ? bias[cb + tx * 4 + j] : 0.f;
+        for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+            const int n = row / H, h = row - n * H;
+            __syncthreads();
+            stem_load_rows<T, CIN>(sh, x, n, h, H, W);
+            __syncthreads();
+            T* yrow = y + ((long long)row * W) * Cout + cb + tx * 4;
+            for (int w = ty * 4; w < W; w += kStemThreads / 4) {   // 4 adjacent pixels per thread: 16 independent FMA chains
+                float xw[3][6 * CIN + 2];
+                stem_window<CIN>(sh, RP, w, xw);
+                float acc[4][4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[p][j] = b4[j];
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float xv = xw[t / 3][(p + t % 3) * CIN + c];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[p][j] = fmaf(xv, wr[t * CIN + c][j], acc[p][j]);
+                        }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[p][j] = fmaxf(acc[p][j], 0.f);
+                    }
+                    T* dst = yrow + (long long)(w + p) * Cout;
+                    if (sizeof(T) == 4) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+                    } else {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(acc[p][0], acc[p][1]), hi = __floats2bfloat162_rn(acc[p][2], acc[p][3]);
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <class T, int CIN>
+static int launch_stem_fwd(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cout, int relu,
+                           cudaStream_t st) {
+    size_t smem = sizeof(float) * 3 * (size_t)stem_pitch(W, CIN);
+    if (smem > 200 * 1024 || W % 4 != 0) return 1;   // caller falls back to the generic engine
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(stem_fwd_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    int rows = N * H;
+    int grid = rows < kNumSMs * 12 ? rows : kNumSMs * 12;
+    stem_fwd_kernel<T, CIN><<<grid, kStemThreads, smem, st>>>((const T*)x, (const T*)wp, bias, (T*)y, N, H, W, Cout, relu);
+    return check_launch("conv3x3_fwd(stem)");
+}
+
 // ------------------------------------------------------------------------------------ stem weight gradient
 // conv3x3 wgrad for the 3(4)-channel input layer (K = 27: far too thin for a GEMM tile): one block walks image rows,
 // the three input rows live in shared memory, a thread owns 4 output channels x all 9*CIN taps in registers.
 template <class T, int CIN>
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwp,
+__global__ void __launch_bounds__(kStemThreads) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwp,
                                                         int N, int H, int W, int Cout) {
-    extern __shared__ float sh[];
-    float* xs = sh;                               // [3][W + 2][CIN]
-    float* sdw = sh + 3 * (W + 2) * CIN;          // [9 * CIN][64]
+    extern __shared__ __align__(16) float sh[];
+    const int RP = stem_pitch(W, CIN);
+    float* sdw = sh + 3 * RP;                     // [9 * CIN][64]
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (int cb = 0; cb < Cout; cb += 64) {
         float acc[9 * CIN][4];
@@ -237,47 +348,53 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x
         for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
             const int n = row / H, h = row - n * H;
             __syncthreads();
-            for (int i = threadIdx.x; i < 3 * (W + 2) * CIN; i += 256) {
-                int c = i % CIN, r = i / CIN;
-                int ww = r % (W + 2) - 1, hh = h + r / (W + 2) - 1;
-                float v = 0.f;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = to_f32(x[(((long long)n * H + hh) * W + ww) * CIN + c]);
-                xs[i] = v;
-            }
+            stem_load_rows<T, CIN>(sh, x, n, h, H, W);
             __syncthreads();
             const T* drow = dy + ((long long)row * W) * Cout + cb + tx * 4;
-            for (int w = ty; w < W; w += 16) {
-                float d[4];
+            for (int w = ty * 4; w < W; w += kStemThreads / 4) {   // 4 adjacent pixels per thread
+                float d[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = to_f32(drow[(long long)w * Cout + j]);
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float* xp = xs + ((t / 3) * (W + 2) + w + (t % 3)) * CIN;
-#pragma unroll
-                    for (int c = 0; c < CIN; ++c) {
-                        const float xv = xp[c];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[t * CIN + c][j] = fmaf(xv, d[j], acc[t * CIN + c][j]);
+                for (int p = 0; p < 4; ++p) {
+                    const T* src = drow + (long long)(w + p) * Cout;
+                    if (sizeof(T) == 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(src);
+                        d[p][0] = v.x; d[p][1] = v.y; d[p][2] = v.z; d[p][3] = v.w;
+                    } else {
+                        const uint2 v = *reinterpret_cast<const uint2*>(src);
+                        d[p][0] = __uint_as_float(v.x << 16); d[p][1] = __uint_as_float(v.x & 0xffff0000u);
+                        d[p][2] = __uint_as_float(v.y << 16); d[p][3] = __uint_as_float(v.y & 0xffff0000u);
                     }
                 }
+                float xw[3][6 * CIN + 2];
+                stem_window<CIN>(sh, RP, w, xw);
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float xv = xw[t / 3][(p + t % 3) * CIN + c];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[t * CIN + c][j] = fmaf(xv, d[p][j], acc[t * CIN + c][j]);
+                        }
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < 9 * CIN * 64; i += 256) sdw[i] = 0.f;
+        for (int i = threadIdx.x; i < 9 * CIN * 64; i += kStemThreads) sdw[i] = 0.f;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 9 * CIN; ++k)
 #pragma unroll
             for (int j = 0; j < 4; ++j) atomicAdd(&sdw[k * 64 + tx * 4 + j], acc[k][j]);
         __syncthreads();
-        for (int i = threadIdx.x; i < 9 * CIN * 64; i += 256) atomicAdd(dwp + (long long)(i / 64) * Cout + cb + (i % 64), sdw[i]);
+        for (int i = threadIdx.x; i < 9 * CIN * 64; i += kStemThreads) atomicAdd(dwp + (long long)(i / 64) * Cout + cb + (i % 64), sdw[i]);
     }
 }
 
 template <class T, int CIN>
 static int launch_stem_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cout, cudaStream_t st) {
-    size_t smem = sizeof(float) * (3 * (size_t)(W + 2) * CIN + 9 * CIN * 64);
-    if (smem > 200 * 1024) return 1;   // caller falls back to the generic engine
+    size_t smem = sizeof(float) * (3 * (size_t)stem_pitch(W, CIN) + 9 * CIN * 64);
+    if (smem > 200 * 1024 || W % 4 != 0) return 1;   // caller falls back to the generic engine
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(stem_wgrad_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -285,7 +402,7 @@ static int launch_stem_wgrad(const void* x, const void* dy, float* dwp, int N, i
     }
     int rows = N * H;
     int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
-    stem_wgrad_kernel<T, CIN><<<grid, 256, smem, st>>>((const T*)x, (const T*)dy, dwp, N, H, W, Cout);
+    stem_wgrad_kernel<T, CIN><<<grid, kStemThreads, smem, st>>>((const T*)x, (const T*)dy, dwp, N, H, W, Cout);
     return check_launch("conv3x3_wgrad(stem)");
 }
 
@@ -299,6 +416,15 @@ int eel_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y, i
                     int Cout, int relu, int flip, int dtype, eel_stream s) {
     EEL_REQUIRE(x && wp && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_fwd: bad argument");
     long long P = (long long)N * H * W;
+    if ((Cin == 3 || Cin == 4) && Cout % 64 == 0 && !flip) {
+        int rc = 1;
+        cudaStream_t st = (cudaStream_t)s;
+        if (dtype == EEL_F32) rc = Cin == 3 ? launch_stem_fwd<float, 3>(x, wp, bias, y, N, H, W, Cout, relu, st)
+                                            : launch_stem_fwd<float, 4>(x, wp, bias, y, N, H, W, Cout, relu, st);
+        else if (dtype == EEL_BF16) rc = Cin == 3 ? launch_stem_fwd<bf16, 3>(x, wp, bias, y, N, H, W, Cout, relu, st)
+                                                  : launch_stem_fwd<bf16, 4>(x, wp, bias, y, N, H, W, Cout, relu, st);
+        if (rc <= 0) return rc;
+    }
     EEL_DISPATCH_DTYPE(dtype, {
         Conv3Acc<T> a{(const T*)x, N, H, W, Cin, flip};
         DenseAcc<T> b{(const T*)wp, 9LL * Cin, Cout, Cout};
