@@ -279,7 +279,24 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int q = warp & 3;
         const int grp = (warp - 2) >> 2;     // epilogue warpgroup 0 / 1
         const int r = q * 32 + lane;
+        // output rows leave through the per-warp transposition buffer (tc_common.cuh): full 32-byte sectors per store
+        const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(full) + 1024 + (warp - 2) * 2048, lane);
         long long tile_no = 0;
+        // C == 64: the epilogue's global operand is double-buffered in registers one tile ahead (32 registers);
+        // C == 128 would need 64 more registers than there are, so there the next tile's rows are pulled into L2
+        constexpr bool DB = EPI != H4_T3 && C <= 64;
+        uint4 nxt[DB ? C / 8 : 1];
+        const int item_first = blockIdx.x + (grp / p.mtiles) * gridDim.x;     // this warpgroup's first tile: tile_no == grp
+        if (DB && item_first < p.items) {
+            const int n0 = item_first / idiv, h0 = item_first - n0 * idiv;
+            const long long rb0 = ((long long)n0 * p.H + h0) * p.W;
+            const int m0 = (p.m_begin + grp % p.mtiles) * 128 + r;
+            const bf16* s0 = FWD ? p.x + (rb0 + (m0 >> 1)) * C : p.x + ((rb0 + m0) * 2) * C;
+            if (!FWD || (m0 & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i < (DB ? C / 8 : 1); ++i) nxt[i] = reinterpret_cast<const uint4*>(s0)[i];
+            }
+        }
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const int n = item / idiv, h = item - n * idiv;
             const long long rowbase = ((long long)n * p.H + h) * p.W;
@@ -294,28 +311,58 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t taddr3 = tmem_base + ((uint32_t)(q * 32) << 16) + slot * C;
                     const int ro = m / p.H, hh = m - ro * p.H;
-                    bf16* dst = p.y + (((long long)n * p.H + hh) * 2 * p.F + (long long)ro * p.F) * p.Cc + (long long)h * 128;
+                    (void)ro; (void)hh;
+                    bf16* dst3[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int mm = (p.m_begin + mt) * 128 + q * 32 + L.row_lo + 8 * i;
+                        const int ro2 = mm / p.H, hh2 = mm - ro2 * p.H;
+                        dst3[i] = p.y + (((long long)n * p.H + hh2) * 2 * p.F + (long long)ro2 * p.F) * p.Cc + (long long)h * 128 + L.slot * 8;
+                    }
 #pragma unroll
                     for (int cc = 0; cc < C; cc += 32) {
-                        float v[32];
-                        tmem_ld32(taddr3 + cc, v);
-                        uint4* dp = reinterpret_cast<uint4*>(dst + cc);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            Vec16<bf16> o;
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) o.set(jj, v[i * 8 + jj]);
-                            dp[i] = o.raw;
-                        }
+                        uint32_t rr[32];
+                        tmem_ld32_async(taddr3 + cc, rr);
+                        tmem_ld_wait();
+                        bf16* d4[4] = {dst3[0] + cc, dst3[1] + cc, dst3[2] + cc, dst3[3] + cc};
+                        epi_store_chunk(L, rr, nullptr, 0, d4);
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&accEmpty[slot]);
                     continue;
                 }
-                // the global operand of the epilogue (x, or the real half of g) is fetched BEFORE waiting for the MMAs
+                // the global operand of the epilogue (x, or the real half of g) is fetched BEFORE waiting for the MMAs; the
+                // rows the NEXT tile of this warpgroup will need are pulled into L2 now (the MMAs are far ahead of the
+                // epilogue, so without this every tile would expose a full DRAM round trip on its first use of `pre`)
                 uint4 pre[C / 8];
+                if (DB) {
+#pragma unroll
+                    for (int i = 0; i < C / 8; ++i) pre[i] = nxt[i < (DB ? C / 8 : 1) ? i : 0];
+                }
                 {
+                    // this warpgroup's next tile is tile_no + 2 in the CTA's linear (item, mt) order
+                    const long long t2 = tile_no + 2;
+                    const int mt2 = (int)(t2 % p.mtiles);
+                    const long long item2 = blockIdx.x + (t2 / p.mtiles) * gridDim.x;
+                    if (item2 < p.items) {
+                        const int n2 = (int)(item2 / idiv), h2 = (int)(item2 - (long long)n2 * idiv);
+                        const long long rb2 = ((long long)n2 * p.H + h2) * p.W;
+                        const int m2 = (p.m_begin + mt2) * 128 + r;
+                        const bf16* nx = FWD ? p.x + (rb2 + (m2 >> 1)) * C : p.x + ((rb2 + m2) * 2) * C;
+                        if (!FWD || (m2 & 1) == 0) {
+                            if (DB) {
+#pragma unroll
+                                for (int i = 0; i < (DB ? C / 8 : 1); ++i) nxt[i] = reinterpret_cast<const uint4*>(nx)[i];
+                            } else {
+#pragma unroll
+                                for (int b = 0; b < C * 2; b += 128)
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + b));
+                            }
+                        }
+                    }
+                }
+                if (!DB) {
                     const bf16* src = FWD ? p.x + (rowbase + (m >> 1)) * C : p.x + ((rowbase + m) * 2) * C;
                     if (!FWD || (m & 1) == 0) {
 #pragma unroll
@@ -344,34 +391,47 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 32; ++i) mine[i] = -v[i];
                         }
-                        Vec16<bf16> om[4], op[4];
+                        // re and im of a pixel sit in adjacent lanes: one shuffle per value, then |z| and z/|z| packed two
+                        // at a time (one F2FP per pair instead of a convert + bit insert per element)
+                        uint32_t pkp[16], pkm[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float other = __shfl_xor_sync(0xffffffffu, mine[i], 1);
-                            const float sq = mine[i] * mine[i] + other * other;
-                            const float inv = sq > 0.f ? rsqrtf(sq) : 0.f;
-                            const float mag = sq * inv;
-                            om[i >> 3].set(i & 7, mag);
-                            op[i >> 3].set(i & 7, mine[i] * inv);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float o0 = __shfl_xor_sync(0xffffffffu, mine[i], 1);
+                            const float o1 = __shfl_xor_sync(0xffffffffu, mine[i + 1], 1);
+                            const float sq0 = fmaf(mine[i], mine[i], o0 * o0), sq1 = fmaf(mine[i + 1], mine[i + 1], o1 * o1);
+                            const float inv0 = sq0 > 0.f ? rsqrtf(sq0) : 0.f, inv1 = sq1 > 0.f ? rsqrtf(sq1) : 0.f;
+                            __nv_bfloat162 hm = __floats2bfloat162_rn(sq0 * inv0, sq1 * inv1);
+                            __nv_bfloat162 hp = __floats2bfloat162_rn(mine[i] * inv0, mine[i + 1] * inv1);
+                            pkm[i >> 1] = *reinterpret_cast<uint32_t*>(&hm);
+                            pkp[i >> 1] = *reinterpret_cast<uint32_t*>(&hp);
                         }
-                        uint4* pp = reinterpret_cast<uint4*>(p.phase + ((rowbase + w) * 2 + ro) * C + cc);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) pp[i] = op[i].raw;
-                        if (ro == 0) {
-                            uint4* yp = reinterpret_cast<uint4*>(p.y + e);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) yp[i] = om[i].raw;
-                        }
-                    } else {
-                        const long long e = (rowbase + m) * C + cc;
-                        uint4* dp = reinterpret_cast<uint4*>(p.y + e);
+                        bf16 *dp[4], *dm[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            Vec16<bf16> gv, o; gv.raw = pre[cc / 8 + i];   // real half of the (re, im) pair
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) o.set(jj, gv.get(jj) - v[i * 8 + jj]);
-                            dp[i] = o.raw;
+                            const int mm = (p.m_begin + mt) * 128 + q * 32 + L.row_lo + 8 * i;
+                            dp[i] = p.phase + (rowbase * 2 + mm) * C + cc + L.slot * 8;
+                            dm[i] = (mm & 1) ? nullptr : p.y + (rowbase + (mm >> 1)) * C + cc + L.slot * 8;
                         }
+                        epi_store_packed(L, pkp, dp);
+                        epi_store_packed(L, pkm, dm);
+                    } else {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            Vec16<bf16> gv; gv.raw = pre[cc / 8 + i];   // real half of the (re, im) pair
+#pragma unroll
+                            for (int jj = 0; jj < 8; jj += 2) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(gv.get(jj) - v[i * 8 + jj], gv.get(jj + 1) - v[i * 8 + jj + 1]);
+                                pk[4 * i + (jj >> 1)] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                        }
+                        bf16* dd[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int mm = (p.m_begin + mt) * 128 + q * 32 + L.row_lo + 8 * i;
+                            dd[i] = p.y + (rowbase + mm) * C + cc + L.slot * 8;
+                        }
+                        epi_store_packed(L, pk, dd);
                     }
                 }
                 tc_fence_before();
@@ -403,11 +463,11 @@ static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p
         p.m_begin = mb;
         p.mtiles = total_tiles - mb < 4 ? total_tiles - mb : 4;
         const int m_bytes = p.mtiles * 2 * 16384;
-        int ns = (kMax - 3072 - m_bytes) / p.stage_bytes;
+        int ns = (kMax - 3072 - 16384 - m_bytes) / p.stage_bytes;   // 16 KB: epilogue transposition buffers
         if (ns > 6) ns = 6;
         if (ns < 2) { set_error("%s: resident matrix leaves no room for the operand ring", what); return EEL_ERR_INVALID; }
         p.n_stages = ns;
-        const int smem = m_bytes + ns * p.stage_bytes + 3072;
+        const int smem = m_bytes + ns * p.stage_bytes + 3072 + 16384;
         const int grid = p.items < kNumSMs ? p.items : kNumSMs;
         hft_tc4_kernel<C, EPI><<<grid, kH4Threads, smem, st>>>(m, t, p);
         if (int rc = check_launch(what)) return rc;

@@ -162,8 +162,23 @@ __device__ __forceinline__ EpiLane epi_lane(uint8_t* staging_2k, int lane) {
     L.rd_base = smem_u32(staging_2k) + L.row_lo * 64 + ((L.slot ^ ((lane >> 3) & 3)) << 4);
     return L;
 }
-// r: the 32 accumulator columns of this thread's row; bias32: 32 floats (16-byte aligned) or null;
-// dst[i]: where row (row_lo + 8 i) keeps these 32 columns (already offset by slot * 8 elements), null = skip
+// pk: this thread's row chunk already packed (32 bf16 = 16 words); dst[i]: where row (row_lo + 8 i) keeps these 32
+// columns (already offset by slot * 8 elements), null = skip
+__device__ __forceinline__ void epi_store_packed(const EpiLane& L, const uint32_t (&pk)[16], __nv_bfloat16* const (&dst)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(L.wr_base + ((c ^ L.wr_sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(L.rd_base + i * 512) : "memory");
+        if (dst[i] != nullptr) *reinterpret_cast<uint4*>(dst[i]) = o;
+    }
+    __syncwarp();
+}
+// r: the 32 accumulator columns of this thread's row; bias32: 32 floats (16-byte aligned) or null
 __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t (&r)[32], const float* bias32, int relu,
                                                 __nv_bfloat16* const (&dst)[4]) {
     float v[32];
@@ -181,25 +196,13 @@ __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
+    uint32_t pk[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(L.wr_base + ((c ^ L.wr_sw) << 4)), "r"(pk[0]), "r"(pk[1]),
-                     "r"(pk[2]), "r"(pk[3]) : "memory");
+    for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(L.rd_base + i * 512) : "memory");
-        if (dst[i] != nullptr) *reinterpret_cast<uint4*>(dst[i]) = o;
-    }
-    __syncwarp();
+    epi_store_packed(L, pk, dst);
 }
 
 // ---- descriptors --------------------------------------------------------------------------------
