@@ -31,6 +31,7 @@ struct ConvParams {
     int na;                 // A stages in shared memory
     const float* bias;
     bf16* out;
+    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (n_tiles == 1)
 };
 
 constexpr int kMaxStages = 8;
@@ -196,6 +197,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
         constexpr int NCH_ALL = MT * BN / 32;
         constexpr int NCH = NCH_ALL / (EW / 4);   // chunks per warp and tile
+        float st[NCH][2];                         // fused BatchNorm statistics: two finished values per chunk (tc_common.cuh)
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) st[ci][0] = st[ci][1] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -225,11 +229,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int h = h0 + j * 16 + i;
                     dst[i] = (h < p.H && w < p.W) ? pix + (long long)(j * 16 + i) * p.W * p.Ntot + cc : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst);
+                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, p.bn_sums ? &st[ci] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
+        }
+        if (p.bn_sums) {
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, ((half * NCH + ci) * 32) % BN, lane, st[ci]);
         }
     }
     tc_fence_before();
@@ -282,6 +290,16 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     p.tiles_w = cdiv(p.W, 8);
     p.m_tiles = p.N * p.tiles_h * p.tiles_w;
     p.n_tiles = Cout / BN;
+    if (p.bn_sums != nullptr) {
+        if (p.n_tiles != 1) {
+            set_error("%s: fused BatchNorm statistics need a single N tile (Cout %d)", what, Cout);
+            return EEL_ERR_INVALID;
+        }
+        if (cudaMemsetAsync(p.bn_sums, 0, sizeof(float) * 2 * Cout, st) != cudaSuccess) {
+            set_error("%s: memset failed", what);
+            return EEL_ERR_CUDA;
+        }
+    }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     if (ew == 8) tc_conv_kernel<BN, MT, RES, 8><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
@@ -298,7 +316,7 @@ using namespace eel::tc;
 extern "C" {
 
 int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                   int relu, int flip, eel_stream s) {
+                   int relu, int flip, float* bn_sums, eel_stream s) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     ConvParams p{};
@@ -307,6 +325,7 @@ int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, in
     p.N = N; p.H = H; p.W = W;
     p.flip = flip; p.relu = relu;
     p.bias = bias; p.out = (bf16*)y;
+    p.bn_sums = bn_sums;
     cudaStream_t st = (cudaStream_t)s;
     const bool tall = H > 16;                  // a 32-row tile would be half empty on 16-row maps
     if (Cin == 64 && Cout == 64)

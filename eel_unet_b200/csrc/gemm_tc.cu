@@ -73,6 +73,7 @@ struct TcParams {
     int res;                // weights resident (n_tiles == 1)
     const float* bias;
     bf16* out;
+    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (dense, n_tiles == 1)
 };
 
 constexpr int kThreads = 320;                     // TMA warp, MMA warp, 8 epilogue warps
@@ -197,6 +198,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = (warp - 2) >> 2;       // which half of the columns
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
         constexpr int NCH = BN / 64;            // 32-column chunks per warp and tile
+        float st[NCH][2];                       // fused BatchNorm statistics (tc_common.cuh)
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) st[ci][0] = st[ci][1] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -238,11 +242,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 bf16* dst[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dst[i] = roff[i] >= 0 ? p.out + roff[i] + coff + L.slot * 8 : nullptr;
-                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst);
+                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, (EPI == EPI_DENSE && p.bn_sums) ? &st[ci] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
+        }
+        if (EPI == EPI_DENSE && p.bn_sums) {
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, half * (BN / 2) + ci * 32, lane, st[ci]);
         }
     }
     tc_fence_before();
@@ -298,7 +306,7 @@ using namespace eel::tc;
 extern "C" {
 
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout, int relu,
-                  eel_stream s) {
+                  float* bn_sums, eel_stream s) {
     EEL_REQUIRE(x && w && y && P > 0, "tc_linear: bad argument");
     EEL_REQUIRE(K % 64 == 0 && Nout % 64 == 0, "tc_linear: K and Nout must be multiples of 64 (got %d, %d)", K, Nout);
     const int bn = pick_bn(Nout);
@@ -321,6 +329,14 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
     p.n_tiles = Nout / bn;
     p.M = P; p.Ntot = Nout;
     p.relu = relu; p.bias = bias; p.out = (bf16*)y;
+    if (bn_sums != nullptr) {
+        EEL_REQUIRE(p.n_tiles == 1, "tc_linear: fused BatchNorm statistics need a single N tile (Nout %d)", Nout);
+        if (cudaMemsetAsync(bn_sums, 0, sizeof(float) * 2 * Nout, (cudaStream_t)s) != cudaSuccess) {
+            set_error("tc_linear: memset failed");
+            return EEL_ERR_CUDA;
+        }
+        p.bn_sums = bn_sums;
+    }
     return dispatch_bn<EPI_DENSE>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_linear");
 }
 

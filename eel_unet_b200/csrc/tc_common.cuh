@@ -162,25 +162,75 @@ __device__ __forceinline__ EpiLane epi_lane(uint8_t* staging_2k, int lane) {
     L.rd_base = smem_u32(staging_2k) + L.row_lo * 64 + ((L.slot ^ ((lane >> 3) & 3)) << 4);
     return L;
 }
+// Per-channel sum / sum of squares of a stored chunk (BatchNorm statistics fused into the producer).  After the
+// transposition a lane holds 8 channels (its slot) of 4 rows; the 16 partial values {sum[8], sumsq[8]} are
+// reduce-scattered over the 8 lanes that share the slot (lane bits 2-4), leaving each lane with TWO finished values:
+//     quantity q = bit 4, channel-in-slot c = 4 * bit3 + 2 * bit2 + {0, 1}
+// which the caller accumulates across tiles and adds to global memory once per CTA (epi_stats_flush).
+__device__ __forceinline__ void epi_stats_chunk(const uint4 (&o)[4], const bool (&ok)[4], int lane, float (&acc)[2]) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) continue;
+        const uint32_t w[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+            a[2 * j] += lo; a[2 * j + 1] += hi;
+            a[8 + 2 * j] = fmaf(lo, lo, a[8 + 2 * j]); a[8 + 2 * j + 1] = fmaf(hi, hi, a[8 + 2 * j + 1]);
+        }
+    }
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+    float b[8], c[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float recv = __shfl_xor_sync(0xffffffffu, h4 ? a[k] : a[k + 8], 16);
+        b[k] = (h4 ? a[k + 8] : a[k]) + recv;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float recv = __shfl_xor_sync(0xffffffffu, h3 ? b[k] : b[k + 4], 8);
+        c[k] = (h3 ? b[k + 4] : b[k]) + recv;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float recv = __shfl_xor_sync(0xffffffffu, h2 ? c[k] : c[k + 2], 4);
+        acc[k] += (h2 ? c[k + 2] : c[k]) + recv;
+    }
+}
+// sums: [2][C] fp32 (zeroed by the host); col0 = first channel of the chunk these accumulators belong to
+__device__ __forceinline__ void epi_stats_flush(float* sums, int C, int col0, int lane, const float (&acc)[2]) {
+    const int q = (lane >> 4) & 1;
+    const int ch = col0 + (lane & 3) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2;
+    atomicAdd(sums + (long long)q * C + ch, acc[0]);
+    atomicAdd(sums + (long long)q * C + ch + 1, acc[1]);
+}
+
 // pk: this thread's row chunk already packed (32 bf16 = 16 words); dst[i]: where row (row_lo + 8 i) keeps these 32
-// columns (already offset by slot * 8 elements), null = skip
-__device__ __forceinline__ void epi_store_packed(const EpiLane& L, const uint32_t (&pk)[16], __nv_bfloat16* const (&dst)[4]) {
+// columns (already offset by slot * 8 elements), null = skip.  stats != null: fold the stored values into (*stats)[2].
+__device__ __forceinline__ void epi_store_packed(const EpiLane& L, const uint32_t (&pk)[16], __nv_bfloat16* const (&dst)[4],
+                                                 float (*stats)[2] = nullptr, int lane = 0) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(L.wr_base + ((c ^ L.wr_sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                      "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
     __syncwarp();
+    uint4 o[4];
+    bool ok[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(L.rd_base + i * 512) : "memory");
-        if (dst[i] != nullptr) *reinterpret_cast<uint4*>(dst[i]) = o;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o[i].x), "=r"(o[i].y), "=r"(o[i].z), "=r"(o[i].w) : "r"(L.rd_base + i * 512) : "memory");
+        ok[i] = dst[i] != nullptr;
+        if (ok[i]) *reinterpret_cast<uint4*>(dst[i]) = o[i];
     }
+    if (stats != nullptr) epi_stats_chunk(o, ok, lane, *stats);
     __syncwarp();
 }
 // r: the 32 accumulator columns of this thread's row; bias32: 32 floats (16-byte aligned) or null
 __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t (&r)[32], const float* bias32, int relu,
-                                                __nv_bfloat16* const (&dst)[4]) {
+                                                __nv_bfloat16* const (&dst)[4], float (*stats)[2] = nullptr, int lane = 0) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -202,7 +252,7 @@ __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t
         __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    epi_store_packed(L, pk, dst);
+    epi_store_packed(L, pk, dst, stats, lane);
 }
 
 // ---- descriptors --------------------------------------------------------------------------------

@@ -166,29 +166,44 @@ class EELUnet(nn.Module):
                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias)
 
     @staticmethod
-    def _capmlp(m, x):
-        """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch."""
+    def _capmlp(m, x, bn=None):
+        """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch.
+        bn: the BatchNorm that consumes the result (its training statistics come out of to_space's epilogue)."""
         t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
         ca = m.channel_attention
         t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias)
         t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
         t = ops.Gelu.apply(t)
         t = ops.Linear.apply(t, m.mlp[2].weight, m.mlp[2].bias, False)
-        return ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+        ops.expect_bn(bn is not None and (bn.training or bn.running_mean is None))
+        try:
+            return ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+        finally:
+            ops.expect_bn(False)
+
+    @staticmethod
+    def _conv_bn(conv, bn, x, relu=True):
+        """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
+        ops.expect_bn(bn.training or bn.running_mean is None)
+        try:
+            z = ops.Conv3x3.apply(x, conv.weight, conv.bias, False)
+        finally:
+            ops.expect_bn(False)
+        return EELUnet._bn(bn, z, relu)
 
     def _conv_block(self, blk, x):
-        x = self._bn(blk[1], ops.Conv3x3.apply(x, blk[0].weight, blk[0].bias, False), True)
-        return self._bn(blk[4], ops.Conv3x3.apply(x, blk[3].weight, blk[3].bias, False), True)
+        x = self._conv_bn(blk[0], blk[1], x)
+        return self._conv_bn(blk[3], blk[4], x)
 
     def _mlp_conv_block(self, blk, x):
-        x = self._bn(blk[1], ops.Conv3x3.apply(x, blk[0].weight, blk[0].bias, False), True)
-        return self._bn(blk[4], self._capmlp(blk[3], x), True)
+        x = self._conv_bn(blk[0], blk[1], x)
+        return self._bn(blk[4], self._capmlp(blk[3], x, bn=blk[4]), True)
 
     def _upconv(self, blk, x):
         return self._bn(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), False)
 
     def _mlp_upconv(self, blk, x):
-        return self._bn(blk[2], self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias)), False)
+        return self._bn(blk[2], self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2]), False)
 
     @staticmethod
     def _pgr(m, x):

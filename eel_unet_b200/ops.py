@@ -42,6 +42,24 @@ def _reduce_ws(device, channels, quantities, extra=0):
 # bias gradients that a BatchNorm backward already produced (column sums of dz), keyed by the dz buffer address.
 # An entry is written only when the BN's producer is a biased conv / linear whose backward runs next and pops it.
 _DZ_COLSUM = {}
+# BatchNorm sums a tensor-core producer accumulated in its epilogue, keyed by the address of the tensor it wrote;
+# the BatchNorm that consumes that tensor next pops the entry (training mode only)
+_BN_SUMS = {}
+
+
+def _want_bn_sums(x, ncols):
+    """a [2][ncols] fp32 buffer when the next op is a training-mode BatchNorm (see EELUnet._bn) and one N tile covers ncols"""
+    if _BN_NEXT[0] and ncols <= 256:
+        return torch.empty((2, ncols), dtype=F32, device=x.device)
+    return None
+
+
+_BN_NEXT = [False]
+
+
+def expect_bn(flag):
+    """the model announces that the tensor the next GEMM-class op produces goes straight into a training-mode BatchNorm"""
+    _BN_NEXT[0] = bool(flag)
 
 
 def _colsum(x2d, C):
@@ -207,7 +225,11 @@ class Conv3x3(Function):
             wk = _packed(weight, 0)
             if wk is None:
                 wk = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]  (K-major B operand)
-            call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0, stream())
+            sums = _want_bn_sums(x, Cout) if not relu else None
+            call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0, ptr(sums), stream())
+            if sums is not None:
+                _BN_SUMS.clear()
+                _BN_SUMS[y.data_ptr()] = sums
         else:
             wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
             call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
@@ -234,7 +256,7 @@ class Conv3x3(Function):
                 wk = _packed(weight, 1)
                 if wk is None:
                     wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
-                call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, st)
+                call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, None, st)
             else:
                 wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
                 call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
@@ -320,7 +342,11 @@ class Linear(Function):
         if ctx.tc:
             if shift:
                 x = _shift(x, False)           # saved shifted: wgrad then needs no gather
-            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, stream())
+            sums = _want_bn_sums(x, Nout)
+            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, ptr(sums), stream())
+            if sums is not None:
+                _BN_SUMS.clear()
+                _BN_SUMS[y.data_ptr()] = sums
         else:
             sh, sw = (H, W) if shift else (0, 0)
             call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
@@ -344,7 +370,7 @@ class Linear(Function):
                 wt = _packed(weight, 1)
                 if wt is None:
                     wt = _pack(weight.detach().view(1, 1, Nout, K), (0, 1, 3, 2), x.dtype)   # [K][Nout]
-                call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, st)
+                call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, None, st)
                 if ctx.shift:
                     dx = _shift(dx, True)
             else:
@@ -374,7 +400,11 @@ class BNAct(Function):
         mean = torch.empty(C, dtype=F32, device=dev)
         rstd = torch.empty(C, dtype=F32, device=dev)
         st = stream()
-        if training:
+        sums = _BN_SUMS.pop(z.data_ptr(), None)
+        if training and sums is not None and sums.shape[1] == C:
+            call("eel_bn_stats_from_sums", ptr(sums), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
+                 float(momentum), float(eps), st)
+        elif training:
             ws, n = _reduce_ws(dev, C, 2)
             call("eel_bn_stats", ptr(z), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
                  float(momentum), float(eps), ptr(ws), n, dtype_code(z), st)

@@ -81,10 +81,13 @@ int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int 
 /* ---- bf16 tensor-core (tcgen05 + TMEM + TMA) versions of the heavy GEMM-class ops; bf16 storage only,
  * channel counts multiples of 64.  wk layouts are K-major: conv3x3 wk:[9][Cout][Cin] (flip != 0: the data
  * gradient, wk:[9][Cin_of_layer][Cout_of_layer] with mirrored taps); linear w:[Nout][K]; convt wk:[2][2][Cout][Cin]. */
+/* bn_sums (optional, fp32 [2][Cout], overwritten): per-channel sum and sum of squares of the STORED output, for the
+ * BatchNorm that follows (nn.BatchNorm2d training statistics without another pass over z); needs Cout <= 256
+ * (one N tile) -- finish with eel_bn_stats_from_sums. */
 int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin,
-                   int Cout, int relu, int flip, eel_stream s);
+                   int Cout, int relu, int flip, float* bn_sums, eel_stream s);
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
-                  int relu, eel_stream s);
+                  int relu, float* bn_sums, eel_stream s);
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin,
                         int Cout, eel_stream s);
 /* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */
@@ -116,6 +119,9 @@ int eel_colsum(const void* x, float* out, long long P, int C, void* ws, size_t w
 int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, float* running_mean,
                  float* running_var, float momentum, float eps, void* ws, size_t ws_bytes, int dtype,
                  eel_stream s);
+/* same outputs from the [2][C] sums a tensor-core producer left behind (eel_tc_conv3x3 / eel_tc_linear bn_sums) */
+int eel_bn_stats_from_sums(const float* sums, long long P, int C, float* mean, float* rstd, float* running_mean,
+                           float* running_var, float momentum, float eps, eel_stream s);
 int eel_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean,
                       float* rstd, int C, eel_stream s);
 /* y = [relu](gamma * (z - mean) * rstd + beta) */
