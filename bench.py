@@ -244,6 +244,15 @@ def run_ours(args):
             ach = d["bytes"] / d["ms"] / 1e6
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                     "traffic": None, "peak_source": peak_src + " (copy)", "share_of_step": top[3] / 100.0}
+        # DRAM traffic of the dominant family from the committed ncu --set full capture of the same step (bytes per launch,
+        # like `achieved`); null when no capture of this family is on file
+        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tj):
+            t = json.load(open(tj)).get(top[0])
+            if t:
+                roof["traffic"] = t["dram_bytes_per_launch"]
+                roof["traffic_algorithmic"] = d["bytes"] / max(1, d["calls"])
+                roof["traffic_source"] = t["source"]
         # the best bandwidth-bound kernel family, for the north_star's ">= 70 % of HBM roofline" target
         ew = [r for r in rows if r[0] not in profiling.GEMM_CLASS and fam[r[0]]["bytes"] > 1e8]
         if ew:
