@@ -59,7 +59,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-enum { EPI_DENSE = 0, EPI_CONVT = 2 };
+enum { EPI_DENSE = 0, EPI_SCATTER = 1 /* dense + adjoint ShiftedChannel row scatter */, EPI_CONVT = 2 };
 
 struct TcParams {
     int kchunks;            // 64-wide K chunks
@@ -73,6 +73,7 @@ struct TcParams {
     int res;                // weights resident (n_tiles == 1)
     const float* bias;
     bf16* out;
+    int shH, shW;           // dense: > 0 scatters output rows through the adjoint of ShiftedChannel (rows = pixels of [*, shH, shW])
     float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (dense, n_tiles == 1)
 };
 
@@ -208,11 +209,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int n0 = nt * BN + half * (BN / 2);
             long long roff[4];           // element offset of output row (row_lo + 8 i); -1 = out of range
+            int hrow[4], wcol[4];        // shH > 0: the row's (h, w) inside its image
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const long long m = (long long)mt * 128 + q * 32 + L.row_lo + 8 * i;
+                hrow[i] = 0; wcol[i] = 0;
+                if (EPI == EPI_SCATTER) {
+                    wcol[i] = (int)(m % p.shW);
+                    hrow[i] = (int)((m / p.shW) % p.shH);
+                }
                 if (m >= p.M) roff[i] = -1;
-                else if (EPI == EPI_DENSE) roff[i] = m * p.Ntot;
+                else if (EPI != EPI_CONVT) roff[i] = m * p.Ntot;
                 else {
                     const long long ny = m / p.W;
                     const int x = (int)(m - ny * p.W);
@@ -240,8 +247,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.bias) bp = p.bias + gcol;
                 }
                 bf16* dst[4];
+                int dh = 0, dw = 0;          // ShiftedChannel adjoint: this 32-column chunk lies in one channel quarter
+                if (EPI == EPI_SCATTER) {
+                    const int qd = gcol / (p.Ntot >> 2);
+                    dh = qd == 0 ? -1 : (qd == 1 ? 1 : 0);
+                    dw = qd == 2 ? -1 : 0;
+                }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = roff[i] >= 0 ? p.out + roff[i] + coff + L.slot * 8 : nullptr;
+                for (int i = 0; i < 4; ++i) {
+                    long long o = roff[i];
+                    if (EPI == EPI_SCATTER) {
+                        int hh = hrow[i] + dh, ww = wcol[i] + dw;
+                        hh = hh < 0 ? hh + p.shH : (hh >= p.shH ? hh - p.shH : hh);
+                        ww = ww < 0 ? ww + p.shW : ww;
+                        o += ((long long)(hh - hrow[i]) * p.shW + (ww - wcol[i])) * p.Ntot;
+                    }
+                    dst[i] = roff[i] >= 0 ? p.out + o + coff + L.slot * 8 : nullptr;
+                }
                 epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, (EPI == EPI_DENSE && p.bn_sums) ? &st[ci] : nullptr, lane);
             }
             tc_fence_before();
@@ -306,7 +328,7 @@ using namespace eel::tc;
 extern "C" {
 
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout, int relu,
-                  float* bn_sums, eel_stream s) {
+                  float* bn_sums, int scatterH, int scatterW, eel_stream s) {
     EEL_REQUIRE(x && w && y && P > 0, "tc_linear: bad argument");
     EEL_REQUIRE(K % 64 == 0 && Nout % 64 == 0, "tc_linear: K and Nout must be multiples of 64 (got %d, %d)", K, Nout);
     const int bn = pick_bn(Nout);
@@ -329,6 +351,11 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
     p.n_tiles = Nout / bn;
     p.M = P; p.Ntot = Nout;
     p.relu = relu; p.bias = bias; p.out = (bf16*)y;
+    if (scatterH > 0 || scatterW > 0) {
+        EEL_REQUIRE(scatterH > 0 && scatterW > 0 && P % ((long long)scatterH * scatterW) == 0 && Nout % 128 == 0,
+                    "tc_linear: scatter needs P = images * H * W and Nout a multiple of 128 (32-column chunks inside one quarter)");
+        p.shH = scatterH; p.shW = scatterW;
+    }
     if (bn_sums != nullptr) {
         EEL_REQUIRE(p.n_tiles == 1, "tc_linear: fused BatchNorm statistics need a single N tile (Nout %d)", Nout);
         if (cudaMemsetAsync(bn_sums, 0, sizeof(float) * 2 * Nout, (cudaStream_t)s) != cudaSuccess) {
@@ -337,6 +364,7 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
         }
         p.bn_sums = bn_sums;
     }
+    if (p.shH > 0) return dispatch_bn<EPI_SCATTER>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_linear(scatter)");
     return dispatch_bn<EPI_DENSE>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_linear");
 }
 

@@ -343,7 +343,7 @@ class Linear(Function):
             if shift:
                 x = _shift(x, False)           # saved shifted: wgrad then needs no gather
             sums = _want_bn_sums(x, Nout)
-            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, ptr(sums), stream())
+            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, ptr(sums), 0, 0, stream())
             if sums is not None:
                 _BN_SUMS.clear()
                 _BN_SUMS[y.data_ptr()] = sums
@@ -370,8 +370,9 @@ class Linear(Function):
                 wt = _packed(weight, 1)
                 if wt is None:
                     wt = _pack(weight.detach().view(1, 1, Nout, K), (0, 1, 3, 2), x.dtype)   # [K][Nout]
-                call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, None, st)
-                if ctx.shift:
+                fold = ctx.shift and K % 128 == 0          # the epilogue stores through the adjoint shift
+                call("eel_tc_linear", ptr(dy), ptr(wt), None, ptr(dx), P, Nout, K, 0, None, H if fold else 0, W if fold else 0, st)
+                if ctx.shift and not fold:
                     dx = _shift(dx, True)
             else:
                 w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)

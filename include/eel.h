@@ -86,8 +86,10 @@ int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int 
  * (one N tile) -- finish with eel_bn_stats_from_sums. */
 int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin,
                    int Cout, int relu, int flip, float* bn_sums, eel_stream s);
+/* scatterH/scatterW > 0: rows are pixels of [*, scatterH, scatterW] images and every output row is stored through the
+ * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
-                  int relu, float* bn_sums, eel_stream s);
+                  int relu, float* bn_sums, int scatterH, int scatterW, eel_stream s);
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin,
                         int Cout, eel_stream s);
 /* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */

@@ -49,7 +49,7 @@ def cases(B, S, only):
                        (B * (S // 8) ** 2, 256, 512), (B * (S // 16) ** 2, 1024, 1024)]:
         def mk(P=P, K=K, No=No):
             x, w, b, y = rnd(P, K), rnd(No, K), rnd(No, dtype=F32), torch.empty(P, No, device=DEV, dtype=BF16)
-            return "eel_tc_linear", (ptr(x), ptr(w), ptr(b), ptr(y), P, K, No, int(os.environ.get("EEL_RELU", "0")), None, st()), (x, w, b, y)
+            return "eel_tc_linear", (ptr(x), ptr(w), ptr(b), ptr(y), P, K, No, int(os.environ.get("EEL_RELU", "0")), None, 0, 0, st()), (x, w, b, y)
         add("linear", "linear P=%d %d->%d" % (P, K, No), mk)
 
         def mkw(P=P, K=K, No=No):
