@@ -2,13 +2,15 @@
 
     from eel_unet_b200 import EELUnet, edge_BceDiceLoss      # drop-ins for the reference classes
     from eel_unet_b200 import edges                          # GPU Canny / Sobel edge maps
+    from eel_unet_b200 import data                           # GPU Resize / ToTensor / Normalize of uint8 batches
 
 Importing this package loads libeel.so; if it has not been built the import fails (no fallback).
 """
 from . import _lib  # noqa: F401  (fails loudly when libeel.so is missing)
+from . import data  # noqa: F401
 from . import edges  # noqa: F401
 from .loss import edge_BceDiceLoss  # noqa: F401
 from .model import EELUnet  # noqa: F401
 from .unet import Unet  # noqa: F401
 
-__all__ = ["EELUnet", "Unet", "edge_BceDiceLoss", "edges"]
+__all__ = ["EELUnet", "Unet", "edge_BceDiceLoss", "edges", "data"]

@@ -622,33 +622,69 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------ GELU (erf)
+// cdf(a) = 0.5 (1 + erf(a / sqrt 2)) and e = exp(-a^2 / 2).  fp32 storage: erff.  bf16 storage: Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below bf16 rounding) on the SAME exponential the derivative's density term needs -- the exact
+// erff made these kernels ALU-bound at half of the HBM roofline.
+template <class T> __device__ __forceinline__ void gelu_cdf(float a, float& cdf, float& e) {
+    e = __expf(-0.5f * a * a);
+    if (sizeof(T) == 4) {
+        cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752f));
+    } else {
+        const float z = fabsf(a) * 0.70710678118654752f;
+        const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+        const float half_erfc = 0.5f * poly * e;          // 0.5 * erfc(|a| / sqrt 2)
+        cdf = a >= 0.f ? 1.0f - half_erfc : half_erfc;
+    }
+}
+
 template <class T>
 __global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec) {
-    constexpr int V = Vec16<T>::N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        Vec16<T> v = ld16(x + i * V), o;
+    constexpr int V = Vec16<T>::N, U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += U * stride) {
+        Vec16<T> v[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float a = v.get(j);
-            o.set(j, 0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) v[u] = ld16(x + (i + u * stride) * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) break;
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float a = v[u].get(j);
+                float cdf, e;
+                gelu_cdf<T>(a, cdf, e);
+                o.set(j, a * cdf);
+            }
+            st16(y + (i + u * stride) * V, o);
         }
-        st16(y + i * V, o);
     }
 }
 
 template <class T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long nvec) {
-    constexpr int V = Vec16<T>::N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        Vec16<T> v = ld16(x + i * V), g = ld16(dy + i * V), o;
+    constexpr int V = Vec16<T>::N, U = 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += U * stride) {
+        Vec16<T> v[U], g[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float a = v.get(j);
-            float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752f));
-            float pdf = 0.39894228040143268f * expf(-0.5f * a * a);
-            o.set(j, g.get(j) * (cdf + a * pdf));
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) { v[u] = ld16(x + (i + u * stride) * V); g[u] = ld16(dy + (i + u * stride) * V); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) break;
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float a = v[u].get(j);
+                float cdf, e;
+                gelu_cdf<T>(a, cdf, e);
+                o.set(j, g[u].get(j) * (cdf + a * 0.39894228040143268f * e));
+            }
+            st16(dx + (i + u * stride) * V, o);
         }
-        st16(dx + i * V, o);
     }
 }
 

@@ -111,6 +111,17 @@ int eel_copy_cols(const void* src, long long src_ld, int src_c0, void* dst, long
 /* ShiftedChannel (models/EELUnet.py:88-97) as a standalone gather; inverse != 0 applies the adjoint shifts */
 int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int inverse, int dtype, eel_stream s);
 
+/* ------------------------------------------------------------------ input pipeline
+ * data/ToothDataset.py:58-61 + train.py:249-252 on a whole batch: transforms.Resize((H, W)) (= PIL.Image.resize BILINEAR,
+ * reproduced bit-exactly: antialiased support, 22-bit fixed point, horizontal pass rounded to uint8 before the vertical
+ * one) -> ToTensor (/255, CHW) -> Normalize(mean, std) (mean == std == NULL: none, the mask branch).
+ * in: uint8 NHWC [N,Hs,Ws,C] (C = 1, 3 or 4); out_nchw: fp32 [N,C,H,W] (or NULL); out_u8_nhwc: the resized uint8 image
+ * [N,H,W,C] (or NULL); mean/stdv: device arrays of C floats. */
+size_t eel_preprocess_workspace_bytes(int Hs, int Ws, int H, int W);
+int eel_preprocess_u8(const unsigned char* in, int N, int Hs, int Ws, int C, int H, int W, const float* mean,
+                      const float* stdv, float* out_nchw, unsigned char* out_u8_nhwc, void* ws, size_t ws_bytes,
+                      eel_stream s);
+
 /* ------------------------------------------------------------------ reductions / normalisation */
 size_t eel_reduce_workspace_bytes(int channels, int quantities);
 /* out[c] = sum_p x[p][c]   (bias gradients) */

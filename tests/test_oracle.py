@@ -148,3 +148,21 @@ def test_oracle_matches_live_reference():
     after = m.state_dict()
     for k, v in ns.items():
         assert rel(v, after[k]) < 1e-12, k
+
+
+def test_resize_oracle_matches_pillow_goldens():
+    """oracle/resize_np.py (restated Pillow Resample.c + ToTensor + Normalize) against outputs of Pillow / torchvision
+    themselves (tests/golden/make_golden_resize.py)."""
+    import os
+
+    import numpy as np
+
+    from oracle import resize_np as R
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_pil.npz"))
+    for name in ["down2", "down_frac", "up", "square", "same_w", "tooth"]:
+        oh, ow = (int(v) for v in g[name + "_size"])
+        assert np.array_equal(R.resize_bilinear_u8(g[name + "_img"], oh, ow), g[name + "_img_resized"])
+        assert np.array_equal(R.resize_bilinear_u8(g[name + "_mask"], oh, ow), g[name + "_mask_resized"])
+        assert np.array_equal(R.preprocess_image(g[name + "_img"], (oh, ow)), g[name + "_img_tensor"])
+        assert np.array_equal(R.preprocess_mask(g[name + "_mask"], (oh, ow)), g[name + "_mask_tensor"])
