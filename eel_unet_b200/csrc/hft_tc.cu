@@ -194,6 +194,13 @@ struct Hft4Params {
 
 enum { H4_FWD = 0, H4_BWD = 1, H4_T3 = 2 };
 
+// one MUFU.RSQ (2 ulp), no denormal fix-up: the epilogue is instruction-issue bound and its results are rounded to bf16
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 constexpr int kH4Threads = 320;   // TMA warp, MMA warp, two epilogue warpgroups of 4 warps that alternate tiles
 
 template <int C, int EPI>
@@ -252,7 +259,7 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         mbar_wait(mFull, 0);
         int st = 0;
         uint32_t ph = 0;
-        long long tile_no = 0;
+        int tile_no = 0;                     // tiles per CTA stay far below 2^31: 32-bit divisions in the hot loops
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             mbar_wait(&full[st], ph);
             tc_fence_after();
@@ -281,7 +288,7 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int r = q * 32 + lane;
         // output rows leave through the per-warp transposition buffer (tc_common.cuh): full 32-byte sectors per store
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(full) + 1024 + (warp - 2) * 2048, lane);
-        long long tile_no = 0;
+        int tile_no = 0;                     // tiles per CTA stay far below 2^31: 32-bit divisions in the hot loops
         // C == 64: the epilogue's global operand is double-buffered in registers one tile ahead (32 registers);
         // C == 128 would need 64 more registers than there are, so there the next tile's rows are pulled into L2
         constexpr bool DB = EPI != H4_T3 && C <= 64;
@@ -342,11 +349,11 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                 }
                 {
                     // this warpgroup's next tile is tile_no + 2 in the CTA's linear (item, mt) order
-                    const long long t2 = tile_no + 2;
-                    const int mt2 = (int)(t2 % p.mtiles);
-                    const long long item2 = blockIdx.x + (t2 / p.mtiles) * gridDim.x;
+                    const int t2 = tile_no + 2;
+                    const int mt2 = t2 % p.mtiles;
+                    const int item2 = (int)blockIdx.x + (t2 / p.mtiles) * (int)gridDim.x;
                     if (item2 < p.items) {
-                        const int n2 = (int)(item2 / idiv), h2 = (int)(item2 - (long long)n2 * idiv);
+                        const int n2 = item2 / idiv, h2 = item2 - n2 * idiv;
                         const long long rb2 = ((long long)n2 * p.H + h2) * p.W;
                         const int m2 = (p.m_begin + mt2) * 128 + r;
                         const bf16* nx = FWD ? p.x + (rb2 + (m2 >> 1)) * C : p.x + ((rb2 + m2) * 2) * C;
@@ -399,18 +406,23 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                             const float o0 = __shfl_xor_sync(0xffffffffu, mine[i], 1);
                             const float o1 = __shfl_xor_sync(0xffffffffu, mine[i + 1], 1);
                             const float sq0 = fmaf(mine[i], mine[i], o0 * o0), sq1 = fmaf(mine[i + 1], mine[i + 1], o1 * o1);
-                            const float inv0 = sq0 > 0.f ? rsqrtf(sq0) : 0.f, inv1 = sq1 > 0.f ? rsqrtf(sq1) : 0.f;
+                            const float inv0 = sq0 > 0.f ? rsqrt_approx(sq0) : 0.f, inv1 = sq1 > 0.f ? rsqrt_approx(sq1) : 0.f;
                             __nv_bfloat162 hm = __floats2bfloat162_rn(sq0 * inv0, sq1 * inv1);
                             __nv_bfloat162 hp = __floats2bfloat162_rn(mine[i] * inv0, mine[i + 1] * inv1);
                             pkm[i >> 1] = *reinterpret_cast<uint32_t*>(&hm);
                             pkp[i >> 1] = *reinterpret_cast<uint32_t*>(&hp);
                         }
                         bf16 *dp[4], *dm[4];
+                        {
+                            // rows (row_lo + 8 i) of this warp: phase rows are 8 * C apart, |z| rows 4 * C (even rows only)
+                            const int mm0 = (p.m_begin + mt) * 128 + q * 32 + L.row_lo;
+                            bf16* pb = p.phase + (rowbase * 2 + mm0) * C + cc + L.slot * 8;
+                            bf16* yb = p.y + (rowbase + (mm0 >> 1)) * C + cc + L.slot * 8;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int mm = (p.m_begin + mt) * 128 + q * 32 + L.row_lo + 8 * i;
-                            dp[i] = p.phase + (rowbase * 2 + mm) * C + cc + L.slot * 8;
-                            dm[i] = (mm & 1) ? nullptr : p.y + (rowbase + (mm >> 1)) * C + cc + L.slot * 8;
+                            for (int i = 0; i < 4; ++i) {
+                                dp[i] = pb + i * 8 * C;
+                                dm[i] = (mm0 & 1) ? nullptr : yb + i * 4 * C;
+                            }
                         }
                         epi_store_packed(L, pkp, dp);
                         epi_store_packed(L, pkm, dm);
