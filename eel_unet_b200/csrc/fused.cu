@@ -79,6 +79,63 @@ __global__ void __launch_bounds__(kPixThreads) pgr_fwd_kernel(const T* __restric
     }
 }
 
+// ITERS vectors per lane and pixel, U pixels per lane group in flight: x is loaded once into registers (U*ITERS independent
+// 16-byte loads per thread) and reused for the gate and the output
+template <class T, int ITERS, int U>
+__global__ void __launch_bounds__(kPixThreads) pgr_fwd_kernel2(const T* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ b, T* __restrict__ y,
+                                                             float* __restrict__ sg, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const float bias = b[0];
+    float wreg[ITERS][V];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j) wreg[k][j] = w[(gl + k * G) * V + j];
+    const long long stride = (long long)gridDim.x * groups_per_block * U;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block * U; p0 < P; p0 += stride) {
+        Vec16<T> vx[U][ITERS];
+        float dot[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            ok[u] = p < P;
+            if (ok[u])
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k) vx[u][k] = ld16(x + p * C + (gl + k * G) * V);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            dot[u] = 0.f;
+            if (ok[u])
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) dot[u] += vx[u][k].get(j) * wreg[k][j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] = group_sum(dot[u], G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            const float sv = sigmoidf_(dot[u] + bias);
+            if (gl == 0) sg[p] = sv;
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o.set(j, vx[u][k].get(j) * (1.f + sv));
+                st16(y + p * C + (gl + k * G) * V, o);
+            }
+        }
+    }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel(const T* __restrict__ x, const float* __restrict__ sg,
                                                             const float* __restrict__ w, const T* __restrict__ dy,
@@ -402,7 +459,12 @@ int eel_pgr_fwd(const void* x, const float* w, const float* b, void* y, float* s
         int gpb = kPixThreads / G;
         long long blocks = (P + gpb - 1) / gpb;
         int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
-        pgr_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
+        const int iters = C / V / G;
+        cudaStream_t st2 = (cudaStream_t)s;
+        if (iters == 1) pgr_fwd_kernel2<T, 1, 4><<<grid, kPixThreads, 0, st2>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
+        else if (iters == 2) pgr_fwd_kernel2<T, 2, 2><<<grid, kPixThreads, 0, st2>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
+        else if (iters == 4) pgr_fwd_kernel2<T, 4, 1><<<grid, kPixThreads, 0, st2>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
+        else pgr_fwd_kernel<T><<<grid, kPixThreads, 0, st2>>>((const T*)x, w, b, (T*)y, sgm, P, C, G);
         return check_launch("pgr_fwd");
     });
 }
