@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(kPixThreads) head_fwd_kernel(const T* __restri
             for (int j = 0; j < V; ++j) d += w[o * kHeadC + c0 + j] * nv[j];
             d = group_sum(d, G);
             if (ok && gl == 0) {
-                long long n = p / HW, hw = p - n * HW;
+                // P < 2^31 (checked by the host): a 32-bit division instead of the ~100-instruction 64-bit one per pixel
+                const unsigned nu = (unsigned)p / (unsigned)HW;
+                const long long n = nu, hw = (long long)((unsigned)p - nu * (unsigned)HW);
                 prob[(n * O + o) * HW + hw] = sigmoidf_(d + b[o]);
             }
         }
@@ -337,8 +339,10 @@ __global__ void __launch_bounds__(kPixThreads) head_fwd_kernel(const T* __restri
 }
 
 // partial row layout: dlnw[64] dlnb[64] dw[O][64] db[O]
-template <class T>
-__global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+// MO = compile-time bound on the output channels O (1 for the reference's binary segmentation: the per-output register
+// arrays then cost 9 registers instead of 36, which is the difference between 2 and 3-4 resident blocks per SM)
+template <class T, int MO>
+__global__ void __launch_bounds__(kPixThreads, 3) head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
                                                              const float* __restrict__ lnb, const float* __restrict__ w,
                                                              const float* __restrict__ prob, const float* __restrict__ dprob,
                                                              T* __restrict__ dx, float* __restrict__ partial, long long P,
@@ -352,16 +356,15 @@ __global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restri
     const int c0 = gl * V;
     for (int i = threadIdx.x; i < width; i += kPixThreads) sh[i] = 0.f;
     __syncthreads();
-    float aw[V], ab[V], awo[kHeadMaxO][V], abo[kHeadMaxO];
+    float aw[V], ab[V], awo[MO][V], abo[MO];
 #pragma unroll
     for (int j = 0; j < V; ++j) { aw[j] = 0.f; ab[j] = 0.f; }
 #pragma unroll
-    for (int o = 0; o < kHeadMaxO; ++o) {
+    for (int o = 0; o < MO; ++o) {
         abo[o] = 0.f;
 #pragma unroll
         for (int j = 0; j < V; ++j) awo[o][j] = 0.f;
     }
-#pragma unroll 2
     for (long long p0 = (long long)blockIdx.x * groups_per_block; p0 < P; p0 += (long long)gridDim.x * groups_per_block) {
         long long p = p0 + g_in_block;
         bool ok = p < P;
@@ -384,9 +387,10 @@ __global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restri
         float xh[V], dn[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) { xh[j] = (xv[j] - mu) * r; dn[j] = 0.f; }
-        long long n = ok ? p / HW : 0, hw = ok ? p - n * HW : 0;
+        const unsigned nu = ok ? (unsigned)p / (unsigned)HW : 0u;      // P < 2^31 (checked by the host)
+        const long long n = nu, hw = ok ? (long long)((unsigned)p - nu * (unsigned)HW) : 0;
 #pragma unroll
-        for (int o = 0; o < kHeadMaxO; ++o) {
+        for (int o = 0; o < MO; ++o) {
             if (o < O) {
                 float dl = 0.f;
                 if (ok) {
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(kPixThreads) head_bwd_kernel(const T* __restri
         atomicAdd(&sh[kHeadC + c0 + j], ab[j]);
     }
 #pragma unroll
-    for (int o = 0; o < kHeadMaxO; ++o) {
+    for (int o = 0; o < MO; ++o) {
         if (o < O) {
 #pragma unroll
             for (int j = 0; j < V; ++j) atomicAdd(&sh[(2 + o) * kHeadC + c0 + j], awo[o][j]);
@@ -500,6 +504,7 @@ int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float*
                  long long HW, int O, int dtype, eel_stream s) {
     EEL_REQUIRE(x && lnw && lnb && w && b && prob && N > 0 && HW > 0 && O > 0 && O <= kHeadMaxO, "head_fwd: bad argument (1 <= O <= 4)");
     long long P = (long long)N * HW;
+    EEL_REQUIRE(P < (1LL << 31), "head_fwd: more than 2^31 pixels");
     EEL_DISPATCH_DTYPE(dtype, {
         constexpr int G = kHeadC / Vec16<T>::N;
         int gpb = kPixThreads / G;
@@ -517,6 +522,7 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
     EEL_REQUIRE(x && lnw && lnb && w && prob && dprob && dx && dlnw && dlnb && dw && db && N > 0 && HW > 0 && O > 0 && O <= kHeadMaxO,
                 "head_bwd: bad argument (1 <= O <= 4)");
     long long P = (long long)N * HW;
+    EEL_REQUIRE(P < (1LL << 31), "head_bwd: more than 2^31 pixels");
     EEL_DISPATCH_DTYPE(dtype, {
         constexpr int G = kHeadC / Vec16<T>::N;
         int gpb = kPixThreads / G;
@@ -526,8 +532,8 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         size_t need = sizeof(float) * ((size_t)grid + 1) * width;
         if (need > ws_bytes || !ws) { set_error("head_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
         float* partial = (float*)ws;
-        head_bwd_kernel<T><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx,
-                                                                                       partial, P, HW, O);
+        if (O == 1) head_bwd_kernel<T, 1><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
+        else head_bwd_kernel<T, kHeadMaxO><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
         if (int rc = check_launch("head_bwd")) return rc;
         RowSegs segs{{dlnw, dlnb, dw, db}, {kHeadC, 2 * kHeadC, (2 + O) * kHeadC, (2 + O) * kHeadC + O}};
         finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, width, segs);

@@ -5,6 +5,8 @@
 // and an epilogue into the engine.
 #include "gemm_simt.cuh"
 
+#include <type_traits>
+
 namespace eel {
 
 // ------------------------------------------------------------------------------------ accessors
@@ -351,19 +353,30 @@ __global__ void __launch_bounds__(kStemThreads) stem_wgrad_kernel(const T* __res
             stem_load_rows<T, CIN>(sh, x, n, h, H, W);
             __syncthreads();
             const T* drow = dy + ((long long)row * W) * Cout + cb + tx * 4;
+            // the four dy vectors of the NEXT window are fetched while this one is multiplied (two 4-warp blocks per SM
+            // cannot hide a DRAM round trip per window otherwise)
+            typedef typename std::conditional<sizeof(T) == 4, float4, uint2>::type DV;
+            DV dnext[4];
+            if (ty * 4 < W) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) dnext[p] = *reinterpret_cast<const DV*>(drow + (long long)(ty * 4 + p) * Cout);
+            }
             for (int w = ty * 4; w < W; w += kStemThreads / 4) {   // 4 adjacent pixels per thread
                 float d[4][4];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const T* src = drow + (long long)(w + p) * Cout;
                     if (sizeof(T) == 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(src);
+                        const float4 v = *reinterpret_cast<const float4*>(&dnext[p]);
                         d[p][0] = v.x; d[p][1] = v.y; d[p][2] = v.z; d[p][3] = v.w;
                     } else {
-                        const uint2 v = *reinterpret_cast<const uint2*>(src);
+                        const uint2 v = *reinterpret_cast<const uint2*>(&dnext[p]);
                         d[p][0] = __uint_as_float(v.x << 16); d[p][1] = __uint_as_float(v.x & 0xffff0000u);
                         d[p][2] = __uint_as_float(v.y << 16); d[p][3] = __uint_as_float(v.y & 0xffff0000u);
                     }
+                }
+                if (w + kStemThreads / 4 < W) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) dnext[p] = *reinterpret_cast<const DV*>(drow + (long long)(w + kStemThreads / 4 + p) * Cout);
                 }
                 float xw[3][6 * CIN + 2];
                 stem_window<CIN>(sh, RP, w, xw);
@@ -401,7 +414,7 @@ static int launch_stem_wgrad(const void* x, const void* dy, float* dwp, int N, i
         configured = true;
     }
     int rows = N * H;
-    int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
+    int grid = rows < kNumSMs * 3 ? rows : kNumSMs * 3;   // three 128-thread blocks (168 registers) are resident per SM: one wave
     stem_wgrad_kernel<T, CIN><<<grid, kStemThreads, smem, st>>>((const T*)x, (const T*)dy, dwp, N, H, W, Cout);
     return check_launch("conv3x3_wgrad(stem)");
 }
