@@ -441,6 +441,133 @@ __global__ void __launch_bounds__(kPixThreads, 3) head_bwd_kernel(const T* __res
     for (int i = threadIdx.x; i < width; i += kPixThreads) partial[(long long)blockIdx.x * width + i] = sh[i];
 }
 
+// ---- head, one THREAD per pixel (O == 1, the reference's binary segmentation) -------------------------------------------
+// The lane-group kernels above spend most of their issue slots on shuffles and on per-lane copies of scalar work (ncu:
+// 67 % issue-active at 23 % of DRAM bandwidth).  With the pixel's 64 channels in one thread's registers LayerNorm needs no
+// shuffle at all, and for O == 1 every parameter gradient follows from S0 = sum_p dl_p and S1[c] = sum_p dl_p * xhat_pc:
+//     dlnw[c] = w[c] S1[c],  dlnb[c] = w[c] S0,  dw[c] = lnw[c] S1[c] + lnb[c] S0,  db = S0      (dl = dprob * p (1 - p))
+constexpr int kTpThreads = 128;
+
+template <class T> __device__ __forceinline__ void tp_load64(const T* __restrict__ src, float (&v)[kHeadC]) {
+    constexpr int V = Vec16<T>::N;
+#pragma unroll
+    for (int k = 0; k < kHeadC / V; ++k) {
+        const Vec16<T> q = ld16(src + k * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[k * V + j] = q.get(j);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kTpThreads) head_fwd_tp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                               const float* __restrict__ lnb, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ prob, long long P) {
+    __shared__ float swl[kHeadC];   // w[c] * lnw[c]
+    __shared__ float sc[2];         // sum_c w[c] * lnb[c] + b,  unused
+    if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
+    if (threadIdx.x == 0) {
+        float t = b[0];
+        for (int c = 0; c < kHeadC; ++c) t += w[c] * lnb[c];
+        sc[0] = t;
+    }
+    __syncthreads();
+    const float cb = sc[0];
+    for (long long p = blockIdx.x * (long long)kTpThreads + threadIdx.x; p < P; p += (long long)gridDim.x * kTpThreads) {
+        float v[kHeadC];
+        tp_load64<T>(x + p * kHeadC, v);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) s += v[c];
+        const float mu = s * (1.f / kHeadC);
+        float q = 0.f, d = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) {
+            const float t = v[c] - mu;
+            q = fmaf(t, t, q);
+            d = fmaf(swl[c], t, d);
+        }
+        const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
+        prob[p] = sigmoidf_(fmaf(d, r, cb));       // sum_c w (lnw xhat + lnb) + b
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kTpThreads) head_bwd_tp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                               const float* __restrict__ lnb, const float* __restrict__ w,
+                                                               const float* __restrict__ prob, const float* __restrict__ dprob,
+                                                               T* __restrict__ dx, float* __restrict__ partial, long long P) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float swl[kHeadC];           // w[c] * lnw[c]
+    __shared__ float sacc[kHeadC + 1];      // S1[c], S0
+    __shared__ float swm;
+    if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
+    if (threadIdx.x <= kHeadC) sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int c = 0; c < kHeadC; ++c) t += swl[c];
+        swm = t * (1.f / kHeadC);
+    }
+    __syncthreads();
+    const float wm = swm;
+    float S1[kHeadC], S0 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHeadC; ++c) S1[c] = 0.f;
+    for (long long p = blockIdx.x * (long long)kTpThreads + threadIdx.x; p < P; p += (long long)gridDim.x * kTpThreads) {
+        float v[kHeadC];
+        tp_load64<T>(x + p * kHeadC, v);
+        const float pr = prob[p];
+        const float dl = dprob[p] * pr * (1.f - pr);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) s += v[c];
+        const float mu = s * (1.f / kHeadC);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) { v[c] -= mu; q = fmaf(v[c], v[c], q); }
+        const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) {
+            v[c] *= r;                              // xhat
+            m2 = fmaf(swl[c], v[c], m2);
+            S1[c] = fmaf(dl, v[c], S1[c]);
+        }
+        S0 += dl;
+        m2 *= (1.f / kHeadC);
+        const float k = r * dl;
+        T* dst = dx + p * kHeadC;
+#pragma unroll
+        for (int kk = 0; kk < kHeadC / V; ++kk) {
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.set(j, k * (swl[kk * V + j] - wm - v[kk * V + j] * m2));
+            st16(dst + kk * V, o);
+        }
+    }
+    // block reduction of S1 / S0: warp shuffles, then one shared atomic per warp and value
+#pragma unroll
+    for (int c = 0; c < kHeadC; ++c) {
+        const float t = warp_sum(S1[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[c], t);
+    }
+    {
+        const float t = warp_sum(S0);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[kHeadC], t);
+    }
+    __syncthreads();
+    // partial row layout: dlnw[64] dlnb[64] dw[64] db[1]
+    float* row = partial + (long long)blockIdx.x * (3 * kHeadC + 1);
+    if (threadIdx.x < kHeadC) {
+        const int c = threadIdx.x;
+        const float s1 = sacc[c], s0 = sacc[kHeadC];
+        row[c] = w[c] * s1;
+        row[kHeadC + c] = w[c] * s0;
+        row[2 * kHeadC + c] = lnw[c] * s1 + lnb[c] * s0;
+        if (c == 0) row[3 * kHeadC] = s0;
+    }
+}
+
 static int pix_group(int C, int V) {
     int nv = C / V;
     return nv >= 32 ? 32 : nv;
@@ -510,6 +637,12 @@ int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float*
         int gpb = kPixThreads / G;
         long long blocks = (P + gpb - 1) / gpb;
         int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+        if (O == 1) {
+            long long tb = (P + kTpThreads - 1) / kTpThreads;
+            int g1 = (int)(tb < (long long)kNumSMs * 16 ? tb : (long long)kNumSMs * 16);
+            head_fwd_tp_kernel<T><<<g1, kTpThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P);
+            return check_launch("head_fwd(tp)");
+        }
         head_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P, HW, O);
         return check_launch("head_fwd");
     });
@@ -532,8 +665,12 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         size_t need = sizeof(float) * ((size_t)grid + 1) * width;
         if (need > ws_bytes || !ws) { set_error("head_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
         float* partial = (float*)ws;
-        if (O == 1) head_bwd_kernel<T, 1><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
-        else head_bwd_kernel<T, kHeadMaxO><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
+        if (O == 1) {
+            // thread-per-pixel kernel: the grid is bounded by the partial rows the workspace holds (same bound as above)
+            long long tb = (P + kTpThreads - 1) / kTpThreads;
+            grid = (int)(tb < (long long)grid ? tb : (long long)grid);
+            head_bwd_tp_kernel<T><<<grid, kTpThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P);
+        } else head_bwd_kernel<T, kHeadMaxO><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
         if (int rc = check_launch("head_bwd")) return rc;
         RowSegs segs{{dlnw, dlnb, dw, db}, {kHeadC, 2 * kHeadC, (2 + O) * kHeadC, (2 + O) * kHeadC + O}};
         finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, width, segs);
