@@ -209,9 +209,10 @@ static int hft_run(const SmallA& a, const BL& b, const Epi& e, int M, int N, int
 
 namespace tc {
 bool hft_tc_supported(int H, int W, int C, int r);
+bool hft_tc_supported_fwd(int H, int W, int C, int r);
 size_t hft_tc_matrix_elems(int W);
 int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, bf16* Tb, int N, int H, int W, int C, int r, cudaStream_t st);
-int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, int N, int H, int C, int r, cudaStream_t st);
+int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, float* T2f, int N, int H, int C, int r, cudaStream_t st);
 int hft_tc_step3(const bf16* T2b, bf16* mat_ws, bf16* T3b, int N, int H, int C, int r, cudaStream_t st);
 int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf16* y_or_dx, bf16* phase, int N, int H, int W, int C,
                  int r, cudaStream_t st);
@@ -300,12 +301,15 @@ int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C,
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
     if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
-    if (dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, F / 2)) {
-        // bf16 mode: the two large projections run on the tensor cores (hft_tc.cu); the small H-axis steps stay SIMT fp32
-        // every step on the tensor cores; T1 / T2 / T3 live in bf16 (the fp32 regions T1, T2 are reused as storage)
-        if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, nullptr, (bf16*)w.T1, N, H, W, C, F / 2, st)) return rc;
-        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, N, H, C, F / 2, st)) return rc;
-        if (int rc = tc::hft_tc_step3((const bf16*)w.T2, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
+    if (dtype == EEL_BF16 && tc::hft_tc_supported_fwd(H, W, C, F / 2)) {
+        // every step on the tensor cores; T1 / T2 / T3 live in bf16 (the fp32 regions T1, T2 are reused as storage).
+        // H > 512: step 2 splits its reduction and needs the whole fp32 T2 region for partial sums, so the bf16 T2 goes to
+        // the unused second half of the T1 region.
+        bf16* T1b = (bf16*)w.T1;
+        bf16* T2b = H > 512 ? T1b + (size_t)N * H * 2 * F * C : (bf16*)w.T2;
+        if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, nullptr, T1b, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step2(T1b, w.M2, T2b, w.T2, N, H, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step3(T2b, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
         return tc::hft_tc_step4(w.T3b, w.M4, true, (const bf16*)x, (bf16*)y, (bf16*)phase, N, H, W, C, F / 2, st);
     }
     EEL_DISPATCH_DTYPE(dtype, {
@@ -338,7 +342,7 @@ int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W
         hft_grad_pairs_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)phase, w.G, nvec, C);
         if (int rc = check_launch("hft_bwd.pairs")) return rc;
         if (int rc = tc::hft_tc_step1(w.G, 2 * W, w.M1, 1, nullptr, (bf16*)w.T1, N, H, W, C, F / 2, st)) return rc;
-        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, N, H, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, w.T2, N, H, C, F / 2, st)) return rc;
         if (int rc = tc::hft_tc_step3((const bf16*)w.T2, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
         return tc::hft_tc_step4(w.T3b, w.M4, false, w.G, (bf16*)dx, nullptr, N, H, W, C, F / 2, st);
     }

@@ -28,6 +28,8 @@ struct HftTcParams {
     int mtiles;         // mode 1: 128-blocks of the F*C axis
     int hc;             // mode 1: 64-row chunks per re/im half (H / 64)
     long long Cst;      // output channel extent (C, or F*C in mode 1)
+    int kc_begin;       // first GLOBAL 64-wide K chunk of this launch (K split over launches when the matrix does not fit)
+    int accumulate;     // HEPI_T: add the fp32 T already in memory (second launch of a K split) before storing
     float* T;           // fp32 output [rows][ncols][Cst] (or null)
     bf16* Tb;           // bf16 output, same layout (or null)
     const bf16* x;      // HEPI_ABS: input x [N,H,W,C];  HEPI_SUB: g [N,H,W,2,C]
@@ -77,7 +79,7 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // ===================================================================== TMA producer
         mbar_expect_tx(bFull, b_bytes);
         for (int kc = 0; kc < p.kchunks; ++kc)
-            for (int nb = 0; nb < p.nblocks; ++nb) tma_load_2d(sB + (kc * p.nblocks + nb) * BT, &tmB, bFull, kc * 64, nb * NB);
+            for (int nb = 0; nb < p.nblocks; ++nb) tma_load_2d(sB + (kc * p.nblocks + nb) * BT, &tmB, bFull, (p.kc_begin + kc) * 64, nb * NB);
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -89,8 +91,9 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 uint8_t* a = sA + st * kAStage;
                 if (p.mode == 1) {
                     const int mt = item - n * hb;
-                    tma_load_4d(a, &tmA, &full[st], mt * 128, (kc % p.hc) * 64, kc / p.hc, n);
-                    tma_load_4d(a + 8192, &tmA, &full[st], mt * 128 + 64, (kc % p.hc) * 64, kc / p.hc, n);
+                    const int g = p.kc_begin + kc;     // global K chunk: (ri, h) = (g / hc, 64 * (g % hc))
+                    tma_load_4d(a, &tmA, &full[st], mt * 128, (g % p.hc) * 64, g / p.hc, n);
+                    tma_load_4d(a + 8192, &tmA, &full[st], mt * 128 + 64, (g % p.hc) * 64, g / p.hc, n);
                 } else if (p.rows_per_item == 2) {
                     tma_load_4d(a, &tmA, &full[st], 0, kc * 64, h0, n);
                     tma_load_4d(a + 8192, &tmA, &full[st], 0, kc * 64, h0 + 1, n);
@@ -153,6 +156,10 @@ hft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (int cc = 0; cc < p.ncols; cc += 16) {
                     float v[32];
                     tmem_ld32(taddr + cc, v);    // reads 32 columns; only the first 16 are consumed per step (80 = 5 x 16)
+                    if (p.accumulate) {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) v[t] += p.T[off + (long long)(cc + t) * p.Cst];
+                    }
                     if (p.Tb != nullptr) {
 #pragma unroll
                         for (int t = 0; t < 16; ++t) p.Tb[off + (long long)(cc + t) * p.Cst] = __float2bfloat16_rn(v[t]);
@@ -557,6 +564,12 @@ static int make_b_map(CUtensorMap* m, const void* base, int Kp, int rows, int nb
 bool hft_tc_supported(int H, int W, int C, int r) {
     return (C == 64 || C == 128) && r == 20 && (W == 128 || W == 256 || W == 512) && (H == 128 || H == 256 || H == 512);
 }
+// forward only: 1024-wide planes too (step 1's [80][W] matrix still fits; step 2 splits K; steps 3 / 4 already run in passes
+// of four resident tiles).  The backward's step 1 reduces over 2W and would need the same split.
+bool hft_tc_supported_fwd(int H, int W, int C, int r) {
+    auto ok = [](int v) { return v == 128 || v == 256 || v == 512 || v == 1024; };
+    return (C == 64 || C == 128) && r == 20 && ok(W) && ok(H);
+}
 
 size_t hft_tc_matrix_elems(int W) { return (size_t)80 * 2 * W + (size_t)2 * W * 128; }
 
@@ -579,7 +592,7 @@ int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, b
 }
 
 // step 2: T2b[n][(ro,g)][(f,c)] = sum_(ri,h) A2[(ro,g)][(ri,h)] * T1b[n][h][ri*F + f][c]      (bf16 in, bf16 out)
-int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, int N, int H, int C, int r, cudaStream_t st) {
+int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, float* T2f, int N, int H, int C, int r, cudaStream_t st) {
     const int F = 2 * r;
     const long long FC = (long long)F * C;
     hft_tc_matrix_kernel<<<cdiv(2 * F * 2 * H, 256), 256, 0, st>>>(mat_ws, 5, 2 * F, 2 * H, F, r, H);
@@ -597,9 +610,19 @@ int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, int N, int H, int C, 
     p.mode = 1; p.mtiles = (int)(FC / 128); p.hc = H / 64;
     p.items = N * p.mtiles;
     p.H = H; p.C = C;
-    p.kchunks = 2 * H / 64; p.k16_last = 4;
-    p.nblocks = 1; p.ncols = 2 * F; p.Tb = T2b; p.Cst = FC;
-    return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step2");
+    p.k16_last = 4;
+    p.nblocks = 1; p.ncols = 2 * F; p.Cst = FC;
+    if (H <= 512) {
+        p.kchunks = 2 * H / 64; p.Tb = T2b;
+        return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step2");
+    }
+    // K = 2H = (ri, h) no longer fits next to the operand ring (80 x 2H x 2 B resident): split over ri -- the first launch
+    // leaves fp32 partial sums, the second adds its half and stores bf16
+    p.kchunks = H / 64;
+    p.kc_begin = 0; p.accumulate = 0; p.T = T2f; p.Tb = nullptr;
+    if (int rc = launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step2(ri=0)")) return rc;
+    p.kc_begin = H / 64; p.accumulate = 1; p.T = T2f; p.Tb = T2b;
+    return launch_hft<80, HEPI_T>(tmA, tmB, p, st, "hft_tc.step2(ri=1)");
 }
 
 // step 3: T3b[n][h][ro*F + f][c] = sum_(ri,g) A3[(ro,h)][(ri,g)] * T2b[n][(ri,g)][(f,c)]

@@ -290,7 +290,7 @@ def ref_hft(x, mask_range=20):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 8, 64, 64), (1, 16, 48, 80), (1, 8, 16, 16), (2, 64, 128, 128), (1, 128, 64, 256),
-                                   (1, 64, 48, 192), (1, 64, 512, 512), (1, 128, 256, 128)])
+                                   (1, 64, 48, 192), (1, 64, 512, 512), (1, 128, 256, 128), (1, 64, 1024, 1024)])
 def test_hft(dtype, shape):
     from eel_unet_b200 import ops
 
