@@ -47,7 +47,9 @@ struct PackJob {           // mirrors eel_pack_job in eel.h (64 bytes)
     bf16* dst;
     int d[4];
     int p[4];
-    long long pad[2];
+    const float* scale;    // optional: multiply by scale[index of output dimension scale_pos] (BatchNorm folded into the weight)
+    int scale_pos;
+    int pad;
 };
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs) {
     const PackJob j = jobs[blockIdx.y];
@@ -60,7 +62,30 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs) {
         const int o3 = (int)(r % od3); r /= od3;
         const int o2 = (int)(r % od2); r /= od2;
         const int o1 = (int)(r % od1); r /= od1;
-        j.dst[i] = __float2bfloat16_rn(j.src[r * s0 + o1 * s1 + o2 * s2 + o3 * s3]);
+        float v = j.src[r * s0 + o1 * s1 + o2 * s2 + o3 * s3];
+        if (j.scale != nullptr) v *= j.scale[j.scale_pos == 0 ? (int)r : (j.scale_pos == 1 ? o1 : (j.scale_pos == 2 ? o2 : o3))];
+        j.dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// Inference-time BatchNorm folding: scale[c] = gamma / sqrt(running_var + eps), bias_out[c] = (bias - running_mean) * scale + beta
+struct FoldJob {           // mirrors eel_fold_job in eel.h (64 bytes)
+    const float* rmean;
+    const float* rvar;
+    const float* gamma;
+    const float* beta;
+    const float* bias;     // producer's bias or null
+    float* scale;
+    float* bias_out;
+    int C;
+    float eps;
+};
+__global__ void bn_fold_batch_kernel(const FoldJob* __restrict__ jobs) {
+    const FoldJob j = jobs[blockIdx.x];
+    for (int c = threadIdx.x; c < j.C; c += blockDim.x) {
+        const float sc = j.gamma[c] / sqrtf(j.rvar[c] + j.eps);
+        j.scale[c] = sc;
+        j.bias_out[c] = ((j.bias ? j.bias[c] : 0.f) - j.rmean[c]) * sc + j.beta[c];
     }
 }
 
@@ -827,6 +852,13 @@ int eel_pack_batch(const void* jobs_device, int njobs, int blocks_per_job, eel_s
     dim3 grid(blocks_per_job, njobs);
     pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const PackJob*)jobs_device);
     return check_launch("pack_batch");
+}
+
+int eel_bn_fold_batch(const void* jobs_device, int njobs, eel_stream s) {
+    EEL_REQUIRE(jobs_device && njobs > 0 && njobs <= 65535, "bn_fold_batch: bad argument");
+    static_assert(sizeof(FoldJob) == 64, "FoldJob must match eel_fold_job");
+    bn_fold_batch_kernel<<<njobs, 256, 0, (cudaStream_t)s>>>((const FoldJob*)jobs_device);
+    return check_launch("bn_fold_batch");
 }
 
 int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0, int d1, int d2, int d3, int p0,

@@ -145,12 +145,44 @@ class EELUnet(nn.Module):
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.compute_dtype = _PRECISIONS[precision]
         self._packer = None
+        self._fpacker = None
         return self
 
     def _weight_packer(self):
         if self._packer is None:
             self._packer = ops.build_packer(self)
         return self._packer
+
+    def _folded_packer(self):
+        """inference: (producer, BatchNorm) pairs whose BatchNorm is folded into the producer's packed weight"""
+        if self._fpacker is None:
+            fp = ops.FoldedPacker()
+
+            def conv(c, bn):
+                co, ci = c.weight.shape[0], c.weight.shape[1]
+                if ci % 64 == 0 and co % 64 == 0:
+                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 0, 1), 0)          # [ky][kx][co][ci], scale over co
+
+            def convt(c, bn):
+                ci, co = c.weight.shape[0], c.weight.shape[1]
+                if ci % 64 == 0 and co % 64 == 0:
+                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 1, 0), 1)          # [ky][kx][co][ci]
+
+            def lin(c, bn):
+                no, k = c.weight.shape[0], c.weight.shape[1]
+                if no % 64 == 0 and k % 64 == 0:
+                    fp.add(c.weight, c.bias, bn, (1, 1, no, k), (0, 1, 2, 3), 2)
+
+            for blk in (self.enc1[0], self.enc2[0], self.dec2, self.dec1, self.edge_upconv_2[2], self.edge_upconv_1[2]):
+                conv(blk[0], blk[1]); conv(blk[3], blk[4])
+            for blk in (self.enc3[0], self.enc4[0], self.dec4, self.dec3, self.edge_upconv_4[1], self.edge_upconv_3[1]):
+                conv(blk[0], blk[1]); lin(blk[3].to_space, blk[4])
+            for blk in (self.upconv2, self.upconv1, self.edge_upconv_2[0], self.edge_upconv_1[0]):
+                convt(blk[0], blk[1])
+            for blk in (self.upconv4, self.upconv3, self.edge_upconv_4[0], self.edge_upconv_3[0]):
+                lin(blk[1].to_space, blk[2])
+            self._fpacker = fp
+        return self._fpacker
 
     # ---- fused stages ------------------------------------------------------------------------
     @staticmethod
@@ -166,24 +198,34 @@ class EELUnet(nn.Module):
                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias)
 
     @staticmethod
-    def _capmlp(m, x, bn=None):
+    def _capmlp(m, x, bn=None, relu=False):
         """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch.
-        bn: the BatchNorm that consumes the result (its training statistics come out of to_space's epilogue)."""
+        bn: the BatchNorm (and `relu`) that consume the result -- applied here: in training its statistics come out of
+        to_space's epilogue, in inference it is folded into to_space's weights."""
         t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
         ca = m.channel_attention
         t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias)
         t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
         t = ops.Gelu.apply(t)
         t = ops.Linear.apply(t, m.mlp[2].weight, m.mlp[2].bias, False)
-        ops.expect_bn(bn is not None and (bn.training or bn.running_mean is None))
-        try:
+        if bn is None:
             return ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+        f = ops.folded(m.to_space.weight)
+        if f is not None:
+            return ops.linear_folded(t, f[0], f[1], relu)
+        ops.expect_bn(bn.training or bn.running_mean is None)
+        try:
+            z = ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
         finally:
             ops.expect_bn(False)
+        return EELUnet._bn(bn, z, relu)
 
     @staticmethod
     def _conv_bn(conv, bn, x, relu=True):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
+        f = ops.folded(conv.weight)
+        if f is not None:
+            return ops.conv3x3_folded(x, f[0], f[1], relu)
         ops.expect_bn(bn.training or bn.running_mean is None)
         try:
             z = ops.Conv3x3.apply(x, conv.weight, conv.bias, False)
@@ -197,13 +239,16 @@ class EELUnet(nn.Module):
 
     def _mlp_conv_block(self, blk, x):
         x = self._conv_bn(blk[0], blk[1], x)
-        return self._bn(blk[4], self._capmlp(blk[3], x, bn=blk[4]), True)
+        return self._capmlp(blk[3], x, bn=blk[4], relu=True)
 
     def _upconv(self, blk, x):
+        f = ops.folded(blk[0].weight)
+        if f is not None:
+            return ops.convt2x2_folded(x, f[0], f[1])
         return self._bn(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), False)
 
     def _mlp_upconv(self, blk, x):
-        return self._bn(blk[2], self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2]), False)
+        return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False)
 
     @staticmethod
     def _pgr(m, x):
@@ -215,12 +260,21 @@ class EELUnet(nn.Module):
             raise EelError("eel_unet_b200.EELUnet runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
             raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+        fold = None
         if self.compute_dtype == torch.bfloat16:
             pk = self._weight_packer()
             pk.refresh(x.device)
             ops.set_packer(pk)
+            if not self.training and not torch.is_grad_enabled():
+                # inference: eval-mode BatchNorms are folded into their producers' weights (ops.FoldedPacker)
+                fold = self._folded_packer()
+                if all(not e[2].training and e[2].running_mean is not None for e in fold.entries):
+                    fold.refresh(x.device)
+                else:
+                    fold = None
         else:
             ops.set_packer(None)
+        ops.set_folded(fold)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
         enc1 = self._conv_block(self.enc1[0], a)

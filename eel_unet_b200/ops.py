@@ -143,6 +143,114 @@ class WeightPacker:
         return self.by_param.get(id(w))
 
 
+class FoldedPacker:
+    """Inference only (eval-mode BatchNorm, autograd off): every tensor-core conv / ConvTranspose / to_space Linear that
+    feeds a BatchNorm gets the BatchNorm folded into its packed bf16 weight (x gamma / sqrt(running_var + eps) per output
+    channel) and an fp32 bias ((b - running_mean) * scale + beta); the ReLU that follows is the kernel's fused ReLU.
+    Removes all 33 BatchNorm apply passes of a forward.  Two launches when anything changed (eel_bn_fold_batch,
+    eel_pack_batch), none otherwise."""
+
+    def __init__(self):
+        self.entries = []      # (weight, bias, bn, dims, perm, scale_pos)
+        self.by_weight = {}
+        self.fold_table = self.pack_table = None
+        self.ptrs = self.versions = None
+
+    def add(self, weight, bias, bn, dims, perm, scale_src_dim):
+        perm = tuple(perm)
+        self.entries.append((weight, bias, bn, tuple(int(d) for d in dims), perm, perm.index(scale_src_dim)))
+
+    def _tensors(self, e):
+        w, b, bn = e[0], e[1], e[2]
+        return [w, b, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+    def _build(self, device):
+        import numpy as np
+        n = len(self.entries)
+        fold = np.zeros((n, 8), dtype=np.int64)
+        pack = np.zeros((n, 8), dtype=np.int64)
+        self.by_weight, self._keep = {}, []
+        for k, e in enumerate(self.entries):
+            w, b, bn, dims, perm, spos = e
+            C = bn.num_features
+            scale = torch.empty(C, dtype=F32, device=device)
+            fbias = torch.empty(C, dtype=F32, device=device)
+            dst = torch.empty([dims[i] for i in perm], dtype=BF16, device=device)
+            f = fold[k]
+            f[0], f[1], f[2], f[3] = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr()
+            f[4] = b.data_ptr() if b is not None else 0
+            f[5], f[6] = scale.data_ptr(), fbias.data_ptr()
+            f[7] = int(np.array([C], dtype=np.int32).view(np.uint32)[0]) | (int(np.array([bn.eps], dtype=np.float32).view(np.uint32)[0]) << 32)
+            r = pack[k]
+            r[0], r[1] = w.data_ptr(), dst.data_ptr()
+            r[2:6] = np.array(list(dims) + list(perm), dtype=np.int32).view(np.int64)
+            r[6] = scale.data_ptr()
+            r[7] = spos
+            self.by_weight[id(w)] = (dst, fbias)
+            self._keep.append((scale, fbias, dst))
+        to_dev = lambda a: torch.from_numpy(a.reshape(-1).view(np.uint8).copy()).to(device)
+        self.fold_table, self.pack_table = to_dev(fold), to_dev(pack)
+        self.ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e) if t is not None]
+        self.versions = None
+
+    def refresh(self, device):
+        if not self.entries:
+            return
+        ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e) if t is not None]
+        if self.fold_table is None or self.fold_table.device != device or ptrs != self.ptrs:
+            self._build(device)
+        ver = [_WEIGHT_EPOCH] + [t._version for e in self.entries for t in self._tensors(e) if t is not None]
+        if ver == self.versions:
+            return
+        call("eel_bn_fold_batch", ptr(self.fold_table), len(self.entries), stream())
+        call("eel_pack_batch", ptr(self.pack_table), len(self.entries), 128, stream())
+        self.versions = ver
+
+    def get(self, w):
+        return self.by_weight.get(id(w))
+
+
+_FOLDED = None
+
+
+def set_folded(p):
+    global _FOLDED
+    _FOLDED = p
+
+
+def folded(weight):
+    """(packed bf16 weight with the BatchNorm folded in, fp32 folded bias) or None"""
+    return None if _FOLDED is None else _FOLDED.get(weight)
+
+
+def conv3x3_folded(x, wk, fbias, relu):
+    """inference: conv3x3 + eval-mode BatchNorm (+ ReLU) as ONE tensor-core kernel"""
+    x = _c(x)
+    N, H, W, Cin = x.shape
+    Cout = wk.shape[2]
+    y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+    call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(fbias), ptr(y), N, H, W, Cin, Cout, int(relu), 0, None, stream())
+    return y
+
+
+def convt2x2_folded(x, wk, fbias):
+    x = _c(x)
+    N, h, w, Cin = x.shape
+    Cout = wk.shape[2]
+    y = torch.empty((N, 2 * h, 2 * w, Cout), dtype=x.dtype, device=x.device)
+    call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(fbias), ptr(y), N, h, w, Cin, Cout, stream())
+    return y
+
+
+def linear_folded(x, w2, fbias, relu):
+    x = _c(x)
+    N, H, W, K = x.shape
+    Nout = w2.shape[-2]
+    y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
+    call("eel_tc_linear", ptr(x), ptr(w2), ptr(fbias), ptr(y), N * H * W, K, Nout, int(relu), None, 0, 0, stream())
+    return y
+
+
 _PACKER = None
 _WEIGHT_EPOCH = 0
 

@@ -47,8 +47,13 @@ int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0,
                  int p0, int p1, int p2, int p3, eel_stream s);
 /* one launch packs a table of fp32 weights into bf16 operand layouts (the per-step weight packing of every
  * tensor-core layer): jobs_device = `njobs` records of 64 bytes in DEVICE memory,
- *   { const float* src; bf16* dst; int d[4]; int p[4]; long long pad[2]; }   dst[i_p0][i_p1][i_p2][i_p3] = src[i0][i1][i2][i3] */
+ *   { const float* src; bf16* dst; int d[4]; int p[4]; const float* scale; int scale_pos; int pad; }
+ *   dst[i_p0][i_p1][i_p2][i_p3] = src[i0][i1][i2][i3] (* scale[i_p<scale_pos>] when scale != NULL) */
 int eel_pack_batch(const void* jobs_device, int njobs, int blocks_per_job, eel_stream s);
+/* inference: fold eval-mode nn.BatchNorm2d into the producing conv / linear (models/EELUnet.py:338-344 in model.eval()):
+ * jobs_device = `njobs` 64-byte records { const float *rmean, *rvar, *gamma, *beta, *bias; float *scale, *bias_out; int C; float eps; }
+ * scale = gamma / sqrt(rvar + eps) (then given to eel_pack_batch), bias_out = (bias - rmean) * scale + beta */
+int eel_bn_fold_batch(const void* jobs_device, int njobs, eel_stream s);
 
 /* ------------------------------------------------------------------ GEMM-class ops
  * nn.Conv2d 3x3 pad 1 (models/EELUnet.py:338,341,351,257).  x:[N,H,W,Cin], wp:[9][Cin][Cout] (dtype),

@@ -188,3 +188,33 @@ def test_packed_weights_follow_every_kind_of_update():
         fresh2 = EELUnet(3, 1, precision="bf16").cuda().eval()
         fresh2.load_state_dict(sd)
         assert torch.equal(model(x)[0], fresh2(x)[0]), "packed weights went stale after load_state_dict"
+
+
+def test_inference_batchnorm_folding_matches_unfolded_eval():
+    """bf16 inference folds eval-mode BatchNorms into their producers' packed weights (ops.FoldedPacker).  Same math as the
+    unfolded eval path (taken whenever autograd is on), different rounding points: the two must agree to bf16 accuracy, and
+    the folded copies must follow updates of the BatchNorm buffers."""
+    from eel_unet_b200 import EELUnet
+
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    m = EELUnet(3, 1, precision="bf16").cuda()
+    m.train()
+    with torch.no_grad():
+        for _ in range(2):
+            m(x)                                  # move the running statistics away from (0, 1)
+    m.eval()
+    seg_ref, edges_ref = m(x)                     # autograd on: unfolded eval path
+    with torch.no_grad():
+        seg, edges = m(x)                         # folded
+    assert rel(seg, seg_ref) < 2e-2
+    for a, b in zip(edges, edges_ref):
+        assert rel(a, b) < 2e-2
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.add_(0.05)
+                mod.weight.mul_(1.1)
+        seg2, _ = m(x)
+    seg2_ref, _ = m(x)
+    assert rel(seg2, seg2_ref) < 2e-2 and rel(seg2, seg) > 1e-3   # the folded weights followed the update
