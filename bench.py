@@ -24,6 +24,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner under NCCL_DEBUG=VERSION, warnings):
+# keep a private handle on the real stdout for the result and point file descriptor 1 at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -131,7 +141,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -145,8 +155,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL logs (its version banner included) go to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
@@ -294,7 +302,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
             "loss": float(loss.item()), "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

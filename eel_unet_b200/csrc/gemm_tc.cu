@@ -264,7 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     dst[i] = roff[i] >= 0 ? p.out + o + coff + L.slot * 8 : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, (EPI == EPI_DENSE && p.bn_sums) ? &st[ci] : nullptr, lane);
+                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, (EPI != EPI_SCATTER && p.bn_sums) ? &st[ci] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -273,6 +273,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EPI == EPI_DENSE && p.bn_sums) {
 #pragma unroll
             for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, half * (BN / 2) + ci * 32, lane, st[ci]);
+        }
+        if (EPI == EPI_CONVT && p.bn_sums) {
+            // columns are (dy, dx, co): the four taps of a channel add into the same [2][Co] sums
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (half * (BN / 2) + ci * 32) % p.Co, lane, st[ci]);
         }
     }
     tc_fence_before();
@@ -369,7 +374,7 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
 }
 
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin, int Cout,
-                        eel_stream s) {
+                        float* bn_sums, eel_stream s) {
     EEL_REQUIRE(x && wk && y && N > 0 && h > 0 && w > 0, "tc_convt2x2_fwd: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convt2x2_fwd: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     const long long P = (long long)N * h * w;
@@ -394,6 +399,14 @@ int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* 
     p.n_tiles = ncols / bn;
     p.M = P; p.Ntot = ncols; p.W = w; p.Co = Cout;
     p.bias = bias; p.out = (bf16*)y;
+    if (bn_sums != nullptr) {
+        EEL_REQUIRE(p.n_tiles == 1, "tc_convt2x2_fwd: fused BatchNorm statistics need a single N tile (4 * Cout <= 256, got Cout %d)", Cout);
+        if (cudaMemsetAsync(bn_sums, 0, sizeof(float) * 2 * Cout, (cudaStream_t)s) != cudaSuccess) {
+            set_error("tc_convt2x2_fwd: memset failed");
+            return EEL_ERR_CUDA;
+        }
+        p.bn_sums = bn_sums;
+    }
     return dispatch_bn<EPI_CONVT>(bn, tmA, tmB, p, (cudaStream_t)s, "tc_convt2x2_fwd");
 }
 

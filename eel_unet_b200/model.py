@@ -245,7 +245,12 @@ class EELUnet(nn.Module):
         f = ops.folded(blk[0].weight)
         if f is not None:
             return ops.convt2x2_folded(x, f[0], f[1])
-        return self._bn(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), False)
+        ops.expect_bn(blk[1].training or blk[1].running_mean is None)
+        try:
+            z = ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias)
+        finally:
+            ops.expect_bn(False)
+        return self._bn(blk[1], z, False)
 
     def _mlp_upconv(self, blk, x):
         return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False)

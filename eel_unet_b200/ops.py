@@ -238,7 +238,7 @@ def convt2x2_folded(x, wk, fbias):
     N, h, w, Cin = x.shape
     Cout = wk.shape[2]
     y = torch.empty((N, 2 * h, 2 * w, Cout), dtype=x.dtype, device=x.device)
-    call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(fbias), ptr(y), N, h, w, Cin, Cout, stream())
+    call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(fbias), ptr(y), N, h, w, Cin, Cout, None, stream())
     return y
 
 
@@ -392,7 +392,11 @@ class ConvT2x2(Function):
             wk = _packed(weight, 0)
             if wk is None:
                 wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
-            call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, stream())
+            sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_BN_NEXT[0] and 4 * Cout <= 256) else None
+            call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, ptr(sums), stream())
+            if sums is not None:
+                _BN_SUMS.clear()
+                _BN_SUMS[y.data_ptr()] = sums
         else:
             wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
             call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())

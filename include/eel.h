@@ -95,8 +95,9 @@ int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, in
  * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
                   int relu, float* bn_sums, int scatterH, int scatterW, eel_stream s);
+/* bn_sums as above ([2][Cout]; needs 4 * Cout <= 256) */
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin,
-                        int Cout, eel_stream s);
+                        int Cout, float* bn_sums, eel_stream s);
 /* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */
 int eel_tc_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h, int w, int Cin, int Cout,
                           eel_stream s);

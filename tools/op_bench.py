@@ -61,7 +61,7 @@ def cases(B, S, only):
     for (s, ci, co) in [(S // 2, 128, 64), (S // 4, 256, 128), (S // 8, 512, 256), (S // 16, 1024, 512)]:
         def mk(s=s, ci=ci, co=co):
             x, w, b, y = rnd(B, s, s, ci), rnd(2, 2, co, ci), rnd(co, dtype=F32), torch.empty(B, 2 * s, 2 * s, co, device=DEV, dtype=BF16)
-            return "eel_tc_convt2x2_fwd", (ptr(x), ptr(w), ptr(b), ptr(y), B, s, s, ci, co, st()), (x, w, b, y)
+            return "eel_tc_convt2x2_fwd", (ptr(x), ptr(w), ptr(b), ptr(y), B, s, s, ci, co, None, st()), (x, w, b, y)
         add("convt", "convT %dx%d %d->%d" % (s, s, ci, co), mk)
     for (s, c) in [(S, 64), (S // 2, 128), (S // 4, 256), (S // 8, 512)]:
         P = B * s * s
