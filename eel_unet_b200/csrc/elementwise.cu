@@ -555,15 +555,33 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
 }
 
 // ------------------------------------------------------------------------------------ add + interleave
+// out[:, 2c] = a[:, c] + b[:, c], out[:, 2c+1] = e[:, c].  mean != null: `a` is a pre-BatchNorm tensor and is normalised on
+// the fly (a * gamma * rstd + beta - mean * gamma * rstd, no ReLU: the BatchNorm that ends an upconv block).  The launch uses
+// a multiple of C / V threads, so a thread always meets the same channel vector and keeps its constants in registers.
 template <class T>
 __global__ void add_interleave_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ e,
-                                          T* __restrict__ out, long long nvec) {
+                                          T* __restrict__ out, long long nvec, int C, const float* __restrict__ mean,
+                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta) {
     constexpr int V = Vec16<T>::N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float sc[V], sh[V];
+    if (mean != nullptr) {
+        const int c0 = (int)(i0 % (C / V)) * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            sc[j] = gamma[c0 + j] * rstd[c0 + j];
+            sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+    }
+    for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         Vec16<T> va = ld16(a + i * V), vb = ld16(b + i * V), ve = ld16(e + i * V), o0, o1;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            float s = va.get(j) + vb.get(j);
+            float s = fmaf(va.get(j), sc[j], sh[j]) + vb.get(j);
             if (j < V / 2) { o0.set(2 * j, s); o0.set(2 * j + 1, ve.get(j)); }
             else { o1.set(2 * j - V, s); o1.set(2 * j + 1 - V, ve.get(j)); }
         }
@@ -977,13 +995,17 @@ int eel_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int 
     });
 }
 
-int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* out, long long P, int C, int dtype,
-                           eel_stream s) {
+int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* out, long long P, int C, const float* a_mean,
+                           const float* a_rstd, const float* a_gamma, const float* a_beta, int dtype, eel_stream s) {
     EEL_REQUIRE(a && b && e && out && P > 0 && C > 0, "add_interleave_fwd: bad argument");
+    EEL_REQUIRE(a_mean == nullptr || (a_rstd && a_gamma && a_beta), "add_interleave_fwd: mean / rstd / gamma / beta go together");
     EEL_DISPATCH_DTYPE(dtype, {
         EEL_VEC_CHECK(T, C, "add_interleave_fwd");
-        long long nvec = P * C / Vec16<T>::N;
-        add_interleave_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (const T*)e, (T*)out, nvec);
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(a_mean == nullptr || 256 % (C / V) == 0, "add_interleave_fwd: fused BatchNorm needs C / %d to divide 256", V);
+        long long nvec = P * C / V;
+        add_interleave_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (const T*)e, (T*)out, nvec, C,
+                                                                                   a_mean, a_rstd, a_gamma, a_beta);
         return check_launch("add_interleave_fwd");
     });
 }

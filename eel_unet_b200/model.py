@@ -186,19 +186,32 @@ class EELUnet(nn.Module):
 
     # ---- fused stages ------------------------------------------------------------------------
     @staticmethod
-    def _bn(bn, z, relu, producer_bias=True):
+    def _bn_mode(bn):
+        """training flag of a BatchNorm + the bookkeeping nn.BatchNorm2d.forward does (num_batches_tracked)"""
         training = bn.training or bn.running_mean is None
         if training and bn.track_running_stats:
             if bn.momentum is None:
                 raise EelError("BatchNorm momentum=None (cumulative average) is not used by the reference and not supported")
             bn.num_batches_tracked += 1
+        return training
+
+    @staticmethod
+    def _bn_add_interleave(bn, z, b, e):
+        """BatchNorm(z) + b, interleaved with e (decoder skip bridge) without materialising BatchNorm(z)"""
+        training = EELUnet._bn_mode(bn)
+        return ops.BNAddInterleave.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                         bn.momentum if bn.momentum is not None else 0.1, bn.eps, b, e, True)
+
+    @staticmethod
+    def _bn(bn, z, relu, producer_bias=True):
+        training = EELUnet._bn_mode(bn)
         # producer_bias: z comes straight from a biased conv / linear, whose bias gradient (= column sums of dz) the
         # BatchNorm backward then delivers for free
         return ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu,
                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias)
 
     @staticmethod
-    def _capmlp(m, x, bn=None, relu=False):
+    def _capmlp(m, x, bn=None, relu=False, defer=False):
         """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch.
         bn: the BatchNorm (and `relu`) that consume the result -- applied here: in training its statistics come out of
         to_space's epilogue, in inference it is folded into to_space's weights."""
@@ -218,6 +231,8 @@ class EELUnet(nn.Module):
             z = ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
         finally:
             ops.expect_bn(False)
+        if defer:                      # the caller fuses this BatchNorm into its next op (decoder skip bridge)
+            return z, bn
         return EELUnet._bn(bn, z, relu)
 
     @staticmethod
@@ -241,7 +256,8 @@ class EELUnet(nn.Module):
         x = self._conv_bn(blk[0], blk[1], x)
         return self._capmlp(blk[3], x, bn=blk[4], relu=True)
 
-    def _upconv(self, blk, x):
+    def _upconv(self, blk, x, defer=False):
+        """ConvT -> BatchNorm.  defer: return (z, bn) so that the caller fuses the BatchNorm into the skip bridge"""
         f = ops.folded(blk[0].weight)
         if f is not None:
             return ops.convt2x2_folded(x, f[0], f[1])
@@ -250,10 +266,19 @@ class EELUnet(nn.Module):
             z = ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias)
         finally:
             ops.expect_bn(False)
+        if defer:
+            return z, blk[1]
         return self._bn(blk[1], z, False)
 
-    def _mlp_upconv(self, blk, x):
-        return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False)
+    def _mlp_upconv(self, blk, x, defer=False):
+        return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False, defer=defer)
+
+    def _bridge(self, up, b, e):
+        """(upconv output + edge feature) interleaved with the encoder skip (reference models/EELUnet.py:422-426); `up` is
+        either the finished upconv output or (pre-BatchNorm tensor, BatchNorm) when its BatchNorm is fused in here"""
+        if isinstance(up, tuple):
+            return self._bn_add_interleave(up[1], up[0], b, e)
+        return ops.AddInterleave.apply(up, b, e)
 
     @staticmethod
     def _pgr(m, x):
@@ -302,13 +327,13 @@ class EELUnet(nn.Module):
         e1 = self._conv_block(self.edge_upconv_1[2], e1)
 
         # decoder (reference models/EELUnet.py:421-465)
-        d = self._mlp_conv_block(self.dec4, ops.AddInterleave.apply(self._mlp_upconv(self.upconv4, b), e4, enc4))
+        d = self._mlp_conv_block(self.dec4, self._bridge(self._mlp_upconv(self.upconv4, b, defer=True), e4, enc4))
         d, edge_4 = self._pgr(self.pred4, d)
-        d = self._mlp_conv_block(self.dec3, ops.AddInterleave.apply(self._mlp_upconv(self.upconv3, d), e3, enc3))
+        d = self._mlp_conv_block(self.dec3, self._bridge(self._mlp_upconv(self.upconv3, d, defer=True), e3, enc3))
         d, edge_3 = self._pgr(self.pred3, d)
-        d = self._conv_block(self.dec2, ops.AddInterleave.apply(self._upconv(self.upconv2, d), e2, enc2))
+        d = self._conv_block(self.dec2, self._bridge(self._upconv(self.upconv2, d, defer=True), e2, enc2))
         d, edge_2 = self._pgr(self.pred2, d)
-        d = self._conv_block(self.dec1, ops.AddInterleave.apply(self._upconv(self.upconv1, d), e1, enc1))
+        d = self._conv_block(self.dec1, self._bridge(self._upconv(self.upconv1, d, defer=True), e1, enc1))
         d, edge_1 = self._pgr(self.pred1, d)
 
         seg = ops.Head.apply(d, self.final[0].weight, self.final[0].bias, self.final[1].weight, self.final[1].bias)

@@ -500,6 +500,28 @@ class Linear(Function):
         return dx, dw.view(weight.shape), db, None
 
 
+def _bn_statistics(z, running_mean, running_var, training, momentum, eps):
+    """(mean, rstd) of a BatchNorm over z [.., C]: batch statistics (+ running-stat update) in training -- from the sums the
+    tensor-core producer left behind when there are any -- else the running statistics"""
+    C = z.shape[-1]
+    P = z.numel() // C
+    dev = z.device
+    mean = torch.empty(C, dtype=F32, device=dev)
+    rstd = torch.empty(C, dtype=F32, device=dev)
+    st = stream()
+    sums = _BN_SUMS.pop(z.data_ptr(), None)
+    if training and sums is not None and sums.shape[1] == C:
+        call("eel_bn_stats_from_sums", ptr(sums), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
+             float(momentum), float(eps), st)
+    elif training:
+        ws, n = _reduce_ws(dev, C, 2)
+        call("eel_bn_stats", ptr(z), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
+             float(momentum), float(eps), ptr(ws), n, dtype_code(z), st)
+    else:
+        call("eel_bn_eval_stats", ptr(running_mean), ptr(running_var), float(eps), ptr(mean), ptr(rstd), C, st)
+    return mean, rstd
+
+
 # --------------------------------------------------------------------------------------- BatchNorm (+ReLU)
 class BNAct(Function):
     """nn.BatchNorm2d [+ nn.ReLU] (reference models/EELUnet.py:339-344,352-357,365,373,256)."""
@@ -509,20 +531,8 @@ class BNAct(Function):
         z = _c(z)
         C = z.shape[-1]
         P = z.numel() // C
-        dev = z.device
-        mean = torch.empty(C, dtype=F32, device=dev)
-        rstd = torch.empty(C, dtype=F32, device=dev)
         st = stream()
-        sums = _BN_SUMS.pop(z.data_ptr(), None)
-        if training and sums is not None and sums.shape[1] == C:
-            call("eel_bn_stats_from_sums", ptr(sums), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
-                 float(momentum), float(eps), st)
-        elif training:
-            ws, n = _reduce_ws(dev, C, 2)
-            call("eel_bn_stats", ptr(z), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
-                 float(momentum), float(eps), ptr(ws), n, dtype_code(z), st)
-        else:
-            call("eel_bn_eval_stats", ptr(running_mean), ptr(running_var), float(eps), ptr(mean), ptr(rstd), C, st)
+        mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
         y = torch.empty_like(z)
         g, b = gamma.detach(), beta.detach()
         call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
@@ -619,7 +629,7 @@ class AddInterleave(Function):
         a, b, e = _c(a), _c(b), _c(e)
         N, H, W, C = a.shape
         out = torch.empty((N, H, W, 2 * C), dtype=a.dtype, device=a.device)
-        call("eel_add_interleave_fwd", ptr(a), ptr(b), ptr(e), ptr(out), N * H * W, C, dtype_code(a), stream())
+        call("eel_add_interleave_fwd", ptr(a), ptr(b), ptr(e), ptr(out), N * H * W, C, None, None, None, None, dtype_code(a), stream())
         return out
 
     @staticmethod
@@ -631,6 +641,47 @@ class AddInterleave(Function):
         de = torch.empty_like(dab)
         call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), N * H * W, C, dtype_code(dout), stream())
         return dab, dab, de
+
+
+class BNAddInterleave(Function):
+    """nn.BatchNorm2d (no ReLU: the end of an upconv block, reference models/EELUnet.py:365,373) + torch.add +
+    FeatureInterleaveBridge (:422-426) in one pass: the normalised tensor is never written.  Inputs: the pre-BatchNorm
+    tensor z, the edge feature b and the encoder skip e."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, momentum, eps, b, e, producer_bias):
+        z, b, e = _c(z), _c(b), _c(e)
+        N, H, W, C = z.shape
+        mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
+        out = torch.empty((N, H, W, 2 * C), dtype=z.dtype, device=z.device)
+        call("eel_add_interleave_fwd", ptr(z), ptr(b), ptr(e), ptr(out), N * H * W, C, ptr(mean), ptr(rstd), ptr(gamma.detach()),
+             ptr(beta.detach()), dtype_code(z), stream())
+        ctx.training, ctx.producer_bias = training, producer_bias
+        ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, mean, rstd, gamma, beta = ctx.saved_tensors
+        dout = _c(dout)
+        N, H, W, C2 = dout.shape
+        C = C2 // 2
+        P = N * H * W
+        dab = torch.empty((N, H, W, C), dtype=dout.dtype, device=dout.device)
+        de = torch.empty_like(dab)
+        st = stream()
+        call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), P, C, dtype_code(dout), st)
+        dz = torch.empty_like(z)
+        dgamma = torch.empty(C, dtype=F32, device=z.device)
+        dbeta = torch.empty(C, dtype=F32, device=z.device)
+        ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+        dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
+        call("eel_bn_act_bwd", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
+             ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, 0, int(ctx.training), ptr(ws), n, dtype_code(z), st)
+        if dzsum is not None:
+            _DZ_COLSUM.clear()
+            _DZ_COLSUM[dz.data_ptr()] = dzsum
+        return dz, dgamma, dbeta, None, None, None, None, None, dab, de, None
 
 
 class Concat(Function):

@@ -77,7 +77,7 @@ def cost(name, a):
         N, H, W, C, dt = a[3], a[4], a[5], a[6], a[7]
         return 0.75 * N * H * W * C, 2.25 * N * H * W * C * _esz(dt)
     if n == "add_interleave_fwd":
-        P, C, dt = a[4], a[5], a[6]
+        P, C, dt = a[4], a[5], a[10]
         return 1.0 * P * C, 5 * P * C * _esz(dt)
     if n == "add_interleave_bwd":
         P, C, dt = a[3], a[4], a[5]

@@ -159,7 +159,10 @@ int eel_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int 
                      eel_stream s);
 /* torch.add + FeatureInterleaveBridge (models/EELUnet.py:422-426,132-141):
  * out[p][2c] = a[p][c] + b[p][c], out[p][2c+1] = e[p][c] */
+/* a_mean != NULL: `a` is a pre-BatchNorm tensor, normalised on the fly with (a_mean, a_rstd, a_gamma, a_beta) -- the
+ * BatchNorm that ends an upconv block (models/EELUnet.py:365,373) fused into the skip bridge */
 int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* out, long long P, int C,
+                           const float* a_mean, const float* a_rstd, const float* a_gamma, const float* a_beta,
                            int dtype, eel_stream s);
 int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, int C, int dtype,
                            eel_stream s);
