@@ -975,6 +975,24 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
     });
 }
 
+int eel_bn_act_bwd_apply(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         const float* sums, void* dz, float* dz_colsum, long long P, int C, int relu, int train, int dtype,
+                         eel_stream s) {
+    EEL_REQUIRE(dy && z && mean && rstd && gamma && beta && sums && dz && P > 0 && C > 0, "bn_act_bwd_apply: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "bn_act_bwd_apply");
+        RedPlan ps = plan_stream<T>(P, C);
+        dim3 grid(ps.ncb, ps.nrb);
+        if (dz_colsum != nullptr && cudaMemsetAsync(dz_colsum, 0, sizeof(float) * C, (cudaStream_t)s) != cudaSuccess) {
+            set_error("bn_act_bwd_apply: memset failed");
+            return EEL_ERR_CUDA;
+        }
+        bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
+                                                            1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train, dz_colsum);
+        return check_launch("bn_act_bwd_apply");
+    });
+}
+
 int eel_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, eel_stream s) {
     EEL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad argument (H, W must be even)");
     EEL_DISPATCH_DTYPE(dtype, {

@@ -286,6 +286,175 @@ __global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel2(const T* __restri
     for (int i = threadIdx.x; i <= C; i += kPixThreads) partial[(long long)blockIdx.x * (C + 1) + i] = sh[i];
 }
 
+// ---- BatchNorm + ReLU + PredictionGuidedRefinement fused (the end of every decoder block, models/EELUnet.py:343-344 then
+// :200-203).  Forward: the input is the PRE-BatchNorm tensor z; x = relu(gamma * (z - mean) * rstd + beta) exists only in
+// registers.  Backward: x is recomputed from z, and the kernel also accumulates the two per-channel sums the BatchNorm
+// backward needs (sum g, sum g * xhat with g = dx * relu_mask), so that BatchNorm's own reduction pass over (dy, z)
+// disappears -- eel_bn_act_bwd_apply finishes with one pass.
+struct BnConst { const float* mean; const float* rstd; const float* gamma; const float* beta; };
+
+template <class T, int ITERS, int U>
+__global__ void __launch_bounds__(kPixThreads) bn_pgr_fwd_kernel(const T* __restrict__ z, BnConst bn, const float* __restrict__ w,
+                                                               const float* __restrict__ b, T* __restrict__ y,
+                                                               float* __restrict__ sg, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const float bias = b[0];
+    float wreg[ITERS][V], m[ITERS][V], rs[ITERS][V], gm[ITERS][V], bt[ITERS][V];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int c = (gl + k * G) * V + j;
+            wreg[k][j] = w[c]; m[k][j] = bn.mean[c]; rs[k][j] = bn.rstd[c]; gm[k][j] = bn.gamma[c]; bt[k][j] = bn.beta[c];
+        }
+    const long long stride = (long long)gridDim.x * groups_per_block * U;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block * U; p0 < P; p0 += stride) {
+        Vec16<T> vz[U][ITERS];
+        float dot[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            ok[u] = p < P;
+            if (ok[u])
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k) vz[u][k] = ld16(z + p * C + (gl + k * G) * V);
+        }
+        float xf[U][ITERS][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            dot[u] = 0.f;
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float xh = ok[u] ? (vz[u][k].get(j) - m[k][j]) * rs[k][j] : 0.f;
+                    const float x = ok[u] ? fmaxf(gm[k][j] * xh + bt[k][j], 0.f) : 0.f;
+                    xf[u][k][j] = x;
+                    dot[u] += x * wreg[k][j];
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] = group_sum(dot[u], G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            const float sv = sigmoidf_(dot[u] + bias);
+            if (gl == 0) sg[p] = sv;
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o.set(j, xf[u][k][j] * (1.f + sv));
+                st16(y + p * C + (gl + k * G) * V, o);
+            }
+        }
+    }
+}
+
+// partial row layout: dw[C] db[1] sum_g[C] sum_gx[C]
+template <class T, int ITERS, int U>
+__global__ void __launch_bounds__(kPixThreads) bn_pgr_bwd_kernel(const T* __restrict__ z, BnConst bn, const float* __restrict__ sg,
+                                                               const float* __restrict__ w, const T* __restrict__ dy,
+                                                               const float* __restrict__ dsg, T* __restrict__ dx,
+                                                               float* __restrict__ partial, long long P, int C, int G) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float sh[];   // [3 C + 1]
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int groups_per_block = kPixThreads / G;
+    const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
+    const int width = 3 * C + 1;
+    for (int i = threadIdx.x; i < width; i += kPixThreads) sh[i] = 0.f;
+    __syncthreads();
+    float dwacc[ITERS][V], sga[ITERS][V], sgx[ITERS][V], wreg[ITERS][V], m[ITERS][V], rs[ITERS][V], gm[ITERS][V], bt[ITERS][V];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int c = (gl + k * G) * V + j;
+            dwacc[k][j] = 0.f; sga[k][j] = 0.f; sgx[k][j] = 0.f;
+            wreg[k][j] = w[c]; m[k][j] = bn.mean[c]; rs[k][j] = bn.rstd[c]; gm[k][j] = bn.gamma[c]; bt[k][j] = bn.beta[c];
+        }
+    float dbacc = 0.f;
+    const long long stride = (long long)gridDim.x * groups_per_block * U;
+    for (long long p0 = (long long)blockIdx.x * groups_per_block * U; p0 < P; p0 += stride) {
+        Vec16<T> vz[U][ITERS], vd[U][ITERS];
+        float sv[U], ds[U], dot[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            ok[u] = p < P;
+            sv[u] = 0.f; ds[u] = 0.f;
+            if (ok[u]) {
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k) {
+                    const int c0 = (gl + k * G) * V;
+                    vz[u][k] = ld16(z + p * C + c0);
+                    vd[u][k] = ld16(dy + p * C + c0);
+                }
+                sv[u] = sg[p];
+                if (dsg) ds[u] = dsg[p];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            dot[u] = 0.f;
+            if (ok[u])
+#pragma unroll
+                for (int k = 0; k < ITERS; ++k)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float xh = (vz[u][k].get(j) - m[k][j]) * rs[k][j];
+                        const float x = fmaxf(gm[k][j] * xh + bt[k][j], 0.f);
+                        dot[u] += x * vd[u][k].get(j);
+                    }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] = group_sum(dot[u], G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const long long p = p0 + (long long)u * groups_per_block + g_in_block;
+            const float dg = (dot[u] + ds[u]) * sv[u] * (1.f - sv[u]);
+            if (gl == 0) dbacc += dg;
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float xh = (vz[u][k].get(j) - m[k][j]) * rs[k][j];
+                    const float pre = gm[k][j] * xh + bt[k][j];
+                    const float x = fmaxf(pre, 0.f);
+                    o.set(j, vd[u][k].get(j) * (1.f + sv[u]) + wreg[k][j] * dg);
+                    dwacc[k][j] += x * dg;
+                    const float g = pre > 0.f ? o.get(j) : 0.f;     // the BatchNorm backward sees the STORED (rounded) dx
+                    sga[k][j] += g;
+                    sgx[k][j] += g * xh;
+                }
+                st16(dx + p * C + (gl + k * G) * V, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+        const int c0 = (gl + k * G) * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            atomicAdd(&sh[c0 + j], dwacc[k][j]);
+            atomicAdd(&sh[C + 1 + c0 + j], sga[k][j]);
+            atomicAdd(&sh[2 * C + 1 + c0 + j], sgx[k][j]);
+        }
+    }
+    if (gl == 0) atomicAdd(&sh[C], dbacc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += kPixThreads) partial[(long long)blockIdx.x * width + i] = sh[i];
+}
+
 // ------------------------------------------------------------------------------------ head (C = 64)
 constexpr int kHeadC = 64;
 constexpr int kHeadMaxO = 4;
@@ -624,6 +793,55 @@ int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy,
         RowSegs segs{{dw, db, db, db}, {C, C + 1, C + 1, C + 1}};
         finalize_rows_kernel<<<cdiv(C + 1, 32), 1024, 0, (cudaStream_t)s>>>(partial, grid, C + 1, segs);
         return check_launch("pgr_bwd.finalize");
+    });
+}
+
+int eel_bn_pgr_fwd(const void* z, const float* bn_mean, const float* bn_rstd, const float* bn_gamma, const float* bn_beta,
+                   const float* w, const float* b, void* y, float* sgm, long long P, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && bn_mean && bn_rstd && bn_gamma && bn_beta && w && b && y && sgm && P > 0 && C > 0, "bn_pgr_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(C % V == 0 && pow2(C / V), "bn_pgr_fwd: C/vec must be a power of two");
+        const int G = pix_group(C, V), iters = C / V / G;
+        EEL_REQUIRE(iters == 1 || iters == 2, "bn_pgr_fwd: at most 64 channel vectors (C <= %d)", 64 * V);
+        const int gpb = kPixThreads / G;
+        const long long blocks = (P + gpb - 1) / gpb;
+        const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+        const BnConst bn{bn_mean, bn_rstd, bn_gamma, bn_beta};
+        cudaStream_t st2 = (cudaStream_t)s;
+        if (iters == 1) bn_pgr_fwd_kernel<T, 1, 4><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        else bn_pgr_fwd_kernel<T, 2, 2><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        return check_launch("bn_pgr_fwd");
+    });
+}
+
+int eel_bn_pgr_bwd(const void* z, const float* bn_mean, const float* bn_rstd, const float* bn_gamma, const float* bn_beta,
+                   const float* sgm, const float* w, const void* dy, const float* dsgm, void* dx, float* dw, float* db,
+                   float* bn_sums, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && bn_mean && bn_rstd && bn_gamma && bn_beta && sgm && w && dy && dx && dw && db && bn_sums && P > 0 && C > 0,
+                "bn_pgr_bwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(C % V == 0 && pow2(C / V), "bn_pgr_bwd: C/vec must be a power of two");
+        const int G = pix_group(C, V), iters = C / V / G;
+        EEL_REQUIRE(iters == 1 || iters == 2, "bn_pgr_bwd: at most 64 channel vectors (C <= %d)", 64 * V);
+        const int gpb = kPixThreads / G;
+        const long long blocks = (P + gpb - 1) / gpb;
+        const int grid = (int)(blocks < (long long)kNumSMs * 2 ? blocks : (long long)kNumSMs * 2);
+        const int width = 3 * C + 1;
+        const size_t need = sizeof(float) * (size_t)grid * width;
+        if (need > ws_bytes || !ws) { set_error("bn_pgr_bwd: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
+        float* partial = (float*)ws;
+        const BnConst bn{bn_mean, bn_rstd, bn_gamma, bn_beta};
+        const size_t shb = sizeof(float) * width;
+        cudaStream_t st2 = (cudaStream_t)s;
+        if (iters == 1) bn_pgr_bwd_kernel<T, 1, 4><<<grid, kPixThreads, shb, st2>>>((const T*)z, bn, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
+        else bn_pgr_bwd_kernel<T, 2, 2><<<grid, kPixThreads, shb, st2>>>((const T*)z, bn, sgm, w, (const T*)dy, dsgm, (T*)dx, partial, P, C, G);
+        if (int rc = check_launch("bn_pgr_bwd")) return rc;
+        // bn_sums = [2][C]: {sum g, sum g * xhat} (= dbeta, dgamma of the BatchNorm)
+        RowSegs segs{{dw, db, bn_sums, bn_sums + C}, {C, C + 1, 2 * C + 1, 3 * C + 1}};
+        finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, st2>>>(partial, grid, width, segs);
+        return check_launch("bn_pgr_bwd.finalize");
     });
 }
 

@@ -236,7 +236,7 @@ class EELUnet(nn.Module):
         return EELUnet._bn(bn, z, relu)
 
     @staticmethod
-    def _conv_bn(conv, bn, x, relu=True):
+    def _conv_bn(conv, bn, x, relu=True, defer=False):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
         f = ops.folded(conv.weight)
         if f is not None:
@@ -246,15 +246,30 @@ class EELUnet(nn.Module):
             z = ops.Conv3x3.apply(x, conv.weight, conv.bias, False)
         finally:
             ops.expect_bn(False)
+        if defer:
+            return z, bn
         return EELUnet._bn(bn, z, relu)
 
-    def _conv_block(self, blk, x):
+    def _conv_block(self, blk, x, defer=False):
+        """defer: return (pre-BatchNorm tensor, BatchNorm) for the block's LAST BatchNorm + ReLU (fused into the PGR that follows)"""
         x = self._conv_bn(blk[0], blk[1], x)
-        return self._conv_bn(blk[3], blk[4], x)
+        return self._conv_bn(blk[3], blk[4], x, defer=defer)
 
-    def _mlp_conv_block(self, blk, x):
+    def _mlp_conv_block(self, blk, x, defer=False):
         x = self._conv_bn(blk[0], blk[1], x)
-        return self._capmlp(blk[3], x, bn=blk[4], relu=True)
+        return self._capmlp(blk[3], x, bn=blk[4], relu=True, defer=defer)
+
+    def _pgr_block(self, m, d):
+        """PredictionGuidedRefinement on a decoder block's output; `d` is either the finished block output or
+        (pre-BatchNorm tensor, BatchNorm) whose BatchNorm + ReLU are then fused into the PGR pass"""
+        if isinstance(d, tuple):
+            z, bn = d
+            if ops.bn_pgr_supported(z):
+                training = self._bn_mode(bn)
+                return ops.BNReluPGR.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                           bn.momentum if bn.momentum is not None else 0.1, bn.eps, m.conv.weight, m.conv.bias, True)
+            d = self._bn(bn, z, True)
+        return self._pgr(m, d)
 
     def _upconv(self, blk, x, defer=False):
         """ConvT -> BatchNorm.  defer: return (z, bn) so that the caller fuses the BatchNorm into the skip bridge"""
@@ -327,14 +342,14 @@ class EELUnet(nn.Module):
         e1 = self._conv_block(self.edge_upconv_1[2], e1)
 
         # decoder (reference models/EELUnet.py:421-465)
-        d = self._mlp_conv_block(self.dec4, self._bridge(self._mlp_upconv(self.upconv4, b, defer=True), e4, enc4))
-        d, edge_4 = self._pgr(self.pred4, d)
-        d = self._mlp_conv_block(self.dec3, self._bridge(self._mlp_upconv(self.upconv3, d, defer=True), e3, enc3))
-        d, edge_3 = self._pgr(self.pred3, d)
-        d = self._conv_block(self.dec2, self._bridge(self._upconv(self.upconv2, d, defer=True), e2, enc2))
-        d, edge_2 = self._pgr(self.pred2, d)
-        d = self._conv_block(self.dec1, self._bridge(self._upconv(self.upconv1, d, defer=True), e1, enc1))
-        d, edge_1 = self._pgr(self.pred1, d)
+        d = self._mlp_conv_block(self.dec4, self._bridge(self._mlp_upconv(self.upconv4, b, defer=True), e4, enc4), defer=True)
+        d, edge_4 = self._pgr_block(self.pred4, d)
+        d = self._mlp_conv_block(self.dec3, self._bridge(self._mlp_upconv(self.upconv3, d, defer=True), e3, enc3), defer=True)
+        d, edge_3 = self._pgr_block(self.pred3, d)
+        d = self._conv_block(self.dec2, self._bridge(self._upconv(self.upconv2, d, defer=True), e2, enc2), defer=True)
+        d, edge_2 = self._pgr_block(self.pred2, d)
+        d = self._conv_block(self.dec1, self._bridge(self._upconv(self.upconv1, d, defer=True), e1, enc1), defer=True)
+        d, edge_1 = self._pgr_block(self.pred1, d)
 
         seg = ops.Head.apply(d, self.final[0].weight, self.final[0].bias, self.final[1].weight, self.final[1].bias)
         return seg, [edge_5, edge_4, edge_3, edge_2, edge_1]

@@ -763,6 +763,60 @@ class PGR(Function):
         return dx, dw.view(weight.shape), db
 
 
+class BNReluPGR(Function):
+    """nn.BatchNorm2d + nn.ReLU (the end of a decoder block, reference models/EELUnet.py:343-344 / 356-357) followed by
+    PredictionGuidedRefinement (:200-203) in one pass over the pre-BatchNorm tensor z.  The backward recomputes relu(bn(z)),
+    and its PGR pass also produces the BatchNorm's two reduction sums, so BatchNorm backward is a single apply pass.
+    Returns (x * (1 + s), s[N,1,H,W] fp32)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, momentum, eps, weight, bias, producer_bias):
+        z = _c(z)
+        N, H, W, C = z.shape
+        mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
+        y = torch.empty_like(z)
+        s = torch.empty((N, 1, H, W), dtype=F32, device=z.device)
+        call("eel_bn_pgr_fwd", ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(_c(weight.detach())),
+             ptr(bias.detach()), ptr(y), ptr(s), N * H * W, C, dtype_code(z), stream())
+        ctx.training, ctx.producer_bias = training, producer_bias
+        ctx.save_for_backward(z, mean, rstd, gamma, beta, s, weight)
+        return y, s
+
+    @staticmethod
+    def backward(ctx, dy, ds):
+        z, mean, rstd, gamma, beta, s, weight = ctx.saved_tensors
+        N, H, W, C = z.shape
+        P = N * H * W
+        dy = _c(dy)
+        ds = _c(ds.to(F32)) if ds is not None else None
+        dev = z.device
+        dx = torch.empty_like(z)
+        dw = torch.empty(C, dtype=F32, device=dev)
+        db = torch.empty(1, dtype=F32, device=dev)
+        sums = torch.empty((2, C), dtype=F32, device=dev)          # {dbeta, dgamma} of the BatchNorm
+        n = 4 * (2 * _lib_sms()) * (3 * C + 1)
+        ws = workspace(n, dev)
+        st = stream()
+        g, b = gamma.detach(), beta.detach()
+        call("eel_bn_pgr_bwd", ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(s), ptr(_c(weight.detach())), ptr(dy), ptr(ds),
+             ptr(dx), ptr(dw), ptr(db), ptr(sums), P, C, ptr(ws), n, dtype_code(z), st)
+        dz = torch.empty_like(z)
+        dzsum = torch.empty(C, dtype=F32, device=dev) if ctx.producer_bias else None
+        call("eel_bn_act_bwd_apply", ptr(dx), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(sums), ptr(dz), ptr(dzsum), P, C, 1,
+             int(ctx.training), dtype_code(z), st)
+        if dzsum is not None:
+            _DZ_COLSUM.clear()
+            _DZ_COLSUM[dz.data_ptr()] = dzsum
+        return dz, sums[1], sums[0], None, None, None, None, None, dw.view(weight.shape), db, None
+
+
+def bn_pgr_supported(z):
+    """the fused kernel keeps at most two channel vectors per lane (C <= 512 in bf16, 256 in fp32)"""
+    vec = 8 if z.dtype == BF16 else 4
+    C = z.shape[-1]
+    return C % vec == 0 and C // vec <= 64 and (C // vec) & (C // vec - 1) == 0
+
+
 def _lib_sms():
     return 148
 

@@ -88,6 +88,15 @@ def cost(name, a):
     if n == "pgr_bwd":
         P, C, dt = a[8], a[9], a[12]
         return 8.0 * P * C, 3 * P * C * _esz(dt) + 8 * P
+    if n == "bn_pgr_fwd":
+        P, C, dt = a[9], a[10], a[11]
+        return 8.0 * P * C, 2 * P * C * _esz(dt) + 4 * P
+    if n == "bn_pgr_bwd":
+        P, C, dt = a[13], a[14], a[17]
+        return 14.0 * P * C, 3 * P * C * _esz(dt) + 8 * P
+    if n == "bn_act_bwd_apply":
+        P, C, dt = a[9], a[10], a[13]
+        return 8.0 * P * C, 3 * P * C * _esz(dt)
     if n == "head_fwd":
         N, HW, O, dt = a[6], a[7], a[8], a[9]
         return (10.0 + 2 * O) * N * HW * 64, N * HW * (64 * _esz(dt) + 4 * O)

@@ -171,6 +171,18 @@ int eel_pgr_fwd(const void* x, const float* w, const float* b, void* y, float* s
                 int dtype, eel_stream s);
 int eel_pgr_bwd(const void* x, const float* sgm, const float* w, const void* dy, const float* dsgm, void* dx,
                 float* dw, float* db, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+/* BatchNorm + ReLU + PredictionGuidedRefinement in one pass (the end of every decoder block): z is the PRE-BatchNorm tensor,
+ * relu(bn(z)) exists only in registers.  The backward recomputes it, and also leaves bn_sums = [2][C] {sum g, sum g*xhat}
+ * (g = dx * relu_mask = the BatchNorm's dbeta, dgamma), so that the BatchNorm backward is the single apply pass below. */
+int eel_bn_pgr_fwd(const void* z, const float* bn_mean, const float* bn_rstd, const float* bn_gamma, const float* bn_beta,
+                   const float* w, const float* b, void* y, float* sgm, long long P, int C, int dtype, eel_stream s);
+int eel_bn_pgr_bwd(const void* z, const float* bn_mean, const float* bn_rstd, const float* bn_gamma, const float* bn_beta,
+                   const float* sgm, const float* w, const void* dy, const float* dsgm, void* dx, float* dw, float* db,
+                   float* bn_sums, long long P, int C, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+/* second half of eel_bn_act_bwd for callers that already hold sums = [2][C] {sum g, sum g*xhat} */
+int eel_bn_act_bwd_apply(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, const float* sums, void* dz, float* dz_colsum, long long P, int C, int relu,
+                         int train, int dtype, eel_stream s);
 /* LayerNorm(channels_first, eps 1e-6) + conv1x1 64->O + sigmoid (models/EELUnet.py:217-225,330-333,469).
  * x:[N*HW][64] NHWC, prob: fp32 NCHW [N][O][HW] */
 int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float* w, const float* b,
