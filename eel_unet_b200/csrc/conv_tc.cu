@@ -114,7 +114,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, 
 }
 
 
-template <int BN, int MT, bool RES, int EW>
+template <int BN, int MT, bool RES, int EW, bool STATS>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     typedef ConvCfg<BN, MT, RES> Cfg;
@@ -197,9 +197,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
         constexpr int NCH_ALL = MT * BN / 32;
         constexpr int NCH = NCH_ALL / (EW / 4);   // chunks per warp and tile
-        float st[NCH][2];                         // fused BatchNorm statistics: two finished values per chunk (tc_common.cuh)
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) st[ci][0] = st[ci][1] = 0.f;
+        float st[STATS ? NCH : 1][2];             // fused BatchNorm statistics: two finished values per chunk (tc_common.cuh);
+#pragma unroll                                    // a template flag, so that the data-gradient launches carry none of it
+        for (int ci = 0; ci < (STATS ? NCH : 1); ++ci) st[ci][0] = st[ci][1] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -229,15 +229,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int h = h0 + j * 16 + i;
                     dst[i] = (h < p.H && w < p.W) ? pix + (long long)(j * 16 + i) * p.W * p.Ntot + cc : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, p.bn_sums ? &st[ci] : nullptr, lane);
+                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
         }
-        if (p.bn_sums) {
+        if (STATS) {
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, ((half * NCH + ci) * 32) % BN, lane, st[ci]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, ((half * NCH + ci) * 32) % BN, lane, st[STATS ? ci : 0]);
         }
     }
     tc_fence_before();
@@ -263,15 +263,17 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     }
     p.na = na;
     const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + ew * 2048 + 1024 /* alignment slack */;
-    static int configured[2] = {0, 0};
-    if (configured[ew == 8] < smem) {
-        cudaError_t e = ew == 8 ? cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                : cudaFuncSetAttribute(tc_conv_kernel<BN, MT, RES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) {
+    const bool stats = p.bn_sums != nullptr;
+    static int configured[4] = {0, 0, 0, 0};
+    const int variant = (ew == 8 ? 1 : 0) + (stats ? 2 : 0);
+    if (configured[variant] < smem) {
+        const void* fn = stats ? (ew == 8 ? (const void*)tc_conv_kernel<BN, MT, RES, 8, true> : (const void*)tc_conv_kernel<BN, MT, RES, 4, true>)
+                               : (ew == 8 ? (const void*)tc_conv_kernel<BN, MT, RES, 8, false> : (const void*)tc_conv_kernel<BN, MT, RES, 4, false>);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
             return EEL_ERR_CUDA;
         }
-        configured[ew == 8] = smem;
+        configured[variant] = smem;
     }
     CUtensorMap tmA, tmB;
     {
@@ -302,8 +304,13 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (ew == 8) tc_conv_kernel<BN, MT, RES, 8><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
-    else tc_conv_kernel<BN, MT, RES, 4><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
+    if (stats) {
+        if (ew == 8) tc_conv_kernel<BN, MT, RES, 8, true><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
+        else tc_conv_kernel<BN, MT, RES, 4, true><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
+    } else {
+        if (ew == 8) tc_conv_kernel<BN, MT, RES, 8, false><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
+        else tc_conv_kernel<BN, MT, RES, 4, false><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
+    }
     return check_launch(what);
 }
 

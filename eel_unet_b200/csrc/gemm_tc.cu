@@ -82,7 +82,7 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = 16384;                    // 128 rows x 64 bf16
 constexpr int kSmemBudget = 232448 - 1024 /* alignment */ - 1024 /* barriers */ - 16384 /* epilogue staging */;
 
-template <int BN, int EPI, int AGATHER>
+template <int BN, int EPI, int AGATHER, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     constexpr int B_BYTES = BN * 128;
@@ -199,9 +199,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = (warp - 2) >> 2;       // which half of the columns
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
         constexpr int NCH = BN / 64;            // 32-column chunks per warp and tile
-        float st[NCH][2];                       // fused BatchNorm statistics (tc_common.cuh)
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) st[ci][0] = st[ci][1] = 0.f;
+        float st[STATS ? NCH : 1][2];           // fused BatchNorm statistics (tc_common.cuh); STATS is a template flag so
+#pragma unroll                                  // that the common no-statistics launches carry none of its registers / code
+        for (int ci = 0; ci < (STATS ? NCH : 1); ++ci) st[ci][0] = st[ci][1] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -264,20 +264,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     dst[i] = roff[i] >= 0 ? p.out + o + coff + L.slot * 8 : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, (EPI != EPI_SCATTER && p.bn_sums) ? &st[ci] : nullptr, lane);
+                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
         }
-        if (EPI == EPI_DENSE && p.bn_sums) {
+        if (STATS && EPI == EPI_DENSE) {
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, half * (BN / 2) + ci * 32, lane, st[ci]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, half * (BN / 2) + ci * 32, lane, st[STATS ? ci : 0]);
         }
-        if (EPI == EPI_CONVT && p.bn_sums) {
+        if (STATS && EPI == EPI_CONVT) {
             // columns are (dy, dx, co): the four taps of a channel add into the same [2][Co] sums
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (half * (BN / 2) + ci * 32) % p.Co, lane, st[ci]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (half * (BN / 2) + ci * 32) % p.Co, lane, st[STATS ? ci : 0]);
         }
     }
     tc_fence_before();
@@ -285,8 +285,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int EPI, int AGATHER>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t st, const char* what) {
+template <int BN, int EPI, int AGATHER, bool STATS>
+static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t st, const char* what) {
     constexpr int B_BYTES = BN * 128;
     // resident weights: single N tile whose whole K extent fits beside >= 4 A stages
     p.res = (p.n_tiles == 1 && p.kchunks * B_BYTES + 4 * kABytes <= kSmemBudget) ? 1 : 0;
@@ -303,7 +303,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p,
     const int smem = p.na * kABytes + b_bytes + 1024 + 16384 + 1024;
     static int configured = 0;
     if (configured < smem) {
-        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, AGATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, AGATHER, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
             return EEL_ERR_CUDA;
         }
@@ -311,8 +311,14 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p,
     }
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    tc_gemm_kernel<BN, EPI, AGATHER><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    tc_gemm_kernel<BN, EPI, AGATHER, STATS><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
     return check_launch(what);
+}
+
+template <int BN, int EPI, int AGATHER>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st, const char* what) {
+    if (EPI != EPI_SCATTER && AGATHER == 0 && p.bn_sums != nullptr) return launch_tc_impl<BN, EPI, AGATHER, (EPI != EPI_SCATTER && AGATHER == 0)>(tmA, tmB, p, st, what);
+    return launch_tc_impl<BN, EPI, AGATHER, false>(tmA, tmB, p, st, what);
 }
 
 template <int EPI, int AGATHER = 0>
