@@ -149,29 +149,29 @@ class EELUnet(nn.Module):
         return self
 
     def _weight_packer(self):
-        if self._packer is None:
+        if self._packer is None or self._packer.stale():
             self._packer = ops.build_packer(self)
         return self._packer
 
     def _folded_packer(self):
         """inference: (producer, BatchNorm) pairs whose BatchNorm is folded into the producer's packed weight"""
-        if self._fpacker is None:
+        if self._fpacker is None or self._fpacker.stale():
             fp = ops.FoldedPacker()
 
             def conv(c, bn):
                 co, ci = c.weight.shape[0], c.weight.shape[1]
                 if ci % 64 == 0 and co % 64 == 0:
-                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 0, 1), 0)          # [ky][kx][co][ci], scale over co
+                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 0, 1), 0, c)          # [ky][kx][co][ci], scale over co
 
             def convt(c, bn):
                 ci, co = c.weight.shape[0], c.weight.shape[1]
                 if ci % 64 == 0 and co % 64 == 0:
-                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 1, 0), 1)          # [ky][kx][co][ci]
+                    fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 1, 0), 1, c)          # [ky][kx][co][ci]
 
             def lin(c, bn):
                 no, k = c.weight.shape[0], c.weight.shape[1]
                 if no % 64 == 0 and k % 64 == 0:
-                    fp.add(c.weight, c.bias, bn, (1, 1, no, k), (0, 1, 2, 3), 2)
+                    fp.add(c.weight, c.bias, bn, (1, 1, no, k), (0, 1, 2, 3), 2, c)
 
             for blk in (self.enc1[0], self.enc2[0], self.dec2, self.dec1, self.edge_upconv_2[2], self.edge_upconv_1[2]):
                 conv(blk[0], blk[1]); conv(blk[3], blk[4])

@@ -97,13 +97,20 @@ class WeightPacker:
 
     def __init__(self):
         self.entries = []      # (param, dims, perm_fwd, perm_dgrad)
+        self.owners = []
         self.by_param = {}
         self.table = None
         self.ptrs = None
         self.versions = None
 
-    def add(self, param, dims, perm_fwd, perm_dgrad):
+    def add(self, param, dims, perm_fwd, perm_dgrad, owner=None):
         self.entries.append((param, tuple(int(d) for d in dims), perm_fwd, perm_dgrad))
+        self.owners.append(owner)
+
+    def stale(self):
+        """a module's ``weight`` was replaced by another Parameter object (torch.nn.utils.prune.remove, manual surgery):
+        the table must be rebuilt from the module tree"""
+        return any(o is not None and getattr(o, "weight", None) is not e[0] for o, e in zip(self.owners, self.entries))
 
     def _build(self, device):
         import numpy as np
@@ -152,13 +159,19 @@ class FoldedPacker:
 
     def __init__(self):
         self.entries = []      # (weight, bias, bn, dims, perm, scale_pos)
+        self.owners = []
         self.by_weight = {}
         self.fold_table = self.pack_table = None
         self.ptrs = self.versions = None
 
-    def add(self, weight, bias, bn, dims, perm, scale_src_dim):
+    def add(self, weight, bias, bn, dims, perm, scale_src_dim, owner=None):
         perm = tuple(perm)
         self.entries.append((weight, bias, bn, tuple(int(d) for d in dims), perm, perm.index(scale_src_dim)))
+        self.owners.append(owner)
+
+    def stale(self):
+        return any(o is not None and (getattr(o, "weight", None) is not e[0] or getattr(o, "bias", None) is not e[1])
+                   for o, e in zip(self.owners, self.entries))
 
     def _tensors(self, e):
         w, b, bn = e[0], e[1], e[2]
@@ -273,15 +286,15 @@ def build_packer(module):
         if isinstance(m, nn.ConvTranspose2d):
             ci, co = w.shape[0], w.shape[1]
             if ci % 64 == 0 and co % 64 == 0 and m.kernel_size == (2, 2):
-                pk.add(w, w.shape, (2, 3, 1, 0), (0, 2, 3, 1))
+                pk.add(w, w.shape, (2, 3, 1, 0), (0, 2, 3, 1), m)
         elif isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3):
             co, ci = w.shape[0], w.shape[1]
             if ci % 64 == 0 and co % 64 == 0:
-                pk.add(w, w.shape, (2, 3, 0, 1), (2, 3, 1, 0))
+                pk.add(w, w.shape, (2, 3, 0, 1), (2, 3, 1, 0), m)
         elif isinstance(m, nn.Linear) or (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1)):
             no, k = w.shape[0], w.shape[1]
             if no % 64 == 0 and k % 64 == 0:
-                pk.add(w, (1, 1, no, k), (0, 1, 2, 3), (0, 1, 3, 2))
+                pk.add(w, (1, 1, no, k), (0, 1, 2, 3), (0, 1, 3, 2), m)
     return pk
 
 

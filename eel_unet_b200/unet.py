@@ -49,7 +49,7 @@ class Unet(nn.Module):
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
             raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
         if self.compute_dtype == torch.bfloat16:
-            if self._packer is None:
+            if self._packer is None or self._packer.stale():
                 self._packer = ops.build_packer(self)
             self._packer.refresh(x.device)
             ops.set_packer(self._packer)

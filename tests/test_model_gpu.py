@@ -218,3 +218,30 @@ def test_inference_batchnorm_folding_matches_unfolded_eval():
         seg2, _ = m(x)
     seg2_ref, _ = m(x)
     assert rel(seg2, seg2_ref) < 2e-2 and rel(seg2, seg) > 1e-3   # the folded weights followed the update
+
+
+def test_prune_flow_keeps_working():
+    """reference prune.py:251-263: torch.nn.utils.prune.ln_structured on every nn.Conv2d, then prune.remove -- which swaps
+    each ``weight`` for a NEW Parameter object.  The packed-weight tables must notice and follow the pruned weights, in
+    training-style forwards (autograd on) and in folded inference."""
+    import torch.nn.utils.prune as prune
+
+    from eel_unet_b200 import EELUnet
+
+    torch.manual_seed(2)
+    x = torch.randn(1, 3, 32, 32, device="cuda")
+    m = EELUnet(3, 1, precision="bf16").cuda().eval()
+    with torch.no_grad():
+        before = m(x)[0].clone()
+    convs = [mod for mod in m.modules() if isinstance(mod, torch.nn.Conv2d)]
+    for c in convs:
+        prune.ln_structured(c, name="weight", amount=0.3, n=2, dim=0)
+    for c in convs:
+        prune.remove(c, "weight")
+    fresh = EELUnet(3, 1, precision="bf16").cuda().eval()
+    fresh.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        after, ref = m(x)[0], fresh(x)[0]
+    assert torch.equal(after, ref), "folded inference did not pick up the pruned weights"
+    assert rel(after, before) > 1e-3
+    assert torch.equal(m(x)[0], fresh(x)[0]), "unfolded path did not pick up the pruned weights"
