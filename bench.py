@@ -160,7 +160,7 @@ def run_ours(args):
 
     from eel_unet_b200 import EELUnet, _lib, edge_BceDiceLoss, profiling
     from eel_unet_b200.parallel import DataParallel, FusedAdam
-    from oracle import synth  # synthetic-input generator only
+    from eel_unet_b200 import synth  # numpy input generator (nothing under oracle/ is touched by the measured arm)
 
     hbm, tens_sus, tens_burst, peak_src = _peaks()
     B, S = args.batch, args.size

@@ -16,8 +16,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import numpy as np
 import torch
 
-from eel_unet_b200 import EELUnet, Unet, edges
-from oracle import edge_np, synth
+from eel_unet_b200 import EELUnet, Unet, edges, synth
+from oracle import edge_np   # checker for the bit-exactness line only
 
 dev = torch.device("cuda", 0)
 quick = "--quick" in sys.argv
