@@ -809,8 +809,8 @@ int eel_bn_pgr_fwd(const void* z, const float* bn_mean, const float* bn_rstd, co
         const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
         const BnConst bn{bn_mean, bn_rstd, bn_gamma, bn_beta};
         cudaStream_t st2 = (cudaStream_t)s;
-        if (iters == 1) bn_pgr_fwd_kernel<T, 1, 4><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
-        else bn_pgr_fwd_kernel<T, 2, 2><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        if (iters == 1) bn_pgr_fwd_kernel<T, 1, 2><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        else bn_pgr_fwd_kernel<T, 2, 1><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
         return check_launch("bn_pgr_fwd");
     });
 }
