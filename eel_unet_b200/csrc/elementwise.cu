@@ -3,6 +3,8 @@
 // Everything moves 16-byte vectors along the contiguous channel axis of NHWC tensors.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace eel {
 
 static inline int ew_grid(long long work_items, int block) {
@@ -94,6 +96,12 @@ __global__ void bn_fold_batch_kernel(const FoldJob* __restrict__ jobs) {
 // Threads: TX lanes across channel vectors, TY = 256/TX across rows.
 constexpr int kRedThreads = 256;
 constexpr int kRedMaxRowBlocks = 4096;
+// Row-block targets (blocks per SM), measured on B200 with tools/op_bench.py at the model's shapes: the two-input
+// reductions and the BatchNorm backward apply pass run fastest with few, long-lived blocks (less tail and a shorter
+// partial-sum finalize); the one-input BatchNorm apply prefers the full 8 x 256 threads per SM.
+constexpr int kRedBlocksPerSM = 4;
+constexpr int kStreamBpsFwd = 8;
+constexpr int kStreamBpsBwd = 2;
 
 struct RedPlan { int TX, TY, ncb, nrb; long long rows_per_rb; };
 
@@ -103,7 +111,7 @@ template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) 
     p.TX = cv >= 32 ? 32 : (cv >= 16 ? 16 : (cv >= 8 ? 8 : (cv >= 4 ? 4 : (cv >= 2 ? 2 : 1))));
     p.TY = kRedThreads / p.TX;
     p.ncb = cdiv(cv, p.TX);
-    long long want = (8LL * kNumSMs) / ((long long)p.ncb * batch);
+    long long want = (kRedBlocksPerSM * (long long)kNumSMs) / ((long long)p.ncb * batch);
     if (want < 1) want = 1;
     long long maxrb = cdiv(rows, p.TY * 4);
     if (maxrb < 1) maxrb = 1;
@@ -115,9 +123,9 @@ template <class T> static RedPlan plan_reduce(long long rows, int C, int batch) 
 }
 
 // same thread layout for pure streaming kernels: more row blocks (no partial buffer to bound them)
-template <class T> static RedPlan plan_stream(long long rows, int C) {
+template <class T> static RedPlan plan_stream(long long rows, int C, int blocks_per_sm = kStreamBpsFwd) {
     RedPlan p = plan_reduce<T>(rows, C, 1);
-    long long want = (8LL * kNumSMs) / p.ncb;
+    long long want = (blocks_per_sm * (long long)kNumSMs) / p.ncb;
     if (want < 1) want = 1;
     long long maxrb = cdiv(rows, p.TY * 4);
     if (maxrb < 1) maxrb = 1;
@@ -975,7 +983,7 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
                                                    "bn_act_bwd.reduce")) return rc;
         bn_bwd_finalize_kernel<<<cdiv(2 * C, 32), 1024, 0, (cudaStream_t)s>>>(partial, pl.nrb, C, sums, dbeta, dgamma, dz_colsum);
         if (int rc = check_launch("bn_act_bwd.finalize")) return rc;
-        RedPlan ps = plan_stream<T>(P, C);
+        RedPlan ps = plan_stream<T>(P, C, kStreamBpsBwd);
         dim3 grid(ps.ncb, ps.nrb);
         bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
                                                             1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train, dz_colsum);
@@ -989,7 +997,7 @@ int eel_bn_act_bwd_apply(const void* dy, const void* z, const float* mean, const
     EEL_REQUIRE(dy && z && mean && rstd && gamma && beta && sums && dz && P > 0 && C > 0, "bn_act_bwd_apply: bad argument");
     EEL_DISPATCH_DTYPE(dtype, {
         EEL_VEC_CHECK(T, C, "bn_act_bwd_apply");
-        RedPlan ps = plan_stream<T>(P, C);
+        RedPlan ps = plan_stream<T>(P, C, kStreamBpsBwd);
         dim3 grid(ps.ncb, ps.nrb);
         if (dz_colsum != nullptr && cudaMemsetAsync(dz_colsum, 0, sizeof(float) * C, (cudaStream_t)s) != cudaSuccess) {
             set_error("bn_act_bwd_apply: memset failed");
