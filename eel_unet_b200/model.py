@@ -146,12 +146,19 @@ class EELUnet(nn.Module):
         self.compute_dtype = _PRECISIONS[precision]
         self._packer = None
         self._fpacker = None
+        self._cpacker = None
         return self
 
     def _weight_packer(self):
         if self._packer is None or self._packer.stale():
             self._packer = ops.build_packer(self)
         return self._packer
+
+    def _composed_packer(self):
+        """(mlp[2], to_space) pairs of the ChannelAwarePatchedMLP blocks, composed into one matrix per step"""
+        if self._cpacker is None or self._cpacker.dtype != self.compute_dtype or self._cpacker.stale():
+            self._cpacker = ops.build_composed(self, self.compute_dtype)
+        return self._cpacker
 
     def _folded_packer(self):
         """inference: (producer, BatchNorm) pairs whose BatchNorm is folded into the producer's packed weight"""
@@ -168,19 +175,20 @@ class EELUnet(nn.Module):
                 if ci % 64 == 0 and co % 64 == 0:
                     fp.add(c.weight, c.bias, bn, c.weight.shape, (2, 3, 1, 0), 1, c)          # [ky][kx][co][ci]
 
-            def lin(c, bn):
-                no, k = c.weight.shape[0], c.weight.shape[1]
+            def lin(m, bn):
+                # to_space(mlp[2](.)) composed into one matrix, then the BatchNorm folded into that (ops.ComposedPacker)
+                no, k = m.to_space.weight.shape[0], m.mlp[2].weight.shape[1]
                 if no % 64 == 0 and k % 64 == 0:
-                    fp.add(c.weight, c.bias, bn, (1, 1, no, k), (0, 1, 2, 3), 2, c)
+                    fp.composed.add(m.mlp[2], m.to_space, bn)
 
             for blk in (self.enc1[0], self.enc2[0], self.dec2, self.dec1, self.edge_upconv_2[2], self.edge_upconv_1[2]):
                 conv(blk[0], blk[1]); conv(blk[3], blk[4])
             for blk in (self.enc3[0], self.enc4[0], self.dec4, self.dec3, self.edge_upconv_4[1], self.edge_upconv_3[1]):
-                conv(blk[0], blk[1]); lin(blk[3].to_space, blk[4])
+                conv(blk[0], blk[1]); lin(blk[3], blk[4])
             for blk in (self.upconv2, self.upconv1, self.edge_upconv_2[0], self.edge_upconv_1[0]):
                 convt(blk[0], blk[1])
             for blk in (self.upconv4, self.upconv3, self.edge_upconv_4[0], self.edge_upconv_3[0]):
-                lin(blk[1].to_space, blk[2])
+                lin(blk[1], blk[2])
             self._fpacker = fp
         return self._fpacker
 
@@ -220,15 +228,16 @@ class EELUnet(nn.Module):
         t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias)
         t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
         t = ops.Gelu.apply(t)
-        t = ops.Linear.apply(t, m.mlp[2].weight, m.mlp[2].bias, False)
+        # mlp[2] and to_space are two linear maps with nothing in between: ONE GEMM with the composed matrix (ops.ComposedLinear)
+        pair = (m.mlp[2].weight, m.mlp[2].bias, m.to_space.weight, m.to_space.bias)
         if bn is None:
-            return ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+            return ops.ComposedLinear.apply(t, *pair)
         f = ops.folded(m.to_space.weight)
         if f is not None:
             return ops.linear_folded(t, f[0], f[1], relu)
         ops.expect_bn(bn.training or bn.running_mean is None)
         try:
-            z = ops.Linear.apply(t, m.to_space.weight, m.to_space.bias, False)
+            z = ops.ComposedLinear.apply(t, *pair)
         finally:
             ops.expect_bn(False)
         if defer:                      # the caller fuses this BatchNorm into its next op (decoder skip bridge)
@@ -313,13 +322,16 @@ class EELUnet(nn.Module):
             if not self.training and not torch.is_grad_enabled():
                 # inference: eval-mode BatchNorms are folded into their producers' weights (ops.FoldedPacker)
                 fold = self._folded_packer()
-                if all(not e[2].training and e[2].running_mean is not None for e in fold.entries):
+                if all(not b.training and b.running_mean is not None for b in fold.bns()):
                     fold.refresh(x.device)
                 else:
                     fold = None
         else:
             ops.set_packer(None)
         ops.set_folded(fold)
+        cp = self._composed_packer()
+        cp.refresh(x.device)
+        ops.set_composed(cp)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
         enc1 = self._conv_block(self.enc1[0], a)

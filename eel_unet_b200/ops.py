@@ -163,6 +163,10 @@ class FoldedPacker:
         self.by_weight = {}
         self.fold_table = self.pack_table = None
         self.ptrs = self.versions = None
+        self.composed = ComposedPacker(BF16)       # (mlp[2], to_space, BatchNorm) triples: composed, then folded
+
+    def bns(self):
+        return [e[2] for e in self.entries] + self.composed.bns()
 
     def add(self, weight, bias, bn, dims, perm, scale_src_dim, owner=None):
         perm = tuple(perm)
@@ -170,8 +174,9 @@ class FoldedPacker:
         self.owners.append(owner)
 
     def stale(self):
-        return any(o is not None and (getattr(o, "weight", None) is not e[0] or getattr(o, "bias", None) is not e[1])
-                   for o, e in zip(self.owners, self.entries))
+        return self.composed.stale() or any(
+            o is not None and (getattr(o, "weight", None) is not e[0] or getattr(o, "bias", None) is not e[1])
+            for o, e in zip(self.owners, self.entries))
 
     def _tensors(self, e):
         w, b, bn = e[0], e[1], e[2]
@@ -207,6 +212,7 @@ class FoldedPacker:
         self.versions = None
 
     def refresh(self, device):
+        self.composed.refresh(device)
         if not self.entries:
             return
         ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e) if t is not None]
@@ -220,7 +226,117 @@ class FoldedPacker:
         self.versions = ver
 
     def get(self, w):
+        hit = self.by_weight.get(id(w))
+        if hit is None:
+            c = self.composed.get(w)
+            if c is not None:
+                hit = (c[0], c[2])
+        return hit
+
+
+class ComposedPacker:
+    """ChannelAwarePatchedMLP ends in ``mlp[2]`` (Linear 256 -> Cout) followed directly by ``to_space`` (1x1 conv
+    Cout -> Cout) (reference models/EELUnet.py:109-111,121-122): the hot path runs them as ONE GEMM with
+    Wc = W_to_space W_mlp2 and bc = W_to_space b_mlp2 + b_to_space.  This table composes all of a model's pairs with one
+    launch per step (eel_compose_batch, fp32 FFMA) into the forward [Cout][K] and data-gradient [K][Cout] operand layouts
+    of the storage dtype; with ``bn`` given (inference) the eval-mode BatchNorm that follows is folded in as well.
+
+    ``get(to_space.weight)`` -> (wc_fwd, wc_dgrad or None, bc)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.entries = []      # (lin1, lin2, bn)
+        self.by_weight = {}
+        self.table = None
+        self.ptrs = self.versions = self.params = None
+        self.blocks = 1
+
+    def add(self, lin1, lin2, bn=None):
+        self.entries.append((lin1, lin2, bn))
+
+    @staticmethod
+    def _tensors(e):
+        l1, l2, bn = e
+        t = [l2.weight, l2.bias, l1.weight, l1.bias]
+        if bn is not None:
+            t += [bn.running_mean, bn.running_var, bn.weight, bn.bias]
+        return t
+
+    def stale(self):
+        """a parameter object was replaced (prune.remove, manual surgery): rebuild from the module tree"""
+        return self.params is not None and any(a is not b for e, p in zip(self.entries, self.params)
+                                                for a, b in zip(self._tensors(e), p))
+
+    def bns(self):
+        return [e[2] for e in self.entries if e[2] is not None]
+
+    def _build(self, device):
+        import numpy as np
+        n = len(self.entries)
+        rec = np.zeros((n, 16), dtype=np.int64)       # 128-byte records (eel_compose_job)
+        self.by_weight, self._keep = {}, []
+        code = _lib.EEL_BF16 if self.dtype == BF16 else _lib.EEL_F32
+        blocks = 1
+        for k, e in enumerate(self.entries):
+            l1, l2, bn = e
+            cout, cmid, kin = l2.weight.shape[0], l1.weight.shape[0], l1.weight.shape[1]
+            if l2.weight.shape[1] != cmid:
+                raise _lib.EelError("composed linear pair: inner sizes differ (%d vs %d)" % (l2.weight.shape[1], cmid))
+            fwd = torch.empty((cout, kin), dtype=self.dtype, device=device)
+            dgr = torch.empty((kin, cout), dtype=self.dtype, device=device) if bn is None else None
+            bc = torch.empty(cout, dtype=F32, device=device)
+            r = rec[k]
+            r[0], r[1], r[2], r[3] = l2.weight.data_ptr(), l2.bias.data_ptr(), l1.weight.data_ptr(), l1.bias.data_ptr()
+            r[4], r[5], r[6] = fwd.data_ptr(), 0 if dgr is None else dgr.data_ptr(), bc.data_ptr()
+            eps = 0.0
+            if bn is not None:
+                r[7], r[8], r[9], r[10] = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr()
+                eps = bn.eps
+            r[11:13] = np.array([cout, cmid, kin, code], dtype=np.int32).view(np.int64)
+            r[13] = int(np.array([eps], dtype=np.float32).view(np.uint32)[0])
+            self.by_weight[id(l2.weight)] = (fwd, dgr, bc)
+            self._keep.append((fwd, dgr, bc))
+            blocks = max(blocks, ((cout + 63) // 64) * ((kin + 63) // 64 + 1))
+        self.blocks = min(blocks, 128)
+        self.table = torch.from_numpy(rec.reshape(-1).view(np.uint8).copy()).to(device)
+        self.params = [self._tensors(e) for e in self.entries]
+        self.ptrs = [t.data_ptr() for p in self.params for t in p]
+        self.versions = None
+
+    def refresh(self, device):
+        if not self.entries:
+            return
+        ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e)]
+        if self.table is None or self.table.device != device or ptrs != self.ptrs:
+            self._build(device)
+        ver = [_WEIGHT_EPOCH] + [t._version for p in self.params for t in p]
+        if ver == self.versions:
+            return
+        call("eel_compose_batch", ptr(self.table), len(self.entries), self.blocks, stream())
+        self.versions = ver
+
+    def get(self, w):
         return self.by_weight.get(id(w))
+
+
+def build_composed(module, dtype):
+    """table of every (mlp[2], to_space) pair of ``module`` (its ChannelAwarePatchedMLP blocks)"""
+    import torch.nn as nn
+
+    cp = ComposedPacker(dtype)
+    for m in module.modules():
+        mlp, ts = getattr(m, "mlp", None), getattr(m, "to_space", None)
+        if isinstance(mlp, nn.Sequential) and len(mlp) == 3 and isinstance(mlp[2], nn.Linear) and isinstance(ts, nn.Conv2d):
+            cp.add(mlp[2], ts)
+    return cp
+
+
+_COMPOSED = None
+
+
+def set_composed(p):
+    global _COMPOSED
+    _COMPOSED = p
 
 
 _FOLDED = None
@@ -279,9 +395,14 @@ def build_packer(module):
     import torch.nn as nn
 
     pk = WeightPacker()
+    composed = set()           # (mlp[2], to_space) pairs run as one composed matrix (ComposedPacker), never on their own
+    for m in module.modules():
+        mlp, ts = getattr(m, "mlp", None), getattr(m, "to_space", None)
+        if isinstance(mlp, nn.Sequential) and len(mlp) == 3 and isinstance(mlp[2], nn.Linear) and isinstance(ts, nn.Conv2d):
+            composed.update((id(mlp[2]), id(ts)))
     for m in module.modules():
         w = getattr(m, "weight", None)
-        if not isinstance(w, nn.Parameter):
+        if not isinstance(w, nn.Parameter) or id(m) in composed:
             continue
         if isinstance(m, nn.ConvTranspose2d):
             ci, co = w.shape[0], w.shape[1]
@@ -511,6 +632,75 @@ class Linear(Function):
             call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
         db = _colsum(dy, Nout)
         return dx, dw.view(weight.shape), db, None
+
+
+class _Pair:
+    """the two layers of a composed pair as bare tensors (ComposedLinear outside a model's table)"""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class ComposedLinear(Function):
+    """``to_space(mlp[2](x))`` of ChannelAwarePatchedMLP (reference models/EELUnet.py:109-111,121-122) as ONE GEMM:
+    y = (W2 W1) x + (W2 b1 + b2), w1/b1 = mlp[2] ([Cmid, K]), w2/b2 = to_space ([Cout, Cmid(,1,1)]).  The backward runs one
+    data-gradient and one weight-gradient GEMM for the composed matrix; the four parameter gradients of the reference
+    layers follow exactly in weight space (eel_compose_linear_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _c(x)
+        N, H, W, K = x.shape
+        Cout, Cmid = w2.shape[0], w1.shape[0]
+        hit = _COMPOSED.get(w2) if _COMPOSED is not None and _COMPOSED.dtype == x.dtype else None
+        if hit is None:
+            one = ComposedPacker(x.dtype)
+            one.add(_Pair(w1.detach(), b1.detach()), _Pair(w2.detach().view(Cout, Cmid), b2.detach()))
+            one.refresh(x.device)
+            hit = one._keep[0]
+        wc, wct, bc = hit
+        ctx.tc = _tc_ok(x, K, Cout)
+        y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+        if ctx.tc:
+            sums = _want_bn_sums(x, Cout)
+            call("eel_tc_linear", ptr(x), ptr(wc), ptr(bc), ptr(y), N * H * W, K, Cout, 0, ptr(sums), 0, 0, stream())
+            if sums is not None:
+                _BN_SUMS.clear()
+                _BN_SUMS[y.data_ptr()] = sums
+        else:
+            call("eel_linear_fwd", ptr(x), ptr(wc), ptr(bc), ptr(y), N * H * W, K, Cout, 0, 0, dtype_code(x), stream())
+        ctx.save_for_backward(x, w1, b1, w2, wc, wct)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, b1, w2, wc, wct = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, K = x.shape
+        Cout, Cmid = w2.shape[0], w1.shape[0]
+        P = N * H * W
+        st = stream()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if ctx.tc:
+                call("eel_tc_linear", ptr(dy), ptr(wct), None, ptr(dx), P, Cout, K, 0, None, 0, 0, st)
+            else:
+                call("eel_linear_dgrad", ptr(dy), ptr(wc), ptr(dx), P, K, Cout, 0, 0, dtype_code(x), st)
+        dwc = torch.empty((Cout, K), dtype=F32, device=x.device)
+        if ctx.tc and Cout % 128 == 0:
+            call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dwc), P, Cout, K, K, 1, dwc.numel(), 0, st)
+        elif ctx.tc and K % 128 == 0:
+            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 1, K, dwc.numel(), 0, st)
+        else:
+            call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 0, 0, dtype_code(x), st)
+        s = _colsum(dy, Cout)
+        dw2 = torch.empty((Cout, Cmid), dtype=F32, device=x.device)
+        dw1 = torch.empty((Cmid, K), dtype=F32, device=x.device)
+        db1 = torch.empty(Cmid, dtype=F32, device=x.device)
+        call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
+             ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, K, st)
+        return dx, dw1, db1, dw2.view(w2.shape), s
 
 
 def _bn_statistics(z, running_mean, running_var, training, momentum, eps):

@@ -54,6 +54,19 @@ int eel_pack_batch(const void* jobs_device, int njobs, int blocks_per_job, eel_s
  * jobs_device = `njobs` 64-byte records { const float *rmean, *rvar, *gamma, *beta, *bias; float *scale, *bias_out; int C; float eps; }
  * scale = gamma / sqrt(rvar + eps) (then given to eel_pack_batch), bias_out = (bias - rmean) * scale + beta */
 int eel_bn_fold_batch(const void* jobs_device, int njobs, eel_stream s);
+/* ChannelAwarePatchedMLP ends in mlp[2] (nn.Linear 256 -> Cout, models/EELUnet.py:109) followed directly by to_space
+ * (1x1 conv Cout -> Cout, :111,122) -- two linear maps with nothing in between.  The hot path runs them as ONE GEMM with
+ * Wc = W2 W1, bc = W2 b1 + b2 (W1/b1 = mlp[2], W2/b2 = to_space), composed in fp32 here, one launch for all blocks:
+ * jobs_device = `njobs` records of 128 bytes in DEVICE memory,
+ *   { const float *w2 [Cout][Cmid], *b2, *w1 [Cmid][K], *b1; void *out_fwd [Cout][K], *out_dgrad [K][Cout] (dtype, either
+ *     may be NULL); float *bias_out [Cout]; const float *rmean, *rvar, *gamma, *beta (eval-mode BatchNorm over Cout folded
+ *     into Wc / bc as in eel_bn_fold_batch, or all NULL); int Cout, Cmid, K, dtype; float eps; int pad[5]; } */
+int eel_compose_batch(const void* jobs_device, int njobs, int blocks_per_job, eel_stream s);
+/* parameter gradients of the two reference layers from the composed layer's dwc [Cout][K] = sum_p dy_p g_p^T and
+ * colsum [Cout] = sum_p dy_p (exact by linearity): dw2 = dwc W1^T + colsum b1^T, dw1 = W2^T dwc, db1 = W2^T colsum
+ * (db2 = colsum).  All fp32, all overwritten. */
+int eel_compose_linear_bwd(const float* dwc, const float* colsum, const float* w2, const float* w1, const float* b1,
+                           float* dw2, float* dw1, float* db1, int Cout, int Cmid, int K, eel_stream s);
 
 /* ------------------------------------------------------------------ GEMM-class ops
  * nn.Conv2d 3x3 pad 1 (models/EELUnet.py:338,341,351,257).  x:[N,H,W,Cin], wp:[9][Cin][Cout] (dtype),

@@ -157,6 +157,28 @@ def test_linear(dtype, shift, shape):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 256, 8, 16, 256), (1, 256, 16, 16, 512), (2, 24, 5, 7, 40), (1, 256, 4, 8, 1024),
+                                   (1, 64, 8, 8, 72)])
+def test_composed_linear(dtype, shape):
+    """to_space(mlp[2](x)) as one GEMM with the composed matrix (reference models/EELUnet.py:109-111,121-122): forward,
+    input gradient and the FOUR parameter gradients of the two reference layers against the two-layer formulation"""
+    from eel_unet_b200 import ops
+
+    n, k, h, w, cout = shape
+    x = torch.randn(n, k, h, w, device=DEV)
+    w1 = torch.randn(cout, k, device=DEV) / math.sqrt(k)            # mlp[2]: Linear(k -> cout)
+    b1 = torch.randn(cout, device=DEV)
+    w2 = torch.randn(cout, cout, 1, 1, device=DEV) / math.sqrt(cout)  # to_space: 1x1 conv cout -> cout
+    b2 = torch.randn(cout, device=DEV)
+
+    def ref(a, p):
+        t = F.linear(a[0].permute(0, 2, 3, 1), p[0], p[1]).permute(0, 3, 1, 2)
+        return F.conv2d(t, p[2], p[3])
+
+    run_case(lambda a, p: ops.ComposedLinear.apply(a[0], p[0], p[1], p[2], p[3]), ref, [x], [w1, b1, w2, b2], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("training", [True, False])
 def test_bn_act(dtype, relu, training):
