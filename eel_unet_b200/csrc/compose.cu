@@ -50,8 +50,10 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, long long
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < Kd; k0 += kCK) {
-        float ra[4], rb[4];
+    // the global loads of step k0 + 16 are in flight while step k0 is multiplied (these products are latency-bound:
+    // a few dozen blocks, 16-64 steps each)
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int m, k;
@@ -61,6 +63,9 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, long long
             if (sbn == 1) { n = t & 63; kb = (t >> 6) + 4 * i; } else { kb = t & 15; n = (t >> 4) + 16 * i; }
             rb[i] = (n0 + n < N && k0 + kb < Kd) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + n) * sbn] : 0.f;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < Kd; k0 += kCK) {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -68,6 +73,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, long long
             if (sbn == 1) Bs[(t >> 6) + 4 * i][t & 63] = rb[i]; else Bs[t & 15][(t >> 4) + 16 * i] = rb[i];
         }
         __syncthreads();
+        if (k0 + kCK < Kd) fetch(k0 + kCK);
 #pragma unroll
         for (int kk = 0; kk < kCK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

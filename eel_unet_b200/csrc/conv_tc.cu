@@ -31,7 +31,7 @@ struct ConvParams {
     int na;                 // A stages in shared memory
     const float* bias;
     bf16* out;
-    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (n_tiles == 1)
+    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (grid % n_tiles == 0)
 };
 
 constexpr int kMaxStages = 8;
@@ -236,8 +236,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
         }
         if (STATS) {
+            // the grid is a multiple of n_tiles (host check): all tiles of this CTA lie in N tile blockIdx.x % n_tiles
+            const int n_own = (blockIdx.x % p.n_tiles) * BN;
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, ((half * NCH + ci) * 32) % BN, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, n_own + ((half * NCH + ci) * 32) % BN, lane, st[STATS ? ci : 0]);
         }
     }
     tc_fence_before();
@@ -293,8 +295,9 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     p.m_tiles = p.N * p.tiles_h * p.tiles_w;
     p.n_tiles = Cout / BN;
     if (p.bn_sums != nullptr) {
-        if (p.n_tiles != 1) {
-            set_error("%s: fused BatchNorm statistics need a single N tile (Cout %d)", what, Cout);
+        const int all = p.m_tiles * p.n_tiles;
+        if ((all < kNumSMs ? all : kNumSMs) % p.n_tiles != 0) {
+            set_error("%s: fused BatchNorm statistics need a grid that is a multiple of the %d N tiles (Cout %d)", what, p.n_tiles, Cout);
             return EEL_ERR_INVALID;
         }
         if (cudaMemsetAsync(p.bn_sums, 0, sizeof(float) * 2 * Cout, st) != cudaSuccess) {

@@ -293,6 +293,24 @@ template <class T> struct DotF {
     }
 };
 
+// the same plus the plain sum of a: {sum a*b, sum a} (squeeze-excite backward: d att and, through sum_hw dout, the column
+// sums of the op's input gradient = the bias gradient of the to_patch conv in front of it)
+template <class T> struct Dot2F {
+    const T* a; const T* b; int C;
+    static constexpr int NIN = 2;
+    typedef NoState State;
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(long long r, int c0, Vec16<T> (&in)[2]) const { in[0] = ld16(a + r * C + c0); in[1] = ld16(b + r * C + c0); }
+    template <int V> __device__ void accum(const State&, const Vec16<T> (&in)[2], float (&acc)[2][V]) const {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float av = in[0].get(i);
+            acc[0][i] = fmaf(av, in[1].get(i), acc[0][i]);
+            acc[1][i] += av;
+        }
+    }
+};
+
 // shifted moments for BatchNorm: d = z - z[0][c]  ->  sum d, sum d^2 (no catastrophic cancellation)
 template <class T> struct MomentF {
     const T* z; int C;
@@ -747,6 +765,50 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
     }
 }
 
+// GELU backward that also leaves the per-channel column sums of dx (the bias gradient of the Linear that produced x:
+// mlp[0] of ChannelAwarePatchedMLP) -- saves the separate column-sum pass over dx.  The grid stride is a multiple of the
+// C / V channel vectors of a row, so a thread stays on ONE channel vector and accumulates in registers.
+template <class T>
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                                            float* __restrict__ colsum, long long nvec, int cvec) {
+    constexpr int V = Vec16<T>::N, U = 2;
+    __shared__ float sm[256][V + 1];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += U * stride) {
+        Vec16<T> v[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) { v[u] = ld16(x + (i + u * stride) * V); g[u] = ld16(dy + (i + u * stride) * V); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) break;
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float a = v[u].get(j);
+                float cdf, e;
+                gelu_cdf<T>(a, cdf, e);
+                o.set(j, g[u].get(j) * (cdf + a * 0.39894228040143268f * e));
+                acc[j] += o.get(j);           // the STORED (rounded) value, as a separate pass over dx would see it
+            }
+            st16(dx + (i + u * stride) * V, o);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) sm[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    // threads t, t + cvec, t + 2 cvec, ... of the block share a channel vector (256 % cvec == 0)
+    for (int k = threadIdx.x; k < cvec * V; k += blockDim.x) {
+        const int cv = k / V, j = k - cv * V;
+        float sum = 0.f;
+        for (int t = cv; t < 256; t += cvec) sum += sm[t][j];
+        atomicAdd(colsum + k, sum);
+    }
+}
+
 // ------------------------------------------------------------------------------------ squeeze-excite
 // one block per image: hid = relu(W1 mean + b1), att = sigmoid(W2 hid + b2)
 __global__ void se_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -792,14 +854,15 @@ __global__ void scale_rows_kernel(const T* __restrict__ t, const float* __restri
 // in:  datt[n][c] = sum_hw dout*t ; out: dmean_scaled[n][c] = (W1^T dhid_pre)[c] / HW, dpre[n][c], dhid[n][r]
 __global__ void se_mlp_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ att, const float* __restrict__ hid,
                                   const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ dmean_scaled,
-                                  float* __restrict__ dpre_out, float* __restrict__ dhid_out, int C, int R, float inv_hw) {
+                                  float* __restrict__ dpre_out, float* __restrict__ dhid_out, int C, int R, float inv_hw,
+                                  int datt_stride) {
     extern __shared__ float sh[];   // dpre[C] then dhid[R]
     float* dpre = sh;
     float* dhid = sh + C;
     const int t = threadIdx.x, n = blockIdx.x;
     for (int c = t; c < C; c += blockDim.x) {
         float a = att[n * C + c];
-        float d = datt[n * C + c] * a * (1.f - a);
+        float d = datt[n * datt_stride + c] * a * (1.f - a);
         dpre[c] = d;
         dpre_out[n * C + c] = d;
     }
@@ -822,7 +885,9 @@ __global__ void se_mlp_bwd_kernel(const float* __restrict__ datt, const float* _
 // phase B: one thread per parameter-gradient element sums its contributions over the images (deterministic order).
 __global__ void se_param_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ dhid, const float* __restrict__ hid,
                                      const float* __restrict__ mean, float* __restrict__ dw1, float* __restrict__ db1,
-                                     float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R) {
+                                     float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R,
+                                     const float* __restrict__ att, const float* __restrict__ sums, const float* __restrict__ dmean_scaled,
+                                     float hw, float* __restrict__ dt_colsum) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int CR = C * R;
     float s = 0.f;
@@ -842,6 +907,11 @@ __global__ void se_param_grad_kernel(const float* __restrict__ dpre, const float
         const int r = i - 2 * CR - C;
         for (int n = 0; n < N; ++n) s += dhid[n * R + r];
         db1[r] = s;
+    } else if (dt_colsum != nullptr && i < 2 * CR + 2 * C + R) {
+        // column sums of dt = dout * att + dmean over all pixels: sum_n att[n][c] * (sum_hw dout)[n][c] + HW * dmean[n][c]
+        const int c = i - 2 * CR - C - R;
+        for (int n = 0; n < N; ++n) s += att[n * C + c] * sums[(long long)n * 2 * C + C + c] + hw * dmean_scaled[n * C + c];
+        dt_colsum[c] = s;
     }
 }
 
@@ -1117,6 +1187,25 @@ int eel_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype
     });
 }
 
+int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, long long n, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(x && dy && dx && colsum && n > 0 && C > 0 && n % C == 0, "gelu_bwd_colsum: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "gelu_bwd_colsum");
+        const int cvec = C / Vec16<T>::N;
+        EEL_REQUIRE(256 % cvec == 0, "gelu_bwd_colsum: %d channels do not tile a 256-thread block", C);
+        if (cudaMemsetAsync(colsum, 0, sizeof(float) * C, st) != cudaSuccess) {
+            set_error("gelu_bwd_colsum: memset failed");
+            return EEL_ERR_CUDA;
+        }
+        long long nvec = n / Vec16<T>::N;
+        long long blocks = (nvec + 511) / 512;
+        if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+        gelu_bwd_colsum_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, colsum, nvec, cvec);
+        return check_launch("gelu_bwd_colsum");
+    });
+}
+
 int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
                float* mean, float* att, float* hid, int N, long long HW, int C, int R, void* ws, size_t ws_bytes,
                int dtype, eel_stream s) {
@@ -1136,27 +1225,28 @@ int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2,
 }
 
 int eel_se_bwd(const void* t, const void* dout, const float* att, const float* hid, const float* mean, const float* w1,
-               const float* w2, void* dt, float* dw1, float* db1, float* dw2, float* db2, int N, long long HW, int C,
-               int R, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+               const float* w2, void* dt, float* dw1, float* db1, float* dw2, float* db2, float* dt_colsum, int N, long long HW,
+               int C, int R, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
     EEL_REQUIRE(t && dout && att && hid && mean && w1 && w2 && dt && dw1 && db1 && dw2 && db2 && N > 0 && HW > 0 && C > 0 && R > 0,
                 "se_bwd: bad argument");
     cudaStream_t st = (cudaStream_t)s;
-    size_t head = sizeof(float) * 4 * (size_t)N * C;   // datt[N][C], dmean_scaled[N][C], dpre[N][C], dhid[N][R] (R <= C)
+    size_t head = sizeof(float) * 5 * (size_t)N * C;   // sums[N][2C] = {sum dout*t | sum dout}, dmean_scaled[N][C], dpre[N][C], dhid[N][R] (R <= C)
     EEL_REQUIRE(ws_bytes > head && R <= C, "se_bwd: workspace too small");
     EEL_DISPATCH_DTYPE(dtype, {
-        float* datt = (float*)ws;
-        float* dmean = datt + (size_t)N * C;
+        float* sums = (float*)ws;
+        float* dmean = sums + (size_t)2 * N * C;
         float* dpre = dmean + (size_t)N * C;
         float* dhid = dpre + (size_t)N * C;
         float* partial = dhid + (size_t)N * C;
         RedPlan pl;
-        DotF<T> f{(const T*)dout, (const T*)t, C};
-        if (int rc = run_colreduce<T, DotF<T>, 1>(f, HW, C, N, partial, ws_bytes - head, pl, st, "se_bwd.dot")) return rc;
-        if (int rc = run_finalize(partial, pl.nrb, C, N, datt, 1.0f, st, "se_bwd.finalize")) return rc;
-        se_mlp_bwd_kernel<<<N, 64, sizeof(float) * (C + R), st>>>(datt, att, hid, w1, w2, dmean, dpre, dhid, C, R, 1.0f / (float)HW);
+        Dot2F<T> f{(const T*)dout, (const T*)t, C};
+        if (int rc = run_colreduce<T, Dot2F<T>, 2>(f, HW, C, N, partial, ws_bytes - head, pl, st, "se_bwd.dot")) return rc;
+        if (int rc = run_finalize(partial, pl.nrb, 2 * C, N, sums, 1.0f, st, "se_bwd.finalize")) return rc;
+        se_mlp_bwd_kernel<<<N, 64, sizeof(float) * (C + R), st>>>(sums, att, hid, w1, w2, dmean, dpre, dhid, C, R, 1.0f / (float)HW, 2 * C);
         if (int rc = check_launch("se_bwd.mlp")) return rc;
-        const int nout = 2 * C * R + C + R;
-        se_param_grad_kernel<<<cdiv(nout, 128), 128, 0, st>>>(dpre, dhid, hid, mean, dw1, db1, dw2, db2, N, C, R);
+        const int nout = 2 * C * R + 2 * C + R;
+        se_param_grad_kernel<<<cdiv(nout, 128), 128, 0, st>>>(dpre, dhid, hid, mean, dw1, db1, dw2, db2, N, C, R, att, sums, dmean,
+                                                               (float)HW, dt_colsum);
         if (int rc = check_launch("se_bwd.param_grad")) return rc;
         long long nvec = (long long)N * HW * C / Vec16<T>::N;
         scale_rows_kernel<T><<<ew_grid(nvec, 256), 256, 0, st>>>((const T*)dout, att, dmean, (T*)dt, nvec, HW * C / Vec16<T>::N, C);

@@ -74,7 +74,7 @@ struct TcParams {
     const float* bias;
     bf16* out;
     int shH, shW;           // dense: > 0 scatters output rows through the adjoint of ShiftedChannel (rows = pixels of [*, shH, shW])
-    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (dense, n_tiles == 1)
+    float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (grid % n_tiles == 0)
 };
 
 constexpr int kThreads = 320;                     // TMA warp, MMA warp, 8 epilogue warps
@@ -270,14 +270,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmemEmpty[acc]);
         }
+        // the grid is a multiple of n_tiles (host check), so every tile of this CTA lies in the SAME N tile and the
+        // statistics registers belong to fixed columns
+        const int nt_own = blockIdx.x % p.n_tiles;
         if (STATS && EPI == EPI_DENSE) {
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, half * (BN / 2) + ci * 32, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, nt_own * BN + half * (BN / 2) + ci * 32, lane, st[STATS ? ci : 0]);
         }
         if (STATS && EPI == EPI_CONVT) {
             // columns are (dy, dx, co): the four taps of a channel add into the same [2][Co] sums
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (half * (BN / 2) + ci * 32) % p.Co, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (nt_own * BN + half * (BN / 2) + ci * 32) % p.Co, lane, st[STATS ? ci : 0]);
         }
     }
     tc_fence_before();
@@ -328,6 +331,13 @@ static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const
     return launch_tc<64, EPI, AGATHER>(a, b, p, st, what);
 }
 
+// fused BatchNorm statistics keep per-column sums in registers across a CTA's tiles: every tile of a CTA must lie in the
+// same N tile, i.e. the grid (min(tiles, SMs)) must be a multiple of n_tiles
+static bool stats_grid_ok(const TcParams& p) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    return (tiles < kNumSMs ? tiles : kNumSMs) % p.n_tiles == 0;
+}
+
 static int pick_bn(int ncols) { return ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64); }
 
 }  // namespace tc
@@ -368,7 +378,7 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
         p.shH = scatterH; p.shW = scatterW;
     }
     if (bn_sums != nullptr) {
-        EEL_REQUIRE(p.n_tiles == 1, "tc_linear: fused BatchNorm statistics need a single N tile (Nout %d)", Nout);
+        EEL_REQUIRE(stats_grid_ok(p), "tc_linear: fused BatchNorm statistics need 1, 2 or 4 N tiles (Nout %d)", Nout);
         if (cudaMemsetAsync(bn_sums, 0, sizeof(float) * 2 * Nout, (cudaStream_t)s) != cudaSuccess) {
             set_error("tc_linear: memset failed");
             return EEL_ERR_CUDA;
@@ -406,7 +416,7 @@ int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* 
     p.M = P; p.Ntot = ncols; p.W = w; p.Co = Cout;
     p.bias = bias; p.out = (bf16*)y;
     if (bn_sums != nullptr) {
-        EEL_REQUIRE(p.n_tiles == 1, "tc_convt2x2_fwd: fused BatchNorm statistics need a single N tile (4 * Cout <= 256, got Cout %d)", Cout);
+        EEL_REQUIRE(stats_grid_ok(p), "tc_convt2x2_fwd: fused BatchNorm statistics need 1, 2 or 4 N tiles (got Cout %d)", Cout);
         if (cudaMemsetAsync(bn_sums, 0, sizeof(float) * 2 * Cout, (cudaStream_t)s) != cudaSuccess) {
             set_error("tc_convt2x2_fwd: memset failed");
             return EEL_ERR_CUDA;

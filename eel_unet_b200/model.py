@@ -225,9 +225,9 @@ class EELUnet(nn.Module):
         to_space's epilogue, in inference it is folded into to_space's weights."""
         t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
         ca = m.channel_attention
-        t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias)
+        t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias, True)
         t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
-        t = ops.Gelu.apply(t)
+        t = ops.Gelu.apply(t, True)
         # mlp[2] and to_space are two linear maps with nothing in between: ONE GEMM with the composed matrix (ops.ComposedLinear)
         pair = (m.mlp[2].weight, m.mlp[2].bias, m.to_space.weight, m.to_space.bias)
         if bn is None:

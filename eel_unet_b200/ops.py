@@ -47,9 +47,15 @@ _DZ_COLSUM = {}
 _BN_SUMS = {}
 
 
+def _stats_cols_ok(ncols):
+    """fused BatchNorm statistics: the kernel's N tiles (256 wide when ncols allows) must divide its grid of 148 CTAs"""
+    return ncols <= 256 or ncols in (512, 1024)
+
+
 def _want_bn_sums(x, ncols):
-    """a [2][ncols] fp32 buffer when the next op is a training-mode BatchNorm (see EELUnet._bn) and one N tile covers ncols"""
-    if _BN_NEXT[0] and ncols <= 256:
+    """a [2][ncols] fp32 buffer when the next op is a training-mode BatchNorm (see EELUnet._bn) and the producer's
+    epilogue can accumulate its statistics"""
+    if _BN_NEXT[0] and _stats_cols_ok(ncols):
         return torch.empty((2, ncols), dtype=F32, device=x.device)
     return None
 
@@ -526,7 +532,7 @@ class ConvT2x2(Function):
             wk = _packed(weight, 0)
             if wk is None:
                 wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
-            sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_BN_NEXT[0] and 4 * Cout <= 256) else None
+            sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_BN_NEXT[0] and _stats_cols_ok(4 * Cout)) else None
             call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, ptr(sums), stream())
             if sums is not None:
                 _BN_SUMS.clear()
@@ -783,14 +789,16 @@ class Relu(Function):
 
 
 class Gelu(Function):
-    """nn.GELU() (erf form; reference models/EELUnet.py:109)."""
+    """nn.GELU() (erf form; reference models/EELUnet.py:109).  producer_bias: x comes straight from a biased Linear,
+    whose bias gradient (the column sums of dx) the backward kernel then delivers for free."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, producer_bias=False):
         x = _c(x)
         y = torch.empty_like(x)
         call("eel_gelu_fwd", ptr(x), ptr(y), x.numel(), dtype_code(x), stream())
         ctx.save_for_backward(x)
+        ctx.producer_bias = producer_bias
         return y
 
     @staticmethod
@@ -798,8 +806,16 @@ class Gelu(Function):
         (x,) = ctx.saved_tensors
         dy = _c(dy)
         dx = torch.empty_like(x)
-        call("eel_gelu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x), stream())
-        return dx
+        C = x.shape[-1]
+        vec = 8 if x.dtype == BF16 else 4
+        if ctx.producer_bias and C % vec == 0 and 256 % (C // vec) == 0:
+            colsum = torch.empty(C, dtype=F32, device=x.device)
+            call("eel_gelu_bwd_colsum", ptr(x), ptr(dy), ptr(dx), ptr(colsum), x.numel(), C, dtype_code(x), stream())
+            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
+            _DZ_COLSUM[dx.data_ptr()] = colsum
+        else:
+            call("eel_gelu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x), stream())
+        return dx, None
 
 
 class MaxPool2(Function):
@@ -1061,10 +1077,11 @@ class Head(Function):
 
 
 class SE(Function):
-    """ChannelAttention (reference models/EELUnet.py:57-80) on NHWC tokens t:[N,H,W,C]."""
+    """ChannelAttention (reference models/EELUnet.py:57-80) on NHWC tokens t:[N,H,W,C].  producer_bias: t comes straight
+    from a biased conv / linear (to_patch), whose bias gradient (column sums of dt) the backward then delivers for free."""
 
     @staticmethod
-    def forward(ctx, t, w1, b1, w2, b2):
+    def forward(ctx, t, w1, b1, w2, b2, producer_bias=False):
         t = _c(t)
         N, H, W, C = t.shape
         R = w1.shape[0]
@@ -1077,6 +1094,7 @@ class SE(Function):
         call("eel_se_fwd", ptr(t), ptr(_c(w1.detach())), ptr(b1.detach()), ptr(_c(w2.detach())), ptr(b2.detach()), ptr(out),
              ptr(mean), ptr(att), ptr(hid), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
         ctx.save_for_backward(t, mean, att, hid, w1, w2)
+        ctx.producer_bias = producer_bias
         return out
 
     @staticmethod
@@ -1091,10 +1109,14 @@ class SE(Function):
         db1 = torch.empty(R, dtype=F32, device=dev)
         dw2 = torch.empty((C, R), dtype=F32, device=dev)
         db2 = torch.empty(C, dtype=F32, device=dev)
-        ws, n = _reduce_ws(dev, C, 1, extra=16 * N * C)
+        dtsum = torch.empty(C, dtype=F32, device=dev) if ctx.producer_bias else None
+        ws, n = _reduce_ws(dev, C, 2, extra=20 * N * C)
         call("eel_se_bwd", ptr(t), ptr(dout), ptr(att), ptr(hid), ptr(mean), ptr(_c(w1.detach())), ptr(_c(w2.detach())),
-             ptr(dt), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
-        return dt, dw1.view(w1.shape), db1, dw2.view(w2.shape), db2
+             ptr(dt), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dtsum), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
+        if dtsum is not None:
+            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
+            _DZ_COLSUM[dt.data_ptr()] = dtsum
+        return dt, dw1.view(w1.shape), db1, dw2.view(w2.shape), db2, None
 
 
 class HFT(Function):

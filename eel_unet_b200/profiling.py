@@ -107,7 +107,7 @@ def cost(name, a):
         N, HW, C, dt = a[9], a[10], a[11], a[15]
         return 2.0 * N * HW * C, 2 * N * HW * C * _esz(dt)
     if n == "se_bwd":
-        N, HW, C, dt = a[12], a[13], a[14], a[18]
+        N, HW, C, dt = a[13], a[14], a[15], a[19]
         return 4.0 * N * HW * C, 3 * N * HW * C * _esz(dt)
     if n in ("gelu_fwd", "relu_fwd"):
         return 8.0 * a[2], 2 * a[2] * _esz(a[3])

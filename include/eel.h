@@ -100,15 +100,15 @@ int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int 
  * channel counts multiples of 64.  wk layouts are K-major: conv3x3 wk:[9][Cout][Cin] (flip != 0: the data
  * gradient, wk:[9][Cin_of_layer][Cout_of_layer] with mirrored taps); linear w:[Nout][K]; convt wk:[2][2][Cout][Cin]. */
 /* bn_sums (optional, fp32 [2][Cout], overwritten): per-channel sum and sum of squares of the STORED output, for the
- * BatchNorm that follows (nn.BatchNorm2d training statistics without another pass over z); needs Cout <= 256
- * (one N tile) -- finish with eel_bn_stats_from_sums. */
+ * BatchNorm that follows (nn.BatchNorm2d training statistics without another pass over z); the output's N tiles (256
+ * columns wide when Cout allows) must number 1, 2 or 4 (Cout <= 256, 512, 1024) -- finish with eel_bn_stats_from_sums. */
 int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin,
                    int Cout, int relu, int flip, float* bn_sums, eel_stream s);
 /* scatterH/scatterW > 0: rows are pixels of [*, scatterH, scatterW] images and every output row is stored through the
  * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,
                   int relu, float* bn_sums, int scatterH, int scatterW, eel_stream s);
-/* bn_sums as above ([2][Cout]; needs 4 * Cout <= 256) */
+/* bn_sums as above ([2][Cout]; the 4 * Cout output columns must make 1, 2 or 4 N tiles: Cout <= 64, 128, 256) */
 int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* y, int N, int h, int w, int Cin,
                         int Cout, float* bn_sums, eel_stream s);
 /* wp:[Cin][2][2][Cout] (the eel_convt2x2_fwd packing); input width w must divide, or be a multiple of, 128 */
@@ -207,15 +207,20 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
 int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
                float* mean, float* att, float* hid, int N, long long HW, int C, int R, void* ws,
                size_t ws_bytes, int dtype, eel_stream s);
+/* dt_colsum (optional, [C]): column sums of dt over all N*HW pixels -- the bias gradient of the to_patch conv in front
+ * of the block (models/EELUnet.py:105,118) without another pass over dt */
 int eel_se_bwd(const void* t, const void* dout, const float* att, const float* hid, const float* mean,
                const float* w1, const float* w2, void* dt, float* dw1, float* db1, float* dw2, float* db2,
-               int N, long long HW, int C, int R, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+               float* dt_colsum, int N, long long HW, int C, int R, void* ws, size_t ws_bytes, int dtype, eel_stream s);
 /* standalone nn.ReLU (models/EELUnet.py:258,260); backward masks with the OUTPUT y */
 int eel_relu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s);
 int eel_relu_bwd(const void* y, const void* dy, void* dx, long long n, int dtype, eel_stream s);
 /* exact (erf) GELU (models/EELUnet.py:109) */
 int eel_gelu_fwd(const void* x, void* y, long long n, int dtype, eel_stream s);
 int eel_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, eel_stream s);
+/* eel_gelu_bwd that also leaves colsum[C] = per-channel column sums of the stored dx (rows of C channels): the bias
+ * gradient of the nn.Linear that produced x (mlp[0], models/EELUnet.py:107) without another pass; 256 % (C / vector) == 0 */
+int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, long long n, int C, int dtype, eel_stream s);
 
 /* HighFourierTransform (models/EELUnet.py:153-191) as an exact low-rank projection:
  * y = | x - U_H (U_H^H x conj(U_W)) U_W^T |, frequencies -r..r-1, r = min(mask_range, H/2, W/2).

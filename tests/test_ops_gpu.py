@@ -219,6 +219,20 @@ def test_maxpool_relu_gelu(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 64, 8, 8, 256), (1, 16, 5, 6, 32), (1, 64, 4, 4, 48)])
+def test_linear_gelu_bias_gradient_from_gelu_backward(dtype, shape):
+    """mlp[0] -> GELU (reference models/EELUnet.py:107-108): the fused GELU backward hands the Linear its bias gradient"""
+    from eel_unet_b200 import ops
+
+    n, k, h, w, nout = shape
+    x = torch.randn(n, k, h, w, device=DEV)
+    wt = torch.randn(nout, k, device=DEV) / math.sqrt(k)
+    b = torch.randn(nout, device=DEV)
+    run_case(lambda a, p: ops.Gelu.apply(ops.Linear.apply(a[0], p[0], p[1], False), True),
+             lambda a, p: F.gelu(F.conv2d(a[0], p[0][:, :, None, None], p[1])), [x], [wt, b], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_maxpool_ties_go_to_first_max(dtype):
     from eel_unet_b200 import ops
 
@@ -298,6 +312,30 @@ def test_se(dtype):
         return a[0] * g
 
     run_case(lambda a, p: ops.SE.apply(a[0], p[0], p[1], p[2], p[3]), ref, [x], [w1, b1, w2, b2], dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_to_patch_bias_gradient_from_se_backward(dtype):
+    """to_patch -> ChannelAttention (reference models/EELUnet.py:118-119): the squeeze-excite backward hands the 1x1 conv in
+    front of it its bias gradient (column sums of dt, from the per-image sums it reduces anyway)"""
+    from eel_unet_b200 import ops
+
+    x = torch.randn(3, 128, 8, 16, device=DEV)
+    wt = torch.randn(64, 128, 1, 1, device=DEV) / math.sqrt(128)
+    bt = torch.randn(64, device=DEV)
+    w1 = torch.randn(4, 64, 1, 1, device=DEV) / 8
+    b1 = torch.randn(4, device=DEV) * 0.5
+    w2 = torch.randn(64, 4, 1, 1, device=DEV) / 2
+    b2 = torch.randn(64, device=DEV) * 0.5
+
+    def ref(a, p):
+        t = F.conv2d(a[0], p[0], p[1])
+        g = t.mean(dim=(2, 3), keepdim=True)
+        g = torch.sigmoid(F.conv2d(F.relu(F.conv2d(g, p[2], p[3])), p[4], p[5]))
+        return t * g
+
+    run_case(lambda a, p: ops.SE.apply(ops.Linear.apply(a[0], p[0], p[1], False), p[2], p[3], p[4], p[5], True), ref,
+             [x], [wt, bt, w1, b1, w2, b2], dtype)
 
 
 def ref_hft(x, mask_range=20):
