@@ -580,6 +580,163 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------ BatchNorm + ReLU + max-pool 2x2
+// The encoder stages end in BatchNorm -> ReLU whose result feeds BOTH the 2x2 max-pool (next stage) and the decoder's skip
+// bridge (models/EELUnet.py:387-406, 423-459).  Forward: one pass over z writes the activation `a` and the pooled tensor.
+// Backward: the two incoming gradients (da from the bridge, dp from the pool) meet INSIDE the BatchNorm backward passes --
+// no max-pool backward tensor, no gradient-accumulation pass: the pooled gradient is routed to the recomputed arg-max
+// (first maximum in scan order, ATen semantics, on the activation values as stored) while z is read anyway.
+// A "row" is a 2x2 window; a thread owns one 16-byte channel vector of it (per-channel constants in registers).
+template <class T> struct PoolWin {
+    long long base, down;    // element offset of the window's top-left pixel (without the channel offset); +down = next image row
+    __device__ PoolWin(long long wi, int Wo, int C) {
+        const int xo = (int)(wi % Wo);
+        const long long r = wi / Wo;                       // n * Ho + yo
+        base = ((r * 2) * (2LL * Wo) + 2 * xo) * C;
+        down = 2LL * Wo * C;
+    }
+    __device__ long long pix(int k, int C) const { return base + (k >> 1) * down + (k & 1) * C; }
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const T* __restrict__ z, T* __restrict__ a, T* __restrict__ pooled,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             long long wins, int Wo, int C, int TX, long long wins_per_rb) {
+    constexpr int V = Vec16<T>::N;
+    constexpr int U = 2;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    if (c0 >= C) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = gamma[c0 + j] * rstd[c0 + j];
+        sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    }
+    long long w0 = blockIdx.y * wins_per_rb, w1 = w0 + wins_per_rb;
+    if (w1 > wins) w1 = wins;
+    for (long long w = w0 + ty; w < w1; w += (long long)U * TY) {
+        Vec16<T> v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (w + (long long)u * TY < w1) {
+                const PoolWin<T> pw(w + (long long)u * TY, Wo, C);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = ld16(z + pw.pix(k, C) + c0);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (w + (long long)u * TY < w1) {
+                const PoolWin<T> pw(w + (long long)u * TY, Wo, C);
+                Vec16<T> o[4], mx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) o[k].set(j, fmaxf(fmaf(v[u][k].get(j), sc[j], sh[j]), 0.f));
+#pragma unroll
+                for (int j = 0; j < V; ++j)      // the maximum of the STORED (rounded) activations, as a separate pool pass would see them
+                    mx.set(j, fmaxf(fmaxf(o[0].get(j), o[1].get(j)), fmaxf(o[2].get(j), o[3].get(j))));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st16(a + pw.pix(k, C) + c0, o[k]);
+                st16(pooled + (w + (long long)u * TY) * C + c0, mx);
+            }
+    }
+}
+
+// APPLY = false: partial[rb][2][C] = {sum g, sum g * xhat} over the block's windows, g = (da + [arg-max] dp) * relu mask.
+// APPLY = true : dz = gamma * rstd * (g - sum_g / n - xhat * sum_gx / n)   (train)   or   gamma * rstd * g   (frozen statistics)
+template <class T, bool APPLY>
+__global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_kernel(const T* __restrict__ da, const T* __restrict__ dp, const T* __restrict__ z,
+                                                             T* __restrict__ dz, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ sums,
+                                                             float inv_count, long long wins, int Wo, int C, int TX,
+                                                             long long wins_per_rb, int train, float* __restrict__ partial,
+                                                             float* __restrict__ dzsum) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float red[256][2 * V + 1];
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    const bool live = c0 < C;
+    float m[V], rs[V], sc[V], sh[V], k1[V], k2[V], acc0[V], acc1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = live ? c0 + j : 0;
+        m[j] = mean[c]; rs[j] = rstd[c];
+        sc[j] = gamma[c] * rs[j];
+        sh[j] = beta[c] - m[j] * sc[j];
+        k1[j] = (APPLY && train) ? sums[c] * inv_count : 0.f;
+        k2[j] = (APPLY && train) ? sums[C + c] * inv_count : 0.f;
+        acc0[j] = acc1[j] = 0.f;
+    }
+    // the apply pass walks the row blocks from the END (the reduction that ran just before left its tail in L2)
+    const long long rb = APPLY ? (long long)(gridDim.y - 1 - blockIdx.y) : (long long)blockIdx.y;
+    long long w0 = rb * wins_per_rb, w1 = w0 + wins_per_rb;
+    if (w1 > wins) w1 = wins;
+    if (!live) w1 = w0;
+    for (long long w = w0 + ty; w < w1; w += TY) {
+        const PoolWin<T> pw(w, Wo, C);
+        Vec16<T> vz[4], vd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { vz[k] = ld16(z + pw.pix(k, C) + c0); vd[k] = ld16(da + pw.pix(k, C) + c0); }
+        const Vec16<T> vp = ld16(dp + w * C + c0);
+        Vec16<T> o[4];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float t[4], av[4];
+            int kmax = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                t[k] = fmaf(vz[k].get(j), sc[j], sh[j]);
+                av[k] = to_f32(from_f32<T>(fmaxf(t[k], 0.f)));        // the activation as the forward stored it
+            }
+            float best = av[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (av[k] > best) { best = av[k]; kmax = k; }
+            const float gp = vp.get(j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float g = vd[k].get(j) + (k == kmax ? gp : 0.f);
+                if (!(t[k] > 0.f)) g = 0.f;
+                const float xh = (vz[k].get(j) - m[j]) * rs[j];
+                if (APPLY) {
+                    const float dzv = sc[j] * (g - k1[j] - xh * k2[j]);
+                    acc0[j] += dzv;
+                    o[k].set(j, dzv);
+                } else {
+                    acc0[j] += g;
+                    acc1[j] = fmaf(g, xh, acc1[j]);
+                }
+            }
+        }
+        if (APPLY) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st16(dz + pw.pix(k, C) + c0, o[k]);
+        }
+    }
+    if (!APPLY || dzsum != nullptr) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { red[threadIdx.x][j] = acc0[j]; red[threadIdx.x][V + j] = acc1[j]; }
+        __syncthreads();
+        if (ty == 0 && live) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float t0 = 0.f, t1 = 0.f;
+                for (int y = 0; y < TY; ++y) { t0 += red[y * TX + tx][j]; t1 += red[y * TX + tx][V + j]; }
+                if (APPLY) atomicAdd(dzsum + c0 + j, t0);
+                else {
+                    partial[((long long)blockIdx.y * 2 + 0) * C + c0 + j] = t0;
+                    partial[((long long)blockIdx.y * 2 + 1) * C + c0 + j] = t1;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ add + interleave
 // out[:, 2c] = a[:, c] + b[:, c], out[:, 2c+1] = e[:, c].  mean != null: `a` is a pre-BatchNorm tensor and is normalised on
 // the fly (a * gamma * rstd + beta - mean * gamma * rstd, no ReLU: the BatchNorm that ends an upconv block).  The launch uses
@@ -1076,6 +1233,49 @@ int eel_bn_act_bwd_apply(const void* dy, const void* z, const float* mean, const
         bn_act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
                                                             1.0f / (float)P, P, C, ps.TX, ps.rows_per_rb, relu, train, dz_colsum);
         return check_launch("bn_act_bwd_apply");
+    });
+}
+
+int eel_bn_relu_pool_fwd(const void* z, void* a, void* pooled, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, int N, int H, int W, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && a && pooled && mean && rstd && gamma && beta && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0,
+                "bn_relu_pool_fwd: bad argument (H, W must be even)");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "bn_relu_pool_fwd");
+        const long long wins = (long long)N * (H / 2) * (W / 2);
+        RedPlan pl = plan_stream<T>(wins, C, kStreamBpsFwd);
+        dim3 grid(pl.ncb, pl.nrb);
+        bn_relu_pool_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)a, (T*)pooled, mean, rstd, gamma, beta, wins,
+                                                                  W / 2, C, pl.TX, pl.rows_per_rb);
+        return check_launch("bn_relu_pool_fwd");
+    });
+}
+
+int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, int N, int H, int W, int C,
+                         int train, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(da && dp && z && mean && rstd && gamma && beta && dz && dgamma && dbeta && N > 0 && H > 0 && W > 0 && C > 0 &&
+                    H % 2 == 0 && W % 2 == 0, "bn_relu_pool_bwd: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "bn_relu_pool_bwd");
+        const long long wins = (long long)N * (H / 2) * (W / 2);
+        const long long P = wins * 4;
+        float* sums = (float*)ws;                   // finished {sum g, sum g*xhat}; partials follow
+        float* partial = sums + 2 * C;
+        RedPlan pr = plan_reduce<T>(wins, C, 1);
+        EEL_REQUIRE(ws_bytes >= sizeof(float) * (2 * (size_t)C + (size_t)pr.nrb * 2 * C), "bn_relu_pool_bwd: workspace too small");
+        dim3 gr(pr.ncb, pr.nrb);
+        bn_relu_pool_bwd_kernel<T, false><<<gr, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, nullptr, mean, rstd, gamma, beta,
+                                                            nullptr, 0.f, wins, W / 2, C, pr.TX, pr.rows_per_rb, train, partial, nullptr);
+        if (int rc = check_launch("bn_relu_pool_bwd.reduce")) return rc;
+        bn_bwd_finalize_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partial, pr.nrb, C, sums, dbeta, dgamma, dz_colsum);
+        if (int rc = check_launch("bn_relu_pool_bwd.finalize")) return rc;
+        RedPlan ps = plan_stream<T>(wins, C, kStreamBpsBwd);
+        dim3 ga(ps.ncb, ps.nrb);
+        bn_relu_pool_bwd_kernel<T, true><<<ga, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
+                                                           1.0f / (float)P, wins, W / 2, C, ps.TX, ps.rows_per_rb, train, nullptr, dz_colsum);
+        return check_launch("bn_relu_pool_bwd");
     });
 }
 

@@ -268,6 +268,19 @@ class EELUnet(nn.Module):
         x = self._conv_bn(blk[0], blk[1], x)
         return self._capmlp(blk[3], x, bn=blk[4], relu=True, defer=defer)
 
+    def _pool(self, d):
+        """end of an encoder stage: (skip tensor, 2x2 max-pooled tensor).  `d` is the finished stage output or
+        (pre-BatchNorm tensor, BatchNorm): then BatchNorm + ReLU + pool are one pass (ops.BNReluPool) and, in the backward,
+        the skip and pool gradients meet inside the BatchNorm backward"""
+        if isinstance(d, tuple):
+            z, bn = d
+            if z.shape[1] % 2 == 0 and z.shape[2] % 2 == 0:
+                training = self._bn_mode(bn)
+                return ops.BNReluPool.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                            bn.momentum if bn.momentum is not None else 0.1, bn.eps, True)
+            d = self._bn(bn, z, True)
+        return d, ops.MaxPool2.apply(d)
+
     def _pgr_block(self, m, d):
         """PredictionGuidedRefinement on a decoder block's output; `d` is either the finished block output or
         (pre-BatchNorm tensor, BatchNorm) whose BatchNorm + ReLU are then fused into the PGR pass"""
@@ -334,13 +347,13 @@ class EELUnet(nn.Module):
         ops.set_composed(cp)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
-        enc1 = self._conv_block(self.enc1[0], a)
-        enc2 = self._conv_block(self.enc2[0], ops.MaxPool2.apply(enc1))
-        enc3 = self._mlp_conv_block(self.enc3[0], ops.MaxPool2.apply(enc2))
-        enc4 = self._mlp_conv_block(self.enc4[0], ops.MaxPool2.apply(enc3))
+        enc1, p = self._pool(self._conv_block(self.enc1[0], a, defer=True))
+        enc2, p = self._pool(self._conv_block(self.enc2[0], p, defer=True))
+        enc3, p = self._pool(self._mlp_conv_block(self.enc3[0], p, defer=True))
+        enc4, p = self._pool(self._mlp_conv_block(self.enc4[0], p, defer=True))
 
         bt = self.bottleneck
-        b = self._bn(bt[0], ops.MaxPool2.apply(enc4), False, producer_bias=False)
+        b = self._bn(bt[0], p, False, producer_bias=False)
         b = ops.Conv3x3.apply(b, bt[1].weight, bt[1].bias, True)
         b = ops.Relu.apply(self._capmlp(bt[3], b))
         b, edge_5 = self._pgr(self.pred5, b)

@@ -768,6 +768,43 @@ class BNAct(Function):
         return dz, dgamma, dbeta, None, None, None, None, None, None, None
 
 
+class BNReluPool(Function):
+    """nn.BatchNorm2d -> nn.ReLU -> {skip tensor, nn.MaxPool2d(2)} at the end of an encoder stage (reference
+    models/EELUnet.py:387-406): returns (a, pooled).  The backward combines the gradient from the skip bridge (da) and from
+    the pool (dp) inside the BatchNorm backward passes -- no max-pool backward tensor, no gradient-accumulation pass."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, momentum, eps, producer_bias=False):
+        z = _c(z)
+        N, H, W, C = z.shape
+        mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
+        a = torch.empty_like(z)
+        pooled = torch.empty((N, H // 2, W // 2, C), dtype=z.dtype, device=z.device)
+        call("eel_bn_relu_pool_fwd", ptr(z), ptr(a), ptr(pooled), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
+             N, H, W, C, dtype_code(z), stream())
+        ctx.training, ctx.producer_bias = training, producer_bias
+        ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        return a, pooled
+
+    @staticmethod
+    def backward(ctx, da, dp):
+        z, mean, rstd, gamma, beta = ctx.saved_tensors
+        N, H, W, C = z.shape
+        da = torch.zeros_like(z) if da is None else _c(da)
+        dp = torch.zeros((N, H // 2, W // 2, C), dtype=z.dtype, device=z.device) if dp is None else _c(dp)
+        dz = torch.empty_like(z)
+        dgamma = torch.empty(C, dtype=F32, device=z.device)
+        dbeta = torch.empty(C, dtype=F32, device=z.device)
+        ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+        dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
+        call("eel_bn_relu_pool_bwd", ptr(da), ptr(dp), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
+             ptr(dz), ptr(dgamma), ptr(dbeta), ptr(dzsum), N, H, W, C, int(ctx.training), ptr(ws), n, dtype_code(z), stream())
+        if dzsum is not None:
+            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
+            _DZ_COLSUM[dz.data_ptr()] = dzsum
+        return dz, dgamma, dbeta, None, None, None, None, None, None
+
+
 class Relu(Function):
     """standalone nn.ReLU (reference models/EELUnet.py:260)."""
 

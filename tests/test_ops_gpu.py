@@ -209,6 +209,40 @@ def test_bn_act(dtype, relu, training):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("shape", [(3, 32, 10, 6), (2, 64, 16, 24), (1, 8, 4, 2)])
+def test_bn_relu_pool(dtype, training, shape):
+    """end of an encoder stage (reference models/EELUnet.py:387-406): BatchNorm -> ReLU -> (skip, MaxPool2d(2)) in one pass;
+    backward with BOTH upstream gradients (skip + pool) meeting inside the BatchNorm backward"""
+    from eel_unet_b200 import ops
+
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, device=DEV) * 2 + 1.0
+    g = torch.rand(c, device=DEV) + 0.5
+    b = torch.randn(c, device=DEV) * 0.5
+    rm0 = torch.randn(c, device=DEV) * 0.1 + 1.0
+    rv0 = torch.rand(c, device=DEV) + 3.5
+    rm, rv = rm0.clone(), rv0.clone()
+    rrm, rrv = rm0.double(), rv0.double()
+
+    def mine(a, p):
+        return ops.BNReluPool.apply(a[0], p[0], p[1], rm, rv, training, 0.1, 1e-5, False)
+
+    def ref(a, p):
+        y = F.relu(F.batch_norm(a[0], rrm, rrv, p[0], p[1], training, 0.1, 1e-5))
+        # the pool sees the activation as stored (rounded to the storage dtype): ties after rounding go to the first maximum
+        ys = y + (y.to(dtype).double() - y).detach()
+        return y, F.max_pool2d(ys, 2)
+
+    run_case(mine, ref, [x], [g, b], dtype)
+    if training:
+        t = 1e-5 if dtype == torch.float32 else 1e-2
+        assert rel(rm, rrm) < t and rel(rv, rrv) < t
+    else:
+        assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_maxpool_relu_gelu(dtype):
     from eel_unet_b200 import ops
 
