@@ -32,6 +32,12 @@ struct ConvParams {
     const float* bias;
     bf16* out;
     float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (grid % n_tiles == 0)
+    // STATS == 2 (data gradient in front of a BatchNorm + ReLU): bn_sums receives the BatchNorm-BACKWARD sums
+    // {sum g, sum g * xhat}, g = stored dy * ReLU mask, from the BatchNorm's input bz (layout of `out`) and bcst[Ntot] = {scale, -shift};
+    // bn_sums[1] then holds sum g * z (bn_sums_fix_kernel turns it into sum g * xhat)
+    const bf16* bz;
+    const float2* bcst;
+    int brelu;
 };
 
 constexpr int kMaxStages = 8;
@@ -114,7 +120,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, 
 }
 
 
-template <int BN, int MT, bool RES, int EW, bool STATS>
+template <int BN, int MT, bool RES, int EW, int STATS>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     typedef ConvCfg<BN, MT, RES> Cfg;
@@ -212,24 +218,61 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // rows (row_lo + 8 i) of this warp's quarter are image rows h0 + i of accumulator j (+ 16 j)
             const int h0 = th * Cfg::TH + q * 4;
             bf16* const pix = p.out + (((long long)n * p.H + h0) * p.W + w) * p.Ntot + n0 + L.slot * 8;
+            // element offset (from `pix`) of row i of chunk ci, or -1 when the pixel lies outside the image
+            auto chunk_off = [&](int ci, int i) -> long long {
+                const int col = (half * NCH + ci) * 32;
+                const int j = col / BN, cc = col - j * BN;
+                const int h = h0 + j * 16 + i;
+                return (h < p.H && w < p.W) ? (long long)(j * 16 + i) * p.W * p.Ntot + cc : -1;
+            };
+            // STATS == 2: the BatchNorm input z is needed at every stored position.  Its lines are pulled into L2 for the
+            // whole tile and the first chunk's vectors are loaded BEFORE waiting for the accumulator; the next chunk's are
+            // loaded while the current one is processed -- no exposed DRAM round trip.
+            const bf16* const zpix = STATS == 2 ? p.bz + (pix - p.out) : nullptr;
+            uint4 zbuf[STATS == 2 ? 2 : 1][4];
+            auto load_z = [&](int ci, uint4 (&dstv)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long o = chunk_off(ci, i);
+                    dstv[i] = o >= 0 ? ldg_early(zpix + o) : make_uint4(0, 0, 0, 0);
+                }
+            };
+            if (STATS == 2) {
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long o = chunk_off(ci, i);
+                        if (o >= 0) prefetch_l2(zpix + o);
+                    }
+                load_z(0, zbuf[0]);
+            }
             mbar_wait(&tmemFull[acc], acc_par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + half * NCH * 32;
-            uint32_t buf[2][32];
+            // STATS == 2 spends its registers on the prefetched z vectors instead of a second TMEM read buffer
+            constexpr int TB = STATS == 2 ? 1 : 2;
+            uint32_t buf[TB][32];
             tmem_ld32_async(taddr, buf[0]);
 #pragma unroll
             for (int ci = 0; ci < NCH; ++ci) {
                 tmem_ld_wait();
-                if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[(ci + 1) & 1]);
+                if (TB == 2 && ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[(ci + 1) % TB]);
+                if (STATS == 2 && ci + 1 < NCH) load_z(ci + 1, zbuf[STATS == 2 ? (ci + 1) & 1 : 0]);
                 const int col = (half * NCH + ci) * 32;       // column within the MT * BN accumulator block
-                const int j = col / BN, cc = col - j * BN;
+                const int cc = col % BN;
                 bf16* dst[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int h = h0 + j * 16 + i;
-                    dst[i] = (h < p.H && w < p.W) ? pix + (long long)(j * 16 + i) * p.W * p.Ntot + cc : nullptr;
+                    const long long o = chunk_off(ci, i);
+                    dst[i] = o >= 0 ? pix + o : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
+                if (STATS == 2) {
+                    const EpiBnBwd bb{zbuf[STATS == 2 ? ci & 1 : 0], p.bcst + n0 + cc + L.slot * 8, p.brelu};
+                    epi_store_chunk(L, buf[0], nullptr, 0, dst, &st[STATS ? ci : 0], lane, &bb);
+                    if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[0]);
+                } else
+                    epi_store_chunk(L, buf[ci % TB], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -265,13 +308,14 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     }
     p.na = na;
     const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + ew * 2048 + 1024 /* alignment slack */;
-    const bool stats = p.bn_sums != nullptr;
-    static int configured[4] = {0, 0, 0, 0};
-    const int variant = (ew == 8 ? 1 : 0) + (stats ? 2 : 0);
+    const int stats = p.bn_sums == nullptr ? 0 : (p.bz != nullptr ? 2 : 1);
+    static int configured[6] = {0, 0, 0, 0, 0, 0};
+    const int variant = (ew == 8 ? 1 : 0) + 2 * stats;
+    const void* fns[6] = {(const void*)tc_conv_kernel<BN, MT, RES, 4, 0>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 0>,
+                          (const void*)tc_conv_kernel<BN, MT, RES, 4, 1>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 1>,
+                          (const void*)tc_conv_kernel<BN, MT, RES, 4, 2>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 2>};
     if (configured[variant] < smem) {
-        const void* fn = stats ? (ew == 8 ? (const void*)tc_conv_kernel<BN, MT, RES, 8, true> : (const void*)tc_conv_kernel<BN, MT, RES, 4, true>)
-                               : (ew == 8 ? (const void*)tc_conv_kernel<BN, MT, RES, 8, false> : (const void*)tc_conv_kernel<BN, MT, RES, 4, false>);
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
             return EEL_ERR_CUDA;
         }
@@ -307,12 +351,10 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (stats) {
-        if (ew == 8) tc_conv_kernel<BN, MT, RES, 8, true><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
-        else tc_conv_kernel<BN, MT, RES, 4, true><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
-    } else {
-        if (ew == 8) tc_conv_kernel<BN, MT, RES, 8, false><<<grid, 64 + 32 * 8, smem, st>>>(tmA, tmB, p);
-        else tc_conv_kernel<BN, MT, RES, 4, false><<<grid, 64 + 32 * 4, smem, st>>>(tmA, tmB, p);
+    void* args[3] = {(void*)&tmA, (void*)&tmB, (void*)&p};
+    if (cudaLaunchKernel(fns[variant], dim3(grid), dim3(64 + 32 * ew), args, smem, st) != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+        return EEL_ERR_CUDA;
     }
     return check_launch(what);
 }
@@ -323,10 +365,23 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
 using namespace eel;
 using namespace eel::tc;
 
-extern "C" {
+// {scale, -shift} per channel (BatchNorm output > 0  <=>  scale * z > -shift), as the fused BatchNorm-backward epilogue reads them
+__global__ void bn_consts_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float2* __restrict__ out, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] * rstd[c];
+    out[c] = make_float2(sc, mean[c] * sc - beta[c]);
+}
+// the epilogue accumulated {sum g, sum g * z}: sum g * xhat = rstd * (sum g z - mean * sum g)
+__global__ void bn_sums_fix_kernel(float* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    sums[C + c] = rstd[c] * (sums[C + c] - mean[c] * sums[c]);
+}
 
-int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                   int relu, int flip, float* bn_sums, eel_stream s) {
+static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                            int relu, int flip, float* bn_sums, const bf16* bz, const float2* bcst, int brelu, cudaStream_t st) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     ConvParams p{};
@@ -336,7 +391,7 @@ int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, in
     p.flip = flip; p.relu = relu;
     p.bias = bias; p.out = (bf16*)y;
     p.bn_sums = bn_sums;
-    cudaStream_t st = (cudaStream_t)s;
+    p.bz = bz; p.bcst = bcst; p.brelu = brelu;
     const bool tall = H > 16;                  // a 32-row tile would be half empty on 16-row maps
     if (Cin == 64 && Cout == 64)
         return tall ? launch_conv<64, 2, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)")
@@ -350,6 +405,28 @@ int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, in
                     : launch_conv<128, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x1)");
     return tall ? launch_conv<64, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x2)")
                 : launch_conv<64, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x1)");
+}
+
+extern "C" {
+
+int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                   int relu, int flip, float* bn_sums, eel_stream s) {
+    return conv3x3_dispatch(x, wk, bias, y, N, H, W, Cin, Cout, relu, flip, bn_sums, nullptr, nullptr, 0, (cudaStream_t)s);
+}
+
+// Data gradient of a conv3x3 whose INPUT came from BatchNorm -> ReLU (models/EELUnet.py:338-344): the same launch as
+// eel_tc_conv3x3(dy, wk, flip = 1) that also accumulates that BatchNorm's backward sums in its epilogue.
+int eel_tc_conv3x3_dgrad_bnsums(const void* dy, const void* wk, void* dx, int N, int H, int W, int Cin, int Cout, const void* z,
+                                const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                                float* sums, void* consts_ws, eel_stream s) {
+    EEL_REQUIRE(dy && wk && dx && z && mean && rstd && gamma && beta && sums && consts_ws && N > 0 && H > 0 && W > 0,
+                "tc_conv3x3_dgrad_bnsums: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    bn_consts_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(mean, rstd, gamma, beta, (float2*)consts_ws, Cout);
+    if (int rc = check_launch("tc_conv3x3_dgrad_bnsums.consts")) return rc;
+    if (int rc = conv3x3_dispatch(dy, wk, nullptr, dx, N, H, W, Cin, Cout, 0, 1, sums, (const bf16*)z, (const float2*)consts_ws, relu, st)) return rc;
+    bn_sums_fix_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(sums, mean, rstd, Cout);
+    return check_launch("tc_conv3x3_dgrad_bnsums.fix");
 }
 
 }  // extern "C"

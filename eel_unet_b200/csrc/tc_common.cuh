@@ -167,21 +167,8 @@ __device__ __forceinline__ EpiLane epi_lane(uint8_t* staging_2k, int lane) {
 // reduce-scattered over the 8 lanes that share the slot (lane bits 2-4), leaving each lane with TWO finished values:
 //     quantity q = bit 4, channel-in-slot c = 4 * bit3 + 2 * bit2 + {0, 1}
 // which the caller accumulates across tiles and adds to global memory once per CTA (epi_stats_flush).
-__device__ __forceinline__ void epi_stats_chunk(const uint4 (&o)[4], const bool (&ok)[4], int lane, float (&acc)[2]) {
-    float a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (!ok[i]) continue;
-        const uint32_t w[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
-            a[2 * j] += lo; a[2 * j + 1] += hi;
-            a[8 + 2 * j] = fmaf(lo, lo, a[8 + 2 * j]); a[8 + 2 * j + 1] = fmaf(hi, hi, a[8 + 2 * j + 1]);
-        }
-    }
+// reduce-scatter of 16 per-lane partial values {q0[8], q1[8]} over the 8 lanes that share a slot (lane bits 2-4)
+__device__ __forceinline__ void epi_reduce16(const float (&a)[16], int lane, float (&acc)[2]) {
     const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
     float b[8], c[4];
 #pragma unroll
@@ -200,6 +187,61 @@ __device__ __forceinline__ void epi_stats_chunk(const uint4 (&o)[4], const bool 
         acc[k] += (h2 ? c[k + 2] : c[k]) + recv;
     }
 }
+__device__ __forceinline__ void epi_stats_chunk(const uint4 (&o)[4], const bool (&ok)[4], int lane, float (&acc)[2]) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) continue;
+        const uint32_t w[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+            a[2 * j] += lo; a[2 * j + 1] += hi;
+            a[8 + 2 * j] = fmaf(lo, lo, a[8 + 2 * j]); a[8 + 2 * j + 1] = fmaf(hi, hi, a[8 + 2 * j + 1]);
+        }
+    }
+    epi_reduce16(a, lane, acc);
+}
+// BatchNorm BACKWARD sums fused into the producer of dy (the data-gradient GEMM in front of a BatchNorm + ReLU): with z the
+// BatchNorm's input at the positions of the stored chunk and cst = this lane's 8 channels x {scale, -shift},
+//     g = dy * [scale * z > -shift],   quantity 0 = sum g,   quantity 1 = sum g * z
+// in the same reduce-scatter layout as epi_stats_chunk (flushed by epi_stats_flush).  The caller turns quantity 1 into
+// sum g * xhat = rstd * (sum g z - mean * sum g) afterwards: two constants per channel and seven instructions per element
+// keep the epilogue under the tile's MMA time.
+__device__ __forceinline__ void epi_bnbwd_chunk(const uint4 (&o)[4], const uint4 (&zv)[4], const bool (&ok)[4],
+                                                const float2* __restrict__ cst, int relu, int lane, float (&acc)[2]) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+    float2 cc[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(cst) + k);
+        cc[2 * k] = make_float2(t.x, t.y);
+        cc[2 * k + 1] = make_float2(t.z, t.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) continue;
+        const uint32_t w[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
+        const uint32_t zw[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 2 * j + h;
+                float g = h ? __uint_as_float(w[j] & 0xffff0000u) : __uint_as_float(w[j] << 16);
+                const float zz = h ? __uint_as_float(zw[j] & 0xffff0000u) : __uint_as_float(zw[j] << 16);
+                if (relu && !(zz * cc[k].x > cc[k].y)) g = 0.f;
+                a[k] += g;
+                a[8 + k] = fmaf(g, zz, a[8 + k]);
+            }
+        }
+    }
+    epi_reduce16(a, lane, acc);
+}
 // sums: [2][C] fp32 (zeroed by the host); col0 = first channel of the chunk these accumulators belong to
 __device__ __forceinline__ void epi_stats_flush(float* sums, int C, int col0, int lane, const float (&acc)[2]) {
     const int q = (lane >> 4) & 1;
@@ -210,8 +252,14 @@ __device__ __forceinline__ void epi_stats_flush(float* sums, int C, int col0, in
 
 // pk: this thread's row chunk already packed (32 bf16 = 16 words); dst[i]: where row (row_lo + 8 i) keeps these 32
 // columns (already offset by slot * 8 elements), null = skip.  stats != null: fold the stored values into (*stats)[2].
+struct EpiBnBwd {              // optional: BatchNorm-backward sums of the stored values (epi_bnbwd_chunk)
+    const uint4* zv;           // the BatchNorm's input at the four positions this lane stores (loaded by the caller well ahead:
+                               // a DRAM round trip per chunk would otherwise serialise the epilogue)
+    const float2* cst;         // this lane's 8 channels x {scale, -shift} for this chunk
+    int relu;
+};
 __device__ __forceinline__ void epi_store_packed(const EpiLane& L, const uint32_t (&pk)[16], __nv_bfloat16* const (&dst)[4],
-                                                 float (*stats)[2] = nullptr, int lane = 0) {
+                                                 float (*stats)[2] = nullptr, int lane = 0, const EpiBnBwd* bb = nullptr) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(L.wr_base + ((c ^ L.wr_sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
@@ -225,12 +273,18 @@ __device__ __forceinline__ void epi_store_packed(const EpiLane& L, const uint32_
         ok[i] = dst[i] != nullptr;
         if (ok[i]) *reinterpret_cast<uint4*>(dst[i]) = o[i];
     }
-    if (stats != nullptr) epi_stats_chunk(o, ok, lane, *stats);
+    if (stats != nullptr) {
+        if (bb != nullptr) {
+            const uint4 zv[4] = {bb->zv[0], bb->zv[1], bb->zv[2], bb->zv[3]};
+            epi_bnbwd_chunk(o, zv, ok, bb->cst, bb->relu, lane, *stats);
+        } else epi_stats_chunk(o, ok, lane, *stats);
+    }
     __syncwarp();
 }
 // r: the 32 accumulator columns of this thread's row; bias32: 32 floats (16-byte aligned) or null
 __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t (&r)[32], const float* bias32, int relu,
-                                                __nv_bfloat16* const (&dst)[4], float (*stats)[2] = nullptr, int lane = 0) {
+                                                __nv_bfloat16* const (&dst)[4], float (*stats)[2] = nullptr, int lane = 0,
+                                                const EpiBnBwd* bb = nullptr) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -252,7 +306,15 @@ __device__ __forceinline__ void epi_store_chunk(const EpiLane& L, const uint32_t
         __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    epi_store_packed(L, pk, dst, stats, lane);
+    epi_store_packed(L, pk, dst, stats, lane, bb);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// a 16-byte read-only load the compiler may not sink towards its use (it is issued HERE, ahead of a long wait)
+__device__ __forceinline__ uint4 ldg_early(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
 // ---- descriptors --------------------------------------------------------------------------------

@@ -211,12 +211,13 @@ class EELUnet(nn.Module):
                                          bn.momentum if bn.momentum is not None else 0.1, bn.eps, b, e, True)
 
     @staticmethod
-    def _bn(bn, z, relu, producer_bias=True):
+    def _bn(bn, z, relu, producer_bias=True, single_conv_consumer=False):
         training = EELUnet._bn_mode(bn)
         # producer_bias: z comes straight from a biased conv / linear, whose bias gradient (= column sums of dz) the
-        # BatchNorm backward then delivers for free
+        # BatchNorm backward then delivers for free.  single_conv_consumer: the result feeds exactly one conv3x3, whose
+        # data-gradient launch then also delivers this BatchNorm's backward sums (ops.Conv3x3.backward)
         return ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu,
-                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias)
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias, single_conv_consumer)
 
     @staticmethod
     def _capmlp(m, x, bn=None, relu=False, defer=False):
@@ -245,7 +246,7 @@ class EELUnet(nn.Module):
         return EELUnet._bn(bn, z, relu)
 
     @staticmethod
-    def _conv_bn(conv, bn, x, relu=True, defer=False):
+    def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
         f = ops.folded(conv.weight)
         if f is not None:
@@ -257,11 +258,11 @@ class EELUnet(nn.Module):
             ops.expect_bn(False)
         if defer:
             return z, bn
-        return EELUnet._bn(bn, z, relu)
+        return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer)
 
     def _conv_block(self, blk, x, defer=False):
         """defer: return (pre-BatchNorm tensor, BatchNorm) for the block's LAST BatchNorm + ReLU (fused into the PGR that follows)"""
-        x = self._conv_bn(blk[0], blk[1], x)
+        x = self._conv_bn(blk[0], blk[1], x, single_conv_consumer=True)
         return self._conv_bn(blk[3], blk[4], x, defer=defer)
 
     def _mlp_conv_block(self, blk, x, defer=False):
@@ -353,7 +354,7 @@ class EELUnet(nn.Module):
         enc4, p = self._pool(self._mlp_conv_block(self.enc4[0], p, defer=True))
 
         bt = self.bottleneck
-        b = self._bn(bt[0], p, False, producer_bias=False)
+        b = self._bn(bt[0], p, False, producer_bias=False, single_conv_consumer=True)
         b = ops.Conv3x3.apply(b, bt[1].weight, bt[1].bias, True)
         b = ops.Relu.apply(self._capmlp(bt[3], b))
         b, edge_5 = self._pgr(self.pred5, b)

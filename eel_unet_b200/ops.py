@@ -61,6 +61,11 @@ def _want_bn_sums(x, ncols):
 
 
 _BN_NEXT = [False]
+# A BatchNorm(+ReLU) whose output feeds ONE conv3x3 (the first BatchNorm of a conv block) registers its saved tensors under
+# the address of its output; the conv picks them up so that its data-gradient launch also accumulates that BatchNorm's
+# backward sums (eel_tc_conv3x3_dgrad_bnsums) and leaves them under the address of dx for the BatchNorm backward.
+_BN_OUT = {}
+_BN_BWD_SUMS = {}
 
 
 def expect_bn(flag):
@@ -483,6 +488,7 @@ class Conv3x3(Function):
             call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
                  dtype_code(x), stream())
         ctx.relu = relu
+        ctx.bn_in = _BN_OUT.pop(x.data_ptr(), None) if _tc_ok(x, Cin, Cout) else None
         ctx.save_for_backward(x, weight, y if relu else None)
         return y
 
@@ -504,7 +510,21 @@ class Conv3x3(Function):
                 wk = _packed(weight, 1)
                 if wk is None:
                     wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
-                call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, None, st)
+                # Measured on B200 (batch 64): the fused epilogue costs +0.12 ms on the 64 -> 64 full-resolution layer and saves
+                # the 0.20 ms reduction pass; on the 128-channel half-resolution layers cost and saving cancel (+0.09 / -0.10),
+                # so those keep the plain launch; small maps (bottleneck) are free.
+                if ctx.bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768):
+                    # x = relu(bn(z)) feeds only this conv: dx is that BatchNorm's whole upstream gradient, and its
+                    # backward sums come out of this launch's epilogue
+                    z, mean, rstd, gamma, beta, bn_relu = ctx.bn_in
+                    sums = torch.empty((2, Cin), dtype=F32, device=x.device)
+                    cws = workspace(16 * Cin, x.device, slot=1)
+                    call("eel_tc_conv3x3_dgrad_bnsums", ptr(dy), ptr(wk), ptr(dx), N, H, W, Cout, Cin, ptr(z), ptr(mean), ptr(rstd),
+                         ptr(gamma.detach()), ptr(beta.detach()), int(bn_relu), ptr(sums), ptr(cws), st)
+                    _BN_BWD_SUMS.clear()
+                    _BN_BWD_SUMS[dx.data_ptr()] = (sums, z.data_ptr())
+                else:
+                    call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, None, st)
             else:
                 wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
                 call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
@@ -736,7 +756,8 @@ class BNAct(Function):
     """nn.BatchNorm2d [+ nn.ReLU] (reference models/EELUnet.py:339-344,352-357,365,373,256)."""
 
     @staticmethod
-    def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps, producer_bias=False):
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps, producer_bias=False,
+                single_conv_consumer=False):
         z = _c(z)
         C = z.shape[-1]
         P = z.numel() // C
@@ -747,6 +768,9 @@ class BNAct(Function):
         call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
         ctx.relu, ctx.training, ctx.producer_bias = relu, training, producer_bias
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        _BN_OUT.clear()
+        if single_conv_consumer and z.dtype == BF16 and ctx.needs_input_grad[0]:
+            _BN_OUT[y.data_ptr()] = (z, mean, rstd, gamma, beta, relu)
         return y
 
     @staticmethod
@@ -756,16 +780,24 @@ class BNAct(Function):
         C = z.shape[-1]
         P = z.numel() // C
         dz = torch.empty_like(z)
-        dgamma = torch.empty(C, dtype=F32, device=z.device)
-        dbeta = torch.empty(C, dtype=F32, device=z.device)
-        ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
-        call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
-             ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
+        hit = _BN_BWD_SUMS.pop(dy.data_ptr(), None)
+        sums = hit[0] if hit is not None and hit[1] == z.data_ptr() else None
+        if sums is not None and sums.shape[1] == C:
+            # the conv that consumed this BatchNorm's output accumulated {dbeta, dgamma} in its data-gradient epilogue
+            call("eel_bn_act_bwd_apply", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(sums),
+                 ptr(dz), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), dtype_code(z), stream())
+            dgamma, dbeta = sums[1], sums[0]
+        else:
+            dgamma = torch.empty(C, dtype=F32, device=z.device)
+            dbeta = torch.empty(C, dtype=F32, device=z.device)
+            ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+            call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
+                 ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
         if dzsum is not None:
             _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
             _DZ_COLSUM[dz.data_ptr()] = dzsum
-        return dz, dgamma, dbeta, None, None, None, None, None, None, None
+        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 class BNReluPool(Function):

@@ -22,6 +22,18 @@ def cost(name, a):
         N, H, W, ci, co = a[4], a[5], a[6], a[7], a[8]
         P = N * H * W
         return 2.0 * P * 9 * ci * co, P * (ci + co) * 2 + 9 * ci * co * 2
+    if n == "tc_conv3x3_dgrad_bnsums":     # the data-gradient launch + one read of the BatchNorm input in its epilogue
+        N, H, W, ci, co = a[3], a[4], a[5], a[6], a[7]
+        P = N * H * W
+        return 2.0 * P * 9 * ci * co, P * (ci + 2 * co) * 2 + 9 * ci * co * 2
+    if n == "bn_relu_pool_fwd":
+        N, H, W, C, dt = a[7], a[8], a[9], a[10], a[11]
+        return 6.0 * N * H * W * C, 2.25 * N * H * W * C * _esz(dt)
+    if n == "bn_relu_pool_bwd":
+        N, H, W, C, dt = a[11], a[12], a[13], a[14], a[18]
+        return 16.0 * N * H * W * C, 3.25 * N * H * W * C * _esz(dt)
+    if n == "gelu_bwd_colsum":
+        return 12.0 * a[4], 3 * a[4] * _esz(a[6])
     if n == "tc_linear":
         P, K, No = a[4], a[5], a[6]
         return 2.0 * P * K * No, P * (K + No) * 2 + K * No * 2
@@ -147,6 +159,9 @@ def cost(name, a):
     return 0.0, 0.0
 
 
+# launches reported under another family's name
+ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd"}
+
 GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}
 
@@ -156,7 +171,7 @@ def summarize(records):
     fam = defaultdict(lambda: {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
     for name, args, s, e in records:
         f, b = cost(name, args)
-        k = name[4:]
+        k = ALIAS.get(name[4:], name[4:])
         d = fam[k]
         d["calls"] += 1
         d["ms"] += s.elapsed_time(e)

@@ -104,6 +104,14 @@ int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int 
  * columns wide when Cout allows) must number 1, 2 or 4 (Cout <= 256, 512, 1024) -- finish with eel_bn_stats_from_sums. */
 int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin,
                    int Cout, int relu, int flip, float* bn_sums, eel_stream s);
+/* The data gradient of a conv3x3 whose input came from nn.BatchNorm2d -> nn.ReLU (models/EELUnet.py:338-344: the block's
+ * first BatchNorm): the same launch as eel_tc_conv3x3(dy, wk, flip = 1) -> dx:[N,H,W,Cout], whose epilogue also accumulates
+ * that BatchNorm's BACKWARD sums over the dx it stores: sums:[2][Cout] = {sum g, sum g * xhat}, g = dx * [bn(z) > 0]
+ * (relu != 0), xhat = (z - mean) * rstd, z:[N,H,W,Cout] the BatchNorm's input -- the reduction pass of eel_bn_act_bwd
+ * disappears (finish with eel_bn_act_bwd_apply).  consts_ws: 16 * Cout bytes of scratch. */
+int eel_tc_conv3x3_dgrad_bnsums(const void* dy, const void* wk, void* dx, int N, int H, int W, int Cin, int Cout, const void* z,
+                                const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                                float* sums, void* consts_ws, eel_stream s);
 /* scatterH/scatterW > 0: rows are pixels of [*, scatterH, scatterW] images and every output row is stored through the
  * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,

@@ -208,6 +208,43 @@ def test_bn_act(dtype, relu, training):
         assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
 
 
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", [(2, 64, 40, 24, 64), (1, 128, 36, 20, 128), (2, 512, 8, 8, 256), (1, 64, 16, 16, 128)])
+def test_bn_backward_sums_from_conv_dgrad_epilogue(relu, shape):
+    """conv_block (reference models/EELUnet.py:338-344): BatchNorm(+ReLU) -> conv3x3.  In bf16 mode the conv's data-gradient
+    launch also accumulates the BatchNorm's backward sums (eel_tc_conv3x3_dgrad_bnsums), the BatchNorm backward is apply-only"""
+    from eel_unet_b200 import _lib, ops
+
+    n, c, h, w, cout = shape
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, device=DEV) * 1.5 + 0.5
+    g = torch.rand(c, device=DEV) + 0.5
+    b = torch.randn(c, device=DEV) * 0.5
+    wt = torch.randn(cout, c, 3, 3, device=DEV) / math.sqrt(9 * c)
+    bias = torch.randn(cout, device=DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+
+    def mine(a, p):
+        y = ops.BNAct.apply(a[0], p[0], p[1], rm, rv, True, relu, 0.1, 1e-5, False, True)
+        return ops.Conv3x3.apply(y, p[2], p[3], False)
+
+    def ref(a, p):
+        y = F.batch_norm(a[0], None, None, p[0], p[1], True, 0.1, 1e-5)
+        y = F.relu(y) if relu else y
+        # the conv reads the activation as stored (bf16)
+        y = y + (y.to(dtype).double() - y).detach()
+        return F.conv2d(y, p[2], p[3], padding=1)
+
+    rec = []
+    _lib.set_profiler(rec)
+    try:
+        run_case(mine, ref, [x], [g, b, wt, bias], dtype, atol_scale=2.0)
+    finally:
+        _lib.set_profiler(None)
+    names = [r[0] for r in rec]
+    assert "eel_tc_conv3x3_dgrad_bnsums" in names and "eel_bn_act_bwd_apply" in names and "eel_bn_act_bwd" not in names
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("shape", [(3, 32, 10, 6), (2, 64, 16, 24), (1, 8, 4, 2)])
