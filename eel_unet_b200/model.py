@@ -253,7 +253,7 @@ class EELUnet(nn.Module):
             return ops.conv3x3_folded(x, f[0], f[1], relu)
         ops.expect_bn(bn.training or bn.running_mean is None)
         try:
-            z = ops.Conv3x3.apply(x, conv.weight, conv.bias, False)
+            z = ops.conv3x3(x, conv.weight, conv.bias, False)
         finally:
             ops.expect_bn(False)
         if defer:

@@ -443,6 +443,13 @@ def _packed(weight, which):
     return None if hit is None else hit[which]
 
 
+def conv3x3(x, weight, bias, relu):
+    """nn.Conv2d(k=3, pad=1): the 3-channel first layer of bf16 mode takes the im2col tensor-core path (StemConv)"""
+    if not relu and StemConv.supported(x, weight) and bias is not None:
+        return StemConv.apply(x, weight, bias)
+    return Conv3x3.apply(x, weight, bias, relu)
+
+
 def _tc_ok(x, *chans):
     """bf16 storage and every channel count a multiple of 64 -> tcgen05 tensor-core kernels (gemm_tc.cu)."""
     return x.dtype == BF16 and all(c % 64 == 0 for c in chans)
@@ -462,6 +469,54 @@ def nchw_to_nhwc(x, dtype):
     y = torch.empty((N, H, W, C), dtype=dtype, device=x.device)
     call("eel_nchw_to_nhwc", ptr(x), ptr(y), N, C, H, W, dtype_code(y), stream())
     return y
+
+
+# --------------------------------------------------------------------------------------- first conv (3 -> 64), bf16
+class StemConv(Function):
+    """The first nn.Conv2d(3, 64, 3, padding=1) (reference models/EELUnet.py:338) in bf16 mode: a compact im2col
+    ([P][32], saved for the weight gradient) feeds the tensor-core GEMM / weight-gradient kernels (csrc/stem.cu).
+    The input image is a leaf: there is no data gradient."""
+
+    @staticmethod
+    def supported(x, weight):
+        N, H, W, Cin = x.shape
+        return x.dtype == BF16 and Cin == 3 and tuple(weight.shape) == (64, 3, 3, 3) and (N * H * W) % 2 == 0
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        N, H, W, _ = x.shape
+        P = N * H * W
+        dev, st = x.device, stream()
+        col = torch.empty((P, 32), dtype=BF16, device=dev)
+        call("eel_stem_im2col", ptr(x), ptr(col), N, H, W, st)
+        wblk = torch.empty((128, 64), dtype=BF16, device=dev)
+        bias2 = torch.empty(128, dtype=F32, device=dev)
+        call("eel_stem_pack", ptr(_c(weight.detach())), ptr(bias.detach()), ptr(wblk), ptr(bias2), st)
+        y = torch.empty((N, H, W, 64), dtype=BF16, device=dev)
+        sums2 = torch.empty((2, 128), dtype=F32, device=dev) if _BN_NEXT[0] else None
+        call("eel_tc_linear", ptr(col), ptr(wblk), ptr(bias2), ptr(y), P // 2, 64, 128, 0, ptr(sums2), 0, 0, st)
+        if sums2 is not None:
+            sums = torch.empty((2, 64), dtype=F32, device=dev)
+            call("eel_stem_fold_sums", ptr(sums2), ptr(sums), st)
+            _BN_SUMS.clear()
+            _BN_SUMS[y.data_ptr()] = sums
+        ctx.save_for_backward(col)
+        ctx.bn_in = None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (col,) = ctx.saved_tensors
+        dy = _c(dy)
+        P = col.shape[0]
+        st = stream()
+        dwblk = torch.empty((128, 64), dtype=F32, device=dy.device)
+        call("eel_tc_wgrad", ptr(dy), ptr(col), ptr(dwblk), P // 2, 128, 64, 64, 1, dwblk.numel(), 0, st)
+        dw = torch.empty((64, 3, 3, 3), dtype=F32, device=dy.device)
+        call("eel_stem_unpack_dw", ptr(dwblk), ptr(dw), st)
+        db = _colsum(dy, 64)
+        return None, dw, db
 
 
 # --------------------------------------------------------------------------------------- conv 3x3

@@ -96,6 +96,18 @@ int eel_linear_dgrad(const void* dy, const void* w, void* dx, long long P, int K
 int eel_linear_wgrad(const void* x, const void* dy, float* dw, long long P, int K, int Nout, int shiftH,
                      int shiftW, int dtype, eel_stream s);
 
+/* The first convolution (models/EELUnet.py:338, in_channels = 3, 64 output channels) in bf16 mode: K = 27 is fed to the
+ * tensor-core GEMM / weight-gradient kernels through a compact im2col.  col:[N*H*W][32] bf16 = taps (ky, kx, c) of a pixel,
+ * zero padded; two pixels side by side make a K = 64 row, the weight is the block-diagonal wblk:[128][64] bf16 with
+ * bias2:[128] = {bias, bias} (eel_stem_pack from the fp32 [64][3][3][3] parameter), so that
+ * eel_tc_linear(col, wblk, bias2, y, P/2, 64, 128) writes y:[N,H,W,64]; its BatchNorm sums come out as [2][128]
+ * (eel_stem_fold_sums -> [2][64]).  Weight gradient: eel_tc_wgrad(dy as [P/2][128], col as [P/2][64]) -> dwblk:[128][64],
+ * eel_stem_unpack_dw adds its two diagonal blocks into dw:[64][3][3][3]. */
+int eel_stem_im2col(const void* x, void* col, int N, int H, int W, eel_stream s);
+int eel_stem_pack(const float* w, const float* bias, void* wblk, float* bias2, eel_stream s);
+int eel_stem_unpack_dw(const float* dwblk, float* dw, eel_stream s);
+int eel_stem_fold_sums(const float* sums128, float* sums64, eel_stream s);
+
 /* ---- bf16 tensor-core (tcgen05 + TMEM + TMA) versions of the heavy GEMM-class ops; bf16 storage only,
  * channel counts multiples of 64.  wk layouts are K-major: conv3x3 wk:[9][Cout][Cin] (flip != 0: the data
  * gradient, wk:[9][Cin_of_layer][Cout_of_layer] with mirrored taps); linear w:[Nout][K]; convt wk:[2][2][Cout][Cin]. */

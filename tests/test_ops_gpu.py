@@ -122,6 +122,39 @@ def test_conv3x3_first_layer_three_channels(dtype):
     assert wt.grad is not None and torch.isfinite(wt.grad).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32), (1, 16, 48), (3, 18, 10)])
+def test_first_conv_tensor_core_path(shape):
+    """bf16 mode runs the 3 -> 64 first conv (reference models/EELUnet.py:338) through a compact im2col + the tcgen05 GEMM /
+    weight-gradient kernels (ops.StemConv): forward, weight and bias gradients, and the fused BatchNorm sums"""
+    from eel_unet_b200 import _lib, ops
+
+    n, h, w = shape
+    x = torch.randn(n, 3, h, w, device=DEV)
+    wt = (torch.randn(64, 3, 3, 3, device=DEV) / math.sqrt(27)).requires_grad_(True)
+    b = torch.randn(64, device=DEV).requires_grad_(True)
+    a = ops.nchw_to_nhwc(x, torch.bfloat16)
+    rec = []
+    _lib.set_profiler(rec)
+    ops.expect_bn(True)
+    try:
+        y = ops.conv3x3(a, wt, b, False)
+    finally:
+        ops.expect_bn(False)
+        _lib.set_profiler(None)
+    assert "eel_stem_im2col" in [r[0] for r in rec]
+    sums = ops._BN_SUMS.pop(y.data_ptr())
+    wr, br = wt.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    r = F.conv2d(nchw(a.double()), wr, br, padding=1)
+    assert rel(nchw(y.float()), r) < 2e-2
+    ys = y.double().reshape(-1, 64)
+    assert rel(sums[0], ys.sum(0)) < 1e-3 and rel(sums[1], (ys * ys).sum(0)) < 1e-3
+    g = torch.randn_like(r)
+    gm = nhwc(g).to(torch.bfloat16)
+    y.backward(gm)
+    r.backward(nchw(gm.double()))
+    assert rel(wt.grad, wr.grad) < 2e-2 and rel(b.grad, br.grad) < 2e-2
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 16, 6, 10, 8), (1, 64, 8, 8, 32), (2, 128, 8, 16, 64), (1, 64, 3, 5, 128),
                                    (1, 256, 16, 16, 128)])
