@@ -600,6 +600,7 @@ template <class T> struct PoolWin {
 
 template <class T>
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const T* __restrict__ z, T* __restrict__ a, T* __restrict__ pooled,
+                                                             unsigned short* __restrict__ argmax,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              long long wins, int Wo, int C, int TX, long long wins_per_rb) {
@@ -607,8 +608,10 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const T* __restri
     constexpr int U = 2;
     const int TY = 256 / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const int c0 = (blockIdx.x * TX + tx) * V;
+    const int cvi = blockIdx.x * TX + tx;
+    const int c0 = cvi * V;
     if (c0 >= C) return;
+    const int cvecs = C / V;
     float sc[V], sh[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -631,24 +634,39 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const T* __restri
             if (w + (long long)u * TY < w1) {
                 const PoolWin<T> pw(w + (long long)u * TY, Wo, C);
                 Vec16<T> o[4], mx;
+                unsigned int idx = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int j = 0; j < V; ++j) o[k].set(j, fmaxf(fmaf(v[u][k].get(j), sc[j], sh[j]), 0.f));
 #pragma unroll
-                for (int j = 0; j < V; ++j)      // the maximum of the STORED (rounded) activations, as a separate pool pass would see them
-                    mx.set(j, fmaxf(fmaxf(o[0].get(j), o[1].get(j)), fmaxf(o[2].get(j), o[3].get(j))));
+                for (int j = 0; j < V; ++j) {    // the maximum of the STORED (rounded) activations, first one in scan order
+                    float best = o[0].get(j);
+                    unsigned int kmax = 0;
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) {
+                        const float t = o[k].get(j);
+                        if (t > best) { best = t; kmax = k; }
+                    }
+                    mx.set(j, best);
+                    idx |= kmax << (2 * j);
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) st16(a + pw.pix(k, C) + c0, o[k]);
                 st16(pooled + (w + (long long)u * TY) * C + c0, mx);
+                argmax[(w + (long long)u * TY) * cvecs + cvi] = (unsigned short)idx;
             }
     }
 }
 
-// APPLY = false: partial[rb][2][C] = {sum g, sum g * xhat} over the block's windows, g = (da + [arg-max] dp) * relu mask.
-// APPLY = true : dz = gamma * rstd * (g - sum_g / n - xhat * sum_gx / n)   (train)   or   gamma * rstd * g   (frozen statistics)
+// With g = (da + [k == arg-max] dp) * [scale * z + shift > 0]:
+// APPLY = false: partial[rb][2][C] = {sum g, sum g * z} over the block's windows (the finalize turns the second into
+//                sum g * xhat = rstd * (sum g z - mean * sum g)).
+// APPLY = true : dz = scale * (g - sum_g / n - xhat * sum_gx / n) = scale * g + A * z + B with per-channel A, B (train);
+//                scale * g with frozen statistics.  Two FMAs per element: the kernel is instruction-bound otherwise.
 template <class T, bool APPLY>
 __global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_kernel(const T* __restrict__ da, const T* __restrict__ dp, const T* __restrict__ z,
+                                                             const unsigned short* __restrict__ argmax,
                                                              T* __restrict__ dz, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ sums,
@@ -659,17 +677,21 @@ __global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_kernel(const T* __res
     __shared__ float red[256][2 * V + 1];
     const int TY = 256 / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const int c0 = (blockIdx.x * TX + tx) * V;
+    const int cvi = blockIdx.x * TX + tx;
+    const int c0 = cvi * V;
     const bool live = c0 < C;
-    float m[V], rs[V], sc[V], sh[V], k1[V], k2[V], acc0[V], acc1[V];
+    const int cvecs = C / V;
+    float sc[V], sh[V], ka[V], kb[V], acc0[V], acc1[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const int c = live ? c0 + j : 0;
-        m[j] = mean[c]; rs[j] = rstd[c];
-        sc[j] = gamma[c] * rs[j];
-        sh[j] = beta[c] - m[j] * sc[j];
-        k1[j] = (APPLY && train) ? sums[c] * inv_count : 0.f;
-        k2[j] = (APPLY && train) ? sums[C + c] * inv_count : 0.f;
+        const float m = mean[c], rs = rstd[c];
+        sc[j] = gamma[c] * rs;
+        sh[j] = beta[c] - m * sc[j];
+        const float k1 = (APPLY && train) ? sums[c] * inv_count : 0.f;
+        const float k2 = (APPLY && train) ? sums[C + c] * inv_count : 0.f;
+        ka[j] = -sc[j] * k2 * rs;
+        kb[j] = -sc[j] * k1 - ka[j] * m;
         acc0[j] = acc1[j] = 0.f;
     }
     // the apply pass walks the row blocks from the END (the reduction that ran just before left its tail in L2)
@@ -683,33 +705,25 @@ __global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_kernel(const T* __res
 #pragma unroll
         for (int k = 0; k < 4; ++k) { vz[k] = ld16(z + pw.pix(k, C) + c0); vd[k] = ld16(da + pw.pix(k, C) + c0); }
         const Vec16<T> vp = ld16(dp + w * C + c0);
+        const unsigned int idx = argmax[w * cvecs + cvi];
         Vec16<T> o[4];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            float t[4], av[4];
-            int kmax = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                t[k] = fmaf(vz[k].get(j), sc[j], sh[j]);
-                av[k] = to_f32(from_f32<T>(fmaxf(t[k], 0.f)));        // the activation as the forward stored it
-            }
-            float best = av[0];
-#pragma unroll
-            for (int k = 1; k < 4; ++k)
-                if (av[k] > best) { best = av[k]; kmax = k; }
+            const unsigned int kmax = (idx >> (2 * j)) & 3u;
             const float gp = vp.get(j);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float g = vd[k].get(j) + (k == kmax ? gp : 0.f);
-                if (!(t[k] > 0.f)) g = 0.f;
-                const float xh = (vz[k].get(j) - m[j]) * rs[j];
+                const float zz = vz[k].get(j);
+                float g = vd[k].get(j);
+                if (k == (int)kmax) g += gp;
+                if (!(fmaf(zz, sc[j], sh[j]) > 0.f)) g = 0.f;
                 if (APPLY) {
-                    const float dzv = sc[j] * (g - k1[j] - xh * k2[j]);
+                    const float dzv = fmaf(sc[j], g, fmaf(ka[j], zz, kb[j]));
                     acc0[j] += dzv;
                     o[k].set(j, dzv);
                 } else {
                     acc0[j] += g;
-                    acc1[j] = fmaf(g, xh, acc1[j]);
+                    acc1[j] = fmaf(g, zz, acc1[j]);
                 }
             }
         }
@@ -735,6 +749,16 @@ __global__ void __launch_bounds__(256, 2) bn_relu_pool_bwd_kernel(const T* __res
             }
         }
     }
+}
+
+// sums = {sum g, sum g * z} -> {sum g, sum g * xhat}, in place and in dgamma (bn_bwd_finalize_kernel wrote the raw values)
+__global__ void bn_pool_fix_kernel(float* __restrict__ sums, float* __restrict__ dgamma, const float* __restrict__ mean,
+                                   const float* __restrict__ rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float v = rstd[c] * (sums[C + c] - mean[c] * sums[c]);
+    sums[C + c] = v;
+    dgamma[c] = v;
 }
 
 // ------------------------------------------------------------------------------------ add + interleave
@@ -1236,25 +1260,25 @@ int eel_bn_act_bwd_apply(const void* dy, const void* z, const float* mean, const
     });
 }
 
-int eel_bn_relu_pool_fwd(const void* z, void* a, void* pooled, const float* mean, const float* rstd, const float* gamma,
-                         const float* beta, int N, int H, int W, int C, int dtype, eel_stream s) {
-    EEL_REQUIRE(z && a && pooled && mean && rstd && gamma && beta && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0,
-                "bn_relu_pool_fwd: bad argument (H, W must be even)");
+int eel_bn_relu_pool_fwd(const void* z, void* a, void* pooled, void* argmax, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, int N, int H, int W, int C, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && a && pooled && argmax && mean && rstd && gamma && beta && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 &&
+                    W % 2 == 0, "bn_relu_pool_fwd: bad argument (H, W must be even)");
     EEL_DISPATCH_DTYPE(dtype, {
         EEL_VEC_CHECK(T, C, "bn_relu_pool_fwd");
         const long long wins = (long long)N * (H / 2) * (W / 2);
         RedPlan pl = plan_stream<T>(wins, C, kStreamBpsFwd);
         dim3 grid(pl.ncb, pl.nrb);
-        bn_relu_pool_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)a, (T*)pooled, mean, rstd, gamma, beta, wins,
-                                                                  W / 2, C, pl.TX, pl.rows_per_rb);
+        bn_relu_pool_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)a, (T*)pooled, (unsigned short*)argmax, mean, rstd,
+                                                                  gamma, beta, wins, W / 2, C, pl.TX, pl.rows_per_rb);
         return check_launch("bn_relu_pool_fwd");
     });
 }
 
-int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const float* mean, const float* rstd, const float* gamma,
-                         const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, int N, int H, int W, int C,
-                         int train, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
-    EEL_REQUIRE(da && dp && z && mean && rstd && gamma && beta && dz && dgamma && dbeta && N > 0 && H > 0 && W > 0 && C > 0 &&
+int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const void* argmax, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, int N,
+                         int H, int W, int C, int train, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(da && dp && z && argmax && mean && rstd && gamma && beta && dz && dgamma && dbeta && N > 0 && H > 0 && W > 0 && C > 0 &&
                     H % 2 == 0 && W % 2 == 0, "bn_relu_pool_bwd: bad argument");
     cudaStream_t st = (cudaStream_t)s;
     EEL_DISPATCH_DTYPE(dtype, {
@@ -1266,15 +1290,19 @@ int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const fl
         RedPlan pr = plan_reduce<T>(wins, C, 1);
         EEL_REQUIRE(ws_bytes >= sizeof(float) * (2 * (size_t)C + (size_t)pr.nrb * 2 * C), "bn_relu_pool_bwd: workspace too small");
         dim3 gr(pr.ncb, pr.nrb);
-        bn_relu_pool_bwd_kernel<T, false><<<gr, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, nullptr, mean, rstd, gamma, beta,
-                                                            nullptr, 0.f, wins, W / 2, C, pr.TX, pr.rows_per_rb, train, partial, nullptr);
+        bn_relu_pool_bwd_kernel<T, false><<<gr, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, (const unsigned short*)argmax, nullptr,
+                                                            mean, rstd, gamma, beta, nullptr, 0.f, wins, W / 2, C, pr.TX, pr.rows_per_rb,
+                                                            train, partial, nullptr);
         if (int rc = check_launch("bn_relu_pool_bwd.reduce")) return rc;
         bn_bwd_finalize_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partial, pr.nrb, C, sums, dbeta, dgamma, dz_colsum);
         if (int rc = check_launch("bn_relu_pool_bwd.finalize")) return rc;
+        bn_pool_fix_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, dgamma, mean, rstd, C);
+        if (int rc = check_launch("bn_relu_pool_bwd.fix")) return rc;
         RedPlan ps = plan_stream<T>(wins, C, kStreamBpsBwd);
         dim3 ga(ps.ncb, ps.nrb);
-        bn_relu_pool_bwd_kernel<T, true><<<ga, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, (T*)dz, mean, rstd, gamma, beta, sums,
-                                                           1.0f / (float)P, wins, W / 2, C, ps.TX, ps.rows_per_rb, train, nullptr, dz_colsum);
+        bn_relu_pool_bwd_kernel<T, true><<<ga, 256, 0, st>>>((const T*)da, (const T*)dp, (const T*)z, (const unsigned short*)argmax, (T*)dz,
+                                                           mean, rstd, gamma, beta, sums, 1.0f / (float)P, wins, W / 2, C, ps.TX,
+                                                           ps.rows_per_rb, train, nullptr, dz_colsum);
         return check_launch("bn_relu_pool_bwd");
     });
 }

@@ -867,15 +867,17 @@ class BNReluPool(Function):
         mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
         a = torch.empty_like(z)
         pooled = torch.empty((N, H // 2, W // 2, C), dtype=z.dtype, device=z.device)
-        call("eel_bn_relu_pool_fwd", ptr(z), ptr(a), ptr(pooled), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
-             N, H, W, C, dtype_code(z), stream())
+        vec = 8 if z.dtype == BF16 else 4
+        amax = torch.empty((N * (H // 2) * (W // 2), C // vec), dtype=torch.int16, device=z.device)   # 2 bits per channel
+        call("eel_bn_relu_pool_fwd", ptr(z), ptr(a), ptr(pooled), ptr(amax), ptr(mean), ptr(rstd), ptr(gamma.detach()),
+             ptr(beta.detach()), N, H, W, C, dtype_code(z), stream())
         ctx.training, ctx.producer_bias = training, producer_bias
-        ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        ctx.save_for_backward(z, mean, rstd, gamma, beta, amax)
         return a, pooled
 
     @staticmethod
     def backward(ctx, da, dp):
-        z, mean, rstd, gamma, beta = ctx.saved_tensors
+        z, mean, rstd, gamma, beta, amax = ctx.saved_tensors
         N, H, W, C = z.shape
         da = torch.zeros_like(z) if da is None else _c(da)
         dp = torch.zeros((N, H // 2, W // 2, C), dtype=z.dtype, device=z.device) if dp is None else _c(dp)
@@ -884,7 +886,7 @@ class BNReluPool(Function):
         dbeta = torch.empty(C, dtype=F32, device=z.device)
         ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
-        call("eel_bn_relu_pool_bwd", ptr(da), ptr(dp), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
+        call("eel_bn_relu_pool_bwd", ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
              ptr(dz), ptr(dgamma), ptr(dbeta), ptr(dzsum), N, H, W, C, int(ctx.training), ptr(ws), n, dtype_code(z), stream())
         if dzsum is not None:
             _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it

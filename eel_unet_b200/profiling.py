@@ -27,10 +27,10 @@ def cost(name, a):
         P = N * H * W
         return 2.0 * P * 9 * ci * co, P * (ci + 2 * co) * 2 + 9 * ci * co * 2
     if n == "bn_relu_pool_fwd":
-        N, H, W, C, dt = a[7], a[8], a[9], a[10], a[11]
+        N, H, W, C, dt = a[8], a[9], a[10], a[11], a[12]
         return 6.0 * N * H * W * C, 2.25 * N * H * W * C * _esz(dt)
     if n == "bn_relu_pool_bwd":
-        N, H, W, C, dt = a[11], a[12], a[13], a[14], a[18]
+        N, H, W, C, dt = a[12], a[13], a[14], a[15], a[19]
         return 16.0 * N * H * W * C, 3.25 * N * H * W * C * _esz(dt)
     if n == "gelu_bwd_colsum":
         return 12.0 * a[4], 3 * a[4] * _esz(a[6])

@@ -190,12 +190,14 @@ int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float
  * (models/EELUnet.py:387-406 with :339-344,352-357; skips at :423-459).  fwd: one pass over z:[N,H,W,C] writes the
  * activation a:[N,H,W,C] and pooled:[N,H/2,W/2,C].  bwd: da (gradient w.r.t. a) and dp (w.r.t. pooled) are combined inside
  * the BatchNorm backward passes (dp goes to the first maximum of each 2x2 window, ATen semantics): dz, dgamma, dbeta and the
- * optional column sums of dz as eel_bn_act_bwd; ws >= (2 + 2 * row blocks) * C floats (eel_reduce_workspace_bytes(C, 2) + 8 C). */
-int eel_bn_relu_pool_fwd(const void* z, void* a, void* pooled, const float* mean, const float* rstd, const float* gamma,
-                         const float* beta, int N, int H, int W, int C, int dtype, eel_stream s);
-int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const float* mean, const float* rstd, const float* gamma,
-                         const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, int N, int H, int W, int C,
-                         int train, void* ws, size_t ws_bytes, int dtype, eel_stream s);
+ * optional column sums of dz as eel_bn_act_bwd; ws >= (2 + 2 * row blocks) * C floats (eel_reduce_workspace_bytes(C, 2) + 8 C).
+ * argmax: [N*H/2*W/2][C / vector] uint16 (vector = 8 bf16 / 4 fp32 channels), 2 bits per channel = position of the window's first
+ * maximum, written by fwd and read by bwd (the backward would otherwise recompute it from the rounded activations). */
+int eel_bn_relu_pool_fwd(const void* z, void* a, void* pooled, void* argmax, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, int N, int H, int W, int C, int dtype, eel_stream s);
+int eel_bn_relu_pool_bwd(const void* da, const void* dp, const void* z, const void* argmax, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta, float* dz_colsum, int N,
+                         int H, int W, int C, int train, void* ws, size_t ws_bytes, int dtype, eel_stream s);
 /* nn.MaxPool2d(2) (models/EELUnet.py:391,396,401,406); x:[N,H,W,C] -> y:[N,H/2,W/2,C] */
 int eel_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, eel_stream s);
 int eel_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
