@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 
 // BatchNorm statistics from sums the producing GEMM kernel accumulated in its epilogue (sums = [2][C]: sum z, sum z^2)
 __global__ void bn_from_sums_kernel(const float* __restrict__ sums, int C, double count, float* mean, float* rstd, float* rmean,
-                                    float* rvar, float momentum, float eps) {
+                                    float* rvar, float momentum, float eps, const float* __restrict__ skipped_bias) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = (double)sums[c] / count;
@@ -409,7 +409,10 @@ __global__ void bn_from_sums_kernel(const float* __restrict__ sums, int C, doubl
     if (var < 0.0) var = 0.0;
     mean[c] = (float)m;
     rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (rmean != nullptr) rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * m);
+    // the producer left its bias out of z (a per-channel constant cancels in a training-mode BatchNorm): only the running
+    // mean, which describes z + bias, has to see it
+    const double mb = skipped_bias != nullptr ? m + (double)skipped_bias[c] : m;
+    if (rmean != nullptr) rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * mb);
     if (rvar != nullptr) {
         const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
         rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unb);
@@ -1194,9 +1197,10 @@ int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, fl
 }
 
 int eel_bn_stats_from_sums(const float* sums, long long P, int C, float* mean, float* rstd, float* running_mean,
-                           float* running_var, float momentum, float eps, eel_stream s) {
+                           float* running_var, float momentum, float eps, const float* skipped_bias, eel_stream s) {
     EEL_REQUIRE(sums && mean && rstd && P > 0 && C > 0, "bn_stats_from_sums: bad argument");
-    bn_from_sums_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>(sums, C, (double)P, mean, rstd, running_mean, running_var, momentum, eps);
+    bn_from_sums_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>(sums, C, (double)P, mean, rstd, running_mean, running_var, momentum, eps,
+                                                                   skipped_bias);
     return check_launch("bn_stats_from_sums");
 }
 

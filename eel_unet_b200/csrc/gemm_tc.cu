@@ -202,28 +202,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float st[STATS ? NCH : 1][2];           // fused BatchNorm statistics (tc_common.cuh); STATS is a template flag so
 #pragma unroll                                  // that the common no-statistics launches carry none of its registers / code
         for (int ci = 0; ci < (STATS ? NCH : 1); ++ci) st[ci][0] = st[ci][1] = 0.f;
+        // Addressing in 32-bit units of one 16-byte vector (8 bf16): ncu showed the epilogue -- not HBM -- bounds the output-heavy
+        // launches, with half of its instructions 64-bit address arithmetic and per-row integer divisions.  Everything that
+        // depends only on the column chunk is computed when the N tile changes (once per CTA when the grid is a multiple of
+        // n_tiles); per tile ONE 32-bit division locates the tile's first row, the rows follow by add / wrap.
+        const uint32_t ntot_v = (uint32_t)p.Ntot >> 3, co_v = (uint32_t)p.Co >> 3;
+        uint32_t coff_v[NCH];                   // column part of the destination offset of chunk ci
+        const float* bp[NCH];                   // its 32 bias values (or null)
+        int sdh[NCH], sdw[NCH];                 // EPI_SCATTER: the ShiftedChannel adjoint of the chunk's channel quarter
+        int nt_cur = -1;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_par = (it >> 1) & 1;
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-            const int n0 = nt * BN + half * (BN / 2);
-            long long roff[4];           // element offset of output row (row_lo + 8 i); -1 = out of range
-            int hrow[4], wcol[4];        // shH > 0: the row's (h, w) inside its image
+            if (nt != nt_cur) {
+                nt_cur = nt;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long m = (long long)mt * 128 + q * 32 + L.row_lo + 8 * i;
-                hrow[i] = 0; wcol[i] = 0;
-                if (EPI == EPI_SCATTER) {
-                    wcol[i] = (int)(m % p.shW);
-                    hrow[i] = (int)((m / p.shW) % p.shH);
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int gcol = nt * BN + half * (BN / 2) + ci * 32;
+                    sdh[ci] = sdw[ci] = 0;
+                    if (EPI == EPI_CONVT) {
+                        const int dy = gcol / (2 * p.Co), rem = gcol - dy * 2 * p.Co;
+                        coff_v[ci] = (uint32_t)dy * (2u * (uint32_t)p.W) * co_v + ((uint32_t)rem >> 3);
+                        bp[ci] = p.bias ? p.bias + (rem % p.Co) : nullptr;
+                    } else {
+                        coff_v[ci] = (uint32_t)gcol >> 3;
+                        bp[ci] = p.bias ? p.bias + gcol : nullptr;
+                        if (EPI == EPI_SCATTER) {
+                            const int qd = gcol / (p.Ntot >> 2);
+                            sdh[ci] = qd == 0 ? -1 : (qd == 1 ? 1 : 0);
+                            sdw[ci] = qd == 2 ? -1 : 0;
+                        }
+                    }
                 }
-                if (m >= p.M) roff[i] = -1;
-                else if (EPI != EPI_CONVT) roff[i] = m * p.Ntot;
-                else {
-                    const long long ny = m / p.W;
-                    const int x = (int)(m - ny * p.W);
-                    roff[i] = ((ny * 2) * (2LL * p.W) + 2 * x) * p.Co;   // (2*ny, 2*x, 0)
+            }
+            const uint32_t m0 = (uint32_t)mt * 128u;
+            const uint32_t rows_left = p.M - (long long)m0 >= 128 ? 128u : (uint32_t)(p.M - (long long)m0);
+            uint32_t roff_v[4];          // vector offset of output row (row_lo + 8 i)
+            bool rok[4];
+            int hrow[4], wcol[4];        // shH > 0: the row's (h, w) inside its image
+            {
+                // the tile's first row: (image row index, column) for the layouts that need them
+                const uint32_t Wd = EPI == EPI_CONVT ? (uint32_t)p.W : (EPI == EPI_SCATTER ? (uint32_t)p.shW : 1u);
+                const uint32_t r0 = EPI == EPI_DENSE ? 0u : m0 / Wd, x0 = EPI == EPI_DENSE ? 0u : m0 - r0 * Wd;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t r = (uint32_t)(q * 32 + L.row_lo + 8 * i);
+                    rok[i] = r < rows_left;
+                    hrow[i] = 0; wcol[i] = 0;
+                    if (EPI == EPI_DENSE) roff_v[i] = (m0 + r) * ntot_v;
+                    else {
+                        uint32_t x = x0 + r, ry = r0;
+                        if (x >= Wd) { const uint32_t k = x / Wd; ry += k; x -= k * Wd; }
+                        if (EPI == EPI_CONVT) roff_v[i] = ((ry * 2u) * (2u * Wd) + 2u * x) * co_v;      // (2*ny, 2*x, 0)
+                        else {
+                            roff_v[i] = (m0 + r) * ntot_v;
+                            wcol[i] = (int)x;
+                            hrow[i] = (int)(ry % (uint32_t)p.shH);
+                        }
+                    }
                 }
             }
             mbar_wait(&tmemFull[acc], acc_par);
@@ -235,36 +273,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int ci = 0; ci < NCH; ++ci) {
                 tmem_ld_wait();
                 if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[(ci + 1) & 1]);
-                const int gcol = n0 + ci * 32;
-                long long coff;              // column part of the destination offset (same for every row)
-                const float* bp = nullptr;
-                if (EPI == EPI_CONVT) {
-                    const int dy = gcol / (2 * p.Co), rem = gcol - dy * 2 * p.Co;
-                    coff = (long long)dy * (2LL * p.W) * p.Co + rem;
-                    if (p.bias) bp = p.bias + (rem % p.Co);
-                } else {
-                    coff = gcol;
-                    if (p.bias) bp = p.bias + gcol;
-                }
                 bf16* dst[4];
-                int dh = 0, dw = 0;          // ShiftedChannel adjoint: this 32-column chunk lies in one channel quarter
-                if (EPI == EPI_SCATTER) {
-                    const int qd = gcol / (p.Ntot >> 2);
-                    dh = qd == 0 ? -1 : (qd == 1 ? 1 : 0);
-                    dw = qd == 2 ? -1 : 0;
-                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    long long o = roff[i];
+                    uint32_t o = roff_v[i] + coff_v[ci] + (uint32_t)L.slot;
                     if (EPI == EPI_SCATTER) {
-                        int hh = hrow[i] + dh, ww = wcol[i] + dw;
+                        int hh = hrow[i] + sdh[ci], ww = wcol[i] + sdw[ci];
                         hh = hh < 0 ? hh + p.shH : (hh >= p.shH ? hh - p.shH : hh);
                         ww = ww < 0 ? ww + p.shW : ww;
-                        o += ((long long)(hh - hrow[i]) * p.shW + (ww - wcol[i])) * p.Ntot;
+                        o += (uint32_t)(((hh - hrow[i]) * p.shW + (ww - wcol[i])) * (int)ntot_v);
                     }
-                    dst[i] = roff[i] >= 0 ? p.out + o + coff + L.slot * 8 : nullptr;
+                    dst[i] = rok[i] ? p.out + (size_t)o * 8 : nullptr;
                 }
-                epi_store_chunk(L, buf[ci & 1], bp, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
+                epi_store_chunk(L, buf[ci & 1], bp[ci], p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -352,6 +373,7 @@ int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long
                   float* bn_sums, int scatterH, int scatterW, eel_stream s) {
     EEL_REQUIRE(x && w && y && P > 0, "tc_linear: bad argument");
     EEL_REQUIRE(K % 64 == 0 && Nout % 64 == 0, "tc_linear: K and Nout must be multiples of 64 (got %d, %d)", K, Nout);
+    EEL_REQUIRE(P * (long long)Nout / 8 < (1LL << 32), "tc_linear: output too large for 32-bit vector offsets");
     const int bn = pick_bn(Nout);
     CUtensorMap tmA, tmB;
     {
@@ -395,6 +417,7 @@ int eel_tc_convt2x2_fwd(const void* x, const void* wk, const float* bias, void* 
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convt2x2_fwd: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     const long long P = (long long)N * h * w;
     const int ncols = 4 * Cout;
+    EEL_REQUIRE(P * (long long)ncols / 8 < (1LL << 32), "tc_convt2x2_fwd: output too large for 32-bit vector offsets");
     const int bn = pick_bn(ncols);
     CUtensorMap tmA, tmB;
     {
@@ -433,6 +456,7 @@ int eel_tc_convt2x2_dgrad(const void* dy, const void* wp, void* dx, int N, int h
     const int gw = w >= 128 ? 128 : w;
     EEL_REQUIRE(128 % gw == 0 && w % gw == 0, "tc_convt2x2_dgrad: input width %d must divide or be a multiple of 128", w);
     const long long P = (long long)N * h * w;
+    EEL_REQUIRE(P * (long long)Cin / 8 < (1LL << 32), "tc_convt2x2_dgrad: output too large for 32-bit vector offsets");
     const int bn = pick_bn(Cin);
     CUtensorMap tmA, tmB;
     {

@@ -495,12 +495,13 @@ class StemConv(Function):
         call("eel_stem_pack", ptr(_c(weight.detach())), ptr(bias.detach()), ptr(wblk), ptr(bias2), st)
         y = torch.empty((N, H, W, 64), dtype=BF16, device=dev)
         sums2 = torch.empty((2, 128), dtype=F32, device=dev) if _BN_NEXT[0] else None
-        call("eel_tc_linear", ptr(col), ptr(wblk), ptr(bias2), ptr(y), P // 2, 64, 128, 0, ptr(sums2), 0, 0, st)
+        call("eel_tc_linear", ptr(col), ptr(wblk), None if sums2 is not None else ptr(bias2), ptr(y), P // 2, 64, 128, 0, ptr(sums2),
+             0, 0, st)
         if sums2 is not None:
             sums = torch.empty((2, 64), dtype=F32, device=dev)
             call("eel_stem_fold_sums", ptr(sums2), ptr(sums), st)
             _BN_SUMS.clear()
-            _BN_SUMS[y.data_ptr()] = sums
+            _BN_SUMS[y.data_ptr()] = (sums, bias.detach())
         ctx.save_for_backward(col)
         ctx.bn_in = None
         return y
@@ -534,10 +535,14 @@ class Conv3x3(Function):
             if wk is None:
                 wk = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]  (K-major B operand)
             sums = _want_bn_sums(x, Cout) if not relu else None
-            call("eel_tc_conv3x3", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0, ptr(sums), stream())
+            # a training-mode BatchNorm follows: the bias cancels in it, z is stored without (one FADD + a load less per
+            # output in the epilogue that bounds these kernels); eel_bn_stats_from_sums adds it to the running mean
+            b = bias.detach() if bias is not None else None
+            call("eel_tc_conv3x3", ptr(x), ptr(wk), None if sums is not None else ptr(b), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
+                 ptr(sums), stream())
             if sums is not None:
                 _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = sums
+                _BN_SUMS[y.data_ptr()] = (sums, b)
         else:
             wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
             call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
@@ -608,10 +613,12 @@ class ConvT2x2(Function):
             if wk is None:
                 wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
             sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_BN_NEXT[0] and _stats_cols_ok(4 * Cout)) else None
-            call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, ptr(sums), stream())
+            b = bias.detach()
+            call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), None if sums is not None else ptr(b), ptr(y), N, h, w, Cin, Cout, ptr(sums),
+                 stream())
             if sums is not None:
                 _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = sums
+                _BN_SUMS[y.data_ptr()] = (sums, b)
         else:
             wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
             call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())
@@ -670,10 +677,12 @@ class Linear(Function):
             if shift:
                 x = _shift(x, False)           # saved shifted: wgrad then needs no gather
             sums = _want_bn_sums(x, Nout)
-            call("eel_tc_linear", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, 0, ptr(sums), 0, 0, stream())
+            b = bias.detach()
+            call("eel_tc_linear", ptr(x), ptr(w2), None if sums is not None else ptr(b), ptr(y), N * H * W, K, Nout, 0, ptr(sums), 0, 0,
+                 stream())
             if sums is not None:
                 _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = sums
+                _BN_SUMS[y.data_ptr()] = (sums, b)
         else:
             sh, sw = (H, W) if shift else (0, 0)
             call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
@@ -744,10 +753,11 @@ class ComposedLinear(Function):
         y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
         if ctx.tc:
             sums = _want_bn_sums(x, Cout)
-            call("eel_tc_linear", ptr(x), ptr(wc), ptr(bc), ptr(y), N * H * W, K, Cout, 0, ptr(sums), 0, 0, stream())
+            call("eel_tc_linear", ptr(x), ptr(wc), None if sums is not None else ptr(bc), ptr(y), N * H * W, K, Cout, 0, ptr(sums), 0, 0,
+                 stream())
             if sums is not None:
                 _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = sums
+                _BN_SUMS[y.data_ptr()] = (sums, bc)
         else:
             call("eel_linear_fwd", ptr(x), ptr(wc), ptr(bc), ptr(y), N * H * W, K, Cout, 0, 0, dtype_code(x), stream())
         ctx.save_for_backward(x, w1, b1, w2, wc, wct)
@@ -793,10 +803,13 @@ def _bn_statistics(z, running_mean, running_var, training, momentum, eps):
     mean = torch.empty(C, dtype=F32, device=dev)
     rstd = torch.empty(C, dtype=F32, device=dev)
     st = stream()
-    sums = _BN_SUMS.pop(z.data_ptr(), None)
-    if training and sums is not None and sums.shape[1] == C:
+    hit = _BN_SUMS.pop(z.data_ptr(), None)
+    sums, skipped_bias = hit if hit is not None else (None, None)
+    if sums is not None and (not training or sums.shape[1] != C):
+        raise _lib.EelError("BatchNorm sums were produced for a tensor that is not consumed by a matching training-mode BatchNorm")
+    if training and sums is not None:
         call("eel_bn_stats_from_sums", ptr(sums), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
-             float(momentum), float(eps), st)
+             float(momentum), float(eps), ptr(skipped_bias), st)
     elif training:
         ws, n = _reduce_ws(dev, C, 2)
         call("eel_bn_stats", ptr(z), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),

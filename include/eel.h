@@ -171,9 +171,11 @@ int eel_colsum(const void* x, float* out, long long P, int C, void* ws, size_t w
 int eel_bn_stats(const void* z, long long P, int C, float* mean, float* rstd, float* running_mean,
                  float* running_var, float momentum, float eps, void* ws, size_t ws_bytes, int dtype,
                  eel_stream s);
-/* same outputs from the [2][C] sums a tensor-core producer left behind (eel_tc_conv3x3 / eel_tc_linear bn_sums) */
+/* same outputs from the [2][C] sums a tensor-core producer left behind (eel_tc_conv3x3 / eel_tc_linear bn_sums).
+ * skipped_bias (optional, [C]): the producer was launched WITHOUT its bias -- a per-channel constant cancels exactly in a
+ * training-mode BatchNorm (models/EELUnet.py:338-339), so z is stored without it and only the running mean adds it back */
 int eel_bn_stats_from_sums(const float* sums, long long P, int C, float* mean, float* rstd, float* running_mean,
-                           float* running_var, float momentum, float eps, eel_stream s);
+                           float* running_var, float momentum, float eps, const float* skipped_bias, eel_stream s);
 int eel_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean,
                       float* rstd, int C, eel_stream s);
 /* y = [relu](gamma * (z - mean) * rstd + beta) */

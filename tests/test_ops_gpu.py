@@ -135,24 +135,31 @@ def test_first_conv_tensor_core_path(shape):
     a = ops.nchw_to_nhwc(x, torch.bfloat16)
     rec = []
     _lib.set_profiler(rec)
-    ops.expect_bn(True)
     try:
         y = ops.conv3x3(a, wt, b, False)
     finally:
-        ops.expect_bn(False)
         _lib.set_profiler(None)
     assert "eel_stem_im2col" in [r[0] for r in rec]
-    sums = ops._BN_SUMS.pop(y.data_ptr())
     wr, br = wt.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
     r = F.conv2d(nchw(a.double()), wr, br, padding=1)
     assert rel(nchw(y.float()), r) < 2e-2
-    ys = y.double().reshape(-1, 64)
-    assert rel(sums[0], ys.sum(0)) < 1e-3 and rel(sums[1], (ys * ys).sum(0)) < 1e-3
     g = torch.randn_like(r)
     gm = nhwc(g).to(torch.bfloat16)
     y.backward(gm)
     r.backward(nchw(gm.double()))
     assert rel(wt.grad, wr.grad) < 2e-2 and rel(b.grad, br.grad) < 2e-2
+    # in front of a training-mode BatchNorm: z is stored WITHOUT the bias (it cancels), its sums come out of the epilogue
+    ops.expect_bn(True)
+    try:
+        z = ops.conv3x3(a, wt.detach(), b.detach(), False)
+    finally:
+        ops.expect_bn(False)
+    sums, skipped = ops._BN_SUMS.pop(z.data_ptr())
+    assert torch.equal(skipped, b.detach())
+    r0 = F.conv2d(nchw(a.double()), wt.detach().double(), None, padding=1)
+    assert rel(nchw(z.float()), r0) < 2e-2
+    zs = z.double().reshape(-1, 64)
+    assert rel(sums[0], zs.sum(0)) < 1e-3 and rel(sums[1], (zs * zs).sum(0)) < 1e-3
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
