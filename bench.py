@@ -63,9 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples taken between wall-clock times t0 and t1 (the timed region); the process is started BEFORE the
+        warm-up so that forking it cannot stall the launching thread inside the timed region"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,7 +76,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.15)]
+        for ln in (inside or [ln for _, ln in self.lines[-3:]]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -192,25 +195,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # before the warm-up: the fork of nvidia-smi must not steal the launching thread's time
     for _ in range(args.warmup):
         step(x_dev, y_dev)
     barrier()
 
     # ---- timed region: inputs resident in HBM --------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.time()
     e0.record()
     for _ in range(args.steps):
         loss = step(x_dev, y_dev)
     e1.record()
     barrier()
+    t_region1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

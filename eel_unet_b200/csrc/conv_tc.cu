@@ -210,20 +210,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_par = (it >> 1) & 1;
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-            const int n0 = nt * BN;
-            const int tw = mt % p.tiles_w, rr = mt / p.tiles_w;
-            const int th = rr % p.tiles_h, n = rr / p.tiles_h;
-            const int w = tw * 8 + L.row_lo;
+            // unsigned 32-bit tile arithmetic; destinations in units of one 16-byte vector (8 bf16) -- the epilogue, not the
+            // MMA, bounds the N = 64 layers and half of its instructions used to be 64-bit address arithmetic
+            const uint32_t mt = (uint32_t)tile / (uint32_t)p.n_tiles, nt = (uint32_t)tile - mt * (uint32_t)p.n_tiles;
+            const int n0 = (int)nt * BN;
+            const uint32_t rr = mt / (uint32_t)p.tiles_w, tw = mt - rr * (uint32_t)p.tiles_w;
+            const uint32_t n = rr / (uint32_t)p.tiles_h, th = rr - n * (uint32_t)p.tiles_h;
+            const int w = (int)tw * 8 + L.row_lo;
             // rows (row_lo + 8 i) of this warp's quarter are image rows h0 + i of accumulator j (+ 16 j)
-            const int h0 = th * Cfg::TH + q * 4;
-            bf16* const pix = p.out + (((long long)n * p.H + h0) * p.W + w) * p.Ntot + n0 + L.slot * 8;
+            const int h0 = (int)th * Cfg::TH + q * 4;
+            const uint32_t ntot_v = (uint32_t)p.Ntot >> 3, rowstep_v = (uint32_t)p.W * ntot_v;
+            const uint32_t pix_v = ((n * (uint32_t)p.H + (uint32_t)h0) * (uint32_t)p.W + (uint32_t)w) * ntot_v + ((uint32_t)n0 >> 3) + (uint32_t)L.slot;
+            bf16* const pix = p.out + (size_t)pix_v * 8;
+            const bool wok = w < p.W;
             // element offset (from `pix`) of row i of chunk ci, or -1 when the pixel lies outside the image
             auto chunk_off = [&](int ci, int i) -> long long {
                 const int col = (half * NCH + ci) * 32;
                 const int j = col / BN, cc = col - j * BN;
                 const int h = h0 + j * 16 + i;
-                return (h < p.H && w < p.W) ? (long long)(j * 16 + i) * p.W * p.Ntot + cc : -1;
+                return (wok && h < p.H) ? (long long)(((uint32_t)(j * 16 + i) * rowstep_v + ((uint32_t)cc >> 3)) << 3) : -1;
             };
             // STATS == 2: the BatchNorm input z is needed at every stored position.  Its lines are pulled into L2 for the
             // whole tile and the first chunk's vectors are loaded BEFORE waiting for the accumulator; the next chunk's are
@@ -384,6 +389,7 @@ static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, vo
                             int relu, int flip, float* bn_sums, const bf16* bz, const float2* bcst, int brelu, cudaStream_t st) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
+    EEL_REQUIRE((long long)N * H * W * Cout / 8 < (1LL << 32), "tc_conv3x3: output too large for 32-bit vector offsets");
     ConvParams p{};
     p.kchunks = Cin / 64;
     p.Ntot = Cout;
