@@ -16,11 +16,42 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _pack(w4, perm, dtype):
+# Flat gradient buffer of parallel.GradBuckets: [flat fp32 tensor, {id(param): (offset, numel)}, ids handed out this step].
+# Backward kernels then write parameter gradients straight into their slots (a FRESH view per call, which autograd's
+# AccumulateGrad adopts without a copy) instead of into temporaries that a copy per parameter moves there afterwards.
+_GRAD_FLAT = None
+
+
+def set_grad_flat(flat, slots):
+    global _GRAD_FLAT
+    _GRAD_FLAT = None if flat is None else [flat, slots, set()]
+
+
+def grads_cleared():
+    """parallel.GradBuckets.zero_grad: every slot may be handed out again"""
+    if _GRAD_FLAT is not None:
+        _GRAD_FLAT[2].clear()
+
+
+def _grad_out(param, shape=None):
+    """fp32 tensor a backward kernel writes ``param``'s gradient into"""
+    shape = tuple(param.shape) if shape is None else tuple(shape)
+    g = _GRAD_FLAT
+    if g is not None and param.grad is None and g[0].device == param.device:
+        slot = g[1].get(id(param))
+        if slot is not None and id(param) not in g[2]:
+            g[2].add(id(param))
+            o, n = slot
+            return g[0][o:o + n].view(shape)
+    return torch.empty(shape, dtype=F32, device=param.device)
+
+
+def _pack(w4, perm, dtype, out=None):
     """permute + cast a 4-D fp32 parameter into the operand layout a kernel wants."""
     w4 = _c(w4.detach())
     d = list(w4.shape)
-    out = torch.empty([d[p] for p in perm], dtype=dtype, device=w4.device)
+    if out is None:
+        out = torch.empty([d[p] for p in perm], dtype=dtype, device=w4.device)
     call("eel_permute4", ptr(w4), dtype_code(w4), ptr(out), dtype_code(out), d[0], d[1], d[2], d[3],
          perm[0], perm[1], perm[2], perm[3], stream())
     return out
@@ -503,6 +534,7 @@ class StemConv(Function):
             _BN_SUMS.clear()
             _BN_SUMS[y.data_ptr()] = (sums, bias.detach())
         ctx.save_for_backward(col)
+        ctx.weight = weight
         ctx.bn_in = None
         return y
 
@@ -514,7 +546,7 @@ class StemConv(Function):
         st = stream()
         dwblk = torch.empty((128, 64), dtype=F32, device=dy.device)
         call("eel_tc_wgrad", ptr(dy), ptr(col), ptr(dwblk), P // 2, 128, 64, 64, 1, dwblk.numel(), 0, st)
-        dw = torch.empty((64, 3, 3, 3), dtype=F32, device=dy.device)
+        dw = _grad_out(ctx.weight)
         call("eel_stem_unpack_dw", ptr(dwblk), ptr(dw), st)
         db = _colsum(dy, 64)
         return None, dw, db
@@ -593,7 +625,7 @@ class Conv3x3(Function):
             call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, st)
         else:
             call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
-        dw = _pack(dwp, (3, 2, 0, 1), F32)
+        dw = _pack(dwp, (3, 2, 0, 1), F32, out=_grad_out(weight))
         db = _colsum(dy, Cout)
         return dx, dw, db, None
 
@@ -649,7 +681,7 @@ class ConvT2x2(Function):
             call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwp), N * h * w, Cin, 4 * Cout, 4 * Cout, 1, dwp.numel(), w, st)
         else:
             call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
-        dw = _pack(dwp, (0, 3, 1, 2), F32)
+        dw = _pack(dwp, (0, 3, 1, 2), F32, out=_grad_out(weight))
         db = _colsum(dy, Cout)
         return dx, dw, db
 
@@ -713,7 +745,7 @@ class Linear(Function):
             else:
                 w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
                 call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
-        dw = torch.empty((Nout, K), dtype=F32, device=x.device)
+        dw = _grad_out(weight, (Nout, K))
         if ctx.tc and Nout % 128 == 0:
             call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dw), P, Nout, K, K, 1, dw.numel(), 0, st)      # D[m=nout][n=k]
         elif ctx.tc and K % 128 == 0:
@@ -786,9 +818,9 @@ class ComposedLinear(Function):
         else:
             call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 0, 0, dtype_code(x), st)
         s = _colsum(dy, Cout)
-        dw2 = torch.empty((Cout, Cmid), dtype=F32, device=x.device)
-        dw1 = torch.empty((Cmid, K), dtype=F32, device=x.device)
-        db1 = torch.empty(Cmid, dtype=F32, device=x.device)
+        dw2 = _grad_out(w2, (Cout, Cmid))
+        dw1 = _grad_out(w1, (Cmid, K))
+        db1 = _grad_out(b1)
         call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
              ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, K, st)
         return dx, dw1, db1, dw2.view(w2.shape), s
@@ -857,8 +889,7 @@ class BNAct(Function):
                  ptr(dz), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), dtype_code(z), stream())
             dgamma, dbeta = sums[1], sums[0]
         else:
-            dgamma = torch.empty(C, dtype=F32, device=z.device)
-            dbeta = torch.empty(C, dtype=F32, device=z.device)
+            dgamma, dbeta = _grad_out(gamma), _grad_out(beta)
             ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
             call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
                  ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
@@ -895,8 +926,7 @@ class BNReluPool(Function):
         da = torch.zeros_like(z) if da is None else _c(da)
         dp = torch.zeros((N, H // 2, W // 2, C), dtype=z.dtype, device=z.device) if dp is None else _c(dp)
         dz = torch.empty_like(z)
-        dgamma = torch.empty(C, dtype=F32, device=z.device)
-        dbeta = torch.empty(C, dtype=F32, device=z.device)
+        dgamma, dbeta = _grad_out(gamma), _grad_out(beta)
         ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
         call("eel_bn_relu_pool_bwd", ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
@@ -1030,8 +1060,7 @@ class BNAddInterleave(Function):
         st = stream()
         call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), P, C, dtype_code(dout), st)
         dz = torch.empty_like(z)
-        dgamma = torch.empty(C, dtype=F32, device=z.device)
-        dbeta = torch.empty(C, dtype=F32, device=z.device)
+        dgamma, dbeta = _grad_out(gamma), _grad_out(beta)
         ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
         call("eel_bn_act_bwd", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
@@ -1203,10 +1232,8 @@ class Head(Function):
         dprob = _c(dprob.to(F32))
         dev = x.device
         dx = torch.empty_like(x)
-        dlnw = torch.empty(64, dtype=F32, device=dev)
-        dlnb = torch.empty(64, dtype=F32, device=dev)
-        dw = torch.empty((O, 64), dtype=F32, device=dev)
-        db = torch.empty(O, dtype=F32, device=dev)
+        dlnw, dlnb = _grad_out(lnw), _grad_out(lnb)
+        dw, db = _grad_out(weight, (O, 64)), _grad_out(bias)
         n = 4 * (4 * _lib_sms() + 1) * ((2 + O) * 64 + O)
         ws = workspace(n, dev)
         call("eel_head_bwd", ptr(x), ptr(lnw.detach()), ptr(lnb.detach()), ptr(_c(weight.detach())), ptr(bias.detach()),
@@ -1244,9 +1271,8 @@ class SE(Function):
         R = w1.shape[0]
         dev = t.device
         dt = torch.empty_like(t)
-        dw1 = torch.empty((R, C), dtype=F32, device=dev)
+        dw1, dw2 = _grad_out(w1, (R, C)), _grad_out(w2, (C, R))
         db1 = torch.empty(R, dtype=F32, device=dev)
-        dw2 = torch.empty((C, R), dtype=F32, device=dev)
         db2 = torch.empty(C, dtype=F32, device=dev)
         dtsum = torch.empty(C, dtype=F32, device=dev) if ctx.producer_bias else None
         ws, n = _reduce_ws(dev, C, 2, extra=20 * N * C)

@@ -61,13 +61,18 @@ class GradBuckets:
             b.pending = len(b.params)
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        if dev.type == "cuda":
+            from . import ops
+            ops.set_grad_flat(self.flat_grad, self._slot)
 
     # ------------------------------------------------------------------------------------------
     def _on_grad(self, p):
         o, n = self._slot[id(p)]
         slot = self.flat_grad[o:o + n].view(p.shape)
-        slot.copy_(p.grad)
-        p.grad = slot                      # the user-visible gradient now lives in the flat buffer
+        if p.grad.data_ptr() != slot.data_ptr():
+            # (the backward kernels of eel_unet_b200.ops write most gradients straight into their slot: ops._grad_out)
+            slot.copy_(p.grad)
+            p.grad = slot                  # the user-visible gradient now lives in the flat buffer
         b = self._bucket_of[id(p)]
         b.pending -= 1
         if b.pending == 0:
@@ -108,11 +113,17 @@ class GradBuckets:
         """set_to_none semantics: the next backward writes fresh gradients (no accumulate kernel per tensor)."""
         for p in self.params:
             p.grad = None
+        if self.device.type == "cuda":
+            from . import ops
+            ops.grads_cleared()
 
     def remove(self):
         for h in self._handles:
             h.remove()
         self._handles = []
+        if self.device.type == "cuda":
+            from . import ops
+            ops.set_grad_flat(None, None)
 
 
 class DataParallel(torch.nn.Module):

@@ -190,6 +190,43 @@ def test_packed_weights_follow_every_kind_of_update():
         assert torch.equal(model(x)[0], fresh2(x)[0]), "packed weights went stale after load_state_dict"
 
 
+def test_flat_gradient_buffer_receives_the_same_gradients():
+    """parallel.GradBuckets: the backward kernels write most parameter gradients straight into their slot of the flat
+    gradient buffer (ops._grad_out); every gradient must equal the one a plain backward (fresh tensors) produces, and
+    ``p.grad`` must live in the flat buffer afterwards.  Values are compared in fp32 mode (exact arithmetic up to the order
+    of fp32 atomics); at default init a bf16 step is chaotic from run to run even between two identical plain models
+    (rounding flips amplified by the BatchNorms), so bf16 only checks placement and finiteness."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+    from eel_unet_b200.parallel import DataParallel
+
+    _, _, x, y = _setup(2, 128, 128)
+    x, y = x.cuda(), y.cuda()
+    crit = edge_BceDiceLoss(1, 1)
+    for precision in ("fp32", "bf16"):
+        torch.manual_seed(4)
+        plain = EELUnet(3, 1, precision=precision).cuda().train()
+        flat = EELUnet(3, 1, precision=precision).cuda().train()
+        flat.load_state_dict(plain.state_dict())
+        seg, edges = plain(x)
+        crit(edges, seg, y).backward()
+        dp = DataParallel(flat)
+        try:
+            for _ in range(2):                      # the second step re-uses the slots after zero_grad
+                dp.zero_grad()
+                seg, edges = dp(x)
+                crit(edges, seg, y).backward()
+                dp.finish_backward()
+            lo, hi = dp.buckets.flat_grad.data_ptr(), dp.buckets.flat_grad.data_ptr() + 4 * dp.buckets.flat_grad.numel()
+            gmax = max(p.grad.norm().item() for p in plain.parameters())
+            for (n, p), q in zip(plain.named_parameters(), flat.parameters()):
+                assert lo <= q.grad.data_ptr() < hi, n
+                assert torch.isfinite(q.grad).all(), n
+                if precision == "fp32" and p.grad.norm().item() > 1e-4 * gmax:     # skip analytically-zero gradients (pure noise)
+                    assert rel(q.grad, p.grad) < 1e-3, (n, rel(q.grad, p.grad))
+        finally:
+            dp.buckets.remove()
+
+
 def test_inference_batchnorm_folding_matches_unfolded_eval():
     """bf16 inference folds eval-mode BatchNorms into their producers' packed weights (ops.FoldedPacker).  Same math as the
     unfolded eval path (taken whenever autograd is on), different rounding points: the two must agree to bf16 accuracy, and
