@@ -1432,7 +1432,7 @@ int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, 
         }
         long long nvec = n / Vec16<T>::N;
         long long blocks = (nvec + 511) / 512;
-        if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+        if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
         gelu_bwd_colsum_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, colsum, nvec, cvec);
         return check_launch("gelu_bwd_colsum");
     });
