@@ -293,6 +293,13 @@ __global__ void __launch_bounds__(kPixThreads) pgr_bwd_kernel2(const T* __restri
 // disappears -- eel_bn_act_bwd_apply finishes with one pass.
 struct BnConst { const float* mean; const float* rstd; const float* gamma; const float* beta; };
 
+// sums = {sum g, sum g * z} -> {sum g, sum g * xhat}
+__global__ void bn_raw_sums_fix_kernel(float* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    sums[C + c] = rstd[c] * (sums[C + c] - mean[c] * sums[c]);
+}
+
 template <class T, int ITERS, int U>
 __global__ void __launch_bounds__(kPixThreads) bn_pgr_fwd_kernel(const T* __restrict__ z, BnConst bn, const float* __restrict__ w,
                                                                const float* __restrict__ b, T* __restrict__ y,
@@ -302,13 +309,16 @@ __global__ void __launch_bounds__(kPixThreads) bn_pgr_fwd_kernel(const T* __rest
     const int groups_per_block = kPixThreads / G;
     const int g_in_block = (threadIdx.x >> 5) * (32 / G) + gi;
     const float bias = b[0];
-    float wreg[ITERS][V], m[ITERS][V], rs[ITERS][V], gm[ITERS][V], bt[ITERS][V];
+    // x = relu(sc * z + sh): two constants per channel (one FMA per element; fewer registers leave room for U pixels in flight)
+    float wreg[ITERS][V], sc[ITERS][V], sh[ITERS][V];
 #pragma unroll
     for (int k = 0; k < ITERS; ++k)
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int c = (gl + k * G) * V + j;
-            wreg[k][j] = w[c]; m[k][j] = bn.mean[c]; rs[k][j] = bn.rstd[c]; gm[k][j] = bn.gamma[c]; bt[k][j] = bn.beta[c];
+            wreg[k][j] = w[c];
+            sc[k][j] = bn.gamma[c] * bn.rstd[c];
+            sh[k][j] = bn.beta[c] - bn.mean[c] * sc[k][j];
         }
     const long long stride = (long long)gridDim.x * groups_per_block * U;
     for (long long p0 = (long long)blockIdx.x * groups_per_block * U; p0 < P; p0 += stride) {
@@ -331,10 +341,9 @@ __global__ void __launch_bounds__(kPixThreads) bn_pgr_fwd_kernel(const T* __rest
             for (int k = 0; k < ITERS; ++k)
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float xh = ok[u] ? (vz[u][k].get(j) - m[k][j]) * rs[k][j] : 0.f;
-                    const float x = ok[u] ? fmaxf(gm[k][j] * xh + bt[k][j], 0.f) : 0.f;
+                    const float x = ok[u] ? fmaxf(fmaf(vz[u][k].get(j), sc[k][j], sh[k][j]), 0.f) : 0.f;
                     xf[u][k][j] = x;
-                    dot[u] += x * wreg[k][j];
+                    dot[u] = fmaf(x, wreg[k][j], dot[u]);
                 }
         }
 #pragma unroll
@@ -370,14 +379,18 @@ __global__ void __launch_bounds__(kPixThreads) bn_pgr_bwd_kernel(const T* __rest
     const int width = 3 * C + 1;
     for (int i = threadIdx.x; i < width; i += kPixThreads) sh[i] = 0.f;
     __syncthreads();
-    float dwacc[ITERS][V], sga[ITERS][V], sgx[ITERS][V], wreg[ITERS][V], m[ITERS][V], rs[ITERS][V], gm[ITERS][V], bt[ITERS][V];
+    // sums over raw z (sgx = sum g * z; the finalize turns it into sum g * xhat = rstd * (sum g z - mean * sum g)) and
+    // x = relu(sc * z + sh): the kernel was instruction-bound with the four-constant form
+    float dwacc[ITERS][V], sga[ITERS][V], sgx[ITERS][V], wreg[ITERS][V], sc[ITERS][V], shf[ITERS][V];
 #pragma unroll
     for (int k = 0; k < ITERS; ++k)
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int c = (gl + k * G) * V + j;
             dwacc[k][j] = 0.f; sga[k][j] = 0.f; sgx[k][j] = 0.f;
-            wreg[k][j] = w[c]; m[k][j] = bn.mean[c]; rs[k][j] = bn.rstd[c]; gm[k][j] = bn.gamma[c]; bt[k][j] = bn.beta[c];
+            wreg[k][j] = w[c];
+            sc[k][j] = bn.gamma[c] * bn.rstd[c];
+            shf[k][j] = bn.beta[c] - bn.mean[c] * sc[k][j];
         }
     float dbacc = 0.f;
     const long long stride = (long long)gridDim.x * groups_per_block * U;
@@ -409,9 +422,8 @@ __global__ void __launch_bounds__(kPixThreads) bn_pgr_bwd_kernel(const T* __rest
                 for (int k = 0; k < ITERS; ++k)
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const float xh = (vz[u][k].get(j) - m[k][j]) * rs[k][j];
-                        const float x = fmaxf(gm[k][j] * xh + bt[k][j], 0.f);
-                        dot[u] += x * vd[u][k].get(j);
+                        const float x = fmaxf(fmaf(vz[u][k].get(j), sc[k][j], shf[k][j]), 0.f);
+                        dot[u] = fmaf(x, vd[u][k].get(j), dot[u]);
                     }
         }
 #pragma unroll
@@ -427,14 +439,14 @@ __global__ void __launch_bounds__(kPixThreads) bn_pgr_bwd_kernel(const T* __rest
                 Vec16<T> o;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float xh = (vz[u][k].get(j) - m[k][j]) * rs[k][j];
-                    const float pre = gm[k][j] * xh + bt[k][j];
+                    const float zz = vz[u][k].get(j);
+                    const float pre = fmaf(zz, sc[k][j], shf[k][j]);
                     const float x = fmaxf(pre, 0.f);
-                    o.set(j, vd[u][k].get(j) * (1.f + sv[u]) + wreg[k][j] * dg);
-                    dwacc[k][j] += x * dg;
+                    o.set(j, fmaf(vd[u][k].get(j), 1.f + sv[u], wreg[k][j] * dg));
+                    dwacc[k][j] = fmaf(x, dg, dwacc[k][j]);
                     const float g = pre > 0.f ? o.get(j) : 0.f;     // the BatchNorm backward sees the STORED (rounded) dx
                     sga[k][j] += g;
-                    sgx[k][j] += g * xh;
+                    sgx[k][j] = fmaf(g, zz, sgx[k][j]);
                 }
                 st16(dx + p * C + (gl + k * G) * V, o);
             }
@@ -809,8 +821,8 @@ int eel_bn_pgr_fwd(const void* z, const float* bn_mean, const float* bn_rstd, co
         const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
         const BnConst bn{bn_mean, bn_rstd, bn_gamma, bn_beta};
         cudaStream_t st2 = (cudaStream_t)s;
-        if (iters == 1) bn_pgr_fwd_kernel<T, 1, 2><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
-        else bn_pgr_fwd_kernel<T, 2, 1><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        if (iters == 1) bn_pgr_fwd_kernel<T, 1, 4><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
+        else bn_pgr_fwd_kernel<T, 2, 2><<<grid, kPixThreads, 0, st2>>>((const T*)z, bn, w, b, (T*)y, sgm, P, C, G);
         return check_launch("bn_pgr_fwd");
     });
 }
@@ -841,7 +853,9 @@ int eel_bn_pgr_bwd(const void* z, const float* bn_mean, const float* bn_rstd, co
         // bn_sums = [2][C]: {sum g, sum g * xhat} (= dbeta, dgamma of the BatchNorm)
         RowSegs segs{{dw, db, bn_sums, bn_sums + C}, {C, C + 1, 2 * C + 1, 3 * C + 1}};
         finalize_rows_kernel<<<cdiv(width, 32), 1024, 0, st2>>>(partial, grid, width, segs);
-        return check_launch("bn_pgr_bwd.finalize");
+        if (int rc = check_launch("bn_pgr_bwd.finalize")) return rc;
+        bn_raw_sums_fix_kernel<<<cdiv(C, 128), 128, 0, st2>>>(bn_sums, bn_mean, bn_rstd, C);
+        return check_launch("bn_pgr_bwd.fix");
     });
 }
 
