@@ -51,22 +51,27 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(LossPtrs preds, const
     }
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ sums, int N, int H, int W, float wb, float wd,
-                                     float* __restrict__ loss) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double total = 0.0;
-    for (int map = 0; map < kLossMaps; ++map) {
-        int s = kMapStride[map];
-        double M = (double)(H / s) * (double)(W / s);
-        double dice = 0.0, bce = 0.0;
-        for (int n = 0; n < N; ++n) {
-            const double* q = sums + ((long long)map * N + n) * 4;
-            dice += (2.0 * q[0] + 1.0) / (q[1] + q[2] + 1.0);
-            bce += q[3];
-        }
-        total += (double)kMapWeight[map] * ((double)wd * (1.0 - dice / N) + (double)wb * bce / (N * M));
+// one thread per (map, sample) term, fixed-order tree reduction in fp64 (a single thread walking the 6 N terms spent ~0.5 us
+// of load latency on each: 0.2 ms at batch 64)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ sums, int N, int H, int W, float wb, float wd,
+                                                          float* __restrict__ loss) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int idx = threadIdx.x; idx < kLossMaps * N; idx += 256) {
+        const int map = idx / N;
+        const int s = kMapStride[map];
+        const double M = (double)(H / s) * (double)(W / s);
+        const double* q = sums + (long long)idx * 4;
+        const double dice = (2.0 * q[0] + 1.0) / (q[1] + q[2] + 1.0);
+        acc += (double)kMapWeight[map] * ((double)wd * (1.0 - dice) / N + (double)wb * q[3] / (N * M));
     }
-    loss[0] = (float)total;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)red[0];
 }
 
 __global__ void __launch_bounds__(256) loss_bwd_kernel(LossPtrs preds, const float* __restrict__ target,
@@ -123,7 +128,7 @@ int eel_edge_loss_fwd(const float* const* preds_host, const float* target, int N
     dim3 grid(bx, N, kLossMaps);
     loss_partial_kernel<<<grid, 256, 0, st>>>(lp, target, H, W, sums);
     if (int rc = check_launch("edge_loss_fwd.partial")) return rc;
-    loss_finalize_kernel<<<1, 32, 0, st>>>(sums, N, H, W, wb, wd, loss);
+    loss_finalize_kernel<<<1, 256, 0, st>>>(sums, N, H, W, wb, wd, loss);
     return check_launch("edge_loss_fwd.finalize");
 }
 
