@@ -114,6 +114,41 @@ def test_train_step_matches_oracle(precision):
     assert float(np.median(ratios)) <= 2.0
 
 
+def test_four_channel_input_and_multi_class_head():
+    """the AddCannyEdge wiring feeds RGB + edge map: EELUnet(in_channels=4, ...) (reference augmentation/AddCannyEdge.py:29-41,
+    data/ToothDataset.py:52); out_channels > 1 exercises the general head.  fp32 train step against the fp64 oracle, bf16 finite."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    torch.manual_seed(5)
+    model = EELUnet(4, 1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    xs, ys, _ = synth.batch(2, 128, 128, 5)
+    x = torch.cat([torch.from_numpy(xs), torch.from_numpy(ys) * 0.5 - 0.1], 1)          # a 4th (edge-like) channel
+    y = torch.from_numpy(ys)
+    sdd = {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in sd.items()}
+    l64, seg64, e64, g64, _ = O.train_step(sdd, x.double(), y.double())
+    model = model.cuda().train()
+    seg, edges = model(x.cuda())
+    loss = edge_BceDiceLoss(1, 1)(edges, seg, y.cuda())
+    loss.backward()
+    assert rel(seg, seg64) < 1e-3 and abs(loss.item() - l64.item()) < 1e-3 * abs(l64.item())
+    w = model.enc1[0][0].weight
+    g = g64["enc1.0.0.weight"].flatten()
+    cos = torch.dot(w.grad.double().cpu().flatten(), g) / (w.grad.double().norm().cpu() * g.norm())
+    assert tuple(w.shape) == (64, 4, 3, 3) and cos > 0.95, cos      # deepest gradient of an ill-conditioned step: direction, not digits
+    for precision in ("fp32", "bf16"):
+        m3 = EELUnet(4, 3, precision=precision).cuda().eval()
+        with torch.no_grad():
+            s3, e3 = m3(x.cuda())
+        assert tuple(s3.shape) == (2, 3, 128, 128) and torch.isfinite(s3).all() and len(e3) == 5
+        if precision == "fp32":
+            sd3 = {k: (v.double().cpu() if v.dtype.is_floating_point else v.cpu().clone()) for k, v in m3.state_dict().items()}
+            r3, _ = O.forward(sd3, x.double(), False, {})
+            assert rel(s3, r3) < 1e-4
+
+
 def test_eval_mode_forward_is_tight():
     """Inference path (running statistics): well conditioned, so the literal 1e-4 bar applies."""
     from oracle import eelunet_torch as O
