@@ -83,6 +83,26 @@ def cases(B, S, only):
             return "eel_bn_act_bwd", (ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dz), ptr(dg), ptr(db), ptr(dzs), P, c, 1, 1,
                                       ptr(ws), n, 1, st()), (z, dy, dz, mean, rstd, g, b, dg, db, dzs, ws)
         add("bn", "bn_act_bwd P=%d C=%d" % (P, c), mk_bwd)
+
+        def mk_pool_fwd(s=s, c=c):
+            z, a_, pooled = rnd(B, s, s, c), torch.empty(B, s, s, c, device=DEV, dtype=BF16), torch.empty(B, s // 2, s // 2, c, device=DEV, dtype=BF16)
+            amax = torch.empty(B * (s // 2) * (s // 2), c // 8, device=DEV, dtype=torch.int16)
+            mean, rstd, g, b = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+            return "eel_bn_relu_pool_fwd", (ptr(z), ptr(a_), ptr(pooled), ptr(amax), ptr(mean), ptr(rstd), ptr(g), ptr(b), B, s, s, c, 1, st()), \
+                (z, a_, pooled, amax, mean, rstd, g, b)
+        add("pool", "bn_relu_pool_fwd %dx%d C=%d" % (s, s, c), mk_pool_fwd)
+
+        def mk_pool_bwd(s=s, c=c):
+            z, da, dz = rnd(B, s, s, c), rnd(B, s, s, c), torch.empty(B, s, s, c, device=DEV, dtype=BF16)
+            dp = rnd(B, s // 2, s // 2, c)
+            amax = torch.randint(0, 1 << 15, (B * (s // 2) * (s // 2), c // 8), device=DEV, dtype=torch.int16)
+            mean, rstd, g, b = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+            dg, db, dzs = torch.empty(c, device=DEV), torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+            n = _lib.lib.eel_reduce_workspace_bytes(c, 2) + 8 * c
+            ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+            return "eel_bn_relu_pool_bwd", (ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dz), ptr(dg), ptr(db),
+                                            ptr(dzs), B, s, s, c, 1, ptr(ws), n, 1, st()), (z, da, dz, dp, amax, mean, rstd, g, b, dg, db, dzs, ws)
+        add("pool", "bn_relu_pool_bwd %dx%d C=%d" % (s, s, c), mk_pool_bwd)
     return out
 
 
