@@ -93,6 +93,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _workload(precision, world, B, S):
+    """the `config` both arms print: the reference arm reports the SAME workload (its bounded sample is described in
+    `cpu_baseline.sample`), so the driver compares like with like"""
+    return {"workload": "EELUnet %s training (fwd + edge_BceDiceLoss + bwd + Adam%s), batch %d per GPU at 3x%dx%d"
+                        % (precision, " + NCCL allreduce" if world > 1 else "", B, S, S),
+            "global_batch": world * B, "parallelism": "dp%d" % world,
+            "l2": "no flush needed: per-step activation working set is GBs >> 126 MB L2"}
+
+
+def _oracle_params(device="cpu"):
+    """seed-0 default-init weights in the reference's state_dict format from oracle/params.py -- NOT through the product
+    package, whose import maps libeel.so"""
+    import torch
+
+    from oracle import params as P
+
+    torch.manual_seed(0)
+    sd = P.eelunet_state_dict(3, 1)
+    return {k: v.to(device).requires_grad_(v.dtype.is_floating_point and "running_" not in k) for k, v in sd.items()}
+
+
 def cpu_step_rate(batch, size, iters, warmup, seed=0):
     """images/s of the CPU oracle port (fp32, fwd + loss + bwd + Adam) on all host threads."""
     import torch
@@ -100,11 +121,7 @@ def cpu_step_rate(batch, size, iters, warmup, seed=0):
     from oracle import eelunet_torch as O
     from oracle import synth
 
-    torch.manual_seed(0)
-    from eel_unet_b200.model import EELUnet as Tree  # parameter container only (never run on CPU)
-
-    sd = {k: v for k, v in Tree(3, 1).state_dict().items()}
-    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running_" not in k) for k, v in sd.items()}
+    params = _oracle_params()
     opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=1e-5)
     xs, ys, _ = synth.batch(batch, size, size, seed)
     x, y = torch.from_numpy(xs), torch.from_numpy(ys)
@@ -122,27 +139,97 @@ def cpu_step_rate(batch, size, iters, warmup, seed=0):
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
+def gpu_eager_rate(dev, batch, size, mode, iters=4, warmup=2):
+    """The bar SURVEY.md section 2a / 8d names: the same step as stock PyTorch eager on THIS GPU (cuDNN / cuBLAS / cuFFT
+    Blackwell kernels) -- the oracle port on `cuda`, forward + edge_BceDiceLoss + backward + torch.optim.Adam(fused=True).
+    mode 'fp32': plain eager.  mode 'bf16': torch.autocast(bfloat16) + channels_last input and conv weights (cuDNN's
+    tensor-core NHWC path).  cudnn.benchmark on (the faster setting; the reference's train.py:32-33 turns it off).
+    CUDA-event timed; halves the batch on out-of-memory.  Returns a dict or {'error': ...}."""
+    import torch
+
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    torch.backends.cudnn.benchmark = True
+    out = {"mode": mode, "size": size}
+    while batch >= 1:
+        params = opt = x = y = None
+        try:
+            params = _oracle_params(dev)
+            if mode == "bf16":
+                for k, v in params.items():
+                    if v.dim() == 4:
+                        v.data = v.data.contiguous(memory_format=torch.channels_last)
+            opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=1e-5, fused=True)
+            xs, ys, _ = synth.batch(min(batch, 16), size, size, 0)
+            reps = (batch + xs.shape[0] - 1) // xs.shape[0]
+            x = torch.from_numpy(xs).repeat(reps, 1, 1, 1)[:batch].to(dev)
+            y = torch.from_numpy(ys).repeat(reps, 1, 1, 1)[:batch].to(dev)
+            if mode == "bf16":
+                x = x.contiguous(memory_format=torch.channels_last)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                    seg, edges = O.forward(params, x, True, {})
+                loss = O.edge_bce_dice_loss([e.float() for e in edges], seg.float(), y)
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / iters
+            out.update(batch=batch, ms_per_step=ms, value=batch / (ms / 1e3), unit="images/s", loss=float(loss.item()),
+                       peak_mem_gb=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2))
+            return out
+        except torch.OutOfMemoryError:
+            batch //= 2
+        except Exception as e:          # a baseline must never take the bench line down with it
+            out["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+            return out
+        finally:
+            del params, opt, x, y
+            torch.cuda.empty_cache()
+    out["error"] = "out of memory at batch 1"
+    return out
+
+
 def run_reference(args):
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: this arm is rank 0 alone on the whole host
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     # bounded sample: keep (K + W) CPU steps inside ~150 s at ~0.05 img/s/core
     per_step = 150.0 / max(1, args.steps + args.warmup)
-    b = int(max(1, min(8, per_step * 0.055 * cores)))
+    b = int(max(1, min(8, per_step * 0.055 * cores * (256.0 / args.size) ** 2)))
     rate, sec = cpu_step_rate(b, args.size, args.steps, args.warmup)
     line = {
         "metric": "EELUnet train images/sec @%d^2" % args.size, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "EELUnet fp32 fwd+loss+bwd+Adam on host CPU, 3x%dx%d" % (args.size, args.size),
-                   "sample": "batch %d per step (bounded sample of the batch-%d workload)" % (b, args.batch)},
+        "config": _workload(args.precision, world, args.batch, args.size),
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "oracle/eelunet_torch.py, batch %d at %d^2, %d timed steps" % (b, args.size, args.steps)},
+                         "sample": "oracle/eelunet_torch.py on host CPU, fp32 fwd+loss+bwd+Adam, batch %d per step at %d^2 (a bounded "
+                                   "sample of the batch-%d workload; images/s does not depend on N: one host), %d timed steps"
+                                   % (b, args.size, args.batch, args.steps)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # self-check: nothing of the product may be mapped into this process (only oracle/ + torch CPU)
+        "native_so_loaded": sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ROOT in ln and ".so" in ln}),
+        "product_imported": "eel_unet_b200" in sys.modules,
     }
     emit(line)
 
@@ -293,19 +380,35 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "oracle/eelunet_torch.py fp32 fwd+loss+bwd+Adam, batch %d at %d^2, 1 warm-up + 1 timed step" % (b, S)}
 
+    # ---- the real bar: stock PyTorch eager (cuDNN / cuBLAS / cuFFT) on this same GPU, same step, same batch --------------
+    eager = None
+    final_loss = float(loss.item())
+    peak_mem = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        dp.buckets.remove()
+        del dp, opt, model, x_dev, y_dev, loss
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        eager = {"what": "oracle/eelunet_torch.py (the reference's op sequence) as stock PyTorch eager on this GPU: fwd + "
+                         "edge_BceDiceLoss + bwd + torch.optim.Adam(fused=True), cudnn.benchmark on, CUDA-event timed in this process",
+                 "fp32": gpu_eager_rate(dev, B, S, "fp32"),
+                 "bf16_autocast_channels_last": gpu_eager_rate(dev, B, S, "bf16")}
+        for k in ("fp32", "bf16_autocast_channels_last"):
+            if eager[k].get("value"):
+                eager[k]["ours_over_eager"] = round(value / eager[k]["value"], 3)
+
     if rank == 0:
         line = {
             "metric": "EELUnet train images/sec @%d^2" % S, "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "EELUnet %s training (fwd + edge_BceDiceLoss + bwd + Adam%s), batch %d per GPU at 3x%dx%d"
-                                   % (args.precision, " + NCCL allreduce" if world > 1 else "", B, S, S),
-                       "global_batch": world * B, "parallelism": "dp%d" % world,
-                       "l2": "no flush needed: per-step activation working set is GBs >> 126 MB L2"},
+            "config": _workload(args.precision, world, B, S),
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4,
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
-            "loss": float(loss.item()), "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
+            "kernels": breakdown, "loss": final_loss, "peak_mem_gb": peak_mem,
         }
         emit(line)
     if world > 1:
@@ -322,6 +425,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
     ap.add_argument("--profile-shapes", default=None)
     args = ap.parse_args()

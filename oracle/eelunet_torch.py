@@ -97,6 +97,8 @@ def hft(x, mask_range=20):
     same mask is built directly in unshifted frequency order.
     """
     h, w = x.shape[-2:]
+    if x.dtype in (torch.bfloat16, torch.float16):
+        x = x.float()          # torch.fft has no half-precision kernels for these sizes (autocast keeps FFTs in fp32)
     r = min(mask_range, h // 2, w // 2)
     mh = torch.ones(h)
     mw = torch.ones(w)

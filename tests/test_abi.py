@@ -56,3 +56,20 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "/root/reference" not in src, f
+
+
+def test_reference_arm_of_bench_runs_without_the_product():
+    """bench.py --impl reference times the CPU oracle port only: the product package (and so libeel.so) must not even be
+    imported into that process, also under torchrun's OMP_NUM_THREADS=1 it must use every host core."""
+    import json
+    import sys
+
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--size", "32"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["native_so_loaded"] == [] and line["product_imported"] is False
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["workload"].startswith("EELUnet bf16 training")        # the same workload string as the measured arm

@@ -15,11 +15,32 @@ def rel(a, b):
 
 
 def _weights():
-    """Seed-0 default-init weights via the drop-in's parameter tree (same construction order as the reference)."""
-    from eel_unet_b200.model import EELUnet
+    """Seed-0 default-init weights from the oracle's own layer table (oracle/params.py: the reference's construction order)."""
+    from oracle import params
 
     torch.manual_seed(0)
-    return {k: v.clone() for k, v in EELUnet(3, 1).state_dict().items()}
+    return params.eelunet_state_dict(3, 1)
+
+
+def test_drop_in_module_tree_initialises_like_the_oracle_table():
+    """eel_unet_b200.EELUnet / Unet (the nn.Module trees a user constructs) and oracle/params.py draw the same weights
+    from the same seed -- key order, shapes, values."""
+    from eel_unet_b200.model import EELUnet
+    from eel_unet_b200.unet import Unet
+    from oracle import params
+
+    for cin, cout, seed in ((3, 1, 0), (4, 3, 5)):
+        torch.manual_seed(seed)
+        a = EELUnet(cin, cout).state_dict()
+        torch.manual_seed(seed)
+        b = params.eelunet_state_dict(cin, cout)
+        assert list(a.keys()) == list(b.keys()) and len(a) == 365
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    torch.manual_seed(2)
+    a = Unet(3, 2).state_dict()
+    torch.manual_seed(2)
+    b = params.unet_state_dict(3, 2)
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
 
 
 def test_seed0_weights_match_reference_checksums():
