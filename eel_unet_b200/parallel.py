@@ -60,6 +60,8 @@ class GradBuckets:
         for b in self.buckets:
             b.pending = len(b.params)
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._got = set()              # ids of the parameters whose gradient landed this step
+        self.missing = []              # parameters that received no gradient in the step `finish()` closed last
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         if dev.type == "cuda":
             from . import ops
@@ -73,6 +75,7 @@ class GradBuckets:
             # (the backward kernels of eel_unet_b200.ops write most gradients straight into their slot: ops._grad_out)
             slot.copy_(p.grad)
             p.grad = slot                  # the user-visible gradient now lives in the flat buffer
+        self._got.add(id(p))
         b = self._bucket_of[id(p)]
         b.pending -= 1
         if b.pending == 0:
@@ -98,9 +101,17 @@ class GradBuckets:
 
     def finish(self):
         """Call after backward: waits for every bucket; gradients are then the mean over ranks."""
+        # Parameters that received no gradient this step (frozen sub-graph, unused branch): their slot still holds the
+        # PREVIOUS step's (possibly already averaged) gradient.  Zero it before anything reads the flat buffer; the optimizer
+        # skips these parameters altogether, like torch.optim.Adam skips ``p.grad is None``.
+        self.missing = [p for p in self.params if id(p) not in self._got] if len(self._got) != len(self.params) else []
+        for p in self.missing:
+            o, n = self._slot[id(p)]
+            self.flat_grad[o:o + n].zero_()
+        self._got = set()
         for b in self.buckets:
             if b.pending != 0 and self.world > 1:
-                # parameters that received no gradient this step: reduce the bucket anyway so ranks stay in step
+                # reduce the bucket anyway so ranks stay in step
                 self._launch(b)
             if b.work is not None:
                 b.work.wait()
@@ -151,27 +162,119 @@ class DataParallel(torch.nn.Module):
         self.buckets.zero_grad()
 
 
-class FusedAdam:
-    """optim.Adam(lr, weight_decay) with L2-coupled decay (reference train.py:312) as one kernel over the flat buffers."""
+class FusedAdam(torch.optim.Optimizer):
+    """``optim.Adam(model.parameters(), lr, weight_decay=1e-5)`` (reference train.py:312: L2-coupled decay) as ONE kernel over
+    the flat parameter / gradient buffers of a ``GradBuckets``.
+
+    A genuine ``torch.optim.Optimizer``: one ``param_groups`` entry over every parameter, whose ``lr`` / ``betas`` / ``eps`` /
+    ``weight_decay`` are read at every ``step()`` -- so ``StepLR(optimizer, 30, 0.5)`` (train.py:315,118) schedules it -- and
+    ``state_dict()`` / ``load_state_dict()`` in ``torch.optim.Adam``'s own format (``step``, ``exp_avg``, ``exp_avg_sq`` per
+    parameter index), so an optimizer checkpoint moves between the two.  Parameters that received no gradient in a step are
+    skipped (no decay, no moment update, their step count does not advance), like ``torch.optim.Adam`` does for
+    ``p.grad is None``."""
 
     def __init__(self, buckets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
         from . import _lib
 
         self._lib = _lib
         self.b = buckets
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        super().__init__([{"params": list(buckets.params)}], dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.m = torch.zeros_like(buckets.flat_param)
         self.v = torch.zeros_like(buckets.flat_param)
         self.t = 0
+        self._lag = {}                 # id(param) -> number of steps it was skipped in (no gradient)
 
-    def step(self):
-        self.t += 1
+    # hyper-parameters live in param_groups[0] (what LR schedulers rewrite); these names are kept for older callers
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    wd = property(lambda self: self.param_groups[0]["weight_decay"])
+
+    def _ranges(self):
+        """[(start, end, step)] element ranges of the flat buffers to update: everything in ONE range normally; when some
+        parameters have missed gradients (now or earlier) the ranges leave out the ones missing now and carry a per-range
+        step count, exactly like torch.optim.Adam's per-parameter ``state['step']``"""
         b = self.b
-        self._lib.call("eel_adam_step", b.flat_param.data_ptr(), b.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                       b.flat_param.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                       float(self.wd), int(self.t), self._lib.stream())
+        total = b.flat_param.numel()
+        if not b.missing and not self._lag:
+            return [(0, total, self.t)]
+        missing = {id(p) for p in b.missing}
+        out = []
+        for p in sorted(b.params, key=lambda q: b._slot[id(q)][0]):
+            if id(p) in missing:
+                continue
+            o, n = b._slot[id(p)]
+            end = (o + n + 3) // 4 * 4
+            t = self.t - self._lag.get(id(p), 0)
+            if out and out[-1][1] == o and out[-1][2] == t:
+                out[-1] = (out[-1][0], end, t)
+            else:
+                out.append((o, end, t))
+        return out
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.t += 1
+        g = self.param_groups[0]
+        b = self.b
+        for p in b.missing:
+            self._lag[id(p)] = self._lag.get(id(p), 0) + 1
+        if b.flat_param.is_cuda:
+            st = torch.cuda.current_stream(b.flat_param.device).cuda_stream
+            with torch.cuda.device(b.flat_param.device):
+                for lo, hi, t in self._ranges():
+                    if t < 1:
+                        continue
+                    self._lib.call("eel_adam_step", b.flat_param.data_ptr() + 4 * lo, b.flat_grad.data_ptr() + 4 * lo,
+                                   self.m.data_ptr() + 4 * lo, self.v.data_ptr() + 4 * lo, hi - lo, float(g["lr"]),
+                                   float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                   int(t), st)
+        else:
+            raise self._lib.EelError("FusedAdam runs on CUDA only (no CPU fallback)")
         from . import ops
         ops.weights_changed()      # the kernel rewrote the parameters through raw pointers: packed copies are stale
+        return loss
 
     def zero_grad(self, set_to_none=True):
         self.b.zero_grad()
+
+    # ---- checkpointing in torch.optim.Adam's format (the reference saves no optimizer state, train.py:157-197; a user who
+    # adds it gets files that torch.optim.Adam reads, and vice versa)
+    def state_dict(self):
+        state = {}
+        if self.t > 0:
+            for i, p in enumerate(self.b.params):
+                o, n = self.b._slot[id(p)]
+                t = self.t - self._lag.get(id(p), 0)
+                if t < 1:
+                    continue
+                state[i] = {"step": torch.tensor(float(t)), "exp_avg": self.m[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[o:o + n].view(p.shape).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.b.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.b.params):
+            raise ValueError("FusedAdam.load_state_dict: expected one param group over %d parameters" % len(self.b.params))
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = tuple(v) if k == "betas" else v
+        self.m.zero_()
+        self.v.zero_()
+        steps = {}
+        for i, p in enumerate(self.b.params):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            steps[id(p)] = 0 if st is None else int(float(st["step"]))
+            if st is None:
+                continue
+            o, n = self.b._slot[id(p)]
+            self.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+        self.t = max(steps.values()) if steps else 0
+        self._lag = {k: self.t - v for k, v in steps.items() if v != self.t}

@@ -42,3 +42,20 @@ def evaluate_batches(batches):
     dfg = 2 * TP / (2 * TP + FP + FN + e); dbg = 2 * TN / (2 * TN + FP + FN + e)
     ioub = TN / (TN + FP + FN + e)
     return acc, prec, rec, f1, iou, dfg, (iou + ioub) / 2, bf / (cnt + e), (dfg + dbg) / 2
+
+
+def seeded_batches():
+    """the seeded (probabilities, labels) batches shared by tests/golden/make_golden_r2.py (which runs the reference's own
+    evaluate() on them) and the metric tests; includes an empty prediction (boundary precision 0/0 path)"""
+    from . import synth
+
+    rng = np.random.default_rng(0)
+    batches = []
+    for k, (n, h, w) in enumerate([(3, 256, 256), (2, 96, 160), (1, 48, 48)]):
+        _, lab, _ = synth.batch(n, h, w, seed=10 + k)
+        _, other, _ = synth.batch(n, h, w, seed=20 + k)
+        seg = np.clip(0.7 * other + 0.25 * lab + rng.uniform(-0.2, 0.2, size=lab.shape), 0, 1).astype(np.float32)
+        if k == 1:
+            seg[0] = 0.0
+        batches.append((seg, lab))
+    return batches

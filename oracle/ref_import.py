@@ -45,6 +45,7 @@ def load():
     if not available():
         raise RuntimeError("reference not present at %s (it only exists in the build container)" % REFERENCE_ROOT)
     sys.dont_write_bytecode = True
+    import torch  # noqa: F401  (before the stubs: torch's import walks sys.modules with inspect, which chokes on attribute sinks)
     try:
         import torchsummary  # noqa: F401
     except Exception:
@@ -55,7 +56,13 @@ def load():
         mpl = _stub("matplotlib")
         plt = _stub("matplotlib.pyplot")
         sink = _Anything()
-        plt.__getattr__ = lambda name: sink  # type: ignore[attr-defined]
+
+        def _attr(name):
+            if name.startswith("__"):          # inspect.getmodule() probes __file__ etc. on every entry of sys.modules
+                raise AttributeError(name)
+            return sink
+
+        plt.__getattr__ = _attr  # type: ignore[attr-defined]
         mpl.pyplot = plt
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
@@ -73,3 +80,16 @@ def load_module():
     import models.EELUnet as ref_model
 
     return ref_model
+
+
+def load_evaluate():
+    """The reference's ``evaluate`` python module (evaluate.py: ``seg2bnd`` :25, ``boundary_f1_score`` :43, ``evaluate`` :62).
+    Its top-level imports pull in comparison models that need timm / mmcv (not installed, out of scope): those three modules
+    are replaced by empty stubs -- evaluate()'s arithmetic does not touch them."""
+    load()
+    for mod, names in (("models.egeunet", ["EGEUNet"]), ("models.malunet", ["MALUNet"]), ("models.unext", ["UNext", "UNext_S"])):
+        if mod not in sys.modules:
+            _stub(mod, **{n: type(n, (), {}) for n in names})
+    import evaluate as ref_evaluate
+
+    return ref_evaluate

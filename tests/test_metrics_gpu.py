@@ -36,3 +36,30 @@ def test_evaluate_function_signature():
     xs, ys, _ = synth.batch(2, 64, 64, 0)
     out = evaluate(model, [(torch.from_numpy(xs), torch.from_numpy(ys))], "cuda")
     assert len(out) == 9 and all(0.0 <= float(v) <= 1.0 for v in out)
+
+
+def test_metrics_match_reference_evaluate_golden():
+    """the GPU metrics against the 9-tuple the reference's OWN evaluate() returned on the same batches
+    (tests/golden/metrics_eval.npz, made by tests/golden/make_golden_r2.py from evaluate.py:62-124), and the per-sample
+    boundary counts against its seg2bnd()."""
+    import os
+
+    from eel_unet_b200.metrics import SegmentationMetrics
+    from oracle import metrics_np
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_eval.npz"))
+    m = SegmentationMetrics("cuda")
+    batches = metrics_np.seeded_batches()
+    for seg, lab in batches:
+        m.update(torch.from_numpy(seg).cuda(), torch.from_numpy(lab).cuda())
+    got = np.array(m.compute())
+    assert np.abs(got - g["metrics"]).max() <= 1e-12, (got, g["metrics"])
+    ps = torch.cat(m._per_sample).cpu().numpy()
+    k = 0
+    for seg, lab in batches:
+        for i in range(seg.shape[0]):
+            h, w = seg.shape[-2:]
+            pb = np.unpackbits(g["bnd_pred_%d" % k])[:h * w].astype(bool)
+            gb = np.unpackbits(g["bnd_gt_%d" % k])[:h * w].astype(bool)
+            assert tuple(ps[k]) == (int((pb & gb).sum()), int(pb.sum()), int(gb.sum())), k
+            k += 1

@@ -553,3 +553,82 @@ def test_adam_matches_torch():
         _lib.call("eel_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-5,
                   step, _lib.stream())
     assert rel(p, ref_p.detach()) < 1e-6
+
+
+def test_fused_adam_is_a_torch_optimizer_with_steplr_and_checkpoints():
+    """SURVEY 8f-1 / reference train.py:312-315,118: ``optim.Adam(params, lr, weight_decay=1e-5)`` + ``StepLR(optimizer, 30, 0.5)``.
+    FusedAdam must be schedulable by the stock StepLR, follow torch.optim.Adam step for step through the decays, skip
+    parameters without a gradient like torch does, and exchange optimizer checkpoints with torch.optim.Adam in both directions."""
+    from torch.optim.lr_scheduler import StepLR
+
+    from eel_unet_b200.parallel import FusedAdam, GradBuckets
+
+    def net():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(9, 17), torch.nn.Tanh(), torch.nn.Linear(17, 6), torch.nn.Tanh(),
+                                   torch.nn.Linear(6, 2)).to(DEV)
+
+    ref, mine = net(), net()
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-5)
+    rsch = StepLR(ropt, 3, 0.5)
+    gb = GradBuckets(list(mine.parameters()))
+    try:
+        opt = FusedAdam(gb, lr=1e-2, weight_decay=1e-5)
+        assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1
+        sch = StepLR(opt, 3, 0.5)
+        torch.manual_seed(11)
+        saved = None
+        for it in range(10):
+            x = torch.randn(5, 9, device=DEV)
+            skip_last = it in (4, 5)                 # the last layer gets no gradient in these steps
+            for model, o, is_ref in ((ref, ropt, True), (mine, opt, False)):
+                o.zero_grad()
+                h = model[:4](x) if skip_last else model(x)
+                h.pow(2).mean().backward()
+                if not is_ref:
+                    gb.finish()
+                o.step()
+            rsch.step()
+            sch.step()
+            assert abs(opt.param_groups[0]["lr"] - ropt.param_groups[0]["lr"]) < 1e-15
+            for a, b in zip(mine.parameters(), ref.parameters()):
+                assert rel(a.detach(), b.detach()) < 2e-6, it
+            if it == 6:
+                saved = (opt.state_dict(), ropt.state_dict(), [p.detach().clone() for p in mine.parameters()])
+        assert abs(opt.param_groups[0]["lr"] - 1e-2 * 0.5 ** 3) < 1e-12
+
+        # checkpoint round trips: ours -> torch.optim.Adam, torch.optim.Adam -> ours, ours -> ours; one more step must agree
+        mine_sd, ref_sd, params = saved
+        assert set(mine_sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+        for k in range(6):                           # the skipped layer's step count is 2 behind in both
+            assert rel(mine_sd["state"][k]["exp_avg"], ref_sd["state"][k]["exp_avg"]) < 1e-5
+            assert float(mine_sd["state"][k]["step"]) == float(ref_sd["state"][k]["step"]) == (7.0 if k < 4 else 5.0)
+        x = torch.randn(5, 9, device=DEV)
+        outs = []
+        for kind in ("torch<-ours", "ours<-torch", "ours<-ours"):
+            m2 = net()
+            with torch.no_grad():
+                for a, b in zip(m2.parameters(), params):
+                    a.copy_(b)
+            if kind == "torch<-ours":
+                o2 = torch.optim.Adam(m2.parameters(), lr=1.0)
+                o2.load_state_dict(mine_sd)
+                fin = lambda: None
+            else:
+                gb2 = GradBuckets(list(m2.parameters()))
+                o2 = FusedAdam(gb2, lr=1.0)
+                o2.load_state_dict(ref_sd if kind == "ours<-torch" else mine_sd)
+                fin = gb2.finish
+            assert abs(o2.param_groups[0]["lr"] - mine_sd["param_groups"][0]["lr"]) < 1e-15
+            o2.zero_grad()
+            m2(x).pow(2).mean().backward()
+            fin()
+            o2.step()
+            outs.append([p.detach().clone() for p in m2.parameters()])
+            if kind != "torch<-ours":
+                gb2.remove()
+        for other in outs[1:]:
+            for k, (a, b) in enumerate(zip(other, outs[0])):
+                assert rel(a, b) < 2e-6, k
+    finally:
+        gb.remove()

@@ -152,7 +152,12 @@ def test_oracle_matches_live_reference():
     from oracle import eelunet_torch as O
     from oracle import synth
 
-    EELUnet, EdgeLoss, _ = ref_import.load()
+    EELUnet, EdgeLoss, Unet = ref_import.load()
+    torch.manual_seed(1)
+    u = Unet(3, 1).double()
+    xu = torch.randn(1, 3, 32, 48, dtype=torch.float64)
+    with torch.no_grad():
+        assert rel(O.unet_forward(u.state_dict(), xu), u(xu)) < 1e-12        # models/Unet.py:58-98
     torch.manual_seed(0)
     m = EELUnet(3, 1).double().train()
     sd = {k: v.clone() for k, v in m.state_dict().items()}
@@ -187,3 +192,87 @@ def test_resize_oracle_matches_pillow_goldens():
         assert np.array_equal(R.resize_bilinear_u8(g[name + "_mask"], oh, ow), g[name + "_mask_resized"])
         assert np.array_equal(R.preprocess_image(g[name + "_img"], (oh, ow)), g[name + "_img_tensor"])
         assert np.array_equal(R.preprocess_mask(g[name + "_mask"], (oh, ow)), g[name + "_mask_tensor"])
+
+
+def test_metrics_oracle_matches_reference_evaluate_golden():
+    """oracle/metrics_np.py against what the reference's OWN evaluate() / seg2bnd() / boundary_f1_score() returned
+    (evaluate.py:25-124, run by tests/golden/make_golden_r2.py)."""
+    from oracle import metrics_np
+
+    g = np.load(os.path.join(GOLD, "metrics_eval.npz"))
+    batches = metrics_np.seeded_batches()
+    got = np.array(metrics_np.evaluate_batches(batches))
+    assert np.abs(got - g["metrics"]).max() <= 1e-15, (got, g["metrics"])
+    k = 0
+    for seg, lab in batches:
+        for i in range(seg.shape[0]):
+            pred = (seg[i, 0] > 0.5).astype(np.float32)
+            assert np.array_equal(np.packbits(metrics_np.seg2bnd(pred)), g["bnd_pred_%d" % k])
+            assert np.array_equal(np.packbits(metrics_np.seg2bnd(lab[i, 0])), g["bnd_gt_%d" % k])
+            assert abs(metrics_np.boundary_f1(lab[i, 0], pred) - g["boundary_f1"][k]) <= 1e-15
+            k += 1
+
+
+def test_metrics_oracle_matches_live_reference_evaluate():
+    from oracle import ref_import
+
+    if not ref_import.available():
+        pytest.skip("reference only exists in the build container")
+    from oracle import metrics_np
+
+    ev = ref_import.load_evaluate()
+
+    class Passthrough:
+        name = "eelunet"
+
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return x, []
+
+    rng = np.random.default_rng(5)
+    batches = []
+    for (n, h, w) in [(2, 64, 80), (1, 33, 47)]:
+        lab = (rng.uniform(size=(n, 1, h, w)) > 0.6).astype(np.float32)
+        lab = (torch.nn.functional.avg_pool2d(torch.from_numpy(lab), 5, 1, 2) > 0.5).float().numpy()
+        seg = np.clip(lab * 0.6 + rng.uniform(0, 0.6, size=lab.shape), 0, 1).astype(np.float32)
+        batches.append((seg, lab))
+    ref = ev.evaluate(Passthrough(), [(torch.from_numpy(s), torch.from_numpy(l)) for s, l in batches], torch.device("cpu"))
+    got = metrics_np.evaluate_batches(batches)
+    assert max(abs(a - b) for a, b in zip(got, ref)) <= 1e-15
+
+
+def test_unet_oracle_matches_reference_golden_and_live_reference():
+    """oracle.unet_forward against models/Unet.py: committed fp64 fixture, and the live module when present."""
+    from oracle import eelunet_torch as O
+    from oracle import params, ref_import, synth
+
+    g = np.load(os.path.join(GOLD, "unet_2x64x96.npz"))
+    torch.manual_seed(0)
+    sd = {k: v.double().requires_grad_(True) for k, v in params.unet_state_dict(3, 1).items()}
+    xs, ys, _ = synth.batch(2, 64, 96, 1)
+    x, y = torch.from_numpy(xs).double(), torch.from_numpy(ys).double()
+    out = O.unet_forward(sd, x)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    assert rel(out.detach(), g["logits"]) < 1e-12 and abs(loss.item() - float(g["loss"])) < 1e-13
+    for n, gn, gs in zip([str(s) for s in g["grad_names"]], g["grad_norm"], g["grad_sum"]):
+        assert abs(sd[n].grad.norm().item() - gn) <= 1e-9 * gn + 1e-15, n
+        assert abs(sd[n].grad.sum().item() - gs) <= 1e-8 * gn * sd[n].numel() ** 0.5 + 1e-15, n
+    for key in g.files:
+        if key.startswith("grad:"):
+            assert rel(sd[key[5:]].grad, g[key]) < 1e-9, key
+    if ref_import.available():
+        _, _, Unet = ref_import.load()
+        torch.manual_seed(4)
+        m = Unet(3, 2).double()
+        x2 = torch.randn(1, 3, 48, 80, dtype=torch.float64)
+        ref = m(x2)
+        ref.pow(2).mean().backward()
+        sd2 = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        got = O.unet_forward(sd2, x2)
+        got.pow(2).mean().backward()
+        assert rel(got.detach(), ref.detach()) < 1e-12
+        for n, p in m.named_parameters():
+            assert rel(sd2[n].grad, p.grad) < 1e-9, n

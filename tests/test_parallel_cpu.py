@@ -81,3 +81,49 @@ def test_single_process_buckets_and_views():
     assert all((p.detach() - 1.0).abs().max() < 10 for p in net.parameters())   # ... is seen through the parameters
     gb.zero_grad()
     assert all(p.grad is None for p in net.parameters())
+
+
+def test_fused_adam_optimizer_contract_on_cpu():
+    """Host logic of FusedAdam without launching the kernel: it is a torch.optim.Optimizer whose single param group StepLR
+    rewrites, and its state_dict()/load_state_dict() speak torch.optim.Adam's format."""
+    from torch.optim.lr_scheduler import StepLR
+
+    from eel_unet_b200.parallel import FusedAdam, GradBuckets
+
+    net, ref = _net(), _net()
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-5)
+    for _ in range(3):
+        ropt.zero_grad()
+        ref(torch.randn(4, 7)).pow(2).mean().backward()
+        ropt.step()
+    gb = GradBuckets(list(net.parameters()))
+    opt = FusedAdam(gb, lr=1e-3, weight_decay=1e-5)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sch = StepLR(opt, 30, 0.5)                                    # reference train.py:315
+    assert opt.state_dict()["state"] == {}
+    opt.load_state_dict(ropt.state_dict())
+    assert opt.t == 3
+    back = opt.state_dict()
+    assert back["param_groups"][0]["params"] == list(range(6)) and back["param_groups"][0]["weight_decay"] == 1e-5
+    for i, st in ropt.state_dict()["state"].items():
+        assert torch.equal(back["state"][i]["exp_avg"], st["exp_avg"]) and torch.equal(back["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+        assert float(back["state"][i]["step"]) == 3.0
+    fresh = torch.optim.Adam(_net().parameters(), lr=1.0)
+    fresh.load_state_dict(back)                                   # torch.optim.Adam accepts our checkpoint
+    assert fresh.param_groups[0]["lr"] == 1e-3
+    # ranges the kernel would update when the middle layer got no gradient
+    gb.missing = [list(net.parameters())[2]]
+    r = opt._ranges()
+    o, n = gb._slot[id(gb.missing[0])]
+    assert all(hi <= o or lo >= o + n for lo, hi, _ in r) and sum(hi - lo for lo, hi, _ in r) == gb.flat_param.numel() - (n + 3) // 4 * 4
+    assert all(t == 3 for _, _, t in r)
+    gb.missing = []
+    assert opt._ranges() == [(0, gb.flat_param.numel(), 3)]
+    opt._lag = {id(list(net.parameters())[2]): 2}                 # a parameter that missed two steps runs two steps behind
+    r = opt._ranges()
+    assert sum(hi - lo for lo, hi, _ in r) == gb.flat_param.numel() and sorted({t for _, _, t in r}) == [1, 3]
+    assert float(opt.state_dict()["state"][2]["step"]) == 1.0
+    opt._lag = {}
+    import pytest
+    with pytest.raises(Exception):
+        opt.step()                                                # no CPU fallback for the update kernel
