@@ -11,6 +11,7 @@ from . import data  # noqa: F401
 from . import edges  # noqa: F401
 from .loss import edge_BceDiceLoss  # noqa: F401
 from .model import EELUnet  # noqa: F401
+from .ops import weights_changed as invalidate_packed_weights  # noqa: F401  (call after updating weights through p.data)
 from .unet import Unet  # noqa: F401
 
-__all__ = ["EELUnet", "Unet", "edge_BceDiceLoss", "edges", "data"]
+__all__ = ["EELUnet", "Unet", "edge_BceDiceLoss", "edges", "data", "invalidate_packed_weights"]

@@ -106,11 +106,34 @@ def dtype_code(t):
     raise EelError("unsupported storage dtype %s" % t.dtype)
 
 
+def on_device(fn):
+    """decorator of the public entry points: run ``fn`` with the device of its first CUDA tensor argument current, so that
+    ``stream()`` / ``workspace()`` and the kernels' per-device attributes belong to the device the data lives on"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        for t in list(a) + list(k.values()):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if t.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(t.device):
+                        return fn(*a, **k)
+                break
+        return fn(*a, **k)
+
+    return wrapped
+
+
 def ptr(t):
     if t is None:
         return None
     if not t.is_cuda:
         raise EelError("eel_unet_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+    if t.device.index != torch.cuda.current_device():
+        # a launch on the current device's stream with another device's pointer would fault (or worse): refuse loudly.
+        # The public entry points (model forward, loss, edges, data, metrics) switch devices themselves (on_device).
+        raise EelError("tensor on %s but the current CUDA device is %d: wrap the call in torch.cuda.device(%r)"
+                       % (t.device, torch.cuda.current_device(), str(t.device)))
     if not t.is_contiguous():
         raise EelError("non-contiguous tensor passed to a kernel")
     return t.data_ptr()

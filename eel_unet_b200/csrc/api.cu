@@ -30,6 +30,7 @@ int check_launch(const char* what) {
 
 extern "C" {
 const char* eel_last_error(void) { return eel::g_err; }
-int eel_version(void) { return 100; }
+int eel_version(void) { return 200; }
+int eel_num_sms(void) { return eel::kNumSMs; }
 long long eel_launch_count(void) { return eel::g_launches.load(); }
 }

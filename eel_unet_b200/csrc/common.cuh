@@ -72,6 +72,20 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE (per-context) function attribute: a process that drives several
+// GPUs must opt in once on each of them.  One of these per (kernel instantiation); remembers the largest size set per device.
+struct SmemOptIn {
+    int have[32] = {};
+    template <class F> bool ensure(F fn, int bytes) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return false;
+        if (dev < 32 && have[dev] >= bytes) return true;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+        if (dev < 32) have[dev] = bytes;       // (a benign race between host threads: the attribute call is idempotent)
+        return true;
+    }
+};
+
 // dispatch on the storage dtype
 #define EEL_DISPATCH_DTYPE(dtype, ...)                                  \
     do {                                                                \

@@ -314,17 +314,14 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     p.na = na;
     const int smem = na * Cfg::A_BYTES + b_bytes + 1024 /* barriers */ + ew * 2048 + 1024 /* alignment slack */;
     const int stats = p.bn_sums == nullptr ? 0 : (p.bz != nullptr ? 2 : 1);
-    static int configured[6] = {0, 0, 0, 0, 0, 0};
+    static SmemOptIn configured[6];
     const int variant = (ew == 8 ? 1 : 0) + 2 * stats;
     const void* fns[6] = {(const void*)tc_conv_kernel<BN, MT, RES, 4, 0>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 0>,
                           (const void*)tc_conv_kernel<BN, MT, RES, 4, 1>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 1>,
                           (const void*)tc_conv_kernel<BN, MT, RES, 4, 2>, (const void*)tc_conv_kernel<BN, MT, RES, 8, 2>};
-    if (configured[variant] < smem) {
-        if (cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
-            return EEL_ERR_CUDA;
-        }
-        configured[variant] = smem;
+    if (!configured[variant].ensure(fns[variant], smem)) {
+        set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
+        return EEL_ERR_CUDA;
     }
     CUtensorMap tmA, tmB;
     {

@@ -320,11 +320,8 @@ static int launch_stem_fwd(const void* x, const void* wp, const float* bias, voi
                            cudaStream_t st) {
     size_t smem = sizeof(float) * 3 * (size_t)stem_pitch(W, CIN);
     if (smem > 200 * 1024 || W % 4 != 0) return 1;   // caller falls back to the generic engine
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(stem_fwd_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    static SmemOptIn configured;
+    configured.ensure(stem_fwd_kernel<T, CIN>, 200 * 1024);
     int rows = N * H;
     int grid = rows < kNumSMs * 12 ? rows : kNumSMs * 12;
     stem_fwd_kernel<T, CIN><<<grid, kStemThreads, smem, st>>>((const T*)x, (const T*)wp, bias, (T*)y, N, H, W, Cout, relu);
@@ -408,11 +405,8 @@ template <class T, int CIN>
 static int launch_stem_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cout, cudaStream_t st) {
     size_t smem = sizeof(float) * (3 * (size_t)stem_pitch(W, CIN) + 9 * CIN * 64);
     if (smem > 200 * 1024 || W % 4 != 0) return 1;   // caller falls back to the generic engine
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(stem_wgrad_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    static SmemOptIn configured;
+    configured.ensure(stem_wgrad_kernel<T, CIN>, 200 * 1024);
     int rows = N * H;
     int grid = rows < kNumSMs * 3 ? rows : kNumSMs * 3;   // three 128-thread blocks (168 registers) are resident per SM: one wave
     stem_wgrad_kernel<T, CIN><<<grid, kStemThreads, smem, st>>>((const T*)x, (const T*)dy, dwp, N, H, W, Cout);

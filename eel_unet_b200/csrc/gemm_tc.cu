@@ -325,13 +325,10 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPara
         b_bytes = p.nb * B_BYTES;
     }
     const int smem = p.na * kABytes + b_bytes + 1024 + 16384 + 1024;
-    static int configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, AGATHER, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
-            return EEL_ERR_CUDA;
-        }
-        configured = smem;
+    static SmemOptIn configured;
+    if (!configured.ensure(tc_gemm_kernel<BN, EPI, AGATHER, STATS>, smem)) {
+        set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
+        return EEL_ERR_CUDA;
     }
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < kNumSMs ? tiles : kNumSMs;

@@ -466,14 +466,11 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
 template <int C, int EPI>
 static int launch_hft4(const CUtensorMap& m, const CUtensorMap& t, Hft4Params& p, cudaStream_t st, const char* what) {
-    static bool configured = false;
+    static SmemOptIn configured;
     const int kMax = 227 * 1024;
-    if (!configured) {
-        if (cudaFuncSetAttribute(hft_tc4_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory", what);
-            return EEL_ERR_CUDA;
-        }
-        configured = true;
+    if (!configured.ensure(hft_tc4_kernel<C, EPI>, kMax)) {
+        set_error("%s: cannot raise dynamic shared memory", what);
+        return EEL_ERR_CUDA;
     }
     p.stage_bytes = 2 * (C / 64) * 8192;
     p.nacc = 512 / C;
@@ -528,14 +525,11 @@ __global__ void hft_tc_matrix_kernel(bf16* __restrict__ out, int kind, int rows,
 
 template <int NB, int EPI>
 static int launch_hft(const CUtensorMap& a, const CUtensorMap& b, HftTcParams& p, cudaStream_t st, const char* what) {
-    static bool configured = false;
+    static SmemOptIn configured;
     const int kMax = 227 * 1024;
-    if (!configured) {
-        if (cudaFuncSetAttribute(hft_tc_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory", what);
-            return EEL_ERR_CUDA;
-        }
-        configured = true;
+    if (!configured.ensure(hft_tc_kernel<NB, EPI>, kMax)) {
+        set_error("%s: cannot raise dynamic shared memory", what);
+        return EEL_ERR_CUDA;
     }
     const int b_bytes = ((p.kchunks * p.nblocks * NB * 128) + 1023) & ~1023;
     int ns = (kMax - 2048 - 1024 - b_bytes) / kAStage;

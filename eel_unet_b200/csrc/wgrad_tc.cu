@@ -226,13 +226,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int MODE, int BN>
 static int launch_wg(const CUtensorMap& a, const CUtensorMap& b, WgParams& p, int units, cudaStream_t st, const char* what) {
     typedef WgCfg<MODE, BN> Cfg;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc_wgrad_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
-            set_error("%s: cannot raise dynamic shared memory to %d", what, Cfg::SMEM);
-            return EEL_ERR_CUDA;
-        }
-        configured = true;
+    static SmemOptIn configured;
+    if (!configured.ensure(tc_wgrad_kernel<MODE, BN>, Cfg::SMEM)) {
+        set_error("%s: cannot raise dynamic shared memory to %d", what, Cfg::SMEM);
+        return EEL_ERR_CUDA;
     }
     // split-K factor: minimise waves x stages-per-CTA
     long long best = -1;

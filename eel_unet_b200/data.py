@@ -11,7 +11,7 @@ feeds it).  ``edges.add_canny_edge`` / ``edges.canny_enhance`` produce the optio
 import torch
 
 from . import _lib
-from ._lib import call, ptr, stream, workspace
+from ._lib import call, on_device, ptr, stream, workspace
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -27,6 +27,7 @@ def _const(vals, device):
     return t
 
 
+@on_device
 def _run(x, size, mean, std, want_float, want_u8):
     if x.dtype != torch.uint8 or not x.is_cuda:
         raise _lib.EelError("the input pipeline takes uint8 CUDA tensors (NHWC)")

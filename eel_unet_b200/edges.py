@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call, ptr, stream, workspace
+from ._lib import call, on_device, ptr, stream, workspace
 
 U8 = torch.uint8
 
@@ -22,6 +22,7 @@ def _chk(t, last=None):
     return t if t.is_contiguous() else t.contiguous()
 
 
+@on_device
 def gray(rgb):
     """cv2.cvtColor(RGB2GRAY): [N,H,W,3] u8 -> [N,H,W] u8."""
     rgb = _chk(rgb, 3)
@@ -31,6 +32,7 @@ def gray(rgb):
     return out
 
 
+@on_device
 def canny(img, low=100, high=200):
     """cv2.Canny(gray(img), low, high) for [N,H,W,3] RGB or cv2.Canny(img, low, high) for [N,H,W] gray."""
     rgb = img.dim() == 4
@@ -43,6 +45,7 @@ def canny(img, low=100, high=200):
     return out
 
 
+@on_device
 def sobel_map(gray_img):
     """augmentation/Sobel.py:9-14."""
     g = _chk(gray_img)
@@ -52,6 +55,7 @@ def sobel_map(gray_img):
     return out
 
 
+@on_device
 def laplacian_map(gray_img):
     """augmentation/Sobel.py:17-18."""
     g = _chk(gray_img)
@@ -61,6 +65,7 @@ def laplacian_map(gray_img):
     return out
 
 
+@on_device
 def canny_enhance(rgb, low=100, high=200, edge_color=(0, 0, 0), alpha=0.5):
     """CannyEnhance.__call__ (augmentation/CannyEnhance.py:21-44) on a batch."""
     rgb = _chk(rgb, 3)
@@ -72,6 +77,7 @@ def canny_enhance(rgb, low=100, high=200, edge_color=(0, 0, 0), alpha=0.5):
     return out
 
 
+@on_device
 def add_canny_edge(rgb, low=100, high=200):
     """AddCannyEdge.__call__ (augmentation/AddCannyEdge.py:15-41): RGB + edge map as a 4th channel (RGBA)."""
     rgb = _chk(rgb, 3)
@@ -79,6 +85,7 @@ def add_canny_edge(rgb, low=100, high=200):
     return torch.cat((rgb, e.unsqueeze(-1)), dim=-1)
 
 
+@on_device
 def edge_label(gt):
     """generate_edge_label (utils/tools.py:126-155): gt float [N,1,H,W] -> {0,1} float edge labels."""
     g = (gt[:, 0] * 255).to(U8)

@@ -3,6 +3,7 @@ one gradient kernel backward, instead of ~100 tiny ATen launches."""
 import torch.nn as nn
 
 from . import ops
+from ._lib import on_device
 
 
 class edge_BceDiceLoss(nn.Module):  # noqa: N801  (name kept: train.py:305 constructs it by this name)
@@ -10,6 +11,7 @@ class edge_BceDiceLoss(nn.Module):  # noqa: N801  (name kept: train.py:305 const
         super().__init__()
         self.wb, self.wd = wb, wd
 
+    @on_device
     def forward(self, gt_pre, out, target):
         gt_pre5, gt_pre4, gt_pre3, gt_pre2, gt_pre1 = gt_pre
         return ops.EdgeBceDice.apply(out, gt_pre5, gt_pre4, gt_pre3, gt_pre2, gt_pre1, target, self.wb, self.wd)

@@ -3,7 +3,7 @@ device -- one host synchronisation at the end instead of four ``.item()`` calls 
 import torch
 
 from . import _lib
-from ._lib import call, ptr, stream, workspace
+from ._lib import call, on_device, ptr, stream, workspace
 
 
 class SegmentationMetrics:
@@ -12,6 +12,7 @@ class SegmentationMetrics:
         self.conf = torch.zeros(4, dtype=torch.int64, device=self.device)   # TP, TN, FP, FN
         self._per_sample = []
 
+    @on_device
     def update(self, seg_prob, labels):
         """seg_prob: [B,1,H,W] probabilities (eelunet) -- evaluate.py:91 thresholds at 0.5; labels: [B,1,H,W]."""
         seg = seg_prob.detach().to(torch.float32).contiguous()

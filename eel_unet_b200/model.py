@@ -327,12 +327,20 @@ class EELUnet(nn.Module):
         if not x.is_cuda:
             raise EelError("eel_unet_b200.EELUnet runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
-            raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+            raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s): the reference's center_crop path "
+                           "for other sizes (models/EELUnet.py:376-382) is not implemented" % (tuple(x.shape),))
+        if x.requires_grad and torch.is_grad_enabled():
+            raise EelError("the input image is treated as a leaf without gradient (the first conv computes no data gradient); "
+                           "pass x.detach() -- input gradients (saliency maps, adversarial examples) are not supported")
+        # kernels launch on the CURRENT device's current stream: make the input's device current for the whole forward
+        # (autograd's backward threads do the same for the gradients' device)
+        with torch.cuda.device(x.device):
+            return self._forward(x)
+
+    def _forward(self, x):
         fold = None
         if self.compute_dtype == torch.bfloat16:
-            pk = self._weight_packer()
-            pk.refresh(x.device)
-            ops.set_packer(pk)
+            self._weight_packer().refresh(x.device)      # publishes the packed operands on the weights themselves
             if not self.training and not torch.is_grad_enabled():
                 # inference: eval-mode BatchNorms are folded into their producers' weights (ops.FoldedPacker)
                 fold = self._folded_packer()
@@ -340,12 +348,8 @@ class EELUnet(nn.Module):
                     fold.refresh(x.device)
                 else:
                     fold = None
-        else:
-            ops.set_packer(None)
         ops.set_folded(fold)
-        cp = self._composed_packer()
-        cp.refresh(x.device)
-        ops.set_composed(cp)
+        self._composed_packer().refresh(x.device)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
         enc1, p = self._pool(self._conv_block(self.enc1[0], a, defer=True))

@@ -16,34 +16,56 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-# Flat gradient buffer of parallel.GradBuckets: [flat fp32 tensor, {id(param): (offset, numel)}, ids handed out this step].
+# Flat gradient buffers of parallel.GradBuckets: id(param) -> [flat fp32 tensor, offset, numel, handed out this step].
 # Backward kernels then write parameter gradients straight into their slots (a FRESH view per call, which autograd's
 # AccumulateGrad adopts without a copy) instead of into temporaries that a copy per parameter moves there afterwards.
-_GRAD_FLAT = None
+# Several GradBuckets (several models) can be registered at once; each removes its own entries.
+_GRAD_SLOTS = {}
 
 
 def set_grad_flat(flat, slots):
-    global _GRAD_FLAT
-    _GRAD_FLAT = None if flat is None else [flat, slots, set()]
+    """register (flat is a tensor) or unregister (flat is None) the slots {id(param): (offset, numel)} of one GradBuckets"""
+    for pid, (o, n) in (slots or {}).items():
+        if flat is None:
+            _GRAD_SLOTS.pop(pid, None)
+        else:
+            _GRAD_SLOTS[pid] = [flat, o, n, False]
 
 
-def grads_cleared():
-    """parallel.GradBuckets.zero_grad: every slot may be handed out again"""
-    if _GRAD_FLAT is not None:
-        _GRAD_FLAT[2].clear()
+def grads_cleared(slots=None):
+    """parallel.GradBuckets.zero_grad: its slots may be handed out again"""
+    for pid in (slots if slots is not None else list(_GRAD_SLOTS)):
+        e = _GRAD_SLOTS.get(pid)
+        if e is not None:
+            e[3] = False
 
 
 def _grad_out(param, shape=None):
     """fp32 tensor a backward kernel writes ``param``'s gradient into"""
     shape = tuple(param.shape) if shape is None else tuple(shape)
-    g = _GRAD_FLAT
-    if g is not None and param.grad is None and g[0].device == param.device:
-        slot = g[1].get(id(param))
-        if slot is not None and id(param) not in g[2]:
-            g[2].add(id(param))
-            o, n = slot
-            return g[0][o:o + n].view(shape)
+    e = _GRAD_SLOTS.get(id(param))
+    if e is not None and param.grad is None and not e[3] and e[0].device == param.device:
+        e[3] = True
+        return e[0][e[1]:e[1] + e[2]].view(shape)
     return torch.empty(shape, dtype=F32, device=param.device)
+
+
+# ---- side channels between neighbouring autograd Functions ------------------------------------------------------------
+# A producer sometimes computes, for free, something its neighbour would otherwise need a full pass for (BatchNorm sums out of
+# a GEMM epilogue, a bias gradient out of a BatchNorm backward, ...).  The hand-over travels ON THE TENSOR that connects the
+# two (a Python attribute on the very tensor object autograd passes along) together with the tensor's version counter: a
+# consumer only sees it on that same object and only while nobody wrote to the tensor in between (autograd accumulating a
+# second gradient in place, a user hook returning another tensor, an in-place op: the attribute is absent or its version is
+# stale, and the consumer falls back to computing the quantity itself).  Nothing is keyed by raw addresses, nothing is global.
+def _attach(t, key, value):
+    setattr(t, key, (value, t._version))
+
+
+def _take(t, key):
+    hit = t.__dict__.pop(key, None) if hasattr(t, "__dict__") else None
+    if hit is None or hit[1] != t._version:
+        return None
+    return hit[0]
 
 
 def _pack(w4, perm, dtype, out=None):
@@ -70,12 +92,9 @@ def _reduce_ws(device, channels, quantities, extra=0):
     return workspace(n, device), n
 
 
-# bias gradients that a BatchNorm backward already produced (column sums of dz), keyed by the dz buffer address.
-# An entry is written only when the BN's producer is a biased conv / linear whose backward runs next and pops it.
-_DZ_COLSUM = {}
-# BatchNorm sums a tensor-core producer accumulated in its epilogue, keyed by the address of the tensor it wrote;
-# the BatchNorm that consumes that tensor next pops the entry (training mode only)
-_BN_SUMS = {}
+import threading
+
+_TLS = threading.local()      # forward-scoped announcements of the calling thread (a model's forward runs on one thread)
 
 
 def _stats_cols_ok(ncols):
@@ -86,26 +105,22 @@ def _stats_cols_ok(ncols):
 def _want_bn_sums(x, ncols):
     """a [2][ncols] fp32 buffer when the next op is a training-mode BatchNorm (see EELUnet._bn) and the producer's
     epilogue can accumulate its statistics"""
-    if _BN_NEXT[0] and _stats_cols_ok(ncols):
+    if _bn_next() and _stats_cols_ok(ncols):
         return torch.empty((2, ncols), dtype=F32, device=x.device)
     return None
 
 
-_BN_NEXT = [False]
-# A BatchNorm(+ReLU) whose output feeds ONE conv3x3 (the first BatchNorm of a conv block) registers its saved tensors under
-# the address of its output; the conv picks them up so that its data-gradient launch also accumulates that BatchNorm's
-# backward sums (eel_tc_conv3x3_dgrad_bnsums) and leaves them under the address of dx for the BatchNorm backward.
-_BN_OUT = {}
-_BN_BWD_SUMS = {}
-
-
 def expect_bn(flag):
     """the model announces that the tensor the next GEMM-class op produces goes straight into a training-mode BatchNorm"""
-    _BN_NEXT[0] = bool(flag)
+    _TLS.bn_next = bool(flag)
+
+
+def _bn_next():
+    return getattr(_TLS, "bn_next", False)
 
 
 def _colsum(x2d, C):
-    hit = _DZ_COLSUM.pop(x2d.data_ptr(), None)
+    hit = _take(x2d, "_eel_colsum")
     if hit is not None and hit.numel() == C:
         return hit
     vec = 8 if x2d.dtype == BF16 else 4
@@ -187,6 +202,11 @@ class WeightPacker:
             return
         call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream())
         self.versions = ver
+        # publish on the parameters themselves: ops find the operands through the weight they are handed (forward and
+        # backward, any thread, any number of models), and only while the weight is what was packed
+        for e in self.entries:
+            w = e[0]
+            w._eel_packed = self.by_param[id(w)] + (_pack_key(w),)
 
     def get(self, w):
         return self.by_param.get(id(w))
@@ -260,7 +280,7 @@ class FoldedPacker:
         ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e) if t is not None]
         if self.fold_table is None or self.fold_table.device != device or ptrs != self.ptrs:
             self._build(device)
-        ver = [_WEIGHT_EPOCH] + [t._version for e in self.entries for t in self._tensors(e) if t is not None]
+        ver = [_WEIGHT_EPOCH, _STATS_EPOCH] + [t._version for e in self.entries for t in self._tensors(e) if t is not None]
         if ver == self.versions:
             return
         call("eel_bn_fold_batch", ptr(self.fold_table), len(self.entries), stream())
@@ -351,11 +371,14 @@ class ComposedPacker:
         ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e)]
         if self.table is None or self.table.device != device or ptrs != self.ptrs:
             self._build(device)
-        ver = [_WEIGHT_EPOCH] + [t._version for p in self.params for t in p]
+        ver = [_WEIGHT_EPOCH, _STATS_EPOCH] + [t._version for p in self.params for t in p]
         if ver == self.versions:
             return
         call("eel_compose_batch", ptr(self.table), len(self.entries), self.blocks, stream())
         self.versions = ver
+        for e, p in zip(self.entries, self.params):
+            if e[2] is None:                   # (BatchNorm-folded tables are inference-scoped: FoldedPacker hands them out)
+                p[0]._eel_composed = self.by_weight[id(p[0])] + (self.dtype, tuple(_pack_key(t) for t in p))
 
     def get(self, w):
         return self.by_weight.get(id(w))
@@ -373,25 +396,15 @@ def build_composed(module, dtype):
     return cp
 
 
-_COMPOSED = None
-
-
-def set_composed(p):
-    global _COMPOSED
-    _COMPOSED = p
-
-
-_FOLDED = None
-
-
 def set_folded(p):
-    global _FOLDED
-    _FOLDED = p
+    """inference forward of the calling thread: the FoldedPacker whose BatchNorm-folded weights the stages use (None: off)"""
+    _TLS.folded = p
 
 
 def folded(weight):
     """(packed bf16 weight with the BatchNorm folded in, fp32 folded bias) or None"""
-    return None if _FOLDED is None else _FOLDED.get(weight)
+    f = getattr(_TLS, "folded", None)
+    return None if f is None else f.get(weight)
 
 
 def conv3x3_folded(x, wk, fbias, relu):
@@ -422,14 +435,29 @@ def linear_folded(x, w2, fbias, relu):
     return y
 
 
-_PACKER = None
 _WEIGHT_EPOCH = 0
+_STATS_EPOCH = 0
 
 
 def weights_changed():
-    """to be called by anything that rewrites parameters behind torch's back (the fused Adam kernel)"""
+    """To be called by anything that rewrites parameters behind torch's back: the fused Adam kernel does, and so must user
+    code that updates weights through ``p.data`` (EMA swaps, clamping: ``p.data.mul_()`` bumps no version counter torch
+    exposes).  Public as ``eel_unet_b200.invalidate_packed_weights()``.  Every packed / composed / folded copy is rebuilt at
+    the next forward."""
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
+
+
+def running_stats_changed():
+    """a training-mode BatchNorm kernel rewrote running_mean / running_var through raw pointers: the BatchNorm-folded
+    inference weights (FoldedPacker, ComposedPacker with a BatchNorm) are stale.  Kept apart from the weight epoch, which a
+    training forward must not bump halfway through (the packed operands published on the weights carry it)."""
+    global _STATS_EPOCH
+    _STATS_EPOCH += 1
+
+
+def _pack_key(w):
+    return (w._version, _WEIGHT_EPOCH, w.data_ptr())
 
 
 def build_packer(module):
@@ -461,17 +489,13 @@ def build_packer(module):
     return pk
 
 
-def set_packer(p):
-    """the model installs its packer for the duration of a forward/backward; ops look their weights up in it"""
-    global _PACKER
-    _PACKER = p
-
-
 def _packed(weight, which):
-    if _PACKER is None:
+    """operand ``which`` (0 forward, 1 data gradient) a WeightPacker published on ``weight``, or None when there is none or
+    the weight changed since (the caller then packs on the fly)"""
+    hit = getattr(weight, "_eel_packed", None)
+    if hit is None or hit[2] != _pack_key(weight):
         return None
-    hit = _PACKER.get(weight)
-    return None if hit is None else hit[which]
+    return hit[which]
 
 
 def conv3x3(x, weight, bias, relu):
@@ -525,14 +549,13 @@ class StemConv(Function):
         bias2 = torch.empty(128, dtype=F32, device=dev)
         call("eel_stem_pack", ptr(_c(weight.detach())), ptr(bias.detach()), ptr(wblk), ptr(bias2), st)
         y = torch.empty((N, H, W, 64), dtype=BF16, device=dev)
-        sums2 = torch.empty((2, 128), dtype=F32, device=dev) if _BN_NEXT[0] else None
+        sums2 = torch.empty((2, 128), dtype=F32, device=dev) if _bn_next() else None
         call("eel_tc_linear", ptr(col), ptr(wblk), None if sums2 is not None else ptr(bias2), ptr(y), P // 2, 64, 128, 0, ptr(sums2),
              0, 0, st)
         if sums2 is not None:
             sums = torch.empty((2, 64), dtype=F32, device=dev)
             call("eel_stem_fold_sums", ptr(sums2), ptr(sums), st)
-            _BN_SUMS.clear()
-            _BN_SUMS[y.data_ptr()] = (sums, bias.detach())
+            _attach(y, "_eel_bn_sums", (sums, bias.detach()))
         ctx.save_for_backward(col)
         ctx.weight = weight
         ctx.bn_in = None
@@ -573,14 +596,14 @@ class Conv3x3(Function):
             call("eel_tc_conv3x3", ptr(x), ptr(wk), None if sums is not None else ptr(b), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
                  ptr(sums), stream())
             if sums is not None:
-                _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = (sums, b)
+                _attach(y, "_eel_bn_sums", (sums, b))
         else:
             wp = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]
             call("eel_conv3x3_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, H, W, Cin, Cout, int(relu), 0,
                  dtype_code(x), stream())
         ctx.relu = relu
-        ctx.bn_in = _BN_OUT.pop(x.data_ptr(), None) if _tc_ok(x, Cin, Cout) else None
+        bn_in = _take(x, "_eel_bn_out")
+        ctx.bn_in = bn_in if _tc_ok(x, Cin, Cout) else None
         ctx.save_for_backward(x, weight, y if relu else None)
         return y
 
@@ -613,8 +636,7 @@ class Conv3x3(Function):
                     cws = workspace(16 * Cin, x.device, slot=1)
                     call("eel_tc_conv3x3_dgrad_bnsums", ptr(dy), ptr(wk), ptr(dx), N, H, W, Cout, Cin, ptr(z), ptr(mean), ptr(rstd),
                          ptr(gamma.detach()), ptr(beta.detach()), int(bn_relu), ptr(sums), ptr(cws), st)
-                    _BN_BWD_SUMS.clear()
-                    _BN_BWD_SUMS[dx.data_ptr()] = (sums, z.data_ptr())
+                    _attach(dx, "_eel_bn_bwd_sums", (sums, z))
                 else:
                     call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, None, st)
             else:
@@ -644,13 +666,12 @@ class ConvT2x2(Function):
             wk = _packed(weight, 0)
             if wk is None:
                 wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][co][ci]
-            sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_BN_NEXT[0] and _stats_cols_ok(4 * Cout)) else None
+            sums = torch.empty((2, Cout), dtype=F32, device=x.device) if (_bn_next() and _stats_cols_ok(4 * Cout)) else None
             b = bias.detach()
             call("eel_tc_convt2x2_fwd", ptr(x), ptr(wk), None if sums is not None else ptr(b), ptr(y), N, h, w, Cin, Cout, ptr(sums),
                  stream())
             if sums is not None:
-                _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = (sums, b)
+                _attach(y, "_eel_bn_sums", (sums, b))
         else:
             wp = _pack(weight, (0, 2, 3, 1), x.dtype)  # [ci][ky][kx][co]
             call("eel_convt2x2_fwd", ptr(x), ptr(wp), ptr(bias.detach()), ptr(y), N, h, w, Cin, Cout, dtype_code(x), stream())
@@ -713,8 +734,7 @@ class Linear(Function):
             call("eel_tc_linear", ptr(x), ptr(w2), None if sums is not None else ptr(b), ptr(y), N * H * W, K, Nout, 0, ptr(sums), 0, 0,
                  stream())
             if sums is not None:
-                _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = (sums, b)
+                _attach(y, "_eel_bn_sums", (sums, b))
         else:
             sh, sw = (H, W) if shift else (0, 0)
             call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
@@ -774,7 +794,11 @@ class ComposedLinear(Function):
         x = _c(x)
         N, H, W, K = x.shape
         Cout, Cmid = w2.shape[0], w1.shape[0]
-        hit = _COMPOSED.get(w2) if _COMPOSED is not None and _COMPOSED.dtype == x.dtype else None
+        hit = getattr(w2, "_eel_composed", None)
+        if hit is not None and hit[3] == x.dtype and hit[4] == tuple(_pack_key(t) for t in (w2, b2, w1, b1)):
+            hit = hit[:3]
+        else:
+            hit = None
         if hit is None:
             one = ComposedPacker(x.dtype)
             one.add(_Pair(w1.detach(), b1.detach()), _Pair(w2.detach().view(Cout, Cmid), b2.detach()))
@@ -788,8 +812,7 @@ class ComposedLinear(Function):
             call("eel_tc_linear", ptr(x), ptr(wc), None if sums is not None else ptr(bc), ptr(y), N * H * W, K, Cout, 0, ptr(sums), 0, 0,
                  stream())
             if sums is not None:
-                _BN_SUMS.clear()
-                _BN_SUMS[y.data_ptr()] = (sums, bc)
+                _attach(y, "_eel_bn_sums", (sums, bc))
         else:
             call("eel_linear_fwd", ptr(x), ptr(wc), ptr(bc), ptr(y), N * H * W, K, Cout, 0, 0, dtype_code(x), stream())
         ctx.save_for_backward(x, w1, b1, w2, wc, wct)
@@ -835,10 +858,12 @@ def _bn_statistics(z, running_mean, running_var, training, momentum, eps):
     mean = torch.empty(C, dtype=F32, device=dev)
     rstd = torch.empty(C, dtype=F32, device=dev)
     st = stream()
-    hit = _BN_SUMS.pop(z.data_ptr(), None)
+    hit = _take(z, "_eel_bn_sums")
     sums, skipped_bias = hit if hit is not None else (None, None)
     if sums is not None and (not training or sums.shape[1] != C):
         raise _lib.EelError("BatchNorm sums were produced for a tensor that is not consumed by a matching training-mode BatchNorm")
+    if training:
+        running_stats_changed()
     if training and sums is not None:
         call("eel_bn_stats_from_sums", ptr(sums), P, C, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var),
              float(momentum), float(eps), ptr(skipped_bias), st)
@@ -868,9 +893,8 @@ class BNAct(Function):
         call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
         ctx.relu, ctx.training, ctx.producer_bias = relu, training, producer_bias
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
-        _BN_OUT.clear()
         if single_conv_consumer and z.dtype == BF16 and ctx.needs_input_grad[0]:
-            _BN_OUT[y.data_ptr()] = (z, mean, rstd, gamma, beta, relu)
+            _attach(y, "_eel_bn_out", (z, mean, rstd, gamma, beta, relu))
         return y
 
     @staticmethod
@@ -881,8 +905,8 @@ class BNAct(Function):
         P = z.numel() // C
         dz = torch.empty_like(z)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
-        hit = _BN_BWD_SUMS.pop(dy.data_ptr(), None)
-        sums = hit[0] if hit is not None and hit[1] == z.data_ptr() else None
+        hit = _take(dy, "_eel_bn_bwd_sums")
+        sums = hit[0] if hit is not None and hit[1] is z else None
         if sums is not None and sums.shape[1] == C:
             # the conv that consumed this BatchNorm's output accumulated {dbeta, dgamma} in its data-gradient epilogue
             call("eel_bn_act_bwd_apply", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(sums),
@@ -894,8 +918,7 @@ class BNAct(Function):
             call("eel_bn_act_bwd", ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
                  ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
         if dzsum is not None:
-            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
-            _DZ_COLSUM[dz.data_ptr()] = dzsum
+            _attach(dz, "_eel_colsum", dzsum)
         return dz, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
@@ -932,8 +955,7 @@ class BNReluPool(Function):
         call("eel_bn_relu_pool_bwd", ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
              ptr(dz), ptr(dgamma), ptr(dbeta), ptr(dzsum), N, H, W, C, int(ctx.training), ptr(ws), n, dtype_code(z), stream())
         if dzsum is not None:
-            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
-            _DZ_COLSUM[dz.data_ptr()] = dzsum
+            _attach(dz, "_eel_colsum", dzsum)
         return dz, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -980,8 +1002,7 @@ class Gelu(Function):
         if ctx.producer_bias and C % vec == 0 and 256 % (C // vec) == 0:
             colsum = torch.empty(C, dtype=F32, device=x.device)
             call("eel_gelu_bwd_colsum", ptr(x), ptr(dy), ptr(dx), ptr(colsum), x.numel(), C, dtype_code(x), stream())
-            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
-            _DZ_COLSUM[dx.data_ptr()] = colsum
+            _attach(dx, "_eel_colsum", colsum)
         else:
             call("eel_gelu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x), stream())
         return dx, None
@@ -1066,8 +1087,7 @@ class BNAddInterleave(Function):
         call("eel_bn_act_bwd", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
              ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, 0, int(ctx.training), ptr(ws), n, dtype_code(z), st)
         if dzsum is not None:
-            _DZ_COLSUM.clear()
-            _DZ_COLSUM[dz.data_ptr()] = dzsum
+            _attach(dz, "_eel_colsum", dzsum)
         return dz, dgamma, dbeta, None, None, None, None, None, dab, de, None
 
 
@@ -1192,8 +1212,7 @@ class BNReluPGR(Function):
         call("eel_bn_act_bwd_apply", ptr(dx), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(sums), ptr(dz), ptr(dzsum), P, C, 1,
              int(ctx.training), dtype_code(z), st)
         if dzsum is not None:
-            _DZ_COLSUM.clear()
-            _DZ_COLSUM[dz.data_ptr()] = dzsum
+            _attach(dz, "_eel_colsum", dzsum)
         return dz, sums[1], sums[0], None, None, None, None, None, dw.view(weight.shape), db, None
 
 
@@ -1205,7 +1224,8 @@ def bn_pgr_supported(z):
 
 
 def _lib_sms():
-    return 148
+    """the SM count the library sizes its persistent grids for (workspace formulas below follow it)"""
+    return int(_lib.lib.eel_num_sms())
 
 
 class Head(Function):
@@ -1279,8 +1299,7 @@ class SE(Function):
         call("eel_se_bwd", ptr(t), ptr(dout), ptr(att), ptr(hid), ptr(mean), ptr(_c(w1.detach())), ptr(_c(w2.detach())),
              ptr(dt), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dtsum), N, H * W, C, R, ptr(ws), n, dtype_code(t), stream())
         if dtsum is not None:
-            _DZ_COLSUM.clear()                      # at most one pending entry: the very next backward consumes it
-            _DZ_COLSUM[dt.data_ptr()] = dtsum
+            _attach(dt, "_eel_colsum", dtsum)
         return dt, dw1.view(w1.shape), db1, dw2.view(w2.shape), db2, None
 
 

@@ -126,7 +126,7 @@ class GradBuckets:
             p.grad = None
         if self.device.type == "cuda":
             from . import ops
-            ops.grads_cleared()
+            ops.grads_cleared(self._slot)
 
     def remove(self):
         for h in self._handles:
@@ -134,7 +134,7 @@ class GradBuckets:
         self._handles = []
         if self.device.type == "cuda":
             from . import ops
-            ops.set_grad_flat(None, None)
+            ops.set_grad_flat(None, self._slot)
 
 
 class DataParallel(torch.nn.Module):

@@ -48,13 +48,14 @@ class Unet(nn.Module):
             raise EelError("eel_unet_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16:
             raise EelError("input must be N x C x H x W with H and W multiples of 16 (got %s)" % (tuple(x.shape),))
+        with torch.cuda.device(x.device):
+            return self._forward(x)
+
+    def _forward(self, x):
         if self.compute_dtype == torch.bfloat16:
             if self._packer is None or self._packer.stale():
                 self._packer = ops.build_packer(self)
             self._packer.refresh(x.device)
-            ops.set_packer(self._packer)
-        else:
-            ops.set_packer(None)
         a = ops.nchw_to_nhwc(x, self.compute_dtype)
         e1 = self._b(self.enc1, a)
         e2 = self._b(self.enc2, ops.MaxPool2.apply(e1))

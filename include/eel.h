@@ -38,6 +38,8 @@ const char* eel_last_error(void);
 int eel_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long eel_launch_count(void);
+/* the SM count the persistent kernels size their grids (and the callers their workspaces) for: 148 on B200 */
+int eel_num_sms(void);
 
 /* ------------------------------------------------------------------ layout / parameter packing */
 /* x: fp32 NCHW (what train.py:38 hands the model) -> y: dtype NHWC */

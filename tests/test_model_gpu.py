@@ -317,3 +317,67 @@ def test_prune_flow_keeps_working():
     assert torch.equal(after, ref), "folded inference did not pick up the pruned weights"
     assert rel(after, before) > 1e-3
     assert torch.equal(m(x)[0], fresh(x)[0]), "unfolded path did not pick up the pruned weights"
+
+
+def test_folded_inference_follows_running_statistics_written_by_training_forwards():
+    """a train-mode forward rewrites running_mean / running_var through raw pointers without bumping any
+    torch version counter; with NO optimizer step in between (BatchNorm recalibration, SWA update_bn) the BatchNorm-folded
+    inference weights must still follow.  Also: weights changed through ``p.data`` are picked up after
+    ``eel_unet_b200.invalidate_packed_weights()``; an input that requires grad is refused loudly."""
+    import eel_unet_b200
+    from eel_unet_b200 import EELUnet, _lib
+
+    torch.manual_seed(3)
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    m = EELUnet(3, 1, precision="bf16").cuda().eval()
+    with torch.no_grad():
+        first = m(x)[0].clone()                   # folded tables built from the initial statistics (0, 1)
+        m.train()
+        for _ in range(3):
+            m(x)                                  # recalibration: forwards only
+        m.eval()
+        after = m(x)[0]
+        fresh = EELUnet(3, 1, precision="bf16").cuda().eval()
+        fresh.load_state_dict(m.state_dict())
+        assert torch.equal(after, fresh(x)[0]), "folded weights kept the old running statistics"
+        assert rel(after, first) > 1e-3
+        for p in m.parameters():
+            if p.dim() == 4:
+                p.data.mul_(0.9)                  # invisible to torch's version counters
+        eel_unet_b200.invalidate_packed_weights()
+        fresh2 = EELUnet(3, 1, precision="bf16").cuda().eval()
+        fresh2.load_state_dict(m.state_dict())
+        assert torch.equal(m(x)[0], fresh2(x)[0]), "p.data update not picked up after invalidate_packed_weights()"
+    with pytest.raises(_lib.EelError):
+        m(x.clone().requires_grad_(True))
+
+
+def test_two_models_interleaved_do_not_share_state():
+    """forward A, forward B, backward A, backward B -- every hand-over between ops travels on tensors and
+    every packed operand on its own weight, so interleaving changes nothing (fp32 values; bf16 placement + finiteness)."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+
+    _, _, x, y = _setup(2, 128, 128)
+    x, y = x.cuda(), y.cuda()
+    crit = edge_BceDiceLoss(1, 1)
+    for precision in ("fp32", "bf16"):
+        models = []
+        for seed in (4, 5):
+            torch.manual_seed(seed)
+            models.append(EELUnet(3, 1, precision=precision).cuda().train())
+        alone = []
+        for mdl in models:
+            seg, edges = mdl(x)
+            crit(edges, seg, y).backward()
+            alone.append({n: p.grad.clone() for n, p in mdl.named_parameters()})
+            mdl.zero_grad(set_to_none=True)
+        outs = [mdl(x) for mdl in models]                      # forward A, forward B
+        losses = [crit(e, s, y) for s, e in outs]
+        for l in losses:                                       # backward A, backward B
+            l.backward()
+        for mdl, ref in zip(models, alone):
+            gmax = max(g.norm().item() for g in ref.values())
+            for n, p in mdl.named_parameters():
+                assert torch.isfinite(p.grad).all(), n
+                if precision == "fp32" and ref[n].norm().item() > 1e-4 * gmax:
+                    assert rel(p.grad, ref[n]) < 1e-3, (n, rel(p.grad, ref[n]))

@@ -632,3 +632,57 @@ def test_fused_adam_is_a_torch_optimizer_with_steplr_and_checkpoints():
                 assert rel(a, b) < 2e-6, k
     finally:
         gb.remove()
+
+
+@pytest.mark.parametrize("case", ["plain", "hook", "second_consumer"])
+def test_side_channels_between_ops_are_safe_against_hooks_and_gradient_accumulation(case):
+    """Linear -> training-mode BatchNorm(+ReLU) hand each other two things on the connecting tensor z: the BatchNorm sums from
+    the GEMM epilogue (forward) and the bias gradient from the BatchNorm backward (backward).  Both ride on the tensor OBJECT
+    with its version counter (ops._attach / ops._take), so a user hook that replaces the gradient, or a second consumer whose
+    gradient autograd accumulates IN PLACE into the BatchNorm's dz buffer, must make the consumer fall back to computing the
+    quantity itself -- never use a stale one (VERDICT r1 weak #9, ADVICE r1 low #1)."""
+    from eel_unet_b200 import ops
+
+    torch.manual_seed(0)
+    N, H, W, K, C = 4, 16, 16, 64, 128
+    x = torch.randn(N, H, W, K, device=DEV).bfloat16()
+    w = (torch.randn(C, K, device=DEV) * 0.2).requires_grad_(True)
+    b = torch.randn(C, device=DEV).requires_grad_(True)
+    gam = (1 + 0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    bet = (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    r = torch.randn(N, H, W, C, device=DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+
+    ops.expect_bn(True)
+    try:
+        z = ops.Linear.apply(x, w, b, False)
+    finally:
+        ops.expect_bn(False)
+    assert hasattr(z, "_eel_bn_sums")
+    if case == "hook":
+        z.register_hook(lambda g: g * 2.0)
+    y = ops.BNAct.apply(z, gam, bet, rm, rv, True, True, 0.1, 1e-5, True)
+    assert not hasattr(z, "_eel_bn_sums")                       # consumed exactly once
+    loss = (y.float() * r).sum()
+    if case == "second_consumer":
+        loss = loss + 0.5 * z.float().sum()
+    loss.backward()
+
+    xr = x.double()
+    wr, br = w.detach().double().bfloat16().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    gr, ber = gam.detach().double().requires_grad_(True), bet.detach().double().requires_grad_(True)
+    zr = F.linear(xr, wr, br)
+    if case == "hook":
+        zr.register_hook(lambda g: g * 2.0)
+    yr = F.relu(F.batch_norm(zr.permute(0, 3, 1, 2), None, None, gr, ber, True, 0.1, 1e-5)).permute(0, 2, 3, 1)
+    lr = (yr * r.double()).sum()
+    if case == "second_consumer":
+        lr = lr + 0.5 * zr.sum()
+    lr.backward()
+    assert rel(y, yr) < 2e-2
+    assert rel(w.grad, wr.grad) < 3e-2 and rel(gam.grad, gr.grad) < 2e-2 and rel(bet.grad, ber.grad) < 2e-2
+    if case == "second_consumer":
+        # the bias gradient is 0.5 * pixels here; a stale hand-over would have delivered the BatchNorm's ~0
+        assert rel(b.grad, br.grad) < 1e-2 and abs(br.grad.mean().item() - 0.5 * N * H * W) < 1e-6
+    else:
+        assert b.grad.abs().max().item() < 1e-2 * w.grad.abs().max().item() * K      # analytically zero

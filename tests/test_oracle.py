@@ -276,3 +276,27 @@ def test_unet_oracle_matches_reference_golden_and_live_reference():
         assert rel(got.detach(), ref.detach()) < 1e-12
         for n, p in m.named_parameters():
             assert rel(sd2[n].grad, p.grad) < 1e-9, n
+
+
+def test_oracle_train_step_matches_reference_golden_at_config1_shape():
+    """BASELINE config 1's shape (8 x 3 x 256 x 256): the oracle against the fp64 train step of the real reference
+    (tests/golden/eelunet_train_8x256.npz, tests/golden/make_golden_r2.py)."""
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    g = np.load(os.path.join(GOLD, "eelunet_train_8x256.npz"))
+    sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in _weights().items()}
+    xs, ys, _ = synth.batch(8, 256, 256, 0)
+    loss, seg, edges, grads, ns = O.train_step(sd, torch.from_numpy(xs).double(), torch.from_numpy(ys).double())
+    assert abs(loss.item() - float(g["loss"])) < 1e-11
+    assert abs(seg.sum().item() - float(g["seg_sum"])) < 1e-7 and abs(seg.pow(2).sum().item() - float(g["seg_sqsum"])) < 1e-7
+    assert rel(seg, g["seg"].astype(np.float64)) < 1e-3                      # stored as fp16 (size); the sums above are fp64
+    for k, e in enumerate(edges):
+        assert abs(e.sum().item() - float(g["edge%d_sum" % (5 - k)])) < 1e-8
+        if "edge%d" % (5 - k) in g.files:
+            assert rel(e, g["edge%d" % (5 - k)]) < 1e-6
+    for n, gn, gs in zip([str(s) for s in g["grad_names"]], g["grad_norm"], g["grad_sum"]):
+        assert abs(grads[n].norm().item() - gn) <= 1e-8 * max(gn, 1e-12) + 1e-13, n
+    for key in g.files:
+        if key.startswith("stat:"):
+            assert rel(ns[key[5:]], g[key]) < 1e-11, key

@@ -1,0 +1,280 @@
+"""Whole-path parity (GPU) AT THE SHAPES THAT ARE BENCHMARKED (BASELINE.json configs): 8 x 3 x 256^2 (config 1 / the per-GPU
+tile shapes of config 3), 2 x 3 x 512^2 (config 4's image size: the `tall` / MT=2 conv tiles, 256-wide HFT planes) and
+1 x 3 x 1024^2 inference (config 5: the 1024-wide HFT, 32-bit offset paths) -- forward, loss, gradients, running statistics,
+against (a) the fp64 train step of the REAL reference stored in tests/golden/eelunet_train_8x256.npz and (b) the fp64 oracle.
+
+The fp64 oracle is run on the GPU here (same oracle/eelunet_torch.py code, device = cuda: cuDNN / cuFFT fp64) because these
+sizes take minutes on the host; `test_oracle_on_cuda_equals_the_pinned_cpu_oracle` pins that configuration to the reference
+fixture the CPU oracle is pinned to.
+
+Bars: the north_star's literal tolerances (probabilities 1e-4 fp32 / 2e-2 bf16, gradients 1e-3, Dice 1e-3) wherever the
+problem is well conditioned, else max(bar, k x the reference's own fp32-vs-fp64 deviation stored in the fixture) -- see
+tests/test_model_gpu.py's docstring and DESIGN.md section 5.  `test_bf16_train_forward_meets_the_literal_bar_on_conditioned_weights`
+shows the literal 2e-2 in TRAIN mode once the weights have left the default initialisation.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ["seg", "edge5", "edge4", "edge3", "edge2", "edge1"]
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _weights(seed=0):
+    from oracle import params
+
+    torch.manual_seed(seed)
+    return params.eelunet_state_dict(3, 1)
+
+
+def _oracle_cuda(sd, x, y, dtype, autocast=False):
+    """oracle train step on the GPU in `dtype`; everything comes back on the host"""
+    from oracle import eelunet_torch as O
+
+    dev = torch.device("cuda")
+    sdd = {k: (v.to(dev, dtype) if v.dtype.is_floating_point else v.to(dev)) for k, v in sd.items()}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False           # the yardstick is the reference's fp32 arithmetic, not TF32
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running_" not in k) for k, v in sdd.items()}
+            ns = {}
+            seg, edges = O.forward(params, x.to(dev, dtype), True, ns)
+        loss = O.edge_bce_dice_loss([e.float() if autocast else e for e in edges], seg.float() if autocast else seg, y.to(dev, dtype))
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    grads = {k: v.grad.cpu() for k, v in params.items() if v.requires_grad and v.grad is not None}
+    return loss.detach().cpu(), seg.detach().float().cpu() if autocast else seg.detach().cpu(), \
+        [e.detach().float().cpu() if autocast else e.detach().cpu() for e in edges], grads, {k: v.cpu() for k, v in ns.items()}
+
+
+def _ours(sd, x, y, precision):
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+
+    model = EELUnet(3, 1, precision=precision)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    seg, edges = model(x.cuda())
+    loss = edge_BceDiceLoss(1, 1)(edges, seg, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return model, loss, seg, edges
+
+
+def test_oracle_on_cuda_equals_the_pinned_cpu_oracle():
+    """oracle/eelunet_torch.py with device = cuda, fp64, against the fixture the real reference produced (2 x 128^2)."""
+    from oracle import synth
+
+    g = np.load(os.path.join(GOLD, "eelunet_train_2x128.npz"))
+    xs, ys, _ = synth.batch(2, 128, 128, 0)
+    loss, seg, edges, grads, ns = _oracle_cuda(_weights(), torch.from_numpy(xs), torch.from_numpy(ys), torch.float64)
+    assert abs(loss.item() - float(g["loss"])) < 1e-10
+    assert rel(seg, g["seg"]) < 1e-6
+    for n, gn in zip([str(s) for s in g["grad_names"]], g["grad_norm"]):
+        assert abs(grads[n].norm().item() - gn) <= 1e-7 * max(gn, 1e-12) + 1e-12, n
+    for key in g.files:
+        if key.startswith("stat:"):
+            assert rel(ns[key[5:]], g[key]) < 1e-10, key
+
+
+def _grad_report(model, g64, g32):
+    """(all-parameter rel L2 of ours, of the yardstick, worst tensor, median ratio to the yardstick, per-tensor list)"""
+    num = num32 = den = 0.0
+    per = []
+    gnorm = max(v.norm().item() for v in g64.values())
+    for name, p in model.named_parameters():
+        t = g64[name].double()
+        if t.norm().item() < 1e-6 * gnorm:
+            continue                                   # analytically zero (bias in front of a train-mode BatchNorm): noise only
+        mine = rel(p.grad, t)
+        floor = rel(g32[name], t) if g32 is not None else float("nan")
+        per.append((name, mine, floor))
+        num += (p.grad.double().cpu() - t).pow(2).sum().item()
+        if g32 is not None:
+            num32 += (g32[name].double() - t).pow(2).sum().item()
+        den += t.pow(2).sum().item()
+    return (num / den) ** 0.5, (num32 / den) ** 0.5, per
+
+
+def test_fp32_train_step_8x256_against_the_reference_fixture():
+    """config 1's shape against the REAL reference's fp64 train step (no oracle in the loop): probabilities, loss, running
+    statistics, gradient norms.  Yardstick = the reference's own fp32 deviations stored next to the fp64 values."""
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    g = np.load(os.path.join(GOLD, "eelunet_train_8x256.npz"))
+    xs, ys, _ = synth.batch(8, 256, 256, 0)
+    x, y = torch.from_numpy(xs), torch.from_numpy(ys)
+    model, loss, seg, edges = _ours(_weights(), x, y, "fp32")
+    e_seg = abs(seg.double().sum().item() - float(g["seg_sum"])) / float(g["seg_sum"])
+    r_seg = rel(seg, g["seg"].astype(np.float64))
+    print("8x256 fp32 vs reference fixture: seg rel %.3e (fixture fp16-rounded), sum rel %.3e, reference fp32 itself %.3e; loss %.8f vs %.8f"
+          % (r_seg, e_seg, float(g["seg_f32_relerr"]), loss.item(), float(g["loss"])))
+    assert r_seg <= 6e-4                                # the fixture stores seg as fp16 (2^-11 relative)
+    assert e_seg <= 1e-4
+    assert abs(loss.item() - float(g["loss"])) <= max(1e-4 * float(g["loss"]), 3 * float(g["loss_f32_abserr"]))
+    for k, e in enumerate(edges):
+        key = "edge%d" % (5 - k)
+        if key in g.files:
+            assert rel(e, g[key]) <= max(1e-4, 3 * float(g[key + "_f32_relerr"])), key
+        assert abs(e.double().sum().item() - float(g[key + "_sum"])) <= 1e-4 * float(g[key + "_sum"]), key
+    assert abs(O.dice_metric(seg.cpu(), y) - O.dice_metric(torch.from_numpy(g["seg"].astype(np.float32)), y)) <= 1e-3
+    sd_after = model.state_dict()
+    for key in g.files:
+        if key.startswith("stat:"):
+            assert rel(sd_after[key[5:]], g[key]) <= 1e-4, key
+    grads = dict(model.named_parameters())
+    names = [str(s) for s in g["grad_names"]]
+    gmax = float(g["grad_norm"].max())
+    bad = []
+    for n, gn, floor in zip(names, g["grad_norm"], g["grad_f32_relerr"]):
+        if gn < 1e-6 * gmax:
+            continue
+        d = abs(grads[n].grad.norm().item() - gn) / gn
+        if d > max(1e-3, 3 * floor):
+            bad.append((n, d, floor))
+    assert not bad, bad[:5]
+    for key in g.files:
+        if key.startswith("grad:") and np.linalg.norm(g[key]) > 1e-6 * gmax:
+            n = key[5:]
+            floor = float(g["grad_f32_relerr"][names.index(n)])
+            if floor < 0.05:
+                assert rel(grads[n].grad, g[key]) <= max(1e-3, 5 * floor), (n, rel(grads[n].grad, g[key]), floor)
+
+
+@pytest.mark.parametrize("shape", [(8, 256, 256), (2, 512, 512)], ids=["8x256", "2x512"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_at_benchmark_shapes_matches_fp64_oracle(shape, precision):
+    """forward + loss + every gradient tensor + running statistics against the fp64 oracle; the yardstick is the oracle in the
+    reference's own precision (fp32, or stock torch.autocast(bfloat16) for bf16 mode) on the same GPU."""
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    n, h, w = shape
+    xs, ys, _ = synth.batch(n, h, w, 0)
+    if precision == "bf16":
+        ys = synth.soften(ys)
+    x, y = torch.from_numpy(xs), torch.from_numpy(ys)
+    sd = _weights()
+    l64, seg64, e64, g64, ns64 = _oracle_cuda(sd, x, y, torch.float64)
+    lY, segY, eY, gY, nsY = _oracle_cuda(sd, x, y, torch.float32, autocast=(precision == "bf16"))
+    model, loss, seg, edges = _ours(sd, x, y, precision)
+
+    base_p = 1e-4 if precision == "fp32" else 2e-2
+    base_g = 1e-3 if precision == "fp32" else 5e-2
+    mult = 3 if precision == "fp32" else 1.5
+    errs = {nm: (rel(a, b), rel(c, b)) for nm, a, b, c in zip(NAMES, [seg] + list(edges), [seg64] + e64, [segY] + eY)}
+    print("%s %s: " % (shape, precision) + ", ".join("%s ours %.2e / yardstick %.2e" % (k, v[0], v[1]) for k, v in errs.items()))
+    for nm, (mine, floor) in errs.items():
+        assert mine <= max(base_p, mult * floor), (nm, mine, floor)
+    assert abs(loss.item() - l64.item()) <= max(base_p * abs(l64.item()), mult * abs(lY.item() - l64.item()))
+    if precision == "fp32":
+        assert abs(O.dice_metric(seg.cpu(), y) - O.dice_metric(seg64, y)) <= 1e-3
+    sd_after = model.state_dict()
+    for k, v in ns64.items():
+        if "num_batches" in k:
+            assert int(sd_after[k]) == int(v)
+        else:
+            assert rel(sd_after[k], v) <= (1e-4 if precision == "fp32" else max(2e-2, mult * rel(nsY[k], v))), k
+    tot, totY, per = _grad_report(model, g64, gY)
+    ratios = [m / max(f, 1e-7) for _, m, f in per]
+    print("%s %s gradients: all-parameter rel L2 ours %.3e / yardstick %.3e; worst tensor %.3e; median ratio %.2f"
+          % (shape, precision, tot, totY, max(m for _, m, _ in per), float(np.median(ratios))))
+    assert tot <= max(base_g, 2 * totY)
+    assert float(np.median(ratios)) <= 2.0
+    for name, mine, floor in per:
+        if floor < 0.05:
+            assert mine <= max(base_g, (5 if precision == "fp32" else 2.5) * floor), (name, mine, floor)
+
+
+def test_eval_forward_1024_matches_fp64_oracle():
+    """config 5's image size (1 x 3 x 1024^2, inference): fp32 1e-4, bf16 (BatchNorm-folded inference path) 2e-2."""
+    from eel_unet_b200 import EELUnet
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    sd = _weights(1)
+    # running statistics away from (0, 1), like a trained checkpoint
+    gen = torch.Generator().manual_seed(3)
+    for k, v in sd.items():
+        if k.endswith("running_mean"):
+            v.copy_(0.1 * torch.randn(v.shape, generator=gen))
+        elif k.endswith("running_var"):
+            v.copy_(0.5 + torch.rand(v.shape, generator=gen))
+    xs, _, _ = synth.batch(1, 1024, 1024, 2)
+    x = torch.from_numpy(xs)
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        seg64, e64 = O.forward({k: (v.to(dev, torch.float64) if v.dtype.is_floating_point else v.to(dev)) for k, v in sd.items()},
+                               x.to(dev, torch.float64), False)
+    for precision, bar in (("fp32", 1e-4), ("bf16", 2e-2)):
+        m = EELUnet(3, 1, precision=precision)
+        m.load_state_dict(sd)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            seg, edges = m(x.cuda())
+        errs = [rel(a, b) for a, b in zip([seg] + list(edges), [seg64] + e64)]
+        print("1x1024 eval %s: " % precision + ", ".join("%s %.2e" % (n, e) for n, e in zip(NAMES, errs)))
+        assert tuple(seg.shape) == (1, 1, 1024, 1024) and [e.shape[-1] for e in edges] == [64, 128, 256, 512, 1024]
+        assert max(errs) <= bar, (precision, errs)
+        del m
+
+
+def test_bf16_train_forward_meets_the_literal_bar_on_conditioned_weights():
+    """north_star: "forward ... within 2e-2 in bf16 mode".  At default initialisation a TRAIN-mode forward is chaotic in any
+    16-bit arithmetic (the reference's own autocast is ~24 % off, tests/test_model_gpu.py); once the weights have taken a few
+    Adam steps (fp32 path, reference hyper-parameters train.py:226-228,312: lr 1e-4, wd 1e-5, batch 8 at 256^2) the same
+    train-mode forward meets the literal bar against the fp64 oracle.  tools/bf16_conditioning.py prints the whole curve."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss
+    from eel_unet_b200.parallel import DataParallel, FusedAdam
+    from oracle import eelunet_torch as O
+    from oracle import synth
+
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = EELUnet(3, 1, precision="fp32").to(dev).train()
+    dp = DataParallel(model)
+    try:
+        opt = FusedAdam(dp.buckets, lr=1e-4, weight_decay=1e-5)
+        crit = edge_BceDiceLoss(1, 1)
+        pool = [synth.batch(8, 256, 256, seed=100 + k)[:2] for k in range(4)]
+        pool = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in pool]
+        for step in range(CONDITIONING_STEPS):
+            xb, yb = pool[step % len(pool)]
+            dp.zero_grad()
+            seg, edges = dp(xb)
+            crit(edges, seg, yb).backward()
+            dp.finish_backward()
+            opt.step()
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    finally:
+        dp.buckets.remove()
+    xs, _, _ = synth.batch(8, 256, 256, seed=7)
+    x = torch.from_numpy(xs)
+    with torch.no_grad():
+        seg64, e64 = O.forward({k: (v.to(dev, torch.float64) if v.dtype.is_floating_point else v.to(dev)) for k, v in sd.items()},
+                               x.to(dev, torch.float64), True, {})
+        m = EELUnet(3, 1, precision="bf16")
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        seg, edges = m(x.cuda())
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            segA, eA = O.forward({k: v.to(dev) for k, v in sd.items()}, x.to(dev), True, {})
+    errs = [rel(a, b) for a, b in zip([seg] + list(edges), [seg64] + e64)]
+    errsA = [rel(a.float(), b) for a, b in zip([segA] + list(eA), [seg64] + e64)]
+    print("bf16 train-mode forward after %d fp32 Adam steps: " % CONDITIONING_STEPS +
+          ", ".join("%s ours %.2e / autocast %.2e" % (n, a, b) for n, a, b in zip(NAMES, errs, errsA)))
+    assert errs[0] <= 2e-2, errs                      # the segmentation output: the literal north_star bar
+    assert max(errs) <= 2e-2, errs                    # ... and every side output
+
+
+CONDITIONING_STEPS = 60
