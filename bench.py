@@ -168,11 +168,22 @@ def gpu_eager_rate(dev, batch, size, mode, iters=4, warmup=2):
             if mode == "bf16":
                 x = x.contiguous(memory_format=torch.channels_last)
 
+            def bce_dice(p, t):
+                """utils/Loss.py:28-73 with the ops the reference itself calls (nn.BCELoss: its backward is finite at saturated
+                probabilities, which bf16 produces; the oracle's hand-written log form is not)"""
+                n = p.shape[0]
+                p2, t2 = p.reshape(n, -1), t.reshape(n, -1)
+                dice = 1 - ((2 * (p2 * t2).sum(1) + 1) / (p2.sum(1) + t2.sum(1) + 1)).sum() / n
+                return dice + torch.nn.functional.binary_cross_entropy(p2, t2)
+
             def step():
                 opt.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
                     seg, edges = O.forward(params, x, True, {})
-                loss = O.edge_bce_dice_loss([e.float() for e in edges], seg.float(), y)
+                loss = bce_dice(seg.float(), y)
+                for k, (e, wk) in enumerate(zip(edges, O.EDGE_WEIGHTS)):          # utils/Loss.py:97-113
+                    sc = 16 >> k
+                    loss = loss + wk * bce_dice(e.float(), torch.nn.functional.max_pool2d(y, sc, sc) if sc > 1 else y)
                 loss.backward()
                 opt.step()
                 return loss

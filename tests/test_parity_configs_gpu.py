@@ -277,4 +277,4 @@ def test_bf16_train_forward_meets_the_literal_bar_on_conditioned_weights():
     assert max(errs) <= 2e-2, errs                    # ... and every side output
 
 
-CONDITIONING_STEPS = 60
+CONDITIONING_STEPS = 20      # tools/bf16_conditioning.py: seg error 19 % at step 0, 0.6 % / 0.4 % / 1.0 % / 1.5 % / 2.6 % after 5 / 20 / 60 / 120 / 250 steps
