@@ -43,6 +43,98 @@ __global__ void permute4_kernel(const TI* __restrict__ in, TO* __restrict__ out,
 }
 
 
+// ---- tiled 3-D transposes ------------------------------------------------------------------------------------------------
+// Every weight repacking of a step is a permutation of a [A][B][T] view (A, B channel counts, T = kernel taps: 9, 4 or 1):
+// reference layout <-> operand layouts, and weight-gradient layout -> reference layout.  The generic index-arithmetic kernels
+// above read with strides of T (or A*B) elements -- 4-byte accesses scattered over 36-byte / kilobyte strides, 8 % of the HBM
+// roofline.  Here a block moves a 32 x 32 x T tile through shared memory: both the global reads and the global writes run
+// along whichever index is contiguous on their side.
+struct Tile3 {             // element offsets: a * sa + b * sb + t * st on each side
+    long long sa_in, sb_in, st_in, sa_out, sb_out, st_out;
+    int A, B, T;
+};
+constexpr int kTileT = 9, kTilePitch = 33;
+
+// decompose a 4-D permutation into the [A][B][T] form; false when it is not one of the weight patterns (or dims are ragged)
+__host__ __device__ inline bool tile3_from_perm(const int (&d)[4], const int (&p)[4], Tile3* t) {
+    const long long istr[4] = {(long long)d[1] * d[2] * d[3], (long long)d[2] * d[3], d[3], 1};
+    long long ostr[4];          // stride of SOURCE dim k in the output
+    {
+        long long run = 1;
+        for (int o = 3; o >= 0; --o) { ostr[p[o]] = run; run *= d[p[o]]; }
+    }
+    int ia, ib, t0, t1;         // which source dims play A, B and the (adjacent, in-order on both sides) tap pair
+    if (p[0] == 2 && p[1] == 3 && p[2] == 0 && p[3] == 1) { ia = 0; ib = 1; t0 = 2; t1 = 3; }        // [A][B][T] -> [T][A][B]
+    else if (p[0] == 2 && p[1] == 3 && p[2] == 1 && p[3] == 0) { ia = 0; ib = 1; t0 = 2; t1 = 3; }   // [A][B][T] -> [T][B][A]
+    else if (p[0] == 0 && p[1] == 2 && p[2] == 3 && p[3] == 1) { ia = 0; ib = 1; t0 = 2; t1 = 3; }   // [A][B][T] -> [A][T][B]
+    else if (p[0] == 3 && p[1] == 2 && p[2] == 0 && p[3] == 1) { ia = 3; ib = 2; t0 = 0; t1 = 1; }   // [T][B][A] -> [A][B][T]
+    else if (p[0] == 0 && p[1] == 3 && p[2] == 1 && p[3] == 2) { ia = 0; ib = 3; t0 = 1; t1 = 2; }   // [A][T][B] -> [A][B][T]
+    else return false;
+    t->A = d[ia]; t->B = d[ib]; t->T = d[t0] * d[t1];
+    if (t->A % 32 != 0 || t->B % 32 != 0 || t->T > kTileT) return false;
+    t->sa_in = istr[ia]; t->sb_in = istr[ib]; t->st_in = istr[t1];
+    t->sa_out = ostr[ia]; t->sb_out = ostr[ib]; t->st_out = ostr[t1];
+    return true;
+}
+
+// sm[(t * 32 + a) * 33 + b]
+template <class TI, class TO>
+__device__ __forceinline__ void tile3_move(const TI* __restrict__ in, TO* __restrict__ out, const Tile3& g, int a0, int b0,
+                                           const float* __restrict__ scale, int scale_on_a, float* sm) {
+    const int T = g.T, n = 32 * 32 * T;
+    // ---- read along the side's contiguous index
+    if (g.st_in == 1 && g.sb_in == T) {                       // a-rows of 32 * T contiguous elements
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int a = i / (32 * T), rem = i - a * 32 * T, b = rem / T, t = rem - b * T;
+            sm[(t * 32 + a) * kTilePitch + b] = to_f32(in[(a0 + a) * g.sa_in + (long long)b0 * T + rem]);
+        }
+    } else if (g.sa_in == 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int a = i & 31, b = (i >> 5) & 31, t = i >> 10;
+            sm[(t * 32 + a) * kTilePitch + b] = to_f32(in[(a0 + a) + (b0 + b) * g.sb_in + t * g.st_in]);
+        }
+    } else {                                                  // b contiguous
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int b = i & 31, a = (i >> 5) & 31, t = i >> 10;
+            sm[(t * 32 + a) * kTilePitch + b] = to_f32(in[(a0 + a) * g.sa_in + (b0 + b) * g.sb_in + t * g.st_in]);
+        }
+    }
+    __syncthreads();
+    // ---- write along the other side's contiguous index
+    if (g.st_out == 1 && g.sb_out == T) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int a = i / (32 * T), rem = i - a * 32 * T, b = rem / T, t = rem - b * T;
+            float v = sm[(t * 32 + a) * kTilePitch + b];
+            if (scale) v *= scale[scale_on_a ? a0 + a : b0 + b];
+            out[(a0 + a) * g.sa_out + (long long)b0 * T + rem] = from_f32<TO>(v);
+        }
+    } else if (g.sa_out == 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int a = i & 31, b = (i >> 5) & 31, t = i >> 10;
+            float v = sm[(t * 32 + a) * kTilePitch + b];
+            if (scale) v *= scale[scale_on_a ? a0 + a : b0 + b];
+            out[(a0 + a) + (b0 + b) * g.sb_out + t * g.st_out] = from_f32<TO>(v);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int b = i & 31, a = (i >> 5) & 31, t = i >> 10;
+            float v = sm[(t * 32 + a) * kTilePitch + b];
+            if (scale) v *= scale[scale_on_a ? a0 + a : b0 + b];
+            out[(a0 + a) * g.sa_out + (b0 + b) * g.sb_out + t * g.st_out] = from_f32<TO>(v);
+        }
+    }
+}
+
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) permute_tiled_kernel(const TI* __restrict__ in, TO* __restrict__ out, const Tile3 g) {
+    __shared__ float sm[kTileT * 32 * kTilePitch];
+    const int tb = g.B / 32, tiles = (g.A / 32) * tb;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        __syncthreads();
+        tile3_move(in, out, g, (tile / tb) * 32, (tile % tb) * 32, nullptr, 0, sm);
+    }
+}
+
 // One launch packs a whole table of weights (fp32, reference layout) into their bf16 operand layouts: blockIdx.y = job.
 struct PackJob {           // mirrors eel_pack_job in eel.h (64 bytes)
     const float* src;
@@ -53,8 +145,21 @@ struct PackJob {           // mirrors eel_pack_job in eel.h (64 bytes)
     int scale_pos;
     int pad;
 };
-__global__ void pack_batch_kernel(const PackJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) pack_batch_kernel(const PackJob* __restrict__ jobs) {
+    __shared__ float sm[kTileT * 32 * kTilePitch];
     const PackJob j = jobs[blockIdx.y];
+    Tile3 g;
+    const int dd[4] = {j.d[0], j.d[1], j.d[2], j.d[3]}, pp[4] = {j.p[0], j.p[1], j.p[2], j.p[3]};
+    // (reference layout [A][B][taps] -> operand layout; a scaled output dimension must be A or B of the tile view)
+    if ((pp[0] == 2 || (pp[0] == 0 && pp[1] == 2)) && (j.scale == nullptr || j.p[j.scale_pos] <= 1) && tile3_from_perm(dd, pp, &g)) {
+        const int scale_on_a = j.scale != nullptr && j.p[j.scale_pos] == 0;
+        const int tb = g.B / 32, tiles = (g.A / 32) * tb;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            __syncthreads();
+            tile3_move(j.src, j.dst, g, (tile / tb) * 32, (tile % tb) * 32, j.scale, scale_on_a, sm);
+        }
+        return;
+    }
     const int od1 = j.d[j.p[1]], od2 = j.d[j.p[2]], od3 = j.d[j.p[3]];
     const long long istr[4] = {(long long)j.d[1] * j.d[2] * j.d[3], (long long)j.d[2] * j.d[3], j.d[3], 1};
     const long long s0 = istr[j.p[0]], s1 = istr[j.p[1]], s2 = istr[j.p[2]], s3 = istr[j.p[3]];
@@ -1158,6 +1263,18 @@ int eel_permute4(const void* in, int in_dtype, void* out, int out_dtype, int d0,
     long long total = (long long)d0 * d1 * d2 * d3;
     int g = ew_grid(total, 256);
     cudaStream_t st = (cudaStream_t)s;
+    {   // the weight / weight-gradient patterns go through shared-memory tiles (coalesced on both sides)
+        Tile3 t3;
+        const int dd[4] = {d0, d1, d2, d3}, pp[4] = {p0, p1, p2, p3};
+        if (in_dtype == EEL_F32 && tile3_from_perm(dd, pp, &t3)) {
+            const int tiles = (t3.A / 32) * (t3.B / 32);
+            const int grid = tiles < kNumSMs * 4 ? tiles : kNumSMs * 4;
+            if (out_dtype == EEL_F32) permute_tiled_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, t3);
+            else if (out_dtype == EEL_BF16) permute_tiled_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)in, (bf16*)out, t3);
+            else { set_error("permute4: unsupported dtype"); return EEL_ERR_INVALID; }
+            return check_launch("permute4(tiled)");
+        }
+    }
     if (in_dtype == EEL_F32 && out_dtype == EEL_F32)
         permute4_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, (float*)out, d0, d1, d2, d3, p0, p1, p2, p3);
     else if (in_dtype == EEL_F32 && out_dtype == EEL_BF16)

@@ -485,7 +485,7 @@ def build_packer(module):
         elif isinstance(m, nn.Linear) or (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1)):
             no, k = w.shape[0], w.shape[1]
             if no % 64 == 0 and k % 64 == 0:
-                pk.add(w, (1, 1, no, k), (0, 1, 2, 3), (0, 1, 3, 2), m)
+                pk.add(w, (no, k, 1, 1), (2, 3, 0, 1), (2, 3, 1, 0), m)      # [1][1][no][k] and [1][1][k][no], tiled transposes
     return pk
 
 

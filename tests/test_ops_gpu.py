@@ -688,3 +688,19 @@ def test_side_channels_between_ops_are_safe_against_hooks_and_gradient_accumulat
         assert rel(b.grad, br.grad) < 1e-2 and abs(br.grad.mean().item() - 0.5 * N * H * W) < 1e-6
     else:
         assert b.grad.abs().max().item() < 1e-2 * w.grad.abs().max().item() * K      # analytically zero
+
+
+@pytest.mark.parametrize("dims,perm", [
+    ((128, 64, 3, 3), (2, 3, 0, 1)), ((128, 64, 3, 3), (2, 3, 1, 0)), ((64, 96, 2, 2), (0, 2, 3, 1)), ((64, 96, 2, 2), (2, 3, 1, 0)),
+    ((3, 3, 64, 160), (3, 2, 0, 1)), ((96, 2, 2, 64), (0, 3, 1, 2)), ((256, 64, 1, 1), (2, 3, 1, 0)), ((256, 64, 1, 1), (2, 3, 0, 1)),
+    ((64, 3, 3, 3), (2, 3, 0, 1)), ((5, 7, 3, 2), (3, 1, 0, 2))])
+def test_permute4_tiled_and_generic_paths(dims, perm):
+    """eel_permute4: the weight / weight-gradient layout changes go through shared-memory tiles (csrc/elementwise.cu
+    tile3_*), everything else through the generic kernel; both against torch.permute, fp32 -> fp32 and fp32 -> bf16."""
+    from eel_unet_b200 import ops
+
+    torch.manual_seed(1)
+    w = torch.randn(*dims, device=DEV)
+    ref = w.permute(*perm).contiguous()
+    assert torch.equal(ops._pack(w, perm, torch.float32), ref)
+    assert torch.equal(ops._pack(w, perm, torch.bfloat16), ref.bfloat16())
