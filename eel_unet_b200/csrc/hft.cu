@@ -215,19 +215,24 @@ int hft_tc_step1(const bf16* rows_in, int R, bf16* mat_ws, int kind, float* T, b
 int hft_tc_step2(const bf16* T1b, bf16* mat_ws, bf16* T2b, float* T2f, int N, int H, int C, int r, cudaStream_t st);
 int hft_tc_step3(const bf16* T2b, bf16* mat_ws, bf16* T3b, int N, int H, int C, int r, cudaStream_t st);
 int hft_tc_step4(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_g, bf16* y_or_dx, bf16* phase, int N, int H, int W, int C,
-                 int r, cudaStream_t st);
+                 int r, cudaStream_t st, bool g_re_only = false);
+bool hft_tc_code_path(int H, int W, int C, int r);
+int hft_tc_step1g(const bf16* dy, const uint16_t* code, bf16* mat_ws, bf16* T1b, bf16* gre, int N, int H, int W, int C, int r,
+                  cudaStream_t st);
+int hft_tc_step4p(const bf16* T3b, bf16* mat_ws, bool fwd, const bf16* x_or_dy, const uint16_t* code_in, bf16* y_or_dx,
+                  uint16_t* code_out, int N, int H, int W, int C, int r, cudaStream_t st);
 }  // namespace tc
 
 struct HftWs { float *Cw, *Sw, *Ch, *Sh, *T1, *T2; bf16 *T3b, *G, *M1, *M4, *M2, *M3; };
 
-static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base) {
+static size_t hft_carve(int N, int H, int W, int C, int r, HftWs* ws, void* base, bool need_pairs = true) {
     int F = 2 * r;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off += (n * sizeof(float) + 255) / 256 * 256; return o; };
     size_t oCw = take((size_t)F * W), oSw = take((size_t)F * W), oCh = take((size_t)F * H), oSh = take((size_t)F * H);
     size_t oT1 = take((size_t)N * H * 2 * F * C), oT2 = take((size_t)N * 2 * F * F * C);
     // tensor-core path (bf16): T3 in bf16, the (re, im) gradient pairs, the two resident DFT matrices
-    size_t oT3b = take(((size_t)N * H * 2 * F * C + 1) / 2), oG = take((size_t)N * H * W * C);
+    size_t oT3b = take(((size_t)N * H * 2 * F * C + 1) / 2), oG = take(need_pairs ? (size_t)N * H * W * C : ((size_t)N * H * W * C + 1) / 2);   // (re, im) pairs, or Re(g) only
     size_t oM1 = take(((size_t)80 * 2 * W + 1) / 2), oM4 = take(((size_t)2 * W * 128 + 1) / 2);
     size_t oM2 = take(((size_t)80 * 2 * H + 1) / 2), oM3 = take(((size_t)2 * H * 128 + 1) / 2);
     if (ws && base) {
@@ -277,18 +282,27 @@ extern "C" {
 
 size_t eel_hft_workspace_bytes(int N, int H, int W, int C, int mask_range) {
     int r = hft_radius(H, W, mask_range);
-    return hft_carve(N, H, W, C, r, nullptr, nullptr) + 256;
+    return hft_carve(N, H, W, C, r, nullptr, nullptr, !tc::hft_tc_code_path(H, W, C, r)) + 256;
 }
 
-static int hft_prepare(int N, int H, int W, int C, int mask_range, void* ws, size_t ws_bytes, HftWs* w, int* F, cudaStream_t st) {
+size_t eel_hft_phase_elems(int N, int H, int W, int C, int mask_range, int dtype) {
+    int r = hft_radius(H, W, mask_range);
+    const size_t px = (size_t)N * H * W * C;
+    return (dtype == EEL_BF16 && tc::hft_tc_code_path(H, W, C, r)) ? px : 2 * px;
+}
+
+static int hft_prepare(int N, int H, int W, int C, int mask_range, void* ws, size_t ws_bytes, HftWs* w, int* F, cudaStream_t st,
+                       bool simt_mats) {
     EEL_REQUIRE(N > 0 && H > 1 && W > 1 && C > 0 && mask_range > 0, "hft: bad argument");
     EEL_REQUIRE((long long)N * H <= 65535, "hft: N*H must be <= 65535 per call");
     int r = hft_radius(H, W, mask_range);
     *F = 2 * r;
-    size_t need = hft_carve(N, H, W, C, r, nullptr, nullptr);
+    const bool pairs = !tc::hft_tc_code_path(H, W, C, r);
+    size_t need = hft_carve(N, H, W, C, r, nullptr, nullptr, pairs);
     uintptr_t al = ((uintptr_t)ws + 255) / 256 * 256;
     if (!ws || ws_bytes < need + (al - (uintptr_t)ws)) { set_error("hft: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
-    hft_carve(N, H, W, C, r, w, (void*)al);
+    hft_carve(N, H, W, C, r, w, (void*)al, pairs);
+    if (!simt_mats) return EEL_OK;      // the tensor-core steps build their own bf16 matrices
     hft_init_mats_kernel<<<cdiv(*F * W, 256), 256, 0, st>>>(w->Cw, w->Sw, *F, r, W);
     if (int rc = check_launch("hft.init_w")) return rc;
     hft_init_mats_kernel<<<cdiv(*F * H, 256), 256, 0, st>>>(w->Ch, w->Sh, *F, r, H);
@@ -300,8 +314,9 @@ int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C,
     EEL_REQUIRE(x && y && phase, "hft_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
-    if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
-    if (dtype == EEL_BF16 && tc::hft_tc_supported_fwd(H, W, C, F / 2)) {
+    const bool tcf = dtype == EEL_BF16 && tc::hft_tc_supported_fwd(H, W, C, hft_radius(H, W, mask_range));
+    if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st, !tcf)) return rc;
+    if (tcf) {
         // every step on the tensor cores; T1 / T2 / T3 live in bf16 (the fp32 regions T1, T2 are reused as storage).
         // H > 512: step 2 splits its reduction and needs the whole fp32 T2 region for partial sums, so the bf16 T2 goes to
         // the unused second half of the T1 region.
@@ -310,6 +325,8 @@ int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C,
         if (int rc = tc::hft_tc_step1((const bf16*)x, W, w.M1, 0, nullptr, T1b, N, H, W, C, F / 2, st)) return rc;
         if (int rc = tc::hft_tc_step2(T1b, w.M2, T2b, w.T2, N, H, C, F / 2, st)) return rc;
         if (int rc = tc::hft_tc_step3(T2b, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
+        if (tc::hft_tc_code_path(H, W, C, F / 2))      // |z| and the 16-bit phase code from the pixel-row epilogue
+            return tc::hft_tc_step4p(w.T3b, w.M4, true, (const bf16*)x, nullptr, (bf16*)y, (uint16_t*)phase, N, H, W, C, F / 2, st);
         return tc::hft_tc_step4(w.T3b, w.M4, true, (const bf16*)x, (bf16*)y, (bf16*)phase, N, H, W, C, F / 2, st);
     }
     EEL_DISPATCH_DTYPE(dtype, {
@@ -334,7 +351,16 @@ int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W
     EEL_REQUIRE(dy && phase && dx, "hft_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
-    if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st)) return rc;
+    const bool tcb = dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, hft_radius(H, W, mask_range));
+    if (int rc = hft_prepare(N, H, W, C, mask_range, ws, ws_bytes, &w, &F, st, !tcb)) return rc;
+    if (dtype == EEL_BF16 && tc::hft_tc_code_path(H, W, C, F / 2)) {
+        // phase arrives as the 16-bit code; the complex gradient dy * phase is formed inside the first kernel
+        // (the first kernel also leaves Re(g) in the workspace: the last step then has the light epilogue dx = Re(g) - Re(low))
+        if (int rc = tc::hft_tc_step1g((const bf16*)dy, (const uint16_t*)phase, w.M1, (bf16*)w.T1, w.G, N, H, W, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step2((const bf16*)w.T1, w.M2, (bf16*)w.T2, w.T2, N, H, C, F / 2, st)) return rc;
+        if (int rc = tc::hft_tc_step3((const bf16*)w.T2, w.M3, w.T3b, N, H, C, F / 2, st)) return rc;
+        return tc::hft_tc_step4(w.T3b, w.M4, false, w.G, (bf16*)dx, nullptr, N, H, W, C, F / 2, st, true);
+    }
     if (dtype == EEL_BF16 && tc::hft_tc_supported(H, W, C, F / 2)) {
         const long long nvec = (long long)N * H * W * 2 * C / 8;
         long long blocks = (nvec + 255) / 256;

@@ -260,8 +260,11 @@ int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, 
 
 /* HighFourierTransform (models/EELUnet.py:153-191) as an exact low-rank projection:
  * y = | x - U_H (U_H^H x conj(U_W)) U_W^T |, frequencies -r..r-1, r = min(mask_range, H/2, W/2).
- * phase:[N][H][W][2][C] (dtype) keeps z/|z| for the backward. */
+ * phase keeps the unit vector z/|z| for the backward: eel_hft_phase_elems() elements of the storage dtype --
+ * [N][H][W][2][C] (re, im) pairs, or, for the bf16 tensor-core training shapes (C in {64,128}, H, W in {128,256}, r = 20),
+ * ONE 16-bit code per element [N][H][W][C] (smaller component in biased 14-bit fixed point + two flag bits, csrc/hft_tc.cu). */
 size_t eel_hft_workspace_bytes(int N, int H, int W, int C, int mask_range);
+size_t eel_hft_phase_elems(int N, int H, int W, int C, int mask_range, int dtype);
 int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C, int mask_range, void* ws,
                 size_t ws_bytes, int dtype, eel_stream s);
 int eel_hft_bwd(const void* dy, const void* phase, void* dx, int N, int H, int W, int C, int mask_range,

@@ -34,7 +34,7 @@ def tol(dtype, fwd=True):
     return 2e-5 if fwd else 1e-4
 
 
-def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1.0):
+def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1.0, all_nhwc=False):
     """inputs: list of NCHW fp32 tensors (activations); params: list of fp32 parameter tensors.
 
     fn_mine(nhwc activations (dtype, requires_grad), params) -> NHWC output (or tuple)
@@ -53,7 +53,8 @@ def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1
     routs = routs if isinstance(routs, tuple) else (routs,)
     gs = []
     for o, r in zip(outs, routs):
-        o_cmp = nchw(o.float()) if (o.dim() == 4 and out_nhwc and o.dtype == dtype and o.shape != r.shape) else o.float()
+        # (all_nhwc: every 4-D output is NHWC even when C == H == W makes the shapes coincide)
+        o_cmp = nchw(o.float()) if (o.dim() == 4 and out_nhwc and o.dtype == dtype and (all_nhwc or o.shape != r.shape)) else o.float()
         e = rel(o_cmp, r)
         assert e < tol(dtype) * atol_scale, "forward mismatch %g" % e
         g = torch.randn_like(r)
@@ -61,7 +62,7 @@ def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1
     # backward
     mine_g = []
     for o, g, r in zip(outs, gs, routs):
-        if o.dim() == 4 and o.shape != r.shape:
+        if o.dim() == 4 and (all_nhwc or o.shape != r.shape):
             mine_g.append(nhwc(g).to(o.dtype))
         else:
             mine_g.append(g.to(o.dtype))
@@ -70,7 +71,7 @@ def run_case(fn_mine, fn_ref, inputs, params, dtype, out_nhwc=True, atol_scale=1
     rg = []
     for o, g, r in zip(outs, mine_g, routs):
         gg = g.double()
-        rg.append(nchw(gg) if gg.shape != r.shape else gg)
+        rg.append(nchw(gg) if (all_nhwc or gg.shape != r.shape) else gg)
     torch.autograd.backward(routs, rg)
     for a, ra in zip(acts, racts):
         e = rel(nchw(a.grad.float()), ra.grad)
@@ -461,7 +462,8 @@ def ref_hft(x, mask_range=20):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 8, 64, 64), (1, 16, 48, 80), (1, 8, 16, 16), (2, 64, 128, 128), (1, 128, 64, 256),
-                                   (1, 64, 48, 192), (1, 64, 512, 512), (1, 128, 256, 128), (1, 64, 1024, 1024)])
+                                   (1, 64, 48, 192), (1, 64, 512, 512), (1, 128, 256, 128), (1, 64, 1024, 1024),
+                                   (3, 64, 256, 256), (2, 128, 128, 128), (1, 128, 256, 256), (2, 64, 128, 256)])
 def test_hft(dtype, shape):
     from eel_unet_b200 import ops
 
@@ -473,7 +475,48 @@ def test_hft(dtype, shape):
         assert y.float().abs().max().item() < (1e-4 if dtype == torch.float32 else 5e-2)
         return
     run_case(lambda a, p: ops.HFT.apply(a[0], 20), lambda a, p: ref_hft(a[0]), [x], [], dtype,
-             atol_scale=5.0 if dtype == torch.float32 else 1.5)
+             atol_scale=5.0 if dtype == torch.float32 else 1.5, all_nhwc=True)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 256, 256), (1, 128, 128, 128)])
+def test_hft_phase_code(shape):
+    """bf16 training shapes keep the unit phase z/|z| as one 16-bit code per element (csrc/hft_tc.cu): bit 15 = the smaller
+    component is re, bit 14 = the larger one is negative, bits 13..0 = 8192 + the smaller one in fixed point (step
+    sqrt(1/2)/8191), field 0 = zero vector.  Decoded on the host it must match the phase of the fp64 FFT formulation; |z| likewise."""
+    from eel_unet_b200 import _lib
+    from eel_unet_b200._lib import call, ptr, stream, workspace
+
+    torch.manual_seed(2)
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, device=DEV)
+    x[0, :, :, : w // 2] = 0                                   # large flat regions: small |z|
+    a = nhwc(x).bfloat16()
+    assert _lib.lib.eel_hft_phase_elems(n, h, w, c, 20, _lib.EEL_BF16) == n * h * w * c
+    y = torch.empty_like(a)
+    code = torch.empty((n, h, w, c), dtype=torch.int16, device=DEV)
+    nb = _lib.lib.eel_hft_workspace_bytes(n, h, w, c, 20)
+    ws = workspace(nb, a.device, slot=1)
+    call("eel_hft_fwd", ptr(a), ptr(y), ptr(code), n, h, w, c, 20, ptr(ws), nb, _lib.EEL_BF16, stream())
+    xd = nchw(a.double())
+    crow, ccol, r = h // 2, w // 2, 20
+    mask = torch.ones(h, w, dtype=torch.float64, device=DEV)
+    mask[crow - r:crow + r, ccol - r:ccol + r] = 0
+    z = torch.fft.ifft2(torch.fft.ifftshift(torch.fft.fftshift(torch.fft.fft2(xd), dim=(-2, -1)) * mask, dim=(-2, -1)))
+    z = nhwc(z)
+    assert rel(y.float(), z.abs()) < 1e-2
+    u = code.to(torch.int32) & 0xFFFF
+    q = (u & 0x3FFF) - 8192                                     # biased 14-bit field
+    small = q.double() * (0.5 ** 0.5 / 8191)
+    large = torch.sqrt((1 - small * small).clamp_min(0)) * torch.where((u & 0x4000) != 0, -1.0, 1.0)
+    sel = (u & 0x8000) != 0
+    re, im = torch.where(sel, small, large), torch.where(sel, large, small)
+    zero = (u & 0x3FFF) == 0
+    re, im = torch.where(zero, 0.0, re), torch.where(zero, 0.0, im)
+    ok = z.abs() > 0.05 * z.abs().mean()                        # where the phase is well defined against bf16 input rounding
+    ph = z / z.abs().clamp_min(1e-300)
+    err = torch.sqrt((re - ph.real) ** 2 + (im - ph.imag) ** 2)[ok]
+    assert err.max().item() < 0.3 and err.mean().item() < 1e-2, (err.max().item(), err.mean().item())
+    assert ((re * re + im * im)[~zero] - 1).abs().max().item() < 1e-3
 
 
 @pytest.mark.parametrize("soft", [False, True])

@@ -103,6 +103,18 @@ def cases(B, S, only):
             return "eel_bn_relu_pool_bwd", (ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dz), ptr(dg), ptr(db),
                                             ptr(dzs), B, s, s, c, 1, ptr(ws), n, 1, st()), (z, da, dz, dp, amax, mean, rstd, g, b, dg, db, dzs, ws)
         add("pool", "bn_relu_pool_bwd %dx%d C=%d" % (s, s, c), mk_pool_bwd)
+    for (s, c) in [(S, 64), (S // 2, 128)]:
+        def mk_hft(s=s, c=c, fwd=True):
+            x, y = rnd(B, s, s, c), torch.empty(B, s, s, c, device=DEV, dtype=BF16)
+            ph = torch.empty(_lib.lib.eel_hft_phase_elems(B, s, s, c, 20, 1), device=DEV, dtype=BF16)
+            n = _lib.lib.eel_hft_workspace_bytes(B, s, s, c, 20)
+            ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+            call("eel_hft_fwd", ptr(x), ptr(y), ptr(ph), B, s, s, c, 20, ptr(ws), n, 1, st())     # a valid phase for the backward
+            if fwd:
+                return "eel_hft_fwd", (ptr(x), ptr(y), ptr(ph), B, s, s, c, 20, ptr(ws), n, 1, st()), (x, y, ph, ws)
+            return "eel_hft_bwd", (ptr(x), ptr(ph), ptr(y), B, s, s, c, 20, ptr(ws), n, 1, st()), (x, y, ph, ws)
+        add("hft", "hft_fwd %dx%d C=%d" % (s, s, c), mk_hft)
+        add("hft", "hft_bwd %dx%d C=%d" % (s, s, c), lambda s=s, c=c: mk_hft(s, c, False))
     return out
 
 
