@@ -58,6 +58,11 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            # nvidia-smi attaching to the driver (NVML initialisation) can hold up kernel launches for hundreds of milliseconds:
+            # wait for its first sample so that this happens before the warm-up, never inside the timed region
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 15.0 and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

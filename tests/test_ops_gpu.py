@@ -657,7 +657,7 @@ def test_fused_adam_is_a_torch_optimizer_with_steplr_and_checkpoints():
                     a.copy_(b)
             if kind == "torch<-ours":
                 o2 = torch.optim.Adam(m2.parameters(), lr=1.0)
-                o2.load_state_dict(mine_sd)
+                o2.load_state_dict(copy.deepcopy(mine_sd))      # (torch adopts the given moment tensors and steps them in place)
                 fin = lambda: None
             else:
                 gb2 = GradBuckets(list(m2.parameters()))
