@@ -50,6 +50,10 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # nvidia-smi numbers the PHYSICAL devices: translate the process-local ordinal through CUDA_VISIBLE_DEVICES
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if index < len(vis) and vis[index].isdigit():
+            index = int(vis[index])
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):

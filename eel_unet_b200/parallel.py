@@ -23,7 +23,7 @@ class _Bucket:
 
 
 class GradBuckets:
-    def __init__(self, params, bucket_mb=25.0, process_group=None, average=True):
+    def __init__(self, params, bucket_mb=25.0, process_group=None, average=True, tail_mb=1.0):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("no trainable parameters")
@@ -57,6 +57,23 @@ class GradBuckets:
             self._bucket_of[id(p)] = cur
             cur.end = (o + n + 3) // 4 * 4
         self.buckets.append(cur)
+        # The LAST bucket's all-reduce cannot overlap anything: its final gradient (the first layer's) is the end of backward.
+        # Keep that exposed collective small: the parameters that finish last (the first ~tail_mb of the model) get a bucket of
+        # their own, whatever is in front of them goes out earlier.
+        last = self.buckets[-1]
+        tail_cap = max(1, int(tail_mb * (1 << 20) / 4))
+        if len(last.params) > 1 and last.end - last.start > 2 * tail_cap:
+            k = len(last.params)
+            while k > 1 and last.end - self._slot[id(last.params[k - 1])][0] <= tail_cap:
+                k -= 1
+            if 0 < k < len(last.params):
+                cut = self._slot[id(last.params[k])][0]
+                tail = _Bucket(cut)
+                tail.end, tail.params = last.end, last.params[k:]
+                last.end, last.params = cut, last.params[:k]
+                for p in tail.params:
+                    self._bucket_of[id(p)] = tail
+                self.buckets.append(tail)
         for b in self.buckets:
             b.pending = len(b.params)
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
