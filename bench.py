@@ -160,6 +160,10 @@ def gpu_eager_rate(dev, batch, size, mode, iters=4, warmup=2):
     from oracle import synth
 
     torch.backends.cudnn.benchmark = True
+    # 'fp32' is what a user gets from stock PyTorch: cuDNN convolutions run on TF32 tensor cores.  'fp32_strict' turns TF32 off
+    # (IEEE fp32 FFMA everywhere): the like-for-like partner of this repo's fp32 mode, which is exact FFMA by design
+    torch.backends.cudnn.allow_tf32 = mode != "fp32_strict"
+    torch.backends.cuda.matmul.allow_tf32 = False
     out = {"mode": mode, "size": size}
     while batch >= 1:
         params = opt = x = y = None
@@ -368,7 +372,7 @@ def run_ours(args):
                     "traffic": None, "peak_source": peak_src + " (copy)", "share_of_step": top[3] / 100.0}
         # DRAM traffic of the dominant family from the committed ncu --set full capture of the same step (bytes per launch,
         # like `achieved`); null when no capture of this family is on file
-        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tj):
             t = json.load(open(tj)).get(top[0])
             if t:
@@ -415,7 +419,11 @@ def run_ours(args):
                          "edge_BceDiceLoss + bwd + torch.optim.Adam(fused=True), cudnn.benchmark on, CUDA-event timed in this process",
                  "fp32": gpu_eager_rate(dev, B, S, "fp32"),
                  "bf16_autocast_channels_last": gpu_eager_rate(dev, B, S, "bf16")}
-        for k in ("fp32", "bf16_autocast_channels_last"):
+        if args.precision == "fp32":
+            eager["fp32_strict"] = gpu_eager_rate(dev, B, S, "fp32_strict")
+        for k in list(eager):
+            if not isinstance(eager[k], dict):
+                continue
             if eager[k].get("value"):
                 eager[k]["ours_over_eager"] = round(value / eager[k]["value"], 3)
 

@@ -77,13 +77,17 @@ struct TcParams {
     float* bn_sums;         // optional [2][Ntot]: per-channel sum / sum of squares of the stored output (grid % n_tiles == 0)
 };
 
-constexpr int kThreads = 320;                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr int kABytes = 16384;                    // 128 rows x 64 bf16
-constexpr int kSmemBudget = 232448 - 1024 /* alignment */ - 1024 /* barriers */ - 16384 /* epilogue staging */;
+// EW epilogue warps (8 or 16): these kernels' wide-output launches (64 -> 256 linears, ConvTranspose) are bound by the LATENCY of
+// the epilogue chain (TMEM read -> convert -> transposition -> store), not by its instruction count or by HBM: with 8 warps the
+// four schedulers sit idle three cycles out of four.  Sixteen warps (four per TMEM lane quarter, a quarter of the tile's columns
+// each) double the chains in flight; BN = 64 tiles keep 8.
+constexpr int kSmemBudget8 = 232448 - 1024 /* alignment */ - 1024 /* barriers */ - 16384 /* epilogue staging */;
+constexpr int kSmemBudget16 = kSmemBudget8 - 16384;
 
-template <int BN, int EPI, int AGATHER, bool STATS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EPI, int AGATHER, bool STATS, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     constexpr int B_BYTES = BN * 128;
     constexpr int TMEM_COLS = 2 * BN;
@@ -110,7 +114,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1);
             mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmemFull[i], 1); mbar_init(&tmemEmpty[i], EW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -192,13 +196,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&tmemFull[acc]);
         }
     } else if (warp >= 2) {
-        // ===================================================================== epilogue (8 warps)
-        // Two warps share each TMEM lane quarter and split the tile's columns; the TMEM read of chunk i+1 is in flight
+        // ===================================================================== epilogue (EW warps)
+        // EW / 4 warps share each TMEM lane quarter and split the tile's columns; the TMEM read of chunk i+1 is in flight
         // while chunk i is converted, transposed (epi_store_chunk) and stored.
+        constexpr int PARTS = EW / 4;           // column parts of a tile
+        constexpr int PW = BN / PARTS;          // columns per warp
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;       // which half of the columns
+        const int half = (warp - 2) >> 2;       // which part of the columns
         const EpiLane L = epi_lane(reinterpret_cast<uint8_t*>(tmem_ptr) + 64 + (warp - 2) * 2048, lane);
-        constexpr int NCH = BN / 64;            // 32-column chunks per warp and tile
+        constexpr int NCH = PW / 32;            // 32-column chunks per warp and tile
         float st[STATS ? NCH : 1][2];           // fused BatchNorm statistics (tc_common.cuh); STATS is a template flag so
 #pragma unroll                                  // that the common no-statistics launches carry none of its registers / code
         for (int ci = 0; ci < (STATS ? NCH : 1); ++ci) st[ci][0] = st[ci][1] = 0.f;
@@ -220,7 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 nt_cur = nt;
 #pragma unroll
                 for (int ci = 0; ci < NCH; ++ci) {
-                    const int gcol = nt * BN + half * (BN / 2) + ci * 32;
+                    const int gcol = nt * BN + half * PW + ci * 32;
                     sdh[ci] = sdw[ci] = 0;
                     if (EPI == EPI_CONVT) {
                         const int dy = gcol / (2 * p.Co), rem = gcol - dy * 2 * p.Co;
@@ -266,7 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(&tmemFull[acc], acc_par);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * PW;
             uint32_t buf[2][32];
             tmem_ld32_async(taddr, buf[0]);
 #pragma unroll
@@ -296,12 +302,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt_own = blockIdx.x % p.n_tiles;
         if (STATS && EPI == EPI_DENSE) {
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, nt_own * BN + half * (BN / 2) + ci * 32, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, nt_own * BN + half * PW + ci * 32, lane, st[STATS ? ci : 0]);
         }
         if (STATS && EPI == EPI_CONVT) {
             // columns are (dy, dx, co): the four taps of a channel add into the same [2][Co] sums
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (nt_own * BN + half * (BN / 2) + ci * 32) % p.Co, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Co, (nt_own * BN + half * PW + ci * 32) % p.Co, lane, st[STATS ? ci : 0]);
         }
     }
     tc_fence_before();
@@ -312,6 +318,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int EPI, int AGATHER, bool STATS>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t st, const char* what) {
     constexpr int B_BYTES = BN * 128;
+    // Measured on B200 (tools/op_bench.py, batch 64): 16 warps take the bias-only ConvTranspose forwards from 261 / 142 / 85 us to
+    // 204 / 111 / 70 us, but inside the model most wide launches also carry the fused BatchNorm statistics, whose registers no longer
+    // fit the 113-register budget of 576 threads (spills): tc_linear 1.46 -> 1.64 ms, ConvTranspose forward 0.86 -> 1.0 ms per step.
+    // Until the statistics epilogue is slimmed down, 8 warps stay the default.
+    constexpr int EW = 8;
+    constexpr int kSmemBudget = EW == 16 ? kSmemBudget16 : kSmemBudget8;
     // resident weights: single N tile whose whole K extent fits beside >= 4 A stages
     p.res = (p.n_tiles == 1 && p.kchunks * B_BYTES + 4 * kABytes <= kSmemBudget) ? 1 : 0;
     int b_bytes;
@@ -324,15 +336,15 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPara
         p.na = p.nb = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
         b_bytes = p.nb * B_BYTES;
     }
-    const int smem = p.na * kABytes + b_bytes + 1024 + 16384 + 1024;
+    const int smem = p.na * kABytes + b_bytes + 1024 + 2048 * EW + 1024;
     static SmemOptIn configured;
-    if (!configured.ensure(tc_gemm_kernel<BN, EPI, AGATHER, STATS>, smem)) {
+    if (!configured.ensure(tc_gemm_kernel<BN, EPI, AGATHER, STATS, EW>, smem)) {
         set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
         return EEL_ERR_CUDA;
     }
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    tc_gemm_kernel<BN, EPI, AGATHER, STATS><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    tc_gemm_kernel<BN, EPI, AGATHER, STATS, EW><<<grid, 64 + 32 * EW, smem, st>>>(tmA, tmB, p);
     return check_launch(what);
 }
 

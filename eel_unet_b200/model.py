@@ -103,6 +103,9 @@ _PRECISIONS = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bf
 class EELUnet(nn.Module):
     """B200-native EEL-UNet (reference models/EELUnet.py:228-471)."""
 
+    # token MLP of ChannelAwarePatchedMLP as one kernel (False / EEL_FUSED_MLP=0: the three separate launches; kept for A/B runs)
+    fused_mlp = __import__("os").environ.get("EEL_FUSED_MLP", "1") != "0"
+
     def __init__(self, in_channels, out_channels, precision="fp32"):
         super().__init__()
         self.name = "eelunet"
@@ -227,18 +230,28 @@ class EELUnet(nn.Module):
         t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
         ca = m.channel_attention
         t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias, True)
-        t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
-        t = ops.Gelu.apply(t, True)
-        # mlp[2] and to_space are two linear maps with nothing in between: ONE GEMM with the composed matrix (ops.ComposedLinear)
         pair = (m.mlp[2].weight, m.mlp[2].bias, m.to_space.weight, m.to_space.bias)
+        fused = EELUnet.fused_mlp and ops.mlp_chain_supported(t, m.mlp[0].weight, m.to_space.weight.shape[0])
+        f = ops.folded(m.to_space.weight) if bn is not None else None
+        if f is not None and fused:      # inference: the whole token MLP + folded BatchNorm (+ ReLU) in one kernel
+            return ops.mlp_chain_folded(t, m.mlp[0].weight, m.mlp[0].bias, f[0], f[1], relu)
+        if not fused:
+            t = ops.Linear.apply(t, m.mlp[0].weight, m.mlp[0].bias, False)
+            t = ops.Gelu.apply(t, True)
+            if f is not None:
+                return ops.linear_folded(t, f[0], f[1], relu)
+
+        def tail(u):
+            if fused:                    # mlp[0] -> GELU -> composed (mlp[2], to_space) as ONE kernel (ops.MlpChain, csrc/capmlp_tc.cu)
+                return ops.MlpChain.apply(u, m.mlp[0].weight, m.mlp[0].bias, *pair)
+            # mlp[2] and to_space are two linear maps with nothing in between: ONE GEMM with the composed matrix (ops.ComposedLinear)
+            return ops.ComposedLinear.apply(u, *pair)
+
         if bn is None:
-            return ops.ComposedLinear.apply(t, *pair)
-        f = ops.folded(m.to_space.weight)
-        if f is not None:
-            return ops.linear_folded(t, f[0], f[1], relu)
+            return tail(t)
         ops.expect_bn(bn.training or bn.running_mean is None)
         try:
-            z = ops.ComposedLinear.apply(t, *pair)
+            z = tail(t)
         finally:
             ops.expect_bn(False)
         if defer:                      # the caller fuses this BatchNorm into its next op (decoder skip bridge)

@@ -849,6 +849,100 @@ class ComposedLinear(Function):
         return dx, dw1, db1, dw2.view(w2.shape), s
 
 
+def mlp_chain_supported(t, w0, cout):
+    """the fused token-MLP kernel (csrc/capmlp_tc.cu): bf16, Linear 64 -> 256 first, 256 / 512 / 1024 output channels, whole
+    128-pixel tiles"""
+    N, H, W, K = t.shape
+    return (t.dtype == BF16 and K == 64 and tuple(w0.shape) == (256, 64) and cout in (256, 512, 1024) and (N * H * W) % 128 == 0
+            and t.is_cuda)
+
+
+def mlp_chain_folded(t, w0, b0, wc_folded, fbias, relu):
+    """inference: mlp[0] -> GELU -> composed (mlp[2], to_space, eval-mode BatchNorm) [+ ReLU] as one kernel; no intermediate is kept"""
+    t = _c(t)
+    N, H, W, K = t.shape
+    C = wc_folded.shape[-2]
+    w0p = _packed(w0, 0)
+    if w0p is None:
+        w0p = _as_dtype2d(w0.view(256, 64), BF16)
+    z = torch.empty((N, H, W, C), dtype=BF16, device=t.device)
+    call("eel_tc_capmlp_fwd", ptr(t), ptr(w0p), ptr(b0.detach()), ptr(wc_folded), ptr(fbias), None, None, ptr(z), N * H * W, C, int(relu),
+         None, stream())
+    return z
+
+
+class MlpChain(Function):
+    """``to_space(mlp[2](GELU(mlp[0](u))))`` of ChannelAwarePatchedMLP (reference models/EELUnet.py:107-111,121-122) with the
+    forward as ONE tensor-core kernel (eel_tc_capmlp_fwd): the 256-channel h and a = GELU(h) are written once for the backward
+    and never read back in the forward.  Its outputs are bit-identical to Linear -> Gelu -> ComposedLinear, and the backward IS
+    those three backwards in sequence (same kernels), with the same free bias gradients and BatchNorm hand-overs."""
+
+    @staticmethod
+    def forward(ctx, u, w0, b0, w1, b1, w2, b2):
+        u = _c(u)
+        N, H, W, K = u.shape
+        Cout, Cmid = w2.shape[0], w1.shape[0]
+        P = N * H * W
+        hit = getattr(w2, "_eel_composed", None)
+        if hit is not None and hit[3] == u.dtype and hit[4] == tuple(_pack_key(t) for t in (w2, b2, w1, b1)):
+            wc, wct, bc = hit[:3]
+        else:
+            one = ComposedPacker(u.dtype)
+            one.add(_Pair(w1.detach(), b1.detach()), _Pair(w2.detach().view(Cout, Cmid), b2.detach()))
+            one.refresh(u.device)
+            wc, wct, bc = one._keep[0]
+        w0p = _packed(w0, 0)
+        if w0p is None:
+            w0p = _as_dtype2d(w0.view(256, 64), u.dtype)
+        dev = u.device
+        h = torch.empty((N, H, W, 256), dtype=u.dtype, device=dev)
+        a = torch.empty((N, H, W, 256), dtype=u.dtype, device=dev)
+        z = torch.empty((N, H, W, Cout), dtype=u.dtype, device=dev)
+        sums = _want_bn_sums(u, Cout)
+        call("eel_tc_capmlp_fwd", ptr(u), ptr(w0p), ptr(b0.detach()), ptr(wc), None if sums is not None else ptr(bc), ptr(h), ptr(a), ptr(z),
+             P, Cout, 0, ptr(sums), stream())
+        if sums is not None:
+            _attach(z, "_eel_bn_sums", (sums, bc))
+        ctx.save_for_backward(u, h, a, w0, w1, b1, w2, wc, wct)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        u, h, a, w0, w1, b1, w2, wc, wct = ctx.saved_tensors
+        dz = _c(dz)
+        N, H, W, K = u.shape
+        Cout, Cmid = w2.shape[0], w1.shape[0]
+        P = N * H * W
+        st = stream()
+        dev = u.device
+        # ---- composed layer (ComposedLinear.backward)
+        da = torch.empty_like(a)
+        call("eel_tc_linear", ptr(dz), ptr(wct), None, ptr(da), P, Cout, 256, 0, None, 0, 0, st)
+        dwc = torch.empty((Cout, 256), dtype=F32, device=dev)
+        call("eel_tc_wgrad", ptr(dz), ptr(a), ptr(dwc), P, Cout, 256, 256, 1, dwc.numel(), 0, st)
+        s = _colsum(dz, Cout)
+        dw2 = _grad_out(w2, (Cout, Cmid))
+        dw1 = _grad_out(w1, (Cmid, 256))
+        db1 = _grad_out(b1)
+        call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
+             ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, 256, st)
+        # ---- GELU (Gelu.backward); the column sums of dh are mlp[0]'s bias gradient
+        dh = torch.empty_like(h)
+        db0 = torch.empty(256, dtype=F32, device=dev)
+        call("eel_gelu_bwd_colsum", ptr(h), ptr(da), ptr(dh), ptr(db0), h.numel(), 256, dtype_code(h), st)
+        # ---- mlp[0] (Linear.backward)
+        du = None
+        if ctx.needs_input_grad[0]:
+            w0t = _packed(w0, 1)
+            if w0t is None:
+                w0t = _pack(w0.detach().view(1, 1, 256, 64), (0, 1, 3, 2), u.dtype)
+            du = torch.empty_like(u)
+            call("eel_tc_linear", ptr(dh), ptr(w0t), None, ptr(du), P, 256, 64, 0, None, 0, 0, st)
+        dw0 = _grad_out(w0, (256, 64))
+        call("eel_tc_wgrad", ptr(dh), ptr(u), ptr(dw0), P, 256, 64, 64, 1, dw0.numel(), 0, st)
+        return du, dw0.view(w0.shape), db0, dw1, db1, dw2.view(w2.shape), s
+
+
 def _bn_statistics(z, running_mean, running_var, training, momentum, eps):
     """(mean, rstd) of a BatchNorm over z [.., C]: batch statistics (+ running-stat update) in training -- from the sums the
     tensor-core producer left behind when there are any -- else the running statistics"""

@@ -37,6 +37,9 @@ def cost(name, a):
     if n == "tc_linear":
         P, K, No = a[4], a[5], a[6]
         return 2.0 * P * K * No, P * (K + No) * 2 + K * No * 2
+    if n == "tc_capmlp_fwd":
+        P, C = a[8], a[9]
+        return 2.0 * P * (64 * 256 + 256 * C), P * (64 + (512 if a[5] else 0) + C) * 2 + (64 * 256 + 256 * C) * 2
     if n == "tc_convt2x2_fwd":
         N, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
         P = N * h * w
@@ -162,7 +165,7 @@ def cost(name, a):
 # launches reported under another family's name
 ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd"}
 
-GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
+GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_capmlp_fwd", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}
 
 

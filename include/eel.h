@@ -258,6 +258,14 @@ int eel_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype
  * gradient of the nn.Linear that produced x (mlp[0], models/EELUnet.py:107) without another pass; 256 % (C / vector) == 0 */
 int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, long long n, int C, int dtype, eel_stream s);
 
+/* The token MLP of ChannelAwarePatchedMLP (models/EELUnet.py:107-111,121-122) as ONE tensor-core kernel (bf16):
+ * h = mlp[0](u) (Linear 64 -> 256), a = GELU(h), z = Wc a + bc with Wc / bc the composed mlp[2] + to_space matrix of
+ * eel_compose_batch.  u:[P][64], w0:[256][64] bf16, wc:[C][256] bf16, C in {256, 512, 1024}, P % 128 == 0.  h, a:[P][256] are
+ * kept for the backward (both null: inference, neither is stored); bc null + bn_sums [2][C]: a training-mode BatchNorm follows
+ * (eel_bn_stats_from_sums).  Bit-identical to eel_tc_linear -> eel_gelu_fwd -> eel_tc_linear. */
+int eel_tc_capmlp_fwd(const void* u, const void* w0, const float* b0, const void* wc, const float* bc, void* h, void* a,
+                      void* z, long long P, int C, int relu, float* bn_sums, eel_stream s);
+
 /* HighFourierTransform (models/EELUnet.py:153-191) as an exact low-rank projection:
  * y = | x - U_H (U_H^H x conj(U_W)) U_W^T |, frequencies -r..r-1, r = min(mask_range, H/2, W/2).
  * phase keeps the unit vector z/|z| for the backward: eel_hft_phase_elems() elements of the storage dtype --

@@ -747,3 +747,49 @@ def test_permute4_tiled_and_generic_paths(dims, perm):
     ref = w.permute(*perm).contiguous()
     assert torch.equal(ops._pack(w, perm, torch.float32), ref)
     assert torch.equal(ops._pack(w, perm, torch.bfloat16), ref.bfloat16())
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 256), (1, 16, 32, 512), (1, 16, 16, 1024), (3, 64, 64, 256)])
+@pytest.mark.parametrize("with_bn", [False, True])
+def test_fused_token_mlp_is_bit_identical_to_the_three_launches(shape, with_bn):
+    """ops.MlpChain (csrc/capmlp_tc.cu: mlp[0] -> GELU -> composed mlp[2] + to_space in one tcgen05 kernel, reference
+    models/EELUnet.py:107-111,121-122) against Linear -> Gelu -> ComposedLinear: outputs, BatchNorm statistics and every
+    gradient must agree exactly (same MMA order, same rounding points, same backward kernels); and against the fp64 formulation."""
+    from eel_unet_b200 import ops
+
+    torch.manual_seed(4)
+    N, H, W, C = shape
+    u = torch.randn(N, H, W, 64, device=DEV).bfloat16()
+    w0 = (torch.randn(256, 64, device=DEV) * 0.15)
+    b0 = torch.randn(256, device=DEV) * 0.1
+    w1 = (torch.randn(C, 256, device=DEV) * 0.08)            # mlp[2]
+    b1 = torch.randn(C, device=DEV) * 0.1
+    w2 = (torch.randn(C, C, 1, 1, device=DEV) * (1.0 / C ** 0.5))   # to_space
+    b2 = torch.randn(C, device=DEV) * 0.1
+    r = torch.randn(N, H, W, C, device=DEV).bfloat16()
+    assert ops.mlp_chain_supported(u, w0, C)
+
+    def run(fused):
+        ps = [t.clone().requires_grad_(True) for t in (w0, b0, w1, b1, w2, b2)]
+        uu = u.clone().requires_grad_(True)
+        a = None if fused else ops.Gelu.apply(ops.Linear.apply(uu, ps[0], ps[1], False), True)
+        ops.expect_bn(with_bn)               # (only the LAST layer of the chain feeds the BatchNorm)
+        try:
+            z = ops.MlpChain.apply(uu, *ps) if fused else ops.ComposedLinear.apply(a, *ps[2:])
+        finally:
+            ops.expect_bn(False)
+        sums = ops._take(z, "_eel_bn_sums")
+        z.backward(r)
+        return z.detach(), (None if sums is None else sums[0]), uu.grad, [p.grad for p in ps]
+
+    z1, s1, du1, g1 = run(True)
+    z0, s0, du0, g0 = run(False)
+    assert torch.equal(z1, z0) and torch.equal(du1, du0)
+    assert (s1 is None) == (not with_bn) and (s1 is None or rel(s1, s0) < 1e-5)       # (fp32 atomics: order differs)
+    for a, b in zip(g1, g0):
+        assert rel(a, b) < 1e-5
+    if not with_bn:
+        ud = u.double()
+        hd = F.linear(ud, w0.double().bfloat16().double(), b0.double())
+        zd = F.linear(F.linear(F.gelu(hd), w1.double(), b1.double()), w2.double().view(C, C), b2.double())
+        assert rel(z1, zd) < 2e-2

@@ -103,6 +103,15 @@ def cases(B, S, only):
             return "eel_bn_relu_pool_bwd", (ptr(da), ptr(dp), ptr(z), ptr(amax), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dz), ptr(dg), ptr(db),
                                             ptr(dzs), B, s, s, c, 1, ptr(ws), n, 1, st()), (z, da, dz, dp, amax, mean, rstd, g, b, dg, db, dzs, ws)
         add("pool", "bn_relu_pool_bwd %dx%d C=%d" % (s, s, c), mk_pool_bwd)
+    for (s, c) in [(S // 4, 256), (S // 8, 512), (S // 16, 1024)]:
+        def mk_mlp(s=s, c=c):
+            P = B * s * s
+            u, w0, b0, wc, bc = rnd(P, 64), rnd(256, 64), rnd(256, dtype=F32), rnd(c, 256), rnd(c, dtype=F32)
+            h, a_, z = (torch.empty(P, 256, device=DEV, dtype=BF16), torch.empty(P, 256, device=DEV, dtype=BF16),
+                        torch.empty(P, c, device=DEV, dtype=BF16))
+            return "eel_tc_capmlp_fwd", (ptr(u), ptr(w0), ptr(b0), ptr(wc), ptr(bc), ptr(h), ptr(a_), ptr(z), P, c, 0, None, st()), \
+                (u, w0, b0, wc, bc, h, a_, z)
+        add("mlp", "capmlp_fwd P=%d C=%d" % (B * s * s, c), mk_mlp)
     for (s, c) in [(S, 64), (S // 2, 128)]:
         def mk_hft(s=s, c=c, fwd=True):
             x, y = rnd(B, s, s, c), torch.empty(B, s, s, c, device=DEV, dtype=BF16)
