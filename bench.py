@@ -44,19 +44,66 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Read through NVML from a thread of this
+    process (nvidia_ml_py): three cheap queries every 50 ms.  The earlier `nvidia-smi -lms 100` child process is the fallback --
+    its NVML attach and its polling loop were seen to hold up kernel launches (a timed region 10 % slower than the
+    end-to-end region measured right after it, in which the sampler no longer ran)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        # nvidia-smi numbers the PHYSICAL devices: translate the process-local ordinal through CUDA_VISIBLE_DEVICES
+    def __init__(self, index, mode="nvml"):
+        self.ordinal = index
+        # nvidia-smi / NVML number the PHYSICAL devices: translate the process-local ordinal through CUDA_VISIBLE_DEVICES
         vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
         if index < len(vis) and vis[index].isdigit():
             index = int(vis[index])
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mode = index, None, [], mode
+        self.samples, self.nv, self.stop_flag, self.th = [], None, False, None
+
+    # ---- NVML thread
+    def _nvml_open(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = None
+        try:
+            import torch
+
+            pr = torch.cuda.get_device_properties(self.ordinal)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nv = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _nvml_loop(self):
+        nv, h, _ = self.nv
+        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        cfg = os.environ.get("EEL_BENCH_NVML", "50,cr").split(",")
+        period, what = float(cfg[0]) / 1e3, cfg[1]
+        while not self.stop_flag:
+            try:
+                t_q = time.time()
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM) if "c" in what else 0
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if "r" in what else 0
+                self.samples.append((time.time(), float(mhz), [n for n, b in bits if r & b], time.time() - t_q))
+            except Exception:
+                pass
+            time.sleep(period)
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                self._nvml_open()
+                self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+                self.th.start()
+                return
+            except Exception:
+                self.nv, self.mode = None, "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -75,8 +122,19 @@ class ClockSampler:
             self.lines.append((time.time(), ln.strip()))
 
     def stop(self, t0=None, t1=None):
-        """summary of the samples taken between wall-clock times t0 and t1 (the timed region); the process is started BEFORE the
-        warm-up so that forking it cannot stall the launching thread inside the timed region"""
+        """summary of the samples taken between wall-clock times t0 and t1 (the timed region); the sampler is started BEFORE the
+        warm-up so that starting it cannot stall the launching thread inside the timed region"""
+        if self.mode == "none":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler switched off (--clock-sampler none)"]}
+        if self.nv is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            inside = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1 + 0.05)] or self.samples[-3:]
+            sm = [x[1] for x in inside]
+            reasons = sorted({r for x in inside for r in x[2]})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.nv[2]), "reasons": reasons,
+                    "samples": len(sm), "source": "nvml (in-process thread, 50 ms)",
+                    "slowest_query_ms": round(1e3 * max([x[3] for x in inside] or [0.0]), 2)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +157,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def _workload(precision, world, B, S):
@@ -272,11 +330,12 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
-    from eel_unet_b200 import EELUnet, _lib, edge_BceDiceLoss, profiling
+    from eel_unet_b200 import EELUnet, _lib, edge_BceDiceLoss, ops, profiling
     from eel_unet_b200.parallel import DataParallel, FusedAdam
     from eel_unet_b200 import synth  # numpy input generator (nothing under oracle/ is touched by the measured arm)
 
     hbm, tens_sus, tens_burst, peak_src = _peaks()
+    ops.set_wgrad_stream(not args.no_wgrad_stream)
     B, S = args.batch, args.size
     torch.manual_seed(0)
     model = EELUnet(3, 1, precision=args.precision).to(dev).train()
@@ -306,7 +365,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_sampler)
     if rank == 0:
         sampler.start()          # before the warm-up: the fork of nvidia-smi must not steal the launching thread's time
     for _ in range(args.warmup):
@@ -315,16 +374,26 @@ def run_ours(args):
 
     # ---- timed region: inputs resident in HBM --------------------------------------------------
     l0 = _lib.launch_count()
+    ms0 = torch.cuda.memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_region0 = time.time()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         loss = step(x_dev, y_dev)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()           # (an event record per step: no synchronisation, nothing waits on it)
     e1.record()
     barrier()
     t_region1 = time.time()
     ms = e0.elapsed_time(e1)
+    per_step = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
+    ms1 = torch.cuda.memory_stats(dev)
+    # the caching allocator must be in its steady state inside the timed region: cudaMalloc / cudaFree calls there stall the
+    # launching thread (and synchronise the device)
+    alloc_delta = {k: ms1.get(k, 0) - ms0.get(k, 0) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
+    alloc_delta["reserved_gb"] = round(ms1.get("reserved_bytes.all.current", 0) / 2 ** 30, 2)
     launches = _lib.launch_count() - l0
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     t = torch.tensor([ms], device=dev)
@@ -352,7 +421,11 @@ def run_ours(args):
     rec = []
     if rank == 0:
         _lib.set_profiler(rec)
+    # kernels are timed ALONE here: the weight-gradient stream (ops._Wgrad) is switched off for this one step, otherwise an
+    # event pair around a launch would also span whatever the other stream runs next to it
+    ops.set_wgrad_stream(False)
     step(x_dev, y_dev)            # every rank runs it: the step contains collectives
+    ops.set_wgrad_stream(not args.no_wgrad_stream)
     _lib.set_profiler(None)
     barrier()
     if rank == 0:
@@ -437,6 +510,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
             "kernels": breakdown, "loss": final_loss, "peak_mem_gb": peak_mem,
+            # spread of the timed steps on this rank (`value` is steps / the whole region, as the contract says)
+            "step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step),
+                        "slow": [(i, v) for i, v in enumerate(per_step) if v > 1.15 * statistics.median(per_step)]},
+            "allocator_in_timed_region": alloc_delta,
         }
         emit(line)
     if world > 1:
@@ -454,6 +531,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])
+    ap.add_argument("--no-wgrad-stream", action="store_true", help="weight gradients on the launching stream (A/B of ops._Wgrad)")
     ap.add_argument("--profile-out", default=None)
     ap.add_argument("--profile-shapes", default=None)
     args = ap.parse_args()

@@ -920,6 +920,129 @@ __global__ void add_interleave_bwd_kernel(const T* __restrict__ dout, T* __restr
     }
 }
 
+
+// add + interleave backward that ALSO accumulates the backward sums of the BatchNorms whose whole upstream gradient is dab
+// (the BatchNorm that ends the upconv block, fused into the bridge's forward; at the top level also the BatchNorm + ReLU that
+// ends the edge branch): their reduction passes over (dab, z) disappear, one extra read of z rides on this pass instead.
+// Thread layout of colreduce_kernel (a thread owns one 16-byte channel vector of dab / de, i.e. 32 contiguous bytes of dout,
+// and walks down its row block); partial[rb][2 * NBN][C] = per BatchNorm {sum g, sum g * z}, g = dab * [scale z + shift > 0].
+template <class T> struct BnSumsRef {
+    const T* z; const float* mean; const float* rstd; const float* gamma; const float* beta; float* sums; int relu;
+};
+
+template <class T, int NBN>
+__global__ void __launch_bounds__(kRedThreads) add_interleave_bwd_bn_kernel(const T* __restrict__ dout, T* __restrict__ dab,
+                                                                          T* __restrict__ de, const BnSumsRef<T> b0,
+                                                                          const BnSumsRef<T> b1, long long rows, int C, int TX,
+                                                                          long long rows_per_rb, float* __restrict__ partial) {
+    constexpr int V = Vec16<T>::N;
+    constexpr int U = 2;
+    constexpr int Q = 2 * NBN;
+    __shared__ float sm[kRedThreads][Q * V + 1];
+    const int TY = kRedThreads / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    const bool live = c0 < C;
+    const T* zs[2] = {b0.z, b1.z};
+    float sc[NBN][V], sh[NBN][V], acc[Q][V];
+#pragma unroll
+    for (int k = 0; k < NBN; ++k) {
+        const BnSumsRef<T>& b = k == 0 ? b0 : b1;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int c = live ? c0 + j : 0;
+            // no ReLU: the mask test (scale * z + shift > 0) must always pass
+            sc[k][j] = b.relu ? b.gamma[c] * b.rstd[c] : 0.f;
+            sh[k][j] = b.relu ? b.beta[c] - b.mean[c] * sc[k][j] : 1.f;
+            acc[2 * k][j] = acc[2 * k + 1][j] = 0.f;
+        }
+    }
+    long long r0 = blockIdx.y * rows_per_rb, r1 = r0 + rows_per_rb;
+    if (r1 > rows) r1 = rows;
+    if (!live) r1 = r0;
+    for (long long r = r0 + ty; r < r1; r += (long long)U * TY) {
+        Vec16<T> i0[U], i1[U], vz[U][NBN];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * TY;
+            if (rr < r1) {
+                i0[u] = ld16(dout + (rr * C + c0) * 2);
+                i1[u] = ld16(dout + (rr * C + c0) * 2 + V);
+#pragma unroll
+                for (int k = 0; k < NBN; ++k) vz[u][k] = ld16(zs[k] + rr * C + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * TY;
+            if (rr < r1) {
+                Vec16<T> oa, oe;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (j < V / 2) { oa.set(j, i0[u].get(2 * j)); oe.set(j, i0[u].get(2 * j + 1)); }
+                    else { oa.set(j, i1[u].get(2 * j - V)); oe.set(j, i1[u].get(2 * j + 1 - V)); }
+                }
+                st16(dab + rr * C + c0, oa);
+                st16(de + rr * C + c0, oe);
+#pragma unroll
+                for (int k = 0; k < NBN; ++k)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float zz = vz[u][k].get(j);
+                        float g = oa.get(j);          // the STORED (rounded) gradient: what the apply pass will read
+                        if (!(fmaf(zz, sc[k][j], sh[k][j]) > 0.f)) g = 0.f;
+                        acc[2 * k][j] += g;
+                        acc[2 * k + 1][j] = fmaf(g, zz, acc[2 * k + 1][j]);
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) sm[threadIdx.x][q * V + v] = acc[q][v];
+    __syncthreads();
+    for (int j = ty; j < Q * V; j += TY) {
+        float t = 0.f;
+        for (int y = 0; y < TY; ++y) t += sm[y * TX + tx][j];
+        if (live) partial[((long long)blockIdx.y * Q + j / V) * C + c0 + j % V] = t;
+    }
+}
+
+// BatchNorm blockIdx.y: sums = {sum g, sum g * xhat} from partial[rb][Q][C] rows (2 * blockIdx.y, 2 * blockIdx.y + 1) =
+// raw {sum g, sum g * z}: sum g * xhat = rstd * (sum g z - mean * sum g)   (fp64 accumulation over the row blocks)
+template <class T>
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_raw_kernel(const float* __restrict__ partial, int nrb, int C, int Q,
+                                                                 const BnSumsRef<T> b0, const BnSumsRef<T> b1) {
+    __shared__ double sm0[32][33], sm1[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int k = blockIdx.y;
+    const BnSumsRef<T>& b = k == 0 ? b0 : b1;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < C)
+        for (int r = ty; r < nrb; r += 32 * 4) {
+            float v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = r + 32 * u < nrb;
+                v0[u] = ok ? partial[((long long)(r + 32 * u) * Q + 2 * k) * C + c] : 0.f;
+                v1[u] = ok ? partial[((long long)(r + 32 * u) * Q + 2 * k + 1) * C + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s0 += (double)v0[u]; s1 += (double)v1[u]; }
+        }
+    sm0[ty][tx] = s0;
+    sm1[ty][tx] = s1;
+    __syncthreads();
+    if (ty != 0 || c >= C) return;
+    s0 = 0.0; s1 = 0.0;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) { s0 += sm0[y][tx]; s1 += sm1[y][tx]; }
+    b.sums[c] = (float)s0;
+    b.sums[C + c] = (float)((double)b.rstd[c] * (s1 - (double)b.mean[c] * s0));
+}
+
 // ------------------------------------------------------------------------------------ column-block copy (torch.concat on C)
 template <class T>
 __global__ void copy_cols_kernel(const T* __restrict__ src, long long src_ld, int src_c0, T* __restrict__ dst, long long dst_ld,
@@ -1470,6 +1593,37 @@ int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, i
         long long nvec = P * C / Vec16<T>::N;
         add_interleave_bwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)dout, (T*)dab, (T*)de, nvec);
         return check_launch("add_interleave_bwd");
+    });
+}
+
+int eel_add_interleave_bwd_bnsums(const void* dout, void* dab, void* de, long long P, int C,
+                                  const void* z0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
+                                  int relu0, float* sums0,
+                                  const void* z1, const float* mean1, const float* rstd1, const float* gamma1, const float* beta1,
+                                  int relu1, float* sums1, void* ws, size_t ws_bytes, int dtype, eel_stream s) {
+    EEL_REQUIRE(dout && dab && de && P > 0 && C > 0, "add_interleave_bwd_bnsums: bad argument");
+    EEL_REQUIRE(z0 && mean0 && rstd0 && gamma0 && beta0 && sums0, "add_interleave_bwd_bnsums: the first BatchNorm is incomplete");
+    EEL_REQUIRE(z1 == nullptr || (mean1 && rstd1 && gamma1 && beta1 && sums1), "add_interleave_bwd_bnsums: the second BatchNorm is incomplete");
+    cudaStream_t st = (cudaStream_t)s;
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "add_interleave_bwd_bnsums");
+        const int nbn = z1 != nullptr ? 2 : 1;
+        const int Q = 2 * nbn;
+        RedPlan pl = plan_reduce<T>(P, C, 1);
+        EEL_REQUIRE(ws != nullptr && ws_bytes >= sizeof(float) * (size_t)pl.nrb * Q * C, "add_interleave_bwd_bnsums: workspace too small");
+        float* partial = (float*)ws;
+        BnSumsRef<T> b0{(const T*)z0, mean0, rstd0, gamma0, beta0, sums0, relu0};
+        BnSumsRef<T> b1{(const T*)z1, mean1, rstd1, gamma1, beta1, sums1, relu1};
+        dim3 grid(pl.ncb, pl.nrb);
+        if (nbn == 2)
+            add_interleave_bwd_bn_kernel<T, 2><<<grid, kRedThreads, 0, st>>>((const T*)dout, (T*)dab, (T*)de, b0, b1, P, C, pl.TX,
+                                                                            pl.rows_per_rb, partial);
+        else
+            add_interleave_bwd_bn_kernel<T, 1><<<grid, kRedThreads, 0, st>>>((const T*)dout, (T*)dab, (T*)de, b0, b0, P, C, pl.TX,
+                                                                            pl.rows_per_rb, partial);
+        if (int rc = check_launch("add_interleave_bwd_bnsums")) return rc;
+        bn_bwd_finalize_raw_kernel<T><<<dim3(cdiv(C, 32), nbn), 1024, 0, st>>>(partial, pl.nrb, C, Q, b0, b1);
+        return check_launch("add_interleave_bwd_bnsums.finalize");
     });
 }
 

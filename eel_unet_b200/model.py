@@ -223,7 +223,7 @@ class EELUnet(nn.Module):
                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias, single_conv_consumer)
 
     @staticmethod
-    def _capmlp(m, x, bn=None, relu=False, defer=False):
+    def _capmlp(m, x, bn=None, relu=False, defer=False, single_conv_consumer=False):
         """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch.
         bn: the BatchNorm (and `relu`) that consume the result -- applied here: in training its statistics come out of
         to_space's epilogue, in inference it is folded into to_space's weights."""
@@ -256,7 +256,7 @@ class EELUnet(nn.Module):
             ops.expect_bn(False)
         if defer:                      # the caller fuses this BatchNorm into its next op (decoder skip bridge)
             return z, bn
-        return EELUnet._bn(bn, z, relu)
+        return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer)
 
     @staticmethod
     def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False):
@@ -273,10 +273,11 @@ class EELUnet(nn.Module):
             return z, bn
         return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer)
 
-    def _conv_block(self, blk, x, defer=False):
-        """defer: return (pre-BatchNorm tensor, BatchNorm) for the block's LAST BatchNorm + ReLU (fused into the PGR that follows)"""
+    def _conv_block(self, blk, x, defer=False, single_consumer=False):
+        """defer: return (pre-BatchNorm tensor, BatchNorm) for the block's LAST BatchNorm + ReLU (fused into the PGR that follows);
+        single_consumer: the block's output feeds exactly one skip bridge (whose backward then delivers the last BatchNorm's sums)"""
         x = self._conv_bn(blk[0], blk[1], x, single_conv_consumer=True)
-        return self._conv_bn(blk[3], blk[4], x, defer=defer)
+        return self._conv_bn(blk[3], blk[4], x, defer=defer, single_conv_consumer=single_consumer)
 
     def _mlp_conv_block(self, blk, x, defer=False):
         x = self._conv_bn(blk[0], blk[1], x)
@@ -321,8 +322,9 @@ class EELUnet(nn.Module):
             return z, blk[1]
         return self._bn(blk[1], z, False)
 
-    def _mlp_upconv(self, blk, x, defer=False):
-        return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False, defer=defer)
+    def _mlp_upconv(self, blk, x, defer=False, single_conv_consumer=False):
+        return self._capmlp(blk[1], ops.ConvT2x2.apply(x, blk[0].weight, blk[0].bias), bn=blk[2], relu=False, defer=defer,
+                            single_conv_consumer=single_conv_consumer)
 
     def _bridge(self, up, b, e):
         """(upconv output + edge feature) interleaved with the encoder skip (reference models/EELUnet.py:422-426); `up` is
@@ -377,12 +379,13 @@ class EELUnet(nn.Module):
         b, edge_5 = self._pgr(self.pred5, b)
 
         # edge branch (reference models/EELUnet.py:300-328, 415-418)
-        e4 = self._mlp_conv_block(self.edge_upconv_4[1], self._mlp_upconv(self.edge_upconv_4[0], b))
-        e3 = self._mlp_conv_block(self.edge_upconv_3[1], self._mlp_upconv(self.edge_upconv_3[0], e4))
+        # (the mlp_upconv outputs feed exactly one conv3x3: its data-gradient launch delivers their BatchNorm's backward sums)
+        e4 = self._mlp_conv_block(self.edge_upconv_4[1], self._mlp_upconv(self.edge_upconv_4[0], b, single_conv_consumer=True))
+        e3 = self._mlp_conv_block(self.edge_upconv_3[1], self._mlp_upconv(self.edge_upconv_3[0], e4, single_conv_consumer=True))
         e2 = ops.HFT.apply(self._upconv(self.edge_upconv_2[0], e3), self.edge_upconv_2[1].mask_range)
         e2 = self._conv_block(self.edge_upconv_2[2], e2)
         e1 = ops.HFT.apply(self._upconv(self.edge_upconv_1[0], e2), self.edge_upconv_1[1].mask_range)
-        e1 = self._conv_block(self.edge_upconv_1[2], e1)
+        e1 = self._conv_block(self.edge_upconv_1[2], e1, single_consumer=True)      # e1 feeds only dec1's bridge
 
         # decoder (reference models/EELUnet.py:421-465)
         d = self._mlp_conv_block(self.dec4, self._bridge(self._mlp_upconv(self.upconv4, b, defer=True), e4, enc4), defer=True)

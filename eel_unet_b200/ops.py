@@ -68,6 +68,147 @@ def _take(t, key):
     return hit[0]
 
 
+# ---- weight-gradient stream -------------------------------------------------------------------------------------------
+# Backward is a serial chain of data gradients and BatchNorm backward passes; the WEIGHT gradients hang off it as leaves
+# (nothing in the backward reads them).  They are launched on a second stream per device: the tensor-core weight-gradient
+# kernel of layer i then shares the GPU with the HBM-bound BatchNorm backward of layer i-1 instead of queueing in front of it.
+# Ordering: the side stream waits for everything the launching stream has enqueued so far; the tensors it reads are kept
+# referenced until the launching stream has been ordered behind their use (_Wgrad); the launching (and the caller's) stream
+# join the side stream in a final callback of the autograd engine, and parallel.GradBuckets makes its communication stream
+# wait for it too.
+_WGRAD_ASYNC = __import__("os").environ.get("EEL_WGRAD_STREAM", "1") != "0"
+_SIDE_STREAMS = {}        # device index -> torch.cuda.Stream
+_JOIN_PENDING = {}        # (graph task id, launching stream handle, side stream handle) -> True while a join callback is queued
+_JOIN_LOCK = __import__("threading").Lock()
+
+
+# BatchNorm backward sums out of the producer of the gradient (A/B switches of the two newest producers)
+_BRIDGE_BNSUMS = __import__("os").environ.get("EEL_BRIDGE_BNSUMS", "1") != "0"      # eel_add_interleave_bwd_bnsums
+_BNSUMS_WIDE = __import__("os").environ.get("EEL_BNSUMS_WIDE", "1") != "0"          # conv data-gradient epilogue for every width
+
+
+def set_wgrad_stream(flag):
+    """weight gradients on a second stream (default on; EEL_WGRAD_STREAM=0 turns it off at import)"""
+    global _WGRAD_ASYNC
+    _WGRAD_ASYNC = bool(flag)
+
+
+def wgrad_stream(device_index=None):
+    """the device's weight-gradient stream, or None when it was never used"""
+    return _SIDE_STREAMS.get(torch.cuda.current_device() if device_index is None else device_index)
+
+
+def join_wgrad_stream(waiter):
+    """make ``waiter`` (a torch.cuda.Stream) wait for every weight gradient launched so far on its device"""
+    side = _SIDE_STREAMS.get(waiter.device_index)
+    if side is not None:
+        waiter.wait_stream(side)
+
+
+def _async_ok(*params):
+    """the gradients may be produced on the side stream only if nothing reads them before the end of backward:
+    AccumulateGrad must ADOPT them (p.grad is None, no tensor hooks), and a post-accumulate hook is only tolerated when it is
+    GradBuckets' (the gradient was written into its flat-buffer slot, so the hook launches nothing on it)"""
+    if not _WGRAD_ASYNC:
+        return False
+    for p in params:
+        if p is None:
+            continue
+        if p.grad is not None or p._backward_hooks:
+            return False
+        if getattr(p, "_post_accumulate_grad_hooks", None):
+            e = _GRAD_SLOTS.get(id(p))
+            if e is None or e[3] or e[0].device != p.device:
+                return False
+    return True
+
+
+class _Wgrad:
+    """``with _Wgrad(on, t1, t2, ...):`` -- when ``on``, the launches inside go to the weight-gradient stream, ordered after
+    everything enqueued so far on the current stream; t1, t2, ... are the tensors those launches READ.  Never pass the
+    gradients they write: autograd's AccumulateGrad adopts a returned gradient only while nobody else references it and
+    otherwise CLONES it on the spot -- on the launching stream, before the side stream has produced it.  (A small input that
+    is also returned to autograd, like a bias gradient the side stream reads, may be passed: the clone is then of finished
+    data.)  The outputs need no protection: they are flat-buffer slots or become ``p.grad``.
+
+    Lifetimes are handled HERE, not with ``Tensor.record_stream``: the tensors stay referenced until the launching stream has
+    been made to wait (a few weight gradients later, ``_WGRAD_LAG``) for the event recorded behind their last use, and only
+    then are the references dropped.  Frees therefore happen at fixed points of the program and are ordered like ordinary
+    same-stream frees; with record_stream the caching allocator saw blocks come back at times that depend on how far the side
+    stream had got, kept growing (25 -> 48 GB reserved at batch 64) and cudaMalloc calls inside timed steps stalled them."""
+
+    def __init__(self, on, *tensors):
+        self.on, self.tensors, self.ctx, self.late_join = on, tensors, None, None
+
+    def __enter__(self):
+        if not self.on:
+            return self
+        main = torch.cuda.current_stream()
+        idx = main.device_index
+        side = _SIDE_STREAMS.get(idx)
+        if side is None:
+            side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+        side.wait_stream(main)
+        self.main, self.side, self.idx = main, side, idx
+        key = (torch._C._current_graph_task_id(), main.cuda_stream, side.cuda_stream)      # one join per backward pass
+        with _JOIN_LOCK:
+            if len(_JOIN_PENDING) > 256:       # keys of backward passes that died with an exception (a duplicate join is harmless)
+                _JOIN_PENDING.clear()
+            queued = _JOIN_PENDING.get(key)
+            _JOIN_PENDING[key] = True
+        if not queued:
+            def join(main=main, side=side, key=key, idx=idx):
+                with _JOIN_LOCK:
+                    _JOIN_PENDING.pop(key, None)
+                main.wait_stream(side)
+                cur = torch.cuda.current_stream(idx)        # the stream backward() was called on
+                if cur.cuda_stream != main.cuda_stream:
+                    cur.wait_stream(side)
+                _release_held(idx, main, 0)
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(join)
+            except RuntimeError:
+                # not inside a backward pass (a Function's backward called by hand): no leaf to protect, join right after
+                with _JOIN_LOCK:
+                    _JOIN_PENDING.pop(key, None)
+                self.late_join = True
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is None:
+            return False
+        self.ctx.__exit__(*exc)
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        with _JOIN_LOCK:
+            _HELD.setdefault(self.idx, []).append((ev, self.tensors))
+        if self.late_join:
+            self.main.wait_stream(self.side)
+            _release_held(self.idx, self.main, 0)
+        else:
+            _release_held(self.idx, self.main, _WGRAD_LAG)
+        self.tensors = None
+        return False
+
+
+_HELD = {}            # device index -> [(event behind the last side-stream use, tensors kept alive for it)]
+_WGRAD_LAG = 3        # weight gradients the side stream may fall behind before the launching stream waits for it
+
+
+def _release_held(idx, main, keep):
+    """drop the references of all but the newest ``keep`` side-stream launches, after ordering ``main`` behind them"""
+    with _JOIN_LOCK:
+        q = _HELD.get(idx)
+        if not q or len(q) <= keep:
+            return
+        n = len(q) - keep
+        done, _HELD[idx] = q[:n], q[n:]
+    main.wait_event(done[-1][0])        # events of one stream complete in order: the newest of them covers all
+    del done
+
+
 def _pack(w4, perm, dtype, out=None):
     """permute + cast a 4-D fp32 parameter into the operand layout a kernel wants."""
     w4 = _c(w4.detach())
@@ -567,10 +708,13 @@ class StemConv(Function):
         dy = _c(dy)
         P = col.shape[0]
         st = stream()
-        dwblk = torch.empty((128, 64), dtype=F32, device=dy.device)
-        call("eel_tc_wgrad", ptr(dy), ptr(col), ptr(dwblk), P // 2, 128, 64, 64, 1, dwblk.numel(), 0, st)
+        on = _async_ok(ctx.weight)
         dw = _grad_out(ctx.weight)
-        call("eel_stem_unpack_dw", ptr(dwblk), ptr(dw), st)
+        with _Wgrad(on, dy, col):
+            st = stream()
+            dwblk = torch.empty((128, 64), dtype=F32, device=dy.device)
+            call("eel_tc_wgrad", ptr(dy), ptr(col), ptr(dwblk), P // 2, 128, 64, 64, 1, dwblk.numel(), 0, st)
+            call("eel_stem_unpack_dw", ptr(dwblk), ptr(dw), st)
         db = _colsum(dy, 64)
         return None, dw, db
 
@@ -628,7 +772,7 @@ class Conv3x3(Function):
                 # Measured on B200 (batch 64): the fused epilogue costs +0.12 ms on the 64 -> 64 full-resolution layer and saves
                 # the 0.20 ms reduction pass; on the 128-channel half-resolution layers cost and saving cancel (+0.09 / -0.10),
                 # so those keep the plain launch; small maps (bottleneck) are free.
-                if ctx.bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768):
+                if ctx.bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768 or _BNSUMS_WIDE):
                     # x = relu(bn(z)) feeds only this conv: dx is that BatchNorm's whole upstream gradient, and its
                     # backward sums come out of this launch's epilogue
                     z, mean, rstd, gamma, beta, bn_relu = ctx.bn_in
@@ -642,12 +786,16 @@ class Conv3x3(Function):
             else:
                 wd = _pack(weight, (2, 3, 0, 1), x.dtype)  # [ky][kx][co][ci]
                 call("eel_conv3x3_fwd", ptr(dy), ptr(wd), None, ptr(dx), N, H, W, Cout, Cin, 0, 1, dtype_code(x), st)
-        dwp = torch.empty((3, 3, Cin, Cout), dtype=F32, device=x.device)
-        if _tc_ok(x, Cin, Cout) and (Cin == 64 or Cin % 128 == 0):
-            call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, st)
-        else:
-            call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
-        dw = _pack(dwp, (3, 2, 0, 1), F32, out=_grad_out(weight))
+        on = _async_ok(weight)
+        dw = _grad_out(weight)
+        with _Wgrad(on, x, dy):
+            st = stream()
+            dwp = torch.empty((3, 3, Cin, Cout), dtype=F32, device=x.device)
+            if _tc_ok(x, Cin, Cout) and (Cin == 64 or Cin % 128 == 0):
+                call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, st)
+            else:
+                call("eel_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, Cin, Cout, dtype_code(x), st)
+            _pack(dwp, (3, 2, 0, 1), F32, out=dw)
         db = _colsum(dy, Cout)
         return dx, dw, db, None
 
@@ -696,13 +844,17 @@ class ConvT2x2(Function):
                 call("eel_tc_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, st)
             else:
                 call("eel_convt2x2_dgrad", ptr(dy), ptr(wp), ptr(dx), N, h, w, Cin, Cout, dtype_code(x), st)
-        dwp = torch.empty((Cin, 2, 2, Cout), dtype=F32, device=x.device)
-        gw = min(w, 64)
-        if _tc_ok(x, Cin, Cout) and Cin % 128 == 0 and 64 % gw == 0 and w % gw == 0:
-            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwp), N * h * w, Cin, 4 * Cout, 4 * Cout, 1, dwp.numel(), w, st)
-        else:
-            call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
-        dw = _pack(dwp, (0, 3, 1, 2), F32, out=_grad_out(weight))
+        on = _async_ok(weight)
+        dw = _grad_out(weight)
+        with _Wgrad(on, x, dy):
+            st = stream()
+            dwp = torch.empty((Cin, 2, 2, Cout), dtype=F32, device=x.device)
+            gw = min(w, 64)
+            if _tc_ok(x, Cin, Cout) and Cin % 128 == 0 and 64 % gw == 0 and w % gw == 0:
+                call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwp), N * h * w, Cin, 4 * Cout, 4 * Cout, 1, dwp.numel(), w, st)
+            else:
+                call("eel_convt2x2_wgrad", ptr(x), ptr(dy), ptr(dwp), N, h, w, Cin, Cout, dtype_code(x), st)
+            _pack(dwp, (0, 3, 1, 2), F32, out=dw)
         db = _colsum(dy, Cout)
         return dx, dw, db
 
@@ -765,13 +917,16 @@ class Linear(Function):
             else:
                 w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
                 call("eel_linear_dgrad", ptr(dy), ptr(w2), ptr(dx), P, K, Nout, sh, sw, dtype_code(x), st)
+        on = _async_ok(weight)
         dw = _grad_out(weight, (Nout, K))
-        if ctx.tc and Nout % 128 == 0:
-            call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dw), P, Nout, K, K, 1, dw.numel(), 0, st)      # D[m=nout][n=k]
-        elif ctx.tc and K % 128 == 0:
-            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, 1, K, dw.numel(), 0, st)      # D[m=k][n=nout] -> dw[n][m]
-        else:
-            call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
+        with _Wgrad(on, x, dy):
+            st = stream()
+            if ctx.tc and Nout % 128 == 0:
+                call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dw), P, Nout, K, K, 1, dw.numel(), 0, st)      # D[m=nout][n=k]
+            elif ctx.tc and K % 128 == 0:
+                call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, 1, K, dw.numel(), 0, st)      # D[m=k][n=nout] -> dw[n][m]
+            else:
+                call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dw), P, K, Nout, sh, sw, dtype_code(x), st)
         db = _colsum(dy, Nout)
         return dx, dw.view(weight.shape), db, None
 
@@ -833,19 +988,22 @@ class ComposedLinear(Function):
                 call("eel_tc_linear", ptr(dy), ptr(wct), None, ptr(dx), P, Cout, K, 0, None, 0, 0, st)
             else:
                 call("eel_linear_dgrad", ptr(dy), ptr(wc), ptr(dx), P, K, Cout, 0, 0, dtype_code(x), st)
-        dwc = torch.empty((Cout, K), dtype=F32, device=x.device)
-        if ctx.tc and Cout % 128 == 0:
-            call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dwc), P, Cout, K, K, 1, dwc.numel(), 0, st)
-        elif ctx.tc and K % 128 == 0:
-            call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 1, K, dwc.numel(), 0, st)
-        else:
-            call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 0, 0, dtype_code(x), st)
         s = _colsum(dy, Cout)
+        on = _async_ok(w1, b1, w2)
         dw2 = _grad_out(w2, (Cout, Cmid))
         dw1 = _grad_out(w1, (Cmid, K))
         db1 = _grad_out(b1)
-        call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
-             ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, K, st)
+        with _Wgrad(on, x, dy, s):
+            st = stream()
+            dwc = torch.empty((Cout, K), dtype=F32, device=x.device)
+            if ctx.tc and Cout % 128 == 0:
+                call("eel_tc_wgrad", ptr(dy), ptr(x), ptr(dwc), P, Cout, K, K, 1, dwc.numel(), 0, st)
+            elif ctx.tc and K % 128 == 0:
+                call("eel_tc_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 1, K, dwc.numel(), 0, st)
+            else:
+                call("eel_linear_wgrad", ptr(x), ptr(dy), ptr(dwc), P, K, Cout, 0, 0, dtype_code(x), st)
+            call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
+                 ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, K, st)
         return dx, dw1, db1, dw2.view(w2.shape), s
 
 
@@ -918,14 +1076,17 @@ class MlpChain(Function):
         # ---- composed layer (ComposedLinear.backward)
         da = torch.empty_like(a)
         call("eel_tc_linear", ptr(dz), ptr(wct), None, ptr(da), P, Cout, 256, 0, None, 0, 0, st)
-        dwc = torch.empty((Cout, 256), dtype=F32, device=dev)
-        call("eel_tc_wgrad", ptr(dz), ptr(a), ptr(dwc), P, Cout, 256, 256, 1, dwc.numel(), 0, st)
         s = _colsum(dz, Cout)
+        on = _async_ok(w0, w1, b1, w2)
         dw2 = _grad_out(w2, (Cout, Cmid))
         dw1 = _grad_out(w1, (Cmid, 256))
         db1 = _grad_out(b1)
-        call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
-             ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, 256, st)
+        with _Wgrad(on, dz, a, s):
+            sst = stream()
+            dwc = torch.empty((Cout, 256), dtype=F32, device=dev)
+            call("eel_tc_wgrad", ptr(dz), ptr(a), ptr(dwc), P, Cout, 256, 256, 1, dwc.numel(), 0, sst)
+            call("eel_compose_linear_bwd", ptr(dwc), ptr(s), ptr(_c(w2.detach())), ptr(_c(w1.detach())), ptr(b1.detach()),
+                 ptr(dw2), ptr(dw1), ptr(db1), Cout, Cmid, 256, sst)
         # ---- GELU (Gelu.backward); the column sums of dh are mlp[0]'s bias gradient
         dh = torch.empty_like(h)
         db0 = torch.empty(256, dtype=F32, device=dev)
@@ -939,7 +1100,8 @@ class MlpChain(Function):
             du = torch.empty_like(u)
             call("eel_tc_linear", ptr(dh), ptr(w0t), None, ptr(du), P, 256, 64, 0, None, 0, 0, st)
         dw0 = _grad_out(w0, (256, 64))
-        call("eel_tc_wgrad", ptr(dh), ptr(u), ptr(dw0), P, 256, 64, 64, 1, dw0.numel(), 0, st)
+        with _Wgrad(on, dh, u):
+            call("eel_tc_wgrad", ptr(dh), ptr(u), ptr(dw0), P, 256, 64, 64, 1, dw0.numel(), 0, stream())
         return du, dw0.view(w0.shape), db0, dw1, db1, dw2.view(w2.shape), s
 
 
@@ -987,6 +1149,7 @@ class BNAct(Function):
         call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
         ctx.relu, ctx.training, ctx.producer_bias = relu, training, producer_bias
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        # single_conv_consumer: y feeds exactly one conv3x3 or (as the edge feature) exactly one skip bridge
         if single_conv_consumer and z.dtype == BF16 and ctx.needs_input_grad[0]:
             _attach(y, "_eel_bn_out", (z, mean, rstd, gamma, beta, relu))
         return y
@@ -1160,6 +1323,9 @@ class BNAddInterleave(Function):
         call("eel_add_interleave_fwd", ptr(z), ptr(b), ptr(e), ptr(out), N * H * W, C, ptr(mean), ptr(rstd), ptr(gamma.detach()),
              ptr(beta.detach()), dtype_code(z), stream())
         ctx.training, ctx.producer_bias = training, producer_bias
+        # b = relu(bn(z_b)) with this bridge as its only consumer (the model says so through BNAct's single-consumer flag):
+        # the backward pass below then also delivers THAT BatchNorm's backward sums
+        ctx.b_bn = _take(b, "_eel_bn_out") if ctx.needs_input_grad[8] else None
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
         return out
 
@@ -1173,13 +1339,31 @@ class BNAddInterleave(Function):
         dab = torch.empty((N, H, W, C), dtype=dout.dtype, device=dout.device)
         de = torch.empty_like(dab)
         st = stream()
-        call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), P, C, dtype_code(dout), st)
         dz = torch.empty_like(z)
-        dgamma, dbeta = _grad_out(gamma), _grad_out(beta)
-        ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
         dzsum = torch.empty(C, dtype=F32, device=z.device) if ctx.producer_bias else None
-        call("eel_bn_act_bwd", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()), ptr(dz),
-             ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, 0, int(ctx.training), ptr(ws), n, dtype_code(z), st)
+        g, bt = gamma.detach(), beta.detach()
+        if not _BRIDGE_BNSUMS:
+            call("eel_add_interleave_bwd", ptr(dout), ptr(dab), ptr(de), P, C, dtype_code(dout), st)
+            dgamma, dbeta = _grad_out(gamma), _grad_out(beta)
+            ws, n = _reduce_ws(z.device, C, 2, extra=8 * C)
+            call("eel_bn_act_bwd", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(bt), ptr(dz),
+                 ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, 0, int(ctx.training), ptr(ws), n, dtype_code(z), st)
+        else:
+            # the de-interleaving pass also accumulates this BatchNorm's backward sums (and those of the BatchNorm + ReLU that
+            # produced b, when the bridge is its only consumer): the BatchNorm backward is then a single apply pass
+            sums = torch.empty((2, C), dtype=F32, device=z.device)
+            other = ctx.b_bn
+            sums1 = torch.empty((2, C), dtype=F32, device=z.device) if other is not None else None
+            z1, m1, r1, g1, b1, relu1 = other if other is not None else (None, None, None, None, None, 0)
+            ws, n = _reduce_ws(z.device, C, 4)
+            call("eel_add_interleave_bwd_bnsums", ptr(dout), ptr(dab), ptr(de), P, C, ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(bt), 0,
+                 ptr(sums), ptr(z1), ptr(m1), ptr(r1), ptr(g1.detach()) if g1 is not None else None,
+                 ptr(b1.detach()) if b1 is not None else None, int(relu1), ptr(sums1), ptr(ws), n, dtype_code(dout), st)
+            call("eel_bn_act_bwd_apply", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(bt), ptr(sums), ptr(dz), ptr(dzsum), P, C, 0,
+                 int(ctx.training), dtype_code(z), st)
+            dgamma, dbeta = sums[1], sums[0]
+            if other is not None:
+                _attach(dab, "_eel_bn_bwd_sums", (sums1, z1))
         if dzsum is not None:
             _attach(dz, "_eel_colsum", dzsum)
         return dz, dgamma, dbeta, None, None, None, None, None, dab, de, None

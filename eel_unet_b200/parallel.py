@@ -108,6 +108,9 @@ class GradBuckets:
             ev.record(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if self.device.type == "cuda":
+                    from . import ops
+                    ops.join_wgrad_stream(self.comm_stream)      # weight gradients are produced on a second stream
                 op = dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM
                 b.work = dist.all_reduce(g, op=op, group=self.group, async_op=True)
         else:

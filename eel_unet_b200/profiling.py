@@ -97,6 +97,10 @@ def cost(name, a):
     if n == "add_interleave_bwd":
         P, C, dt = a[3], a[4], a[5]
         return 0.0, 4 * P * C * _esz(dt)
+    if n == "add_interleave_bwd_bnsums":   # + one read of each BatchNorm input whose backward sums ride on the pass
+        P, C, dt = a[3], a[4], a[21]
+        nbn = 2 if a[12] else 1
+        return 4.0 * nbn * P * C, (4 + nbn) * P * C * _esz(dt)
     if n == "pgr_fwd":
         P, C, dt = a[5], a[6], a[7]
         return 4.0 * P * C, 2 * P * C * _esz(dt) + 4 * P
@@ -163,7 +167,7 @@ def cost(name, a):
 
 
 # launches reported under another family's name
-ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd"}
+ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd", "add_interleave_bwd_bnsums": "add_interleave_bwd"}
 
 GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_capmlp_fwd", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}

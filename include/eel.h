@@ -215,6 +215,18 @@ int eel_add_interleave_fwd(const void* a, const void* b, const void* e, void* ou
                            int dtype, eel_stream s);
 int eel_add_interleave_bwd(const void* dout, void* dab, void* de, long long P, int C, int dtype,
                            eel_stream s);
+/* The same, and the pass ALSO accumulates the BatchNorm BACKWARD sums of the (one or two) BatchNorms whose whole upstream
+ * gradient is dab: BatchNorm 0 = the one that ends the upconv block and was applied inside eel_add_interleave_fwd
+ * (models/EELUnet.py:365,373; relu0 = 0); BatchNorm 1 (z1 may be NULL) = the BatchNorm + ReLU that produced the edge feature
+ * `b` when the bridge is its only consumer (edge_upconv_1, :326-328,343-344).  sums_k:[2][C] = {sum g, sum g * xhat},
+ * g = dab * [bn_k(z_k) > 0] (relu_k != 0), xhat = (z_k - mean_k) * rstd_k: finish each with eel_bn_act_bwd_apply -- their
+ * reduction passes over (dab, z_k) disappear.  ws >= eel_reduce_workspace_bytes(C, 4). */
+int eel_add_interleave_bwd_bnsums(const void* dout, void* dab, void* de, long long P, int C,
+                                  const void* z0, const float* mean0, const float* rstd0, const float* gamma0,
+                                  const float* beta0, int relu0, float* sums0,
+                                  const void* z1, const float* mean1, const float* rstd1, const float* gamma1,
+                                  const float* beta1, int relu1, float* sums1,
+                                  void* ws, size_t ws_bytes, int dtype, eel_stream s);
 /* PredictionGuidedRefinement (models/EELUnet.py:200-203): s = sigmoid(w.x + b), y = x (1 + s) */
 int eel_pgr_fwd(const void* x, const float* w, const float* b, void* y, float* sgm, long long P, int C,
                 int dtype, eel_stream s);

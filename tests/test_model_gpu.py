@@ -262,6 +262,58 @@ def test_flat_gradient_buffer_receives_the_same_gradients():
             dp.buckets.remove()
 
 
+def test_weight_gradient_stream_gives_the_same_gradients():
+    """ops._Wgrad: weight gradients are launched on a second stream per device (they are leaves of the backward chain) and
+    joined at the end of backward / before a bucket's all-reduce.  Gradients must equal the single-stream run (fp32 mode:
+    exact arithmetic up to the order of fp32 atomics), with and without the flat gradient buffer, and an optimizer step right
+    after backward must see them complete."""
+    from eel_unet_b200 import EELUnet, edge_BceDiceLoss, ops
+    from eel_unet_b200.parallel import DataParallel, FusedAdam
+
+    _, _, x, y = _setup(2, 128, 128)
+    x, y = x.cuda(), y.cuda()
+    crit = edge_BceDiceLoss(1, 1)
+    torch.manual_seed(5)
+    a = EELUnet(3, 1, precision="fp32").cuda().train()
+    b = EELUnet(3, 1, precision="fp32").cuda().train()
+    c = EELUnet(3, 1, precision="fp32").cuda().train()
+    b.load_state_dict(a.state_dict())
+    c.load_state_dict(a.state_dict())
+    try:
+        ops.set_wgrad_stream(False)
+        seg, edges = a(x)
+        crit(edges, seg, y).backward()
+        ops.set_wgrad_stream(True)
+        seg, edges = b(x)
+        crit(edges, seg, y).backward()
+        assert ops.wgrad_stream() is not None, "the weight-gradient stream was never used"
+        gmax = max(p.grad.norm().item() for p in a.parameters())
+        for (n, p), q in zip(a.named_parameters(), b.parameters()):
+            if p.grad.norm().item() > 1e-4 * gmax:
+                assert rel(q.grad, p.grad) < 1e-3, (n, rel(q.grad, p.grad))
+        # flat gradient buffer + fused Adam: the slots are written on the side stream, the optimizer kernel right after
+        # finish_backward() must find them complete
+        dp = DataParallel(c)
+        opt = FusedAdam(dp.buckets, lr=1e-3)
+        try:
+            for _ in range(2):
+                dp.zero_grad()
+                seg, edges = dp(x)
+                crit(edges, seg, y).backward()
+                dp.finish_backward()
+                if _ == 0:
+                    for (n, p), q in zip(a.named_parameters(), c.parameters()):
+                        if p.grad.norm().item() > 1e-4 * gmax:
+                            assert rel(q.grad, p.grad) < 1e-3, (n, rel(q.grad, p.grad))
+                opt.step()
+            torch.cuda.synchronize()
+            assert all(torch.isfinite(q).all() for q in c.parameters())
+        finally:
+            dp.buckets.remove()
+    finally:
+        ops.set_wgrad_stream(True)
+
+
 def test_inference_batchnorm_folding_matches_unfolded_eval():
     """bf16 inference folds eval-mode BatchNorms into their producers' packed weights (ops.FoldedPacker).  Same math as the
     unfolded eval path (taken whenever autograd is on), different rounding points: the two must agree to bf16 accuracy, and

@@ -372,6 +372,51 @@ def test_add_interleave(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("edge_bn", [False, True])
+@pytest.mark.parametrize("shape", [(2, 64, 12, 20), (1, 128, 16, 8), (3, 16, 6, 10), (1, 512, 4, 6)])
+def test_bn_add_interleave(dtype, edge_bn, shape):
+    """decoder skip bridge (reference models/EELUnet.py:422-426) with the upconv block's BatchNorm (:365,373) applied inside it.
+    Backward: the de-interleaving pass also accumulates that BatchNorm's backward sums (eel_add_interleave_bwd_bnsums) and --
+    edge_bn -- those of the BatchNorm + ReLU that produced the edge feature when the bridge is its only consumer (bf16 mode);
+    both BatchNorm backwards are then single apply passes"""
+    from eel_unet_b200 import _lib, ops
+
+    n, c, h, w = shape
+    z = torch.randn(n, c, h, w, device=DEV) * 1.5 + 0.3
+    zb = torch.randn(n, c, h, w, device=DEV) * 0.7 - 0.2
+    e = torch.randn(n, c, h, w, device=DEV)
+    params = [torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.5]
+    if edge_bn:
+        params += [torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.5]
+    rm0, rv0 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    rm1, rv1 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+
+    def mine(a, p):
+        feat = ops.BNAct.apply(a[1], p[2], p[3], rm1, rv1, True, True, 0.1, 1e-5, False, True) if edge_bn else a[1]
+        return ops.BNAddInterleave.apply(a[0], p[0], p[1], rm0, rv0, True, 0.1, 1e-5, feat, a[2], False)
+
+    def ref(a, p):
+        up = F.batch_norm(a[0], None, None, p[0], p[1], True, 0.1, 1e-5)
+        feat = a[1]
+        if edge_bn:
+            feat = F.relu(F.batch_norm(a[1], None, None, p[2], p[3], True, 0.1, 1e-5))
+            feat = feat + (feat.to(dtype).double() - feat).detach()      # the bridge reads the activation as stored
+        s = up + feat
+        return torch.stack([s, a[2]], dim=2).reshape(n, 2 * c, h, w)
+
+    rec = []
+    _lib.set_profiler(rec)
+    try:
+        run_case(mine, ref, [z, zb, e], params, dtype, atol_scale=2.0)
+    finally:
+        _lib.set_profiler(None)
+    names = [r[0] for r in rec]
+    assert "eel_add_interleave_bwd_bnsums" in names and names.count("eel_bn_act_bwd_apply") >= 1
+    if dtype == torch.bfloat16:
+        assert "eel_bn_act_bwd" not in names and names.count("eel_bn_act_bwd_apply") == (2 if edge_bn else 1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("c", [64, 128, 1024])
 def test_pgr(dtype, c):
     from eel_unet_b200 import ops

@@ -41,6 +41,7 @@ EXPECTED = {
     "eel_se_bwd": {13: "N", 14: "HW", 15: "C", 19: "dtype"},
     "eel_add_interleave_fwd": {4: "P", 5: "C", 10: "dtype"},
     "eel_add_interleave_bwd": {3: "P", 4: "C", 5: "dtype"},
+    "eel_add_interleave_bwd_bnsums": {3: "P", 4: "C", 12: "z1", 21: "dtype"},
     "eel_head_fwd": {6: "N", 7: "HW", 8: "O", 9: "dtype"},
     "eel_head_bwd": {12: "N", 13: "HW", 14: "O", 17: "dtype"},
     "eel_adam_step": {4: "n"},
