@@ -770,12 +770,14 @@ class Conv3x3(Function):
                 if wk is None:
                     wk = _pack(weight, (2, 3, 1, 0), x.dtype)  # [ky][kx][ci][co]: K-major B of the transposed problem
                 # Measured on B200 (batch 64): the fused epilogue costs +0.12 ms on the 64 -> 64 full-resolution layer and saves
-                # the 0.20 ms reduction pass; on the 128-channel half-resolution layers cost and saving cancel (+0.09 / -0.10),
-                # so those keep the plain launch; small maps (bottleneck) are free.
-                if ctx.bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768 or _BNSUMS_WIDE):
+                # the 0.20 ms reduction pass; on the 128-channel half-resolution layers cost and saving cancel in step time
+                # (+0.09 / -0.10) but the two reads of (dy, z) leave the HBM-bound side of the ledger (EEL_BNSUMS_WIDE=0
+                # restores the plain launch there); small maps (bottleneck) are free.
+                bn_in, ctx.bn_in = ctx.bn_in, None      # (not a saved tensor: drop it here, or it lives as long as the graph does)
+                if bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768 or _BNSUMS_WIDE):
                     # x = relu(bn(z)) feeds only this conv: dx is that BatchNorm's whole upstream gradient, and its
                     # backward sums come out of this launch's epilogue
-                    z, mean, rstd, gamma, beta, bn_relu = ctx.bn_in
+                    z, mean, rstd, gamma, beta, bn_relu = bn_in
                     sums = torch.empty((2, Cin), dtype=F32, device=x.device)
                     cws = workspace(16 * Cin, x.device, slot=1)
                     call("eel_tc_conv3x3_dgrad_bnsums", ptr(dy), ptr(wk), ptr(dx), N, H, W, Cout, Cin, ptr(z), ptr(mean), ptr(rstd),
@@ -1352,7 +1354,7 @@ class BNAddInterleave(Function):
             # the de-interleaving pass also accumulates this BatchNorm's backward sums (and those of the BatchNorm + ReLU that
             # produced b, when the bridge is its only consumer): the BatchNorm backward is then a single apply pass
             sums = torch.empty((2, C), dtype=F32, device=z.device)
-            other = ctx.b_bn
+            other, ctx.b_bn = ctx.b_bn, None            # (not a saved tensor: drop it here)
             sums1 = torch.empty((2, C), dtype=F32, device=z.device) if other is not None else None
             z1, m1, r1, g1, b1, relu1 = other if other is not None else (None, None, None, None, None, 0)
             ws, n = _reduce_ws(z.device, C, 4)
