@@ -209,6 +209,37 @@ def _release_held(idx, main, keep):
     del done
 
 
+_PACK_EVENTS = {}     # device index -> event behind the newest weight-packing launches on the side stream
+
+
+def _on_side_stream(fn):
+    """The per-step weight packing (eel_pack_batch, eel_compose_batch: strided fp32 -> bf16 transposes, latency-bound) runs on
+    the side stream, which idles during the forward: its first consumer is several kernels into the step, so it leaves the
+    critical path.  Consumers order themselves behind it through ``_await_packed()``."""
+    if not _WGRAD_ASYNC:
+        fn()
+        return
+    main = torch.cuda.current_stream()
+    idx = main.device_index
+    side = _SIDE_STREAMS.get(idx)
+    if side is None:
+        side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    side.wait_stream(main)          # the optimizer (and the previous step's readers of the packed buffers) ran on `main`
+    with torch.cuda.stream(side):
+        fn()
+    ev = torch.cuda.Event()
+    ev.record(side)
+    _PACK_EVENTS[idx] = ev
+
+
+def _await_packed():
+    """before the first read of a packed / composed operand: order the current stream behind the packing launches"""
+    if _PACK_EVENTS:
+        ev = _PACK_EVENTS.pop(torch.cuda.current_device(), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+
 def _pack(w4, perm, dtype, out=None):
     """permute + cast a 4-D fp32 parameter into the operand layout a kernel wants."""
     w4 = _c(w4.detach())
@@ -341,7 +372,7 @@ class WeightPacker:
         ver = [_WEIGHT_EPOCH] + [e[0]._version for e in self.entries]
         if ver == self.versions:
             return
-        call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream())
+        _on_side_stream(lambda: call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream()))
         self.versions = ver
         # publish on the parameters themselves: ops find the operands through the weight they are handed (forward and
         # backward, any thread, any number of models), and only while the weight is what was packed
@@ -515,7 +546,11 @@ class ComposedPacker:
         ver = [_WEIGHT_EPOCH, _STATS_EPOCH] + [t._version for p in self.params for t in p]
         if ver == self.versions:
             return
-        call("eel_compose_batch", ptr(self.table), len(self.entries), self.blocks, stream())
+        if any(e[2] is not None for e in self.entries):
+            # (BatchNorm-folded inference tables: FoldedPacker reads them right away on the current stream)
+            call("eel_compose_batch", ptr(self.table), len(self.entries), self.blocks, stream())
+        else:
+            _on_side_stream(lambda: call("eel_compose_batch", ptr(self.table), len(self.entries), self.blocks, stream()))
         self.versions = ver
         for e, p in zip(self.entries, self.params):
             if e[2] is None:                   # (BatchNorm-folded tables are inference-scoped: FoldedPacker hands them out)
@@ -636,6 +671,7 @@ def _packed(weight, which):
     hit = getattr(weight, "_eel_packed", None)
     if hit is None or hit[2] != _pack_key(weight):
         return None
+    _await_packed()
     return hit[which]
 
 
@@ -952,6 +988,7 @@ class ComposedLinear(Function):
         N, H, W, K = x.shape
         Cout, Cmid = w2.shape[0], w1.shape[0]
         hit = getattr(w2, "_eel_composed", None)
+        _await_packed()
         if hit is not None and hit[3] == x.dtype and hit[4] == tuple(_pack_key(t) for t in (w2, b2, w1, b1)):
             hit = hit[:3]
         else:
@@ -960,6 +997,7 @@ class ComposedLinear(Function):
             one = ComposedPacker(x.dtype)
             one.add(_Pair(w1.detach(), b1.detach()), _Pair(w2.detach().view(Cout, Cmid), b2.detach()))
             one.refresh(x.device)
+            _await_packed()
             hit = one._keep[0]
         wc, wct, bc = hit
         ctx.tc = _tc_ok(x, K, Cout)
@@ -1044,12 +1082,14 @@ class MlpChain(Function):
         Cout, Cmid = w2.shape[0], w1.shape[0]
         P = N * H * W
         hit = getattr(w2, "_eel_composed", None)
+        _await_packed()
         if hit is not None and hit[3] == u.dtype and hit[4] == tuple(_pack_key(t) for t in (w2, b2, w1, b1)):
             wc, wct, bc = hit[:3]
         else:
             one = ComposedPacker(u.dtype)
             one.add(_Pair(w1.detach(), b1.detach()), _Pair(w2.detach().view(Cout, Cmid), b2.detach()))
             one.refresh(u.device)
+            _await_packed()
             wc, wct, bc = one._keep[0]
         w0p = _packed(w0, 0)
         if w0p is None:
