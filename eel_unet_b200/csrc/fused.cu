@@ -622,64 +622,105 @@ __global__ void __launch_bounds__(kPixThreads, 3) head_bwd_kernel(const T* __res
     for (int i = threadIdx.x; i < width; i += kPixThreads) partial[(long long)blockIdx.x * width + i] = sh[i];
 }
 
-// ---- head, one THREAD per pixel (O == 1, the reference's binary segmentation) -------------------------------------------
+// ---- head, one WARP per 32-pixel tile (O == 1, the reference's binary segmentation) -----------------------------------
 // The lane-group kernels above spend most of their issue slots on shuffles and on per-lane copies of scalar work (ncu:
-// 67 % issue-active at 23 % of DRAM bandwidth).  With the pixel's 64 channels in one thread's registers LayerNorm needs no
+// 67 % issue-active at 23 % of DRAM bandwidth).  With a pixel's 64 channels in ONE thread's registers LayerNorm needs no
 // shuffle at all, and for O == 1 every parameter gradient follows from S0 = sum_p dl_p and S1[c] = sum_p dl_p * xhat_pc:
 //     dlnw[c] = w[c] S1[c],  dlnb[c] = w[c] S0,  dw[c] = lnw[c] S1[c] + lnb[c] S0,  db = S0      (dl = dprob * p (1 - p))
-constexpr int kTpThreads = 128;
+// A first version gave each thread its pixel straight from global memory: 128 (256) contiguous bytes per lane, so every
+// 16-byte access of a warp touched 32 different lines, and the backward's 64 S1 accumulators per thread left 12 warps per
+// SM (36 % of the HBM roofline, 0.47 ms at 64 x 256^2).  Here a warp moves its 32 pixels as 16-byte
+// vectors in lane order (whole 512-byte runs per access) through a shared-memory tile [32][68] fp32 (rows 16-byte aligned,
+// 128-bit accesses conflict-free both ways): phase A stores the vectors, phase B is the thread-per-pixel LayerNorm arithmetic
+// on the pixel's 64 values in registers, phase C walks the tile in vector order again for the dx stores and for S1, of which
+// a lane now only accumulates the 8 (4) channels of its vector slot.  The next tile's vectors are loaded one round ahead.
+constexpr int kHwThreads = 128;               // 4 warps, one tile each per round
+constexpr int kHwRow = kHeadC + 4;
 
-template <class T> __device__ __forceinline__ void tp_load64(const T* __restrict__ src, float (&v)[kHeadC]) {
+template <class T> __device__ __forceinline__ void hw_store_vec(float* row_slot, const Vec16<T>& v, bool ok) {
     constexpr int V = Vec16<T>::N;
 #pragma unroll
-    for (int k = 0; k < kHeadC / V; ++k) {
-        const Vec16<T> q = ld16(src + k * V);
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[k * V + j] = q.get(j);
-    }
+    for (int k = 0; k < V / 4; ++k)
+        *reinterpret_cast<float4*>(row_slot + 4 * k) = ok ? make_float4(v.get(4 * k), v.get(4 * k + 1), v.get(4 * k + 2), v.get(4 * k + 3))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <class T>
-__global__ void __launch_bounds__(kTpThreads) head_fwd_tp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
-                                                               const float* __restrict__ lnb, const float* __restrict__ w,
-                                                               const float* __restrict__ b, float* __restrict__ prob, long long P) {
-    __shared__ float swl[kHeadC];   // w[c] * lnw[c]
-    __shared__ float sc[2];         // sum_c w[c] * lnb[c] + b,  unused
+__global__ void __launch_bounds__(kHwThreads, 3) head_fwd_warp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                                 const float* __restrict__ lnb, const float* __restrict__ w,
+                                                                 const float* __restrict__ b, float* __restrict__ prob, long long P) {
+    constexpr int V = Vec16<T>::N, VPP = kHeadC / V;      // vectors per pixel
+    __shared__ __align__(16) float tile[kHwThreads / 32][32 * kHwRow];
+    __shared__ __align__(16) float swl[kHeadC];
+    __shared__ float scb;
     if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
     if (threadIdx.x == 0) {
         float t = b[0];
         for (int c = 0; c < kHeadC; ++c) t += w[c] * lnb[c];
-        sc[0] = t;
+        scb = t;
     }
     __syncthreads();
-    const float cb = sc[0];
-    for (long long p = blockIdx.x * (long long)kTpThreads + threadIdx.x; p < P; p += (long long)gridDim.x * kTpThreads) {
-        float v[kHeadC];
-        tp_load64<T>(x + p * kHeadC, v);
+    const float cb = scb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane % VPP;
+    float* tl = tile[warp];
+    const long long ntiles = (P + 31) / 32;
+    const long long tstep = (long long)gridDim.x * (kHwThreads / 32);
+    long long t = (long long)blockIdx.x * (kHwThreads / 32) + warp;
+    Vec16<T> v[VPP];
+    auto load_tile = [&](long long tt) {
+        const long long q0 = tt * 32;
+#pragma unroll
+        for (int it = 0; it < VPP; ++it) {
+            const int vi = it * 32 + lane;
+            if (q0 + vi / VPP < P) v[it] = ld16(x + q0 * kHeadC + (long long)vi * V);
+        }
+    };
+    if (t < ntiles) load_tile(t);
+    for (; t < ntiles; t += tstep) {
+        const long long p0 = t * 32;
+#pragma unroll
+        for (int it = 0; it < VPP; ++it) {
+            const int pix = (it * 32 + lane) / VPP;
+            hw_store_vec<T>(tl + pix * kHwRow + slot * V, v[it], p0 + pix < P);
+        }
+        if (t + tstep < ntiles) load_tile(t + tstep);      // the next tile's vectors travel while this one is processed
+        __syncwarp();
+        float xr[kHeadC];
+#pragma unroll
+        for (int k = 0; k < kHeadC / 4; ++k) {
+            const float4 q4 = *reinterpret_cast<const float4*>(tl + lane * kHwRow + 4 * k);
+            xr[4 * k] = q4.x; xr[4 * k + 1] = q4.y; xr[4 * k + 2] = q4.z; xr[4 * k + 3] = q4.w;
+        }
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < kHeadC; ++c) s += v[c];
+        for (int c = 0; c < kHeadC; ++c) s += xr[c];
         const float mu = s * (1.f / kHeadC);
         float q = 0.f, d = 0.f;
 #pragma unroll
-        for (int c = 0; c < kHeadC; ++c) {
-            const float t = v[c] - mu;
-            q = fmaf(t, t, q);
-            d = fmaf(swl[c], t, d);
+        for (int k = 0; k < kHeadC / 4; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4*>(swl + 4 * k);
+            const float u0 = xr[4 * k] - mu, u1 = xr[4 * k + 1] - mu, u2 = xr[4 * k + 2] - mu, u3 = xr[4 * k + 3] - mu;
+            q = fmaf(u0, u0, q); q = fmaf(u1, u1, q); q = fmaf(u2, u2, q); q = fmaf(u3, u3, q);
+            d = fmaf(w4.x, u0, d); d = fmaf(w4.y, u1, d); d = fmaf(w4.z, u2, d); d = fmaf(w4.w, u3, d);
         }
         const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
-        prob[p] = sigmoidf_(fmaf(d, r, cb));       // sum_c w (lnw xhat + lnb) + b
+        if (p0 + lane < P) prob[p0 + lane] = sigmoidf_(fmaf(d, r, cb));
+        __syncwarp();
     }
 }
 
+// partial row layout: dlnw[64] dlnb[64] dw[64] db[1]
 template <class T>
-__global__ void __launch_bounds__(kTpThreads) head_bwd_tp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
-                                                               const float* __restrict__ lnb, const float* __restrict__ w,
-                                                               const float* __restrict__ prob, const float* __restrict__ dprob,
-                                                               T* __restrict__ dx, float* __restrict__ partial, long long P) {
-    constexpr int V = Vec16<T>::N;
-    __shared__ float swl[kHeadC];           // w[c] * lnw[c]
-    __shared__ float sacc[kHeadC + 1];      // S1[c], S0
+__global__ void __launch_bounds__(kHwThreads, 3) head_bwd_warp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                                 const float* __restrict__ lnb, const float* __restrict__ w,
+                                                                 const float* __restrict__ prob, const float* __restrict__ dprob,
+                                                                 T* __restrict__ dx, float* __restrict__ partial, long long P) {
+    constexpr int V = Vec16<T>::N, VPP = kHeadC / V;
+    __shared__ __align__(16) float tile[kHwThreads / 32][32 * kHwRow];
+    __shared__ float pk[kHwThreads / 32][3][32];        // per pixel of a warp's tile: dl, r * dl, m2
+    __shared__ __align__(16) float swl[kHeadC];
+    __shared__ float sacc[kHeadC + 1];                  // S1[c], S0
     __shared__ float swm;
     if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
     if (threadIdx.x <= kHeadC) sacc[threadIdx.x] = 0.f;
@@ -691,53 +732,109 @@ __global__ void __launch_bounds__(kTpThreads) head_bwd_tp_kernel(const T* __rest
     }
     __syncthreads();
     const float wm = swm;
-    float S1[kHeadC], S0 = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tl = tile[warp];
+    float (*pw)[32] = pk[warp];
+    const int slot = lane % VPP;                        // (32 is a multiple of VPP: a lane meets the same slot in every round)
+    float swl_l[V];
 #pragma unroll
-    for (int c = 0; c < kHeadC; ++c) S1[c] = 0.f;
-    for (long long p = blockIdx.x * (long long)kTpThreads + threadIdx.x; p < P; p += (long long)gridDim.x * kTpThreads) {
-        float v[kHeadC];
-        tp_load64<T>(x + p * kHeadC, v);
-        const float pr = prob[p];
-        const float dl = dprob[p] * pr * (1.f - pr);
-        float s = 0.f;
+    for (int j = 0; j < V; ++j) swl_l[j] = swl[slot * V + j] - wm;
+    float S1[V], S0 = 0.f;
 #pragma unroll
-        for (int c = 0; c < kHeadC; ++c) s += v[c];
-        const float mu = s * (1.f / kHeadC);
-        float q = 0.f;
+    for (int j = 0; j < V; ++j) S1[j] = 0.f;
+    const long long ntiles = (P + 31) / 32;
+    const long long tstep = (long long)gridDim.x * (kHwThreads / 32);
+    long long t = (long long)blockIdx.x * (kHwThreads / 32) + warp;
+    Vec16<T> v[VPP];
+    float pr_n = 0.f, dp_n = 0.f;
+    auto load_tile = [&](long long tt) {
+        const long long q0 = tt * 32;
 #pragma unroll
-        for (int c = 0; c < kHeadC; ++c) { v[c] -= mu; q = fmaf(v[c], v[c], q); }
-        const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
-        float m2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kHeadC; ++c) {
-            v[c] *= r;                              // xhat
-            m2 = fmaf(swl[c], v[c], m2);
-            S1[c] = fmaf(dl, v[c], S1[c]);
+        for (int it = 0; it < VPP; ++it) {
+            const int vi = it * 32 + lane;
+            if (q0 + vi / VPP < P) v[it] = ld16(x + q0 * kHeadC + (long long)vi * V);
         }
-        S0 += dl;
-        m2 *= (1.f / kHeadC);
-        const float k = r * dl;
-        T* dst = dx + p * kHeadC;
+        const bool ok = q0 + lane < P;
+        pr_n = ok ? prob[q0 + lane] : 0.f;
+        dp_n = ok ? dprob[q0 + lane] : 0.f;
+    };
+    if (t < ntiles) load_tile(t);
+    for (; t < ntiles; t += tstep) {
+        const long long p0 = t * 32;
+        // ---- A: the tile's vectors (loaded in lane order one round ahead) go to shared memory
+        const float dl = dp_n * pr_n * (1.f - pr_n);
 #pragma unroll
-        for (int kk = 0; kk < kHeadC / V; ++kk) {
+        for (int it = 0; it < VPP; ++it) {
+            const int pix = (it * 32 + lane) / VPP;
+            hw_store_vec<T>(tl + pix * kHwRow + slot * V, v[it], p0 + pix < P);
+        }
+        if (t + tstep < ntiles) load_tile(t + tstep);      // the next tile's vectors travel while this one is processed
+        __syncwarp();
+        // ---- B: LayerNorm statistics of pixel `lane` in registers; the tile row becomes xhat
+        {
+            float xr[kHeadC];
+#pragma unroll
+            for (int k = 0; k < kHeadC / 4; ++k) {
+                const float4 q4 = *reinterpret_cast<const float4*>(tl + lane * kHwRow + 4 * k);
+                xr[4 * k] = q4.x; xr[4 * k + 1] = q4.y; xr[4 * k + 2] = q4.z; xr[4 * k + 3] = q4.w;
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < kHeadC; ++c) s += xr[c];
+            const float mu = s * (1.f / kHeadC);
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < kHeadC; ++c) { xr[c] -= mu; q = fmaf(xr[c], xr[c], q); }
+            const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kHeadC / 4; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(swl + 4 * k);
+                const float4 h4 = make_float4(xr[4 * k] * r, xr[4 * k + 1] * r, xr[4 * k + 2] * r, xr[4 * k + 3] * r);
+                m2 = fmaf(w4.x, h4.x, m2); m2 = fmaf(w4.y, h4.y, m2); m2 = fmaf(w4.z, h4.z, m2); m2 = fmaf(w4.w, h4.w, m2);
+                *reinterpret_cast<float4*>(tl + lane * kHwRow + 4 * k) = h4;
+            }
+            pw[0][lane] = dl;
+            pw[1][lane] = r * dl;
+            pw[2][lane] = m2 * (1.f / kHeadC);
+            S0 += dl;
+        }
+        __syncwarp();
+        // ---- C: dx in vector order; S1 over the lane's slot
+        T* dst = dx + p0 * kHeadC;
+#pragma unroll
+        for (int it = 0; it < VPP; ++it) {
+            const int vi = it * 32 + lane, pix = vi / VPP;
+            const float dlp = pw[0][pix], kk = pw[1][pix], mm = pw[2][pix];
+            float xh[V];
+#pragma unroll
+            for (int k = 0; k < V / 4; ++k) {
+                const float4 q4 = *reinterpret_cast<const float4*>(tl + pix * kHwRow + slot * V + 4 * k);
+                xh[4 * k] = q4.x; xh[4 * k + 1] = q4.y; xh[4 * k + 2] = q4.z; xh[4 * k + 3] = q4.w;
+            }
             Vec16<T> o;
 #pragma unroll
-            for (int j = 0; j < V; ++j) o.set(j, k * (swl[kk * V + j] - wm - v[kk * V + j] * m2));
-            st16(dst + kk * V, o);
+            for (int j = 0; j < V; ++j) {
+                S1[j] = fmaf(dlp, xh[j], S1[j]);
+                o.set(j, kk * fmaf(-xh[j], mm, swl_l[j]));
+            }
+            if (p0 + pix < P) st16(dst + (long long)vi * V, o);
         }
+        __syncwarp();
     }
-    // block reduction of S1 / S0: warp shuffles, then one shared atomic per warp and value
+    // lanes with the same slot hold partial sums of the same channels (lane bits above log2(VPP))
 #pragma unroll
-    for (int c = 0; c < kHeadC; ++c) {
-        const float t = warp_sum(S1[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[c], t);
+    for (int j = 0; j < V; ++j) {
+        float t2 = S1[j];
+#pragma unroll
+        for (int o = VPP; o < 32; o <<= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        if (lane < VPP) atomicAdd(&sacc[slot * V + j], t2);
     }
     {
-        const float t = warp_sum(S0);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[kHeadC], t);
+        const float t2 = warp_sum(S0);
+        if (lane == 0) atomicAdd(&sacc[kHeadC], t2);
     }
     __syncthreads();
-    // partial row layout: dlnw[64] dlnb[64] dw[64] db[1]
     float* row = partial + (long long)blockIdx.x * (3 * kHeadC + 1);
     if (threadIdx.x < kHeadC) {
         const int c = threadIdx.x;
@@ -870,10 +967,10 @@ int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float*
         long long blocks = (P + gpb - 1) / gpb;
         int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
         if (O == 1) {
-            long long tb = (P + kTpThreads - 1) / kTpThreads;
-            int g1 = (int)(tb < (long long)kNumSMs * 16 ? tb : (long long)kNumSMs * 16);
-            head_fwd_tp_kernel<T><<<g1, kTpThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P);
-            return check_launch("head_fwd(tp)");
+            long long tb = (P + kHwThreads - 1) / kHwThreads;
+            int g1 = (int)(tb < (long long)kNumSMs * 6 ? tb : (long long)kNumSMs * 6);
+            head_fwd_warp_kernel<T><<<g1, kHwThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P);
+            return check_launch("head_fwd(warp tile)");
         }
         head_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P, HW, O);
         return check_launch("head_fwd");
@@ -899,9 +996,9 @@ int eel_head_bwd(const void* x, const float* lnw, const float* lnb, const float*
         float* partial = (float*)ws;
         if (O == 1) {
             // thread-per-pixel kernel: the grid is bounded by the partial rows the workspace holds (same bound as above)
-            long long tb = (P + kTpThreads - 1) / kTpThreads;
+            long long tb = (P + kHwThreads - 1) / kHwThreads;
             grid = (int)(tb < (long long)grid ? tb : (long long)grid);
-            head_bwd_tp_kernel<T><<<grid, kTpThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P);
+            head_bwd_warp_kernel<T><<<grid, kHwThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P);
         } else head_bwd_kernel<T, kHeadMaxO><<<grid, kPixThreads, sizeof(float) * width, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, prob, dprob, (T*)dx, partial, P, HW, O);
         if (int rc = check_launch("head_bwd")) return rc;
         RowSegs segs{{dlnw, dlnb, dw, db}, {kHeadC, 2 * kHeadC, (2 + O) * kHeadC, (2 + O) * kHeadC + O}};

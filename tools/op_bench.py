@@ -112,6 +112,21 @@ def cases(B, S, only):
             return "eel_tc_capmlp_fwd", (ptr(u), ptr(w0), ptr(b0), ptr(wc), ptr(bc), ptr(h), ptr(a_), ptr(z), P, c, 0, None, st()), \
                 (u, w0, b0, wc, bc, h, a_, z)
         add("mlp", "capmlp_fwd P=%d C=%d" % (B * s * s, c), mk_mlp)
+    def mk_head(fwd):
+        P = B * S * S
+        x, dx = rnd(B, S, S, 64), torch.empty(B, S, S, 64, device=DEV, dtype=BF16)
+        lnw, lnb, w, b = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), torch.randn(64, device=DEV) / 8, torch.zeros(1, device=DEV)
+        prob, dprob = torch.rand(P, device=DEV), torch.randn(P, device=DEV)
+        g = [torch.empty(64, device=DEV) for _ in range(3)] + [torch.empty(1, device=DEV)]
+        n = 4 * (4 * _lib.lib.eel_num_sms() + 1) * (3 * 64 + 1)
+        ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+        keep = (x, dx, lnw, lnb, w, b, prob, dprob, g, ws)
+        if fwd:
+            return "eel_head_fwd", (ptr(x), ptr(lnw), ptr(lnb), ptr(w), ptr(b), ptr(prob), B, S * S, 1, 1, st()), keep
+        return "eel_head_bwd", (ptr(x), ptr(lnw), ptr(lnb), ptr(w), ptr(b), ptr(prob), ptr(dprob), ptr(dx), ptr(g[0]), ptr(g[1]), ptr(g[2]),
+                                ptr(g[3]), B, S * S, 1, ptr(ws), n, 1, st()), keep
+    add("head", "head_fwd %dx%d" % (S, S), lambda: mk_head(True))
+    add("head", "head_bwd %dx%d" % (S, S), lambda: mk_head(False))
     for (s, c) in [(S, 64), (S // 2, 128)]:
         def mk_hft(s=s, c=c, fwd=True):
             x, y = rnd(B, s, s, c), torch.empty(B, s, s, c, device=DEV, dtype=BF16)
