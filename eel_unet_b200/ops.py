@@ -85,6 +85,7 @@ _JOIN_LOCK = __import__("threading").Lock()
 # BatchNorm backward sums out of the producer of the gradient (A/B switches of the two newest producers)
 _BRIDGE_BNSUMS = __import__("os").environ.get("EEL_BRIDGE_BNSUMS", "1") != "0"      # eel_add_interleave_bwd_bnsums
 _BNSUMS_WIDE = __import__("os").environ.get("EEL_BNSUMS_WIDE", "1") != "0"          # conv data-gradient epilogue for every width
+_BNSUMS_64 = __import__("os").environ.get("EEL_BNSUMS_64", "1") != "0"              # ... for the 64-channel full-resolution layers
 
 
 def set_wgrad_stream(flag):
@@ -810,7 +811,8 @@ class Conv3x3(Function):
                 # (+0.09 / -0.10) but the two reads of (dy, z) leave the HBM-bound side of the ledger (EEL_BNSUMS_WIDE=0
                 # restores the plain launch there); small maps (bottleneck) are free.
                 bn_in, ctx.bn_in = ctx.bn_in, None      # (not a saved tensor: drop it here, or it lives as long as the graph does)
-                if bn_in is not None and _stats_cols_ok(Cin) and (Cin == 64 or N * H * W <= 32768 or _BNSUMS_WIDE):
+                if bn_in is not None and _stats_cols_ok(Cin) and ((Cin == 64 and _BNSUMS_64) or N * H * W <= 32768 or
+                                                                  (Cin != 64 and _BNSUMS_WIDE)):
                     # x = relu(bn(z)) feeds only this conv: dx is that BatchNorm's whole upstream gradient, and its
                     # backward sums come out of this launch's epilogue
                     z, mean, rstd, gamma, beta, bn_relu = bn_in

@@ -50,3 +50,37 @@ def test_rejects_cpu_and_bad_arguments():
         data.preprocess_images(torch.zeros(1, 8, 8, 3, device="cuda"), (4, 4))
     with pytest.raises(_lib.EelError):
         data.preprocess_images(torch.zeros(1, 8, 8, 3, dtype=torch.uint8, device="cuda"), (4, 4), mean=(0.5,), std=(0.5,))
+
+
+def test_device_prefetcher_hands_over_the_batches_in_order():
+    """data.DevicePrefetcher: double-buffered host -> device copies on a copy stream; every batch arrives intact and in order
+    while the compute stream is busy, through the iterator and through put / get"""
+    from eel_unet_b200 import data
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(4, 3, 32, 32, generator=g).pin_memory(), torch.randint(0, 2, (4, 1, 32, 32), generator=g).float().pin_memory())
+               for _ in range(7)]
+    busy = torch.randn(2048, 2048, device=dev)
+    seen = []
+    for x, y in data.DevicePrefetcher(batches, dev):
+        assert x.is_cuda and y.is_cuda
+        busy = busy @ busy * 1e-3                # keep the compute stream occupied between hand-overs
+        seen.append((x.clone(), y.clone()))
+    torch.cuda.synchronize()
+    assert len(seen) == len(batches)
+    for (x, y), (hx, hy) in zip(seen, batches):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
+    pf = data.DevicePrefetcher(device=dev)
+    pf.put(*batches[0])
+    pf.put(*batches[1])
+    with pytest.raises(Exception):
+        pf.put(*batches[2])                      # both slots in flight
+    a = pf.get()
+    pf.put(*batches[2])
+    b = pf.get()
+    c = pf.get()
+    torch.cuda.synchronize()
+    assert torch.equal(b[0].cpu(), batches[1][0]) and torch.equal(c[0].cpu(), batches[2][0])
+    with pytest.raises(Exception):
+        pf.get()
