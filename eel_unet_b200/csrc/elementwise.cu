@@ -3,6 +3,8 @@
 // Everything moves 16-byte vectors along the contiguous channel axis of NHWC tensors.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <stdlib.h>
 
 namespace eel {
@@ -1294,37 +1296,250 @@ __global__ void se_mlp_bwd_kernel(const float* __restrict__ datt, const float* _
     }
 }
 
-// phase B: one thread per parameter-gradient element sums its contributions over the images (deterministic order).
+// phase B: one thread per parameter-gradient element sums its contributions over the images (deterministic order).  The arrays
+// that other blocks of a cooperative launch have just written are read with ld.global.cg (L2 is the point of coherence).
+__device__ void se_param_grad_element(int i, const float* __restrict__ dpre, const float* __restrict__ dhid, const float* __restrict__ hid,
+                                     const float* __restrict__ mean, float* __restrict__ dw1, float* __restrict__ db1,
+                                     float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R,
+                                     const float* __restrict__ att, const float* __restrict__ sums, const float* __restrict__ dmean_scaled,
+                                     float hw, float* __restrict__ dt_colsum) {
+    const int CR = C * R;
+    float s = 0.f;
+    if (i < CR) {                       // dw2[c][r] = sum_n dpre[n][c] * hid[n][r]
+        const int c = i / R, r = i % R;
+        for (int n = 0; n < N; ++n) s += __ldcg(dpre + n * C + c) * hid[n * R + r];
+        dw2[i] = s;
+    } else if (i < 2 * CR) {            // dw1[r][c] = sum_n dhid[n][r] * mean[n][c]
+        const int j = i - CR, r = j / C, c = j % C;
+        for (int n = 0; n < N; ++n) s += __ldcg(dhid + n * R + r) * mean[n * C + c];
+        dw1[j] = s;
+    } else if (i < 2 * CR + C) {        // db2[c]
+        const int c = i - 2 * CR;
+        for (int n = 0; n < N; ++n) s += __ldcg(dpre + n * C + c);
+        db2[c] = s;
+    } else if (i < 2 * CR + C + R) {    // db1[r]
+        const int r = i - 2 * CR - C;
+        for (int n = 0; n < N; ++n) s += __ldcg(dhid + n * R + r);
+        db1[r] = s;
+    } else if (dt_colsum != nullptr && i < 2 * CR + 2 * C + R) {
+        // column sums of dt = dout * att + dmean over all pixels: sum_n att[n][c] * (sum_hw dout)[n][c] + HW * dmean[n][c]
+        const int c = i - 2 * CR - C - R;
+        for (int n = 0; n < N; ++n) s += att[n * C + c] * __ldcg(sums + (long long)n * 2 * C + C + c) + hw * __ldcg(dmean_scaled + n * C + c);
+        dt_colsum[c] = s;
+    }
+}
+
+
 __global__ void se_param_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ dhid, const float* __restrict__ hid,
                                      const float* __restrict__ mean, float* __restrict__ dw1, float* __restrict__ db1,
                                      float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R,
                                      const float* __restrict__ att, const float* __restrict__ sums, const float* __restrict__ dmean_scaled,
                                      float hw, float* __restrict__ dt_colsum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int CR = C * R;
-    float s = 0.f;
-    if (i < CR) {                       // dw2[c][r] = sum_n dpre[n][c] * hid[n][r]
-        const int c = i / R, r = i % R;
-        for (int n = 0; n < N; ++n) s += dpre[n * C + c] * hid[n * R + r];
-        dw2[i] = s;
-    } else if (i < 2 * CR) {            // dw1[r][c] = sum_n dhid[n][r] * mean[n][c]
-        const int j = i - CR, r = j / C, c = j % C;
-        for (int n = 0; n < N; ++n) s += dhid[n * R + r] * mean[n * C + c];
-        dw1[j] = s;
-    } else if (i < 2 * CR + C) {        // db2[c]
-        const int c = i - 2 * CR;
-        for (int n = 0; n < N; ++n) s += dpre[n * C + c];
-        db2[c] = s;
-    } else if (i < 2 * CR + C + R) {    // db1[r]
-        const int r = i - 2 * CR - C;
-        for (int n = 0; n < N; ++n) s += dhid[n * R + r];
-        db1[r] = s;
-    } else if (dt_colsum != nullptr && i < 2 * CR + 2 * C + R) {
-        // column sums of dt = dout * att + dmean over all pixels: sum_n att[n][c] * (sum_hw dout)[n][c] + HW * dmean[n][c]
-        const int c = i - 2 * CR - C - R;
-        for (int n = 0; n < N; ++n) s += att[n * C + c] * sums[(long long)n * 2 * C + C + c] + hw * dmean_scaled[n * C + c];
-        dt_colsum[c] = s;
+    se_param_grad_element(blockIdx.x * blockDim.x + threadIdx.x, dpre, dhid, hid, mean, dw1, db1, dw2, db2, N, C, R, att, sums,
+                          dmean_scaled, hw, dt_colsum);
+}
+
+// ---- squeeze-excite as ONE cooperative launch per direction ---------------------------------------------------------------
+// The multi-launch versions below are latency chains: on the model's 33 MB token tensors the four (forward) / five (backward)
+// dependent launches take 36 / 64 us where the traffic needs 10 / 20.  Here k blocks per image (k * N <= 2 blocks per SM, so
+// that the launch fits beside a weight-gradient kernel of the other stream) reduce their slice, meet at a grid barrier, each
+// repeat the image's tiny 64 -> R -> 64 algebra in shared memory, and scale their slice -- which they have just read, so the
+// second read comes from L2.  The backward needs a second barrier for the parameter gradients (sums over the images).
+
+template <class T, int Q, class LOADACC>
+__device__ __forceinline__ void se_slice_sums(const LOADACC& f, long long row0, long long rows, int C, int TX, float* red /* [256][Q*V+1] */,
+                                              float* __restrict__ dst /* [Q][C] */) {
+    constexpr int V = Vec16<T>::N;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    float acc[Q][V];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[q][v] = 0.f;
+    for (long long r = ty; r < rows; r += 4LL * TY) {
+        Vec16<T> in[4][Q];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r + (long long)u * TY < rows) f.load((row0 + r + (long long)u * TY) * C + tx * V, in[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r + (long long)u * TY < rows) f.accum(in[u], acc);
     }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) red[threadIdx.x * (Q * V + 1) + q * V + v] = acc[q][v];
+    __syncthreads();
+    for (int j = ty; j < Q * V; j += TY) {
+        float t = 0.f;
+        for (int y = 0; y < TY; ++y) t += red[(y * TX + tx) * (Q * V + 1) + j];
+        dst[(j / V) * C + tx * V + j % V] = t;
+    }
+}
+
+template <class T> struct SeSumLoad {
+    const T* t;
+    __device__ void load(long long off, Vec16<T> (&in)[1]) const { in[0] = ld16(t + off); }
+    __device__ void accum(const Vec16<T> (&in)[1], float (&acc)[1][Vec16<T>::N]) const {
+#pragma unroll
+        for (int i = 0; i < Vec16<T>::N; ++i) acc[0][i] += in[0].get(i);
+    }
+};
+template <class T> struct SeDotLoad {      // {sum dout * t, sum dout}
+    const T* dout; const T* t;
+    __device__ void load(long long off, Vec16<T> (&in)[2]) const { in[0] = ld16(dout + off); in[1] = ld16(t + off); }
+    __device__ void accum(const Vec16<T> (&in)[2], float (&acc)[2][Vec16<T>::N]) const {
+#pragma unroll
+        for (int i = 0; i < Vec16<T>::N; ++i) {
+            const float d = in[0].get(i);
+            acc[0][i] = fmaf(d, in[1].get(i), acc[0][i]);
+            acc[1][i] += d;
+        }
+    }
+};
+
+// dynamic shared memory: red[256][Q*V+1] floats, then 3*C + R floats of per-image vectors
+template <class T>
+__global__ void __launch_bounds__(256) se_fwd_coop_kernel(const T* __restrict__ t, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2, T* __restrict__ out,
+                                                        float* __restrict__ mean, float* __restrict__ att, float* __restrict__ hid,
+                                                        float* __restrict__ partial /* [N][k][C] */, long long HW, int C, int R, int k) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float sh[];
+    float* red = sh;
+    float* s_mean = sh + 256 * (V + 1);
+    float* s_att = s_mean + C;
+    float* s_hid = s_att + C;
+    const int TX = C / V, TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.x / k, part = blockIdx.x % k;
+    const long long rows = HW / k, row0 = (long long)n * HW + (long long)part * rows;
+    se_slice_sums<T, 1>(SeSumLoad<T>{t}, row0, rows, C, TX, red, partial + (long long)blockIdx.x * C);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const float inv_hw = 1.0f / (float)HW;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float m = 0.f;
+        for (int p = 0; p < k; ++p) m += __ldcg(partial + ((long long)n * k + p) * C + c);
+        m *= inv_hw;
+        s_mean[c] = m;
+        if (part == 0) mean[(long long)n * C + c] = m;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += 256) {
+        float a = b1[r];
+        for (int c = 0; c < C; ++c) a += w1[r * C + c] * s_mean[c];
+        a = fmaxf(a, 0.f);
+        s_hid[r] = a;
+        if (part == 0) hid[(long long)n * R + r] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = b2[c];
+        for (int r = 0; r < R; ++r) a += w2[c * R + r] * s_hid[r];
+        a = sigmoidf_(a);
+        s_att[c] = a;
+        if (part == 0) att[(long long)n * C + c] = a;
+    }
+    __syncthreads();
+    float av[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) av[j] = s_att[tx * V + j];
+    // the slice is walked from its END: the reduction finished there, those lines are the most likely to still sit in L2
+    for (long long r = rows - 1 - ty; r >= 0; r -= 4LL * TY) {
+        Vec16<T> v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r - (long long)u * TY >= 0) v[u] = ld16(t + (row0 + r - (long long)u * TY) * C + tx * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r - (long long)u * TY >= 0) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o.set(j, v[u].get(j) * av[j]);
+                st16(out + (row0 + r - (long long)u * TY) * C + tx * V, o);
+            }
+    }
+}
+
+// workspace layout as eel_se_bwd: sums[N][2C] | dmean[N][C] | dpre[N][C] | dhid[N][C] | partial[N][k][2][C]
+template <class T>
+__global__ void __launch_bounds__(256) se_bwd_coop_kernel(const T* __restrict__ t, const T* __restrict__ dout, const float* __restrict__ att,
+                                                        const float* __restrict__ hid, const float* __restrict__ mean,
+                                                        const float* __restrict__ w1, const float* __restrict__ w2, T* __restrict__ dt,
+                                                        float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                                        float* __restrict__ db2, float* __restrict__ dt_colsum, float* __restrict__ sums,
+                                                        float* __restrict__ dmean, float* __restrict__ dpre_g, float* __restrict__ dhid_g,
+                                                        float* __restrict__ partial, int N, long long HW, int C, int R, int k) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float sh[];
+    float* red = sh;
+    float* s_dpre = sh + 256 * (2 * V + 1);
+    float* s_dmean = s_dpre + C;
+    float* s_dhid = s_dmean + C;
+    const int TX = C / V, TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.x / k, part = blockIdx.x % k;
+    const long long rows = HW / k, row0 = (long long)n * HW + (long long)part * rows;
+    se_slice_sums<T, 2>(SeDotLoad<T>{dout, t}, row0, rows, C, TX, red, partial + (long long)blockIdx.x * 2 * C);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const float inv_hw = 1.0f / (float)HW;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s_dt = 0.f, s_d = 0.f;
+        for (int p = 0; p < k; ++p) {
+            s_dt += __ldcg(partial + (((long long)n * k + p) * 2 + 0) * C + c);
+            s_d += __ldcg(partial + (((long long)n * k + p) * 2 + 1) * C + c);
+        }
+        const float a = att[(long long)n * C + c];
+        const float d = s_dt * a * (1.f - a);
+        s_dpre[c] = d;
+        if (part == 0) {
+            sums[(long long)n * 2 * C + c] = s_dt;
+            sums[(long long)n * 2 * C + C + c] = s_d;
+            dpre_g[(long long)n * C + c] = d;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += 256) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) a += w2[c * R + r] * s_dpre[c];
+        a = hid[(long long)n * R + r] > 0.f ? a : 0.f;
+        s_dhid[r] = a;
+        if (part == 0) dhid_g[(long long)n * R + r] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a += w1[r * C + c] * s_dhid[r];
+        a *= inv_hw;
+        s_dmean[c] = a;
+        if (part == 0) dmean[(long long)n * C + c] = a;
+    }
+    __syncthreads();
+    float av[V], dm[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { av[j] = att[(long long)n * C + tx * V + j]; dm[j] = s_dmean[tx * V + j]; }
+    for (long long r = rows - 1 - ty; r >= 0; r -= 4LL * TY) {
+        Vec16<T> v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r - (long long)u * TY >= 0) v[u] = ld16(dout + (row0 + r - (long long)u * TY) * C + tx * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r - (long long)u * TY >= 0) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o.set(j, fmaf(v[u].get(j), av[j], dm[j]));
+                st16(dt + (row0 + r - (long long)u * TY) * C + tx * V, o);
+            }
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int nout = 2 * C * R + 2 * C + R;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < nout) se_param_grad_element(i, dpre_g, dhid_g, hid, mean, dw1, db1, dw2, db2, N, C, R, att, sums, dmean, (float)HW, dt_colsum);
 }
 
 // ------------------------------------------------------------------------------------ Adam
@@ -1339,6 +1554,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         p[i] -= (lr / bc1) * (mi / denom);
     }
 }
+
+// blocks per image of the cooperative squeeze-excite launches: a power of two that divides HW, leaves every thread row of a
+// block at least one row, and keeps the grid at <= 2 blocks per SM (0: use the multi-launch path)
+static int se_coop_parts(int N, long long HW, int TY) {
+    if (N <= 0 || N > 2 * kNumSMs) return 0;
+    int k = 1;
+    while (2 * k * N <= 2 * kNumSMs && HW % (2 * k) == 0 && HW / (2 * k) >= TY) k *= 2;
+    return k;
+}
+
+template <class K> static bool se_coop_fits(K kernel, int blocks, int smem) {
+    int dev = 0, per_sm = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess) return false;
+    return (long long)per_sm * sms >= blocks;
+}
+
 
 }  // namespace eel
 
@@ -1709,12 +1942,26 @@ int eel_gelu_bwd_colsum(const void* x, const void* dy, void* dx, float* colsum, 
     });
 }
 
+
 int eel_se_fwd(const void* t, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
                float* mean, float* att, float* hid, int N, long long HW, int C, int R, void* ws, size_t ws_bytes,
                int dtype, eel_stream s) {
     EEL_REQUIRE(t && w1 && b1 && w2 && b2 && out && mean && att && hid && N > 0 && HW > 0 && C > 0 && R > 0, "se_fwd: bad argument");
     cudaStream_t st = (cudaStream_t)s;
     EEL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        if (C % V == 0 && 256 % (C / V) == 0 && C / V <= 256) {
+            const int k = se_coop_parts(N, HW, 256 / (C / V));
+            const int smem = (int)sizeof(float) * (256 * (V + 1) + 2 * C + R);
+            if (k > 0 && smem <= 48 * 1024 && ws != nullptr && ws_bytes >= sizeof(float) * (size_t)N * k * C &&
+                se_coop_fits(se_fwd_coop_kernel<T>, N * k, smem)) {
+                const T* tp = (const T*)t; T* op = (T*)out; float* part = (float*)ws; long long hw = HW; int kk = k;
+                void* args[] = {&tp, &w1, &b1, &w2, &b2, &op, &mean, &att, &hid, &part, &hw, &C, &R, &kk};
+                if (cudaLaunchCooperativeKernel((void*)se_fwd_coop_kernel<T>, dim3(N * k), dim3(256), args, smem, st) == cudaSuccess)
+                    return check_launch("se_fwd(cooperative)");
+                (void)cudaGetLastError();       // (fall through to the multi-launch path)
+            }
+        }
         RedPlan pl;
         SumF<T> f{(const T*)t, C};
         if (int rc = run_colreduce<T, SumF<T>, 1>(f, HW, C, N, (float*)ws, ws_bytes, pl, st, "se_fwd.mean")) return rc;
@@ -1741,6 +1988,21 @@ int eel_se_bwd(const void* t, const void* dout, const float* att, const float* h
         float* dpre = dmean + (size_t)N * C;
         float* dhid = dpre + (size_t)N * C;
         float* partial = dhid + (size_t)N * C;
+        constexpr int V = Vec16<T>::N;
+        if (C % V == 0 && 256 % (C / V) == 0 && C / V <= 256) {
+            const int k = se_coop_parts(N, HW, 256 / (C / V));
+            const int smem = (int)sizeof(float) * (256 * (2 * V + 1) + 2 * C + R);
+            const int nout = 2 * C * R + 2 * C + R;
+            if (k > 0 && smem <= 48 * 1024 && (long long)N * k * 256 >= nout && ws_bytes - head >= sizeof(float) * (size_t)N * k * 2 * C &&
+                se_coop_fits(se_bwd_coop_kernel<T>, N * k, smem)) {
+                const T* tp = (const T*)t; const T* dp = (const T*)dout; T* dtp = (T*)dt; long long hw = HW; int kk = k;
+                void* args[] = {&tp, &dp, &att, &hid, &mean, &w1, &w2, &dtp, &dw1, &db1, &dw2, &db2, &dt_colsum, &sums, &dmean, &dpre, &dhid,
+                                &partial, &N, &hw, &C, &R, &kk};
+                if (cudaLaunchCooperativeKernel((void*)se_bwd_coop_kernel<T>, dim3(N * k), dim3(256), args, smem, st) == cudaSuccess)
+                    return check_launch("se_bwd(cooperative)");
+                (void)cudaGetLastError();
+            }
+        }
         RedPlan pl;
         Dot2F<T> f{(const T*)dout, (const T*)t, C};
         if (int rc = run_colreduce<T, Dot2F<T>, 2>(f, HW, C, N, partial, ws_bytes - head, pl, st, "se_bwd.dot")) return rc;

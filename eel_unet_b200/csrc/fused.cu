@@ -622,6 +622,54 @@ __global__ void __launch_bounds__(kPixThreads, 3) head_bwd_kernel(const T* __res
     for (int i = threadIdx.x; i < width; i += kPixThreads) partial[(long long)blockIdx.x * width + i] = sh[i];
 }
 
+// ---- head forward, one THREAD per pixel (O == 1) -------------------------------------------------------------------------
+// (measured inside the step, where the input was just written and partly sits in L2, this simpler kernel beats the warp-tile
+// forward below: 0.16 against 0.19 ms; the backward is the other way round, 0.47 against 0.39 ms)
+constexpr int kTpThreads = 128;
+
+template <class T> __device__ __forceinline__ void tp_load64(const T* __restrict__ src, float (&v)[kHeadC]) {
+    constexpr int V = Vec16<T>::N;
+#pragma unroll
+    for (int k = 0; k < kHeadC / V; ++k) {
+        const Vec16<T> q = ld16(src + k * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[k * V + j] = q.get(j);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kTpThreads) head_fwd_tp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
+                                                               const float* __restrict__ lnb, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ prob, long long P) {
+    __shared__ float swl[kHeadC];   // w[c] * lnw[c]
+    __shared__ float sc[2];         // sum_c w[c] * lnb[c] + b,  unused
+    if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
+    if (threadIdx.x == 0) {
+        float t = b[0];
+        for (int c = 0; c < kHeadC; ++c) t += w[c] * lnb[c];
+        sc[0] = t;
+    }
+    __syncthreads();
+    const float cb = sc[0];
+    for (long long p = blockIdx.x * (long long)kTpThreads + threadIdx.x; p < P; p += (long long)gridDim.x * kTpThreads) {
+        float v[kHeadC];
+        tp_load64<T>(x + p * kHeadC, v);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) s += v[c];
+        const float mu = s * (1.f / kHeadC);
+        float q = 0.f, d = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) {
+            const float t = v[c] - mu;
+            q = fmaf(t, t, q);
+            d = fmaf(swl[c], t, d);
+        }
+        const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
+        prob[p] = sigmoidf_(fmaf(d, r, cb));       // sum_c w (lnw xhat + lnb) + b
+    }
+}
+
 // ---- head, one WARP per 32-pixel tile (O == 1, the reference's binary segmentation) -----------------------------------
 // The lane-group kernels above spend most of their issue slots on shuffles and on per-lane copies of scalar work (ncu:
 // 67 % issue-active at 23 % of DRAM bandwidth).  With a pixel's 64 channels in ONE thread's registers LayerNorm needs no
@@ -643,71 +691,6 @@ template <class T> __device__ __forceinline__ void hw_store_vec(float* row_slot,
     for (int k = 0; k < V / 4; ++k)
         *reinterpret_cast<float4*>(row_slot + 4 * k) = ok ? make_float4(v.get(4 * k), v.get(4 * k + 1), v.get(4 * k + 2), v.get(4 * k + 3))
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-template <class T>
-__global__ void __launch_bounds__(kHwThreads, 3) head_fwd_warp_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
-                                                                 const float* __restrict__ lnb, const float* __restrict__ w,
-                                                                 const float* __restrict__ b, float* __restrict__ prob, long long P) {
-    constexpr int V = Vec16<T>::N, VPP = kHeadC / V;      // vectors per pixel
-    __shared__ __align__(16) float tile[kHwThreads / 32][32 * kHwRow];
-    __shared__ __align__(16) float swl[kHeadC];
-    __shared__ float scb;
-    if (threadIdx.x < kHeadC) swl[threadIdx.x] = w[threadIdx.x] * lnw[threadIdx.x];
-    if (threadIdx.x == 0) {
-        float t = b[0];
-        for (int c = 0; c < kHeadC; ++c) t += w[c] * lnb[c];
-        scb = t;
-    }
-    __syncthreads();
-    const float cb = scb;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = lane % VPP;
-    float* tl = tile[warp];
-    const long long ntiles = (P + 31) / 32;
-    const long long tstep = (long long)gridDim.x * (kHwThreads / 32);
-    long long t = (long long)blockIdx.x * (kHwThreads / 32) + warp;
-    Vec16<T> v[VPP];
-    auto load_tile = [&](long long tt) {
-        const long long q0 = tt * 32;
-#pragma unroll
-        for (int it = 0; it < VPP; ++it) {
-            const int vi = it * 32 + lane;
-            if (q0 + vi / VPP < P) v[it] = ld16(x + q0 * kHeadC + (long long)vi * V);
-        }
-    };
-    if (t < ntiles) load_tile(t);
-    for (; t < ntiles; t += tstep) {
-        const long long p0 = t * 32;
-#pragma unroll
-        for (int it = 0; it < VPP; ++it) {
-            const int pix = (it * 32 + lane) / VPP;
-            hw_store_vec<T>(tl + pix * kHwRow + slot * V, v[it], p0 + pix < P);
-        }
-        if (t + tstep < ntiles) load_tile(t + tstep);      // the next tile's vectors travel while this one is processed
-        __syncwarp();
-        float xr[kHeadC];
-#pragma unroll
-        for (int k = 0; k < kHeadC / 4; ++k) {
-            const float4 q4 = *reinterpret_cast<const float4*>(tl + lane * kHwRow + 4 * k);
-            xr[4 * k] = q4.x; xr[4 * k + 1] = q4.y; xr[4 * k + 2] = q4.z; xr[4 * k + 3] = q4.w;
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < kHeadC; ++c) s += xr[c];
-        const float mu = s * (1.f / kHeadC);
-        float q = 0.f, d = 0.f;
-#pragma unroll
-        for (int k = 0; k < kHeadC / 4; ++k) {
-            const float4 w4 = *reinterpret_cast<const float4*>(swl + 4 * k);
-            const float u0 = xr[4 * k] - mu, u1 = xr[4 * k + 1] - mu, u2 = xr[4 * k + 2] - mu, u3 = xr[4 * k + 3] - mu;
-            q = fmaf(u0, u0, q); q = fmaf(u1, u1, q); q = fmaf(u2, u2, q); q = fmaf(u3, u3, q);
-            d = fmaf(w4.x, u0, d); d = fmaf(w4.y, u1, d); d = fmaf(w4.z, u2, d); d = fmaf(w4.w, u3, d);
-        }
-        const float r = 1.f / sqrtf(q * (1.f / kHeadC) + 1e-6f);
-        if (p0 + lane < P) prob[p0 + lane] = sigmoidf_(fmaf(d, r, cb));
-        __syncwarp();
-    }
 }
 
 // partial row layout: dlnw[64] dlnb[64] dw[64] db[1]
@@ -967,10 +950,10 @@ int eel_head_fwd(const void* x, const float* lnw, const float* lnb, const float*
         long long blocks = (P + gpb - 1) / gpb;
         int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
         if (O == 1) {
-            long long tb = (P + kHwThreads - 1) / kHwThreads;
-            int g1 = (int)(tb < (long long)kNumSMs * 6 ? tb : (long long)kNumSMs * 6);
-            head_fwd_warp_kernel<T><<<g1, kHwThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P);
-            return check_launch("head_fwd(warp tile)");
+            long long tb = (P + kTpThreads - 1) / kTpThreads;
+            int g1 = (int)(tb < (long long)kNumSMs * 16 ? tb : (long long)kNumSMs * 16);
+            head_fwd_tp_kernel<T><<<g1, kTpThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P);
+            return check_launch("head_fwd(tp)");
         }
         head_fwd_kernel<T><<<grid, kPixThreads, 0, (cudaStream_t)s>>>((const T*)x, lnw, lnb, w, b, prob, P, HW, O);
         return check_launch("head_fwd");

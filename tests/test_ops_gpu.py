@@ -454,14 +454,19 @@ def test_head(dtype, o):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_se(dtype):
+@pytest.mark.parametrize("shape", [(3, 64, 6, 10), (2, 64, 32, 32), (5, 64, 16, 16), (300, 64, 2, 2), (2, 128, 8, 24)])
+def test_se(dtype, shape):
+    """ChannelAttention (reference models/EELUnet.py:57-80).  One cooperative launch per direction (k blocks per image, grid
+    barrier, the tiny MLP repeated per block): shapes with 1, 16 and 4 blocks per image, one with more images than the
+    cooperative grid allows (multi-launch path), and a wider token"""
     from eel_unet_b200 import ops
 
-    x = torch.randn(3, 64, 6, 10, device=DEV)
-    w1 = torch.randn(4, 64, 1, 1, device=DEV) / 8
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, device=DEV)
+    w1 = torch.randn(4, c, 1, 1, device=DEV) / 8
     b1 = torch.randn(4, device=DEV) * 0.5
-    w2 = torch.randn(64, 4, 1, 1, device=DEV) / 2
-    b2 = torch.randn(64, device=DEV) * 0.5
+    w2 = torch.randn(c, 4, 1, 1, device=DEV) / 2
+    b2 = torch.randn(c, device=DEV) * 0.5
 
     def ref(a, p):
         g = a[0].mean(dim=(2, 3), keepdim=True)
