@@ -449,6 +449,14 @@ def run_ours(args):
             ach = d["bytes"] / d["ms"] / 1e6
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                     "traffic": None, "peak_source": peak_src + " (copy)", "share_of_step": top[3] / 100.0}
+        if top[0] == "tc_conv3x3":
+            # the family holds two kinds of launch: plain implicit-GEMM convolutions, and data gradients whose epilogue also reads
+            # the BatchNorm input z and accumulates that BatchNorm's backward sums (HBM work without FLOPs): both rates
+            for tag, names in (("plain_conv_launches", ("eel_tc_conv3x3",)), ("dgrad_with_bn_sums_launches", ("eel_tc_conv3x3_dgrad_bnsums",))):
+                sel = [(profiling.cost(nm, a)[0], s0.elapsed_time(s1)) for nm, a, s0, s1 in rec if nm in names]
+                if sel:
+                    fl, tm = sum(v[0] for v in sel), sum(v[1] for v in sel)
+                    roof[tag] = {"calls": len(sel), "ms": round(tm, 3), "achieved": fl / tm / 1e9, "frac": fl / tm / 1e9 / tens_sus}
         # DRAM traffic of the dominant family from the committed ncu --set full capture of the same step (bytes per launch,
         # like `achieved`); null when no capture of this family is on file
         tj = os.path.join(ROOT, "profiles", "r02_traffic.json")

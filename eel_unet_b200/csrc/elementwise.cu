@@ -1061,23 +1061,41 @@ __global__ void copy_cols_kernel(const T* __restrict__ src, long long src_ld, in
 // ------------------------------------------------------------------------------------ ShiftedChannel
 // y[n,h,w,c] = x[n,(h+dh)%H,(w+dw)%W,c]; quarter 0: dh=-1, quarter 1: dh=+1, quarter 2: dw=-1 (signs flip for the adjoint)
 template <class T>
-__global__ void shift_channels_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, int H, int W, int C, int inverse) {
+__global__ void __launch_bounds__(256) shift_channels_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned int npix, int H, int W, int C,
+                                                           int inverse, int TX, unsigned int pix_per_block) {
+    // Row-streaming layout of the BatchNorm apply kernels: a thread owns one 16-byte channel vector -- so its channel quarter
+    // and with it its (dh, dw) are fixed -- and walks down the pixels with 4 independent loads in flight; 32-bit index
+    // arithmetic (the first version spent ~300 instructions per vector on three 64-bit divisions: 58 % of the HBM roofline).
     constexpr int V = Vec16<T>::N;
-    const int cv = C / V;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * V;
-        long long pix = i / cv;
-        int w = (int)(pix % W);
-        long long r = pix / W;
-        int h = (int)(r % H);
-        long long n = r / H;
-        int q = c / (C / 4);
-        int dh = q == 0 ? -1 : (q == 1 ? 1 : 0), dw = q == 2 ? -1 : 0;
-        if (inverse) { dh = -dh; dw = -dw; }
-        int hh = h + dh, ww = w + dw;
-        hh = hh < 0 ? hh + H : (hh >= H ? hh - H : hh);
-        ww = ww < 0 ? ww + W : (ww >= W ? ww - W : ww);
-        st16(y + i * V, ld16(x + ((n * H + hh) * W + ww) * C + c));
+    constexpr int U = 4;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = (blockIdx.x * TX + tx) * V;
+    if (c >= C) return;
+    const int q = c / (C / 4);
+    int dh = q == 0 ? -1 : (q == 1 ? 1 : 0), dw = q == 2 ? -1 : 0;
+    if (inverse) { dh = -dh; dw = -dw; }
+    const unsigned int p0 = blockIdx.y * pix_per_block;
+    const unsigned int p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+    for (unsigned int p = p0 + ty; p < p1; p += U * TY) {
+        Vec16<T> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int pp = p + u * TY;
+            if (pp < p1) {
+                const unsigned int r = pp / (unsigned int)W, w = pp - r * (unsigned int)W;
+                const unsigned int n = r / (unsigned int)H, h = r - n * (unsigned int)H;
+                int hh = (int)h + dh, ww = (int)w + dw;
+                hh = hh < 0 ? hh + H : (hh >= H ? hh - H : hh);
+                ww = ww < 0 ? ww + W : (ww >= W ? ww - W : ww);
+                v[u] = ld16(x + ((size_t)(n * (unsigned int)H + (unsigned int)hh) * (unsigned int)W + (unsigned int)ww) * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int pp = p + u * TY;
+            if (pp < p1) st16(y + (size_t)pp * C + c, v[u]);
+        }
     }
 }
 
@@ -1877,8 +1895,12 @@ int eel_shift_channels(const void* x, void* y, int N, int H, int W, int C, int i
     EEL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "shift_channels: bad argument");
     EEL_DISPATCH_DTYPE(dtype, {
         EEL_REQUIRE(C % (4 * Vec16<T>::N) == 0, "shift_channels: C/4 must be a multiple of the 16-byte vector");
-        long long nvec = (long long)N * H * W * C / Vec16<T>::N;
-        shift_channels_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, nvec, H, W, C, inverse);
+        const long long npix = (long long)N * H * W;
+        EEL_REQUIRE(npix < (1LL << 32), "shift_channels: more than 2^32 pixels");
+        RedPlan pl = plan_stream<T>(npix, C);
+        dim3 grid(pl.ncb, pl.nrb);
+        shift_channels_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, (unsigned int)npix, H, W, C, inverse, pl.TX,
+                                                                    (unsigned int)pl.rows_per_rb);
         return check_launch("shift_channels");
     });
 }

@@ -210,7 +210,7 @@ def _release_held(idx, main, keep):
     del done
 
 
-_PACK_EVENTS = {}     # device index -> event behind the newest weight-packing launches on the side stream
+# (the event behind the newest weight-packing launches lives in the forward's thread-local state: _TLS.pack_events[device index])
 
 
 def _on_side_stream(fn):
@@ -230,13 +230,18 @@ def _on_side_stream(fn):
         fn()
     ev = torch.cuda.Event()
     ev.record(side)
-    _PACK_EVENTS[idx] = ev
+    pe = getattr(_TLS, "pack_events", None)
+    if pe is None:
+        pe = _TLS.pack_events = {}
+    pe[idx] = ev
 
 
 def _await_packed():
-    """before the first read of a packed / composed operand: order the current stream behind the packing launches"""
-    if _PACK_EVENTS:
-        ev = _PACK_EVENTS.pop(torch.cuda.current_device(), None)
+    """before the first read of a packed / composed operand: order the current stream behind the packing launches (of this
+    thread's forward: the packing and the first consumers run on the thread that calls the model)"""
+    pe = getattr(_TLS, "pack_events", None)
+    if pe:
+        ev = pe.pop(torch.cuda.current_device(), None)
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 

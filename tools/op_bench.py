@@ -112,6 +112,12 @@ def cases(B, S, only):
             return "eel_tc_capmlp_fwd", (ptr(u), ptr(w0), ptr(b0), ptr(wc), ptr(bc), ptr(h), ptr(a_), ptr(z), P, c, 0, None, st()), \
                 (u, w0, b0, wc, bc, h, a_, z)
         add("mlp", "capmlp_fwd P=%d C=%d" % (B * s * s, c), mk_mlp)
+    for (s_, c_) in [(S // 4, 256), (S // 8, 512)]:
+        def mk_shift(s_=s_, c_=c_):
+            x, y = rnd(B, s_, s_, c_), torch.empty(B, s_, s_, c_, device=DEV, dtype=BF16)
+            return "eel_shift_channels", (ptr(x), ptr(y), B, s_, s_, c_, 0, 1, st()), (x, y)
+        add("shift", "shift_channels %dx%d C=%d" % (s_, s_, c_), mk_shift)
+
     def mk_head(fwd):
         P = B * S * S
         x, dx = rnd(B, S, S, 64), torch.empty(B, S, S, 64, device=DEV, dtype=BF16)
