@@ -154,8 +154,10 @@ template <class T> struct AbsEpi {
                 float mag = sqrtf(zr * zr + zi * zi);
                 float inv = mag > 0.f ? 1.0f / mag : 0.f;
                 y[base + n + j] = from_f32<T>(mag);
-                ph[base * 2 + n + j] = from_f32<T>(zr * inv);
-                ph[base * 2 + C + n + j] = from_f32<T>(zi * inv);
+                if (ph != nullptr) {
+                    ph[base * 2 + n + j] = from_f32<T>(zr * inv);
+                    ph[base * 2 + C + n + j] = from_f32<T>(zi * inv);
+                }
             }
         }
     }
@@ -311,7 +313,7 @@ static int hft_prepare(int N, int H, int W, int C, int mask_range, void* ws, siz
 
 int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C, int mask_range, void* ws, size_t ws_bytes,
                 int dtype, eel_stream s) {
-    EEL_REQUIRE(x && y && phase, "hft_fwd: null pointer");
+    EEL_REQUIRE(x && y, "hft_fwd: null pointer");       // phase may be null (inference: nothing is kept for a backward)
     cudaStream_t st = (cudaStream_t)s;
     HftWs w; int F;
     const bool tcf = dtype == EEL_BF16 && tc::hft_tc_supported_fwd(H, W, C, hft_radius(H, W, mask_range));

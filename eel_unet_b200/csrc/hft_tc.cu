@@ -425,11 +425,12 @@ hft_tc4_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                         {
                             // rows (row_lo + 8 i) of this warp: phase rows are 8 * C apart, |z| rows 4 * C (even rows only)
                             const int mm0 = (p.m_begin + mt) * 128 + q * 32 + L.row_lo;
-                            bf16* pb = p.phase + (rowbase * 2 + mm0) * C + cc + L.slot * 8;
+                            // (p.phase null: inference, the unit phase is not kept -- two thirds of this step's writes)
+                            bf16* pb = p.phase != nullptr ? p.phase + (rowbase * 2 + mm0) * C + cc + L.slot * 8 : nullptr;
                             bf16* yb = p.y + (rowbase + (mm0 >> 1)) * C + cc + L.slot * 8;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                dp[i] = pb + i * 8 * C;
+                                dp[i] = pb != nullptr ? pb + i * 8 * C : nullptr;
                                 dm[i] = (mm0 & 1) ? nullptr : yb + i * 4 * C;
                             }
                         }
@@ -718,7 +719,7 @@ hft_tc4p_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
                         bf16* dc_[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            dc_[i] = reinterpret_cast<bf16*>(p.code_out) + (prow + 8 * i) * C + cc + L.slot * 8;
+                            dc_[i] = p.code_out != nullptr ? reinterpret_cast<bf16*>(p.code_out) + (prow + 8 * i) * C + cc + L.slot * 8 : nullptr;
                         epi_store_packed(L, pkm, dy_);
                         epi_store_packed(L, pkc, dc_);
                     } else {

@@ -1638,7 +1638,10 @@ class HFT(Function):
         x = _c(x)
         N, H, W, C = x.shape
         y = torch.empty_like(x)
-        phase = torch.empty(_lib.lib.eel_hft_phase_elems(N, H, W, C, int(mask_range), dtype_code(x)), dtype=x.dtype, device=x.device)
+        # the unit phase z/|z| is only kept when a backward can follow (inference: up to two thirds of the last step's writes)
+        phase = None
+        if ctx.needs_input_grad[0]:
+            phase = torch.empty(_lib.lib.eel_hft_phase_elems(N, H, W, C, int(mask_range), dtype_code(x)), dtype=x.dtype, device=x.device)
         n = _lib.lib.eel_hft_workspace_bytes(N, H, W, C, int(mask_range))
         ws = workspace(n, x.device, slot=1)
         call("eel_hft_fwd", ptr(x), ptr(y), ptr(phase), N, H, W, C, int(mask_range), ptr(ws), n, dtype_code(x), stream())

@@ -282,7 +282,8 @@ int eel_tc_capmlp_fwd(const void* u, const void* w0, const float* b0, const void
  * y = | x - U_H (U_H^H x conj(U_W)) U_W^T |, frequencies -r..r-1, r = min(mask_range, H/2, W/2).
  * phase keeps the unit vector z/|z| for the backward: eel_hft_phase_elems() elements of the storage dtype --
  * [N][H][W][2][C] (re, im) pairs, or, for the bf16 tensor-core training shapes (C in {64,128}, H, W in {128,256}, r = 20),
- * ONE 16-bit code per element [N][H][W][C] (smaller component in biased 14-bit fixed point + two flag bits, csrc/hft_tc.cu). */
+ * ONE 16-bit code per element [N][H][W][C] (smaller component in biased 14-bit fixed point + two flag bits, csrc/hft_tc.cu).
+ * eel_hft_fwd accepts phase == NULL (inference: nothing is kept, the step's phase stores are skipped). */
 size_t eel_hft_workspace_bytes(int N, int H, int W, int C, int mask_range);
 size_t eel_hft_phase_elems(int N, int H, int W, int C, int mask_range, int dtype);
 int eel_hft_fwd(const void* x, void* y, void* phase, int N, int H, int W, int C, int mask_range, void* ws,

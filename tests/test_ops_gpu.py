@@ -528,6 +528,26 @@ def test_hft(dtype, shape):
              atol_scale=5.0 if dtype == torch.float32 else 1.5, all_nhwc=True)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 64, 128, 128), (1, 64, 512, 512), (1, 16, 48, 80), (1, 128, 256, 128)])
+def test_hft_without_a_backward_keeps_no_phase(dtype, shape):
+    """inference (the input needs no gradient): eel_hft_fwd is called with phase == NULL on every path (16-bit code kernels,
+    1024-wide tensor-core step 4, SIMT) and must return the same y"""
+    from eel_unet_b200 import _lib, ops
+
+    a = nhwc(torch.randn(*shape, device=DEV)).to(dtype)
+    with_grad = ops.HFT.apply(a.clone().requires_grad_(True), 20)
+    rec = []
+    _lib.set_profiler(rec)
+    try:
+        with torch.no_grad():
+            plain = ops.HFT.apply(a, 20)
+    finally:
+        _lib.set_profiler(None)
+    assert [r[1][2] for r in rec if r[0] == "eel_hft_fwd"] == [None]         # the phase argument
+    assert torch.equal(plain, with_grad.detach())
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 256, 256), (1, 128, 128, 128)])
 def test_hft_phase_code(shape):
     """bf16 training shapes keep the unit phase z/|z| as one 16-bit code per element (csrc/hft_tc.cu): bit 15 = the smaller
