@@ -574,6 +574,60 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ z
     }
 }
 
+// BatchNorm (+ReLU) whose result is stored through ShiftedChannel (models/EELUnet.py:88-97 in front of to_patch, :118):
+// y[n,h,w,c] = act(bn(z[n,(h+dh)%H,(w+dw)%W,c])) with the quarter shifts of shift_channels_kernel -- the activation the
+// token MLP reads is written in its shifted layout, the separate gather copy (one read + one write of the tensor) disappears.
+template <class T>
+__global__ void __launch_bounds__(256) bn_act_shift_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, unsigned int npix, int H, int W, int C, int TX,
+                                                             unsigned int pix_per_block, int relu) {
+    constexpr int V = Vec16<T>::N;
+    constexpr int U = 4;
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = (blockIdx.x * TX + tx) * V;
+    if (c >= C) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = gamma[c + j] * rstd[c + j];
+        sh[j] = beta[c + j] - mean[c + j] * sc[j];
+    }
+    const int q = c / (C / 4);
+    const int dh = q == 0 ? -1 : (q == 1 ? 1 : 0), dw = q == 2 ? -1 : 0;
+    const unsigned int p0 = blockIdx.y * pix_per_block;
+    const unsigned int p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+    for (unsigned int p = p0 + ty; p < p1; p += U * TY) {
+        Vec16<T> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int pp = p + u * TY;
+            if (pp < p1) {
+                const unsigned int r = pp / (unsigned int)W, w = pp - r * (unsigned int)W;
+                const unsigned int n = r / (unsigned int)H, h = r - n * (unsigned int)H;
+                int hh = (int)h + dh, ww = (int)w + dw;
+                hh = hh < 0 ? hh + H : (hh >= H ? hh - H : hh);
+                ww = ww < 0 ? ww + W : (ww >= W ? ww - W : ww);
+                v[u] = ld16(z + ((size_t)(n * (unsigned int)H + (unsigned int)hh) * (unsigned int)W + (unsigned int)ww) * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int pp = p + u * TY;
+            if (pp < p1) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float t = fmaf(v[u].get(j), sc[j], sh[j]);
+                    o.set(j, relu ? fmaxf(t, 0.f) : t);
+                }
+                st16(y + (size_t)pp * C + c, o);
+            }
+        }
+    }
+}
+
 // dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n)  (train)   or   gamma*rstd*g  (frozen statistics)
 template <class T>
 __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
@@ -1711,6 +1765,21 @@ int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd,
         dim3 grid(pl.ncb, pl.nrb);
         bn_act_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)y, mean, rstd, gamma, beta, P, C, pl.TX, pl.rows_per_rb, relu);
         return check_launch("bn_act_fwd");
+    });
+}
+
+int eel_bn_act_shift_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         int N, int H, int W, int C, int relu, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && y && mean && rstd && gamma && beta && N > 0 && H > 0 && W > 0 && C > 0, "bn_act_shift_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_REQUIRE(C % (4 * Vec16<T>::N) == 0, "bn_act_shift_fwd: C/4 must be a multiple of the 16-byte vector");
+        const long long npix = (long long)N * H * W;
+        EEL_REQUIRE(npix < (1LL << 32), "bn_act_shift_fwd: more than 2^32 pixels");
+        RedPlan pl = plan_stream<T>(npix, C);
+        dim3 grid(pl.ncb, pl.nrb);
+        bn_act_shift_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)z, (T*)y, mean, rstd, gamma, beta, (unsigned int)npix, H, W, C,
+                                                                      pl.TX, (unsigned int)pl.rows_per_rb, relu);
+        return check_launch("bn_act_shift_fwd");
     });
 }
 

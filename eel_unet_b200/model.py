@@ -105,6 +105,7 @@ class EELUnet(nn.Module):
 
     # token MLP of ChannelAwarePatchedMLP as one kernel (False / EEL_FUSED_MLP=0: the three separate launches; kept for A/B runs)
     fused_mlp = __import__("os").environ.get("EEL_FUSED_MLP", "1") != "0"
+    fused_shift = __import__("os").environ.get("EEL_FUSED_SHIFT", "1") != "0"
 
     def __init__(self, in_channels, out_channels, precision="fp32"):
         super().__init__()
@@ -214,20 +215,20 @@ class EELUnet(nn.Module):
                                          bn.momentum if bn.momentum is not None else 0.1, bn.eps, b, e, True)
 
     @staticmethod
-    def _bn(bn, z, relu, producer_bias=True, single_conv_consumer=False):
+    def _bn(bn, z, relu, producer_bias=True, single_conv_consumer=False, shift_out=False):
         training = EELUnet._bn_mode(bn)
         # producer_bias: z comes straight from a biased conv / linear, whose bias gradient (= column sums of dz) the
         # BatchNorm backward then delivers for free.  single_conv_consumer: the result feeds exactly one conv3x3, whose
         # data-gradient launch then also delivers this BatchNorm's backward sums (ops.Conv3x3.backward)
         return ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu,
-                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias, single_conv_consumer)
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, producer_bias, single_conv_consumer, shift_out)
 
     @staticmethod
-    def _capmlp(m, x, bn=None, relu=False, defer=False, single_conv_consumer=False):
+    def _capmlp(m, x, bn=None, relu=False, defer=False, single_conv_consumer=False, pre_shifted=False):
         """ChannelAwarePatchedMLP (reference models/EELUnet.py:114-123); the channel shift is folded into to_patch.
         bn: the BatchNorm (and `relu`) that consume the result -- applied here: in training its statistics come out of
         to_space's epilogue, in inference it is folded into to_space's weights."""
-        t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, True)
+        t = ops.Linear.apply(x, m.to_patch.weight, m.to_patch.bias, "pre" if pre_shifted else True)
         ca = m.channel_attention
         t = ops.SE.apply(t, ca.fc1.weight, ca.fc1.bias, ca.fc2.weight, ca.fc2.bias, True)
         pair = (m.mlp[2].weight, m.mlp[2].bias, m.to_space.weight, m.to_space.bias)
@@ -259,7 +260,7 @@ class EELUnet(nn.Module):
         return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer)
 
     @staticmethod
-    def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False):
+    def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False, shift_out=False):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
         f = ops.folded(conv.weight)
         if f is not None:
@@ -271,7 +272,7 @@ class EELUnet(nn.Module):
             ops.expect_bn(False)
         if defer:
             return z, bn
-        return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer)
+        return EELUnet._bn(bn, z, relu, single_conv_consumer=single_conv_consumer, shift_out=shift_out)
 
     def _conv_block(self, blk, x, defer=False, single_consumer=False):
         """defer: return (pre-BatchNorm tensor, BatchNorm) for the block's LAST BatchNorm + ReLU (fused into the PGR that follows);
@@ -280,8 +281,13 @@ class EELUnet(nn.Module):
         return self._conv_bn(blk[3], blk[4], x, defer=defer, single_conv_consumer=single_consumer)
 
     def _mlp_conv_block(self, blk, x, defer=False):
-        x = self._conv_bn(blk[0], blk[1], x)
-        return self._capmlp(blk[3], x, bn=blk[4], relu=True, defer=defer)
+        # bf16 training path: the BatchNorm + ReLU in front of the token MLP stores its result through ShiftedChannel, so
+        # to_patch reads it as is (no eel_shift_channels copy); inference folds that BatchNorm into the conv instead
+        C = blk[0].weight.shape[0]
+        pre = (EELUnet.fused_shift and self.compute_dtype == torch.bfloat16 and ops.folded(blk[0].weight) is None and C % 128 == 0
+               and blk[0].weight.shape[1] % 64 == 0)
+        x = self._conv_bn(blk[0], blk[1], x, shift_out=pre)
+        return self._capmlp(blk[3], x, bn=blk[4], relu=True, defer=defer, pre_shifted=pre)
 
     def _pool(self, d):
         """end of an encoder stage: (skip tensor, 2x2 max-pooled tensor).  `d` is the finished stage output or

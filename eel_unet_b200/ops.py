@@ -908,7 +908,8 @@ class ConvT2x2(Function):
 class Linear(Function):
     """nn.Linear / nn.Conv2d(k=1) on the channel axis (reference models/EELUnet.py:105-112).
 
-    ``shift=True`` folds ShiftedChannel (reference :88-97) into the operand addressing.
+    ``shift=True`` folds ShiftedChannel (reference :88-97) into the operand addressing; ``shift="pre"``: the input was already
+    stored through the shift by its producer (BNAct shift_out) -- only the backward's adjoint scatter remains.
     weight is [Nout, K] or [Nout, K, 1, 1].
     """
 
@@ -918,13 +919,15 @@ class Linear(Function):
         N, H, W, K = x.shape
         Nout = weight.shape[0]
         ctx.tc = _tc_ok(x, K, Nout)
+        if shift == "pre" and not (ctx.tc and K % 128 == 0):
+            raise _lib.EelError("Linear(shift='pre'): a pre-shifted input needs the tensor-core path with K a multiple of 128")
         w2 = _packed(weight, 0) if ctx.tc else None
         if w2 is None:
             w2 = _as_dtype2d(weight.view(Nout, K), x.dtype)
         w2 = w2.view(Nout, K)
         y = torch.empty((N, H, W, Nout), dtype=x.dtype, device=x.device)
         if ctx.tc:
-            if shift:
+            if shift and shift != "pre":       # "pre": the producer already stored x through the shift (BNAct shift_out)
                 x = _shift(x, False)           # saved shifted: wgrad then needs no gather
             sums = _want_bn_sums(x, Nout)
             b = bias.detach()
@@ -935,7 +938,7 @@ class Linear(Function):
         else:
             sh, sw = (H, W) if shift else (0, 0)
             call("eel_linear_fwd", ptr(x), ptr(w2), ptr(bias.detach()), ptr(y), N * H * W, K, Nout, sh, sw, dtype_code(x), stream())
-        ctx.shift = shift
+        ctx.shift = bool(shift)
         ctx.save_for_backward(x, weight)
         return y
 
@@ -1187,7 +1190,7 @@ class BNAct(Function):
 
     @staticmethod
     def forward(ctx, z, gamma, beta, running_mean, running_var, training, relu, momentum, eps, producer_bias=False,
-                single_conv_consumer=False):
+                single_conv_consumer=False, shift_out=False):
         z = _c(z)
         C = z.shape[-1]
         P = z.numel() // C
@@ -1195,7 +1198,13 @@ class BNAct(Function):
         mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
         y = torch.empty_like(z)
         g, b = gamma.detach(), beta.detach()
-        call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
+        if shift_out:
+            # the result is stored through ShiftedChannel for the to_patch Linear that consumes it (Linear(shift="pre")): that
+            # Linear's data gradient comes back through the adjoint shift, so the backward below is the plain one
+            N, H, W, _ = z.shape
+            call("eel_bn_act_shift_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), N, H, W, C, int(relu), dtype_code(z), st)
+        else:
+            call("eel_bn_act_fwd", ptr(z), ptr(y), ptr(mean), ptr(rstd), ptr(g), ptr(b), P, C, int(relu), dtype_code(z), st)
         ctx.relu, ctx.training, ctx.producer_bias = relu, training, producer_bias
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
         # single_conv_consumer: y feeds exactly one conv3x3 or (as the edge feature) exactly one skip bridge
@@ -1225,7 +1234,7 @@ class BNAct(Function):
                  ptr(dgamma), ptr(dbeta), ptr(dzsum), P, C, int(ctx.relu), int(ctx.training), ptr(ws), n, dtype_code(z), stream())
         if dzsum is not None:
             _attach(dz, "_eel_colsum", dzsum)
-        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class BNReluPool(Function):

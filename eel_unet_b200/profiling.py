@@ -82,6 +82,9 @@ def cost(name, a):
     if n == "bn_act_fwd":
         P, C, dt = a[6], a[7], a[9]
         return 4.0 * P * C, 2 * P * C * _esz(dt)
+    if n == "bn_act_shift_fwd":
+        N, H, W, C, dt = a[6], a[7], a[8], a[9], a[11]
+        return 4.0 * N * H * W * C, 2 * N * H * W * C * _esz(dt)
     if n == "bn_act_bwd":
         P, C, dt = a[10], a[11], a[16]
         return 12.0 * P * C, 3 * P * C * _esz(dt)
@@ -167,7 +170,7 @@ def cost(name, a):
 
 
 # launches reported under another family's name
-ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd", "add_interleave_bwd_bnsums": "add_interleave_bwd"}
+ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd", "add_interleave_bwd_bnsums": "add_interleave_bwd", "bn_act_shift_fwd": "bn_act_fwd"}
 
 GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_capmlp_fwd", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}

@@ -183,6 +183,12 @@ int eel_bn_eval_stats(const float* running_mean, const float* running_var, float
 /* y = [relu](gamma * (z - mean) * rstd + beta) */
 int eel_bn_act_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, long long P, int C, int relu, int dtype, eel_stream s);
+/* the same, stored through ShiftedChannel (models/EELUnet.py:88-97, applied to the input of to_patch, :118):
+ * y[n,h,w,c] = act(bn(z[n,(h+dh)%H,(w+dw)%W,c])), (dh, dw) = (-1,0), (+1,0), (0,-1), (0,0) for the four channel quarters.
+ * The token MLP's first Linear then reads its input without the separate eel_shift_channels copy; the BatchNorm's backward
+ * is unchanged, because that Linear's data gradient is stored through the adjoint shift (eel_tc_linear, shift_h / shift_w). */
+int eel_bn_act_shift_fwd(const void* z, void* y, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, int N, int H, int W, int C, int relu, int dtype, eel_stream s);
 /* train != 0: batch-statistics backward; train == 0: frozen statistics.
  * dz_colsum (nullable, [C]): receives sum_p dz[p][c] = the bias gradient of the conv / linear that produced z. */
 int eel_bn_act_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,

@@ -197,6 +197,43 @@ def test_linear(dtype, shift, shape):
              lambda a, p: F.conv2d(ref_shift(a[0]) if shift else a[0], p[0], p[1]), [x], [wt, b], dtype)
 
 
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", [(2, 256, 8, 12, 64), (1, 512, 5, 7, 64), (3, 128, 4, 4, 64)])
+def test_bn_stored_through_the_shift_feeds_to_patch(relu, shape):
+    """mlp_conv_block (reference models/EELUnet.py:350-357 with :88-97,118): BatchNorm + ReLU -> ShiftedChannel -> to_patch.  In bf16
+    mode the BatchNorm stores its result through the shift (eel_bn_act_shift_fwd) and the Linear takes it as is (shift="pre");
+    the Linear's data gradient comes back through the adjoint shift, the BatchNorm backward is the plain one"""
+    from eel_unet_b200 import _lib, ops
+
+    n, c, h, w, nout = shape
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, device=DEV) * 1.5 + 0.3
+    g = torch.rand(c, device=DEV) + 0.5
+    b = torch.randn(c, device=DEV) * 0.5
+    wt = torch.randn(nout, c, 1, 1, device=DEV) / math.sqrt(c)
+    bias = torch.randn(nout, device=DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+
+    def mine(a, p):
+        y = ops.BNAct.apply(a[0], p[0], p[1], rm, rv, True, relu, 0.1, 1e-5, False, False, True)
+        return ops.Linear.apply(y, p[2], p[3], "pre")
+
+    def ref(a, p):
+        y = F.batch_norm(a[0], None, None, p[0], p[1], True, 0.1, 1e-5)
+        y = F.relu(y) if relu else y
+        y = y + (y.to(dtype).double() - y).detach()          # the Linear reads the activation as stored
+        return F.conv2d(ref_shift(y), p[2], p[3])
+
+    rec = []
+    _lib.set_profiler(rec)
+    try:
+        run_case(mine, ref, [x], [g, b, wt, bias], dtype, atol_scale=2.0)
+    finally:
+        _lib.set_profiler(None)
+    names = [r[0] for r in rec]
+    assert "eel_bn_act_shift_fwd" in names and "eel_shift_channels" not in names
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 256, 8, 16, 256), (1, 256, 16, 16, 512), (2, 24, 5, 7, 40), (1, 256, 4, 8, 1024),
                                    (1, 64, 8, 8, 72)])

@@ -29,6 +29,7 @@ EXPECTED = {
     "eel_tc_conv3x3_wgrad": {3: "N", 4: "H", 5: "W", 6: "Cin", 7: "Cout"},
     "eel_tc_wgrad": {3: "P", 4: "Ma", 5: "Nb"},
     "eel_bn_act_fwd": {6: "P", 7: "C", 9: "dtype"},
+    "eel_bn_act_shift_fwd": {6: "N", 7: "H", 8: "W", 9: "C", 11: "dtype"},
     "eel_bn_act_bwd": {10: "P", 11: "C", 16: "dtype"},
     "eel_bn_act_bwd_apply": {9: "P", 10: "C", 13: "dtype"},
     "eel_bn_relu_pool_fwd": {8: "N", 9: "H", 10: "W", 11: "C", 12: "dtype"},
