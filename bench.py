@@ -79,8 +79,14 @@ class ClockSampler:
 
     def _nvml_loop(self):
         nv, h, _ = self.nv
-        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
-                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        # the other reasons NVML knows (a clock lock shows up as applications_clocks_setting), named when the binding has them
+        for nm, attr in (("hw_power_brake_slowdown", "nvmlClocksEventReasonHwPowerBrakeSlowdown"),
+                         ("applications_clocks_setting", "nvmlClocksEventReasonApplicationsClocksSetting"),
+                         ("sync_boost", "nvmlClocksEventReasonSyncBoost"), ("display_clock_setting", "nvmlClocksEventReasonDisplayClockSetting")):
+            if hasattr(nv, attr):
+                bits.append((nm, getattr(nv, attr)))
         cfg = os.environ.get("EEL_BENCH_NVML", "50,cr").split(",")
         period, what = float(cfg[0]) / 1e3, cfg[1]
         while not self.stop_flag:
