@@ -45,7 +45,7 @@ def _peaks():
 
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Read through NVML from a thread of this
-    process (nvidia_ml_py): three cheap queries every 50 ms.  The earlier `nvidia-smi -lms 100` child process is the fallback --
+    process (nvidia_ml_py): two cheap queries every 25 ms.  The earlier `nvidia-smi -lms 100` child process is the fallback --
     its NVML attach and its polling loop were seen to hold up kernel launches (a timed region 10 % slower than the
     end-to-end region measured right after it, in which the sampler no longer ran)."""
 
@@ -87,7 +87,7 @@ class ClockSampler:
                          ("sync_boost", "nvmlClocksEventReasonSyncBoost"), ("display_clock_setting", "nvmlClocksEventReasonDisplayClockSetting")):
             if hasattr(nv, attr):
                 bits.append((nm, getattr(nv, attr)))
-        cfg = os.environ.get("EEL_BENCH_NVML", "50,cr").split(",")
+        cfg = os.environ.get("EEL_BENCH_NVML", "25,cr").split(",")
         period, what = float(cfg[0]) / 1e3, cfg[1]
         while not self.stop_flag:
             try:
@@ -139,7 +139,7 @@ class ClockSampler:
             sm = [x[1] for x in inside]
             reasons = sorted({r for x in inside for r in x[2]})
             return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.nv[2]), "reasons": reasons,
-                    "samples": len(sm), "source": "nvml (in-process thread, 50 ms)",
+                    "samples": len(sm), "source": "nvml (in-process thread, 25 ms)",
                     "slowest_query_ms": round(1e3 * max([x[3] for x in inside] or [0.0]), 2)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
