@@ -358,13 +358,18 @@ def run_ours(args):
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step(x, y):
-        dp.zero_grad()
         seg, edges = dp(x)
         loss = crit(edges, seg, y)
         loss.backward()
         dp.finish_backward()
         opt.step()
+        # gradients are cleared at the END of a step (pure host work: 365 attribute resets): in the end-to-end loop, which
+        # synchronises on loss.item() after every step, it then runs while the GPU is still busy instead of in front of the
+        # next step's first launch
+        dp.zero_grad()
         return loss
+
+    dp.zero_grad()
 
     def barrier():
         if world > 1:

@@ -359,6 +359,10 @@ class EELUnet(nn.Module):
             return self._forward(x)
 
     def _forward(self, x):
+        # the input conversion is launched before the host-side bookkeeping of the weight tables (version checks over ~70
+        # parameters): after a synchronisation (validation loops, loss.item() per step) the GPU starts a few hundred
+        # microseconds earlier
+        a = ops.nchw_to_nhwc(x, self.compute_dtype)
         fold = None
         if self.compute_dtype == torch.bfloat16:
             self._weight_packer().refresh(x.device)      # publishes the packed operands on the weights themselves
@@ -371,7 +375,6 @@ class EELUnet(nn.Module):
                     fold = None
         ops.set_folded(fold)
         self._composed_packer().refresh(x.device)
-        a = ops.nchw_to_nhwc(x, self.compute_dtype)
 
         enc1, p = self._pool(self._conv_block(self.enc1[0], a, defer=True))
         enc2, p = self._pool(self._conv_block(self.enc2[0], p, defer=True))
