@@ -38,6 +38,12 @@ struct ConvParams {
     const bf16* bz;
     const float2* bcst;
     int brelu;
+    // split > 0 (data gradient of the conv that reads a skip bridge): output columns [0, split) go to `out`, columns
+    // [split, Ntot) to `out2`, both [N,H,W,split] tensors -- the weight operand's rows were de-interleaved, so the two halves
+    // are the gradients of (upconv + edge feature) and of the encoder skip and no interleaved gradient tensor is ever written.
+    // Fused BatchNorm-backward sums (STATS == 2) then cover the first half only (bz / bcst / bn_sums are [.., split]).
+    bf16* out2;
+    int split;
 };
 
 constexpr int kMaxStages = 8;
@@ -219,16 +225,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int w = (int)tw * 8 + L.row_lo;
             // rows (row_lo + 8 i) of this warp's quarter are image rows h0 + i of accumulator j (+ 16 j)
             const int h0 = (int)th * Cfg::TH + q * 4;
-            const uint32_t ntot_v = (uint32_t)p.Ntot >> 3, rowstep_v = (uint32_t)p.W * ntot_v;
-            const uint32_t pix_v = ((n * (uint32_t)p.H + (uint32_t)h0) * (uint32_t)p.W + (uint32_t)w) * ntot_v + ((uint32_t)n0 >> 3) + (uint32_t)L.slot;
+            const uint32_t ntot_v = (uint32_t)(p.split ? p.split : p.Ntot) >> 3, rowstep_v = (uint32_t)p.W * ntot_v;
+            const uint32_t pix_v = ((n * (uint32_t)p.H + (uint32_t)h0) * (uint32_t)p.W + (uint32_t)w) * ntot_v + (uint32_t)L.slot;
             bf16* const pix = p.out + (size_t)pix_v * 8;
+            bf16* const pix2 = p.split ? p.out2 + (size_t)pix_v * 8 : nullptr;
             const bool wok = w < p.W;
-            // element offset (from `pix`) of row i of chunk ci, or -1 when the pixel lies outside the image
+            // chunk ci lies in the second output tensor (split launches only)
+            auto chunk_second = [&](int ci) -> bool {
+                const int col = (half * NCH + ci) * 32;
+                return p.split && n0 + col % BN >= p.split;
+            };
+            // element offset (from `pix` / `pix2`) of row i of chunk ci, or -1 when the pixel lies outside the image
             auto chunk_off = [&](int ci, int i) -> long long {
                 const int col = (half * NCH + ci) * 32;
                 const int j = col / BN, cc = col - j * BN;
                 const int h = h0 + j * 16 + i;
-                return (wok && h < p.H) ? (long long)(((uint32_t)(j * 16 + i) * rowstep_v + ((uint32_t)cc >> 3)) << 3) : -1;
+                int g = n0 + cc;
+                if (p.split && g >= p.split) g -= p.split;
+                return (wok && h < p.H) ? (long long)(((uint32_t)(j * 16 + i) * rowstep_v + ((uint32_t)g >> 3)) << 3) : -1;
             };
             // STATS == 2: the BatchNorm input z is needed at every stored position.  Its lines are pulled into L2 for the
             // whole tile and the first chunk's vectors are loaded BEFORE waiting for the accumulator; the next chunk's are
@@ -236,10 +250,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bf16* const zpix = STATS == 2 ? p.bz + (pix - p.out) : nullptr;
             uint4 zbuf[STATS == 2 ? 2 : 1][4];
             auto load_z = [&](int ci, uint4 (&dstv)[4]) {
+                const bool sec = chunk_second(ci);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const long long o = chunk_off(ci, i);
-                    dstv[i] = o >= 0 ? ldg_early(zpix + o) : make_uint4(0, 0, 0, 0);
+                    dstv[i] = (o >= 0 && !sec) ? ldg_early(zpix + o) : make_uint4(0, 0, 0, 0);
                 }
             };
             if (STATS == 2) {
@@ -248,7 +263,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const long long o = chunk_off(ci, i);
-                        if (o >= 0) prefetch_l2(zpix + o);
+                        if (o >= 0 && !chunk_second(ci)) prefetch_l2(zpix + o);
                     }
                 load_z(0, zbuf[0]);
             }
@@ -267,14 +282,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int col = (half * NCH + ci) * 32;       // column within the MT * BN accumulator block
                 const int cc = col % BN;
                 bf16* dst[4];
+                const bool sec = chunk_second(ci);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const long long o = chunk_off(ci, i);
-                    dst[i] = o >= 0 ? pix + o : nullptr;
+                    dst[i] = o >= 0 ? (sec ? pix2 : pix) + o : nullptr;
                 }
                 if (STATS == 2) {
-                    const EpiBnBwd bb{zbuf[STATS == 2 ? ci & 1 : 0], p.bcst + n0 + cc + L.slot * 8, p.brelu};
-                    epi_store_chunk(L, buf[0], nullptr, 0, dst, &st[STATS ? ci : 0], lane, &bb);
+                    if (!sec) {
+                        const EpiBnBwd bb{zbuf[STATS == 2 ? ci & 1 : 0], p.bcst + n0 + cc + L.slot * 8, p.brelu};
+                        epi_store_chunk(L, buf[0], nullptr, 0, dst, &st[STATS ? ci : 0], lane, &bb);
+                    } else epi_store_chunk(L, buf[0], nullptr, 0, dst, nullptr, lane);      // (the skip's half: no BatchNorm behind it here)
                     if (ci + 1 < NCH) tmem_ld32_async(taddr + (ci + 1) * 32, buf[0]);
                 } else
                     epi_store_chunk(L, buf[ci % TB], p.bias ? p.bias + n0 + cc : nullptr, p.relu, dst, STATS ? &st[STATS ? ci : 0] : nullptr, lane);
@@ -287,7 +305,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the grid is a multiple of n_tiles (host check): all tiles of this CTA lie in N tile blockIdx.x % n_tiles
             const int n_own = (blockIdx.x % p.n_tiles) * BN;
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) epi_stats_flush(p.bn_sums, p.Ntot, n_own + ((half * NCH + ci) * 32) % BN, lane, st[STATS ? ci : 0]);
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int gcol = n_own + ((half * NCH + ci) * 32) % BN;
+                if (!p.split || gcol < p.split) epi_stats_flush(p.bn_sums, p.split ? p.split : p.Ntot, gcol, lane, st[STATS ? ci : 0]);
+            }
         }
     }
     tc_fence_before();
@@ -346,7 +367,7 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
             set_error("%s: fused BatchNorm statistics need a grid that is a multiple of the %d N tiles (Cout %d)", what, p.n_tiles, Cout);
             return EEL_ERR_INVALID;
         }
-        if (cudaMemsetAsync(p.bn_sums, 0, sizeof(float) * 2 * Cout, st) != cudaSuccess) {
+        if (cudaMemsetAsync(p.bn_sums, 0, sizeof(float) * 2 * (p.split ? p.split : Cout), st) != cudaSuccess) {
             set_error("%s: memset failed", what);
             return EEL_ERR_CUDA;
         }
@@ -383,7 +404,8 @@ __global__ void bn_sums_fix_kernel(float* __restrict__ sums, const float* __rest
 }
 
 static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                            int relu, int flip, float* bn_sums, const bf16* bz, const float2* bcst, int brelu, cudaStream_t st) {
+                            int relu, int flip, float* bn_sums, const bf16* bz, const float2* bcst, int brelu, cudaStream_t st,
+                            void* y2 = nullptr, int split = 0) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     EEL_REQUIRE((long long)N * H * W * Cout / 8 < (1LL << 32), "tc_conv3x3: output too large for 32-bit vector offsets");
@@ -395,6 +417,7 @@ static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, vo
     p.bias = bias; p.out = (bf16*)y;
     p.bn_sums = bn_sums;
     p.bz = bz; p.bcst = bcst; p.brelu = brelu;
+    p.out2 = (bf16*)y2; p.split = split;
     const bool tall = H > 16;                  // a 32-row tile would be half empty on 16-row maps
     if (Cin == 64 && Cout == 64)
         return tall ? launch_conv<64, 2, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)")
@@ -430,6 +453,31 @@ int eel_tc_conv3x3_dgrad_bnsums(const void* dy, const void* wk, void* dx, int N,
     if (int rc = conv3x3_dispatch(dy, wk, nullptr, dx, N, H, W, Cin, Cout, 0, 1, sums, (const bf16*)z, (const float2*)consts_ws, relu, st)) return rc;
     bn_sums_fix_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(sums, mean, rstd, Cout);
     return check_launch("tc_conv3x3_dgrad_bnsums.fix");
+}
+
+// Data gradient of the conv that reads a skip bridge (channels interleaved as (upconv + edge feature, encoder skip), models/EELUnet.py:
+// 132-141 then :338): wk is the data-gradient operand with its Cout rows DE-INTERLEAVED (even channels first), so the two halves of
+// the result are stored as two [N,H,W,Cout/2] tensors -- the gradient of the sum and the gradient of the skip -- and
+// eel_add_interleave_bwd never runs; with z given the epilogue also accumulates the upconv BatchNorm's backward sums over the first half.
+int eel_tc_conv3x3_dgrad_split(const void* dy, const void* wk, void* dx0, void* dx1, int N, int H, int W, int Cin, int Cout,
+                               const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                               float* sums, void* consts_ws, eel_stream s) {
+    EEL_REQUIRE(dy && wk && dx0 && dx1 && N > 0 && H > 0 && W > 0, "tc_conv3x3_dgrad_split: bad argument");
+    EEL_REQUIRE(Cout % 128 == 0, "tc_conv3x3_dgrad_split: the two halves must be multiples of 64 channels (Cout %d)", Cout);
+    EEL_REQUIRE(z == nullptr || (mean && rstd && gamma && beta && sums && consts_ws), "tc_conv3x3_dgrad_split: the BatchNorm is incomplete");
+    cudaStream_t st = (cudaStream_t)s;
+    const int C = Cout / 2;
+    if (z != nullptr) {
+        bn_consts_kernel<<<cdiv(C, 128), 128, 0, st>>>(mean, rstd, gamma, beta, (float2*)consts_ws, C);
+        if (int rc = check_launch("tc_conv3x3_dgrad_split.consts")) return rc;
+    }
+    if (int rc = conv3x3_dispatch(dy, wk, nullptr, dx0, N, H, W, Cin, Cout, 0, 1, z != nullptr ? sums : nullptr, (const bf16*)z,
+                                  (const float2*)consts_ws, relu, st, dx1, C)) return rc;
+    if (z != nullptr) {
+        bn_sums_fix_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, mean, rstd, C);
+        return check_launch("tc_conv3x3_dgrad_split.fix");
+    }
+    return EEL_OK;
 }
 
 }  // extern "C"

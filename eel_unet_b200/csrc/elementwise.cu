@@ -1099,6 +1099,20 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_raw_kernel(const float* 
     b.sums[C + c] = (float)((double)b.rstd[c] * (s1 - (double)b.mean[c] * s0));
 }
 
+// dst[g][r'][:] = src[g][perm(r')][:], perm(r') = 2 r' (r' < rows / 2) or 2 (r' - rows / 2) + 1: the rows of every group
+// de-interleaved (even rows first).  Used on the data-gradient operand of the convs that read a skip bridge: their output
+// channels then come out as (gradient of the sum | gradient of the skip) halves (eel_tc_conv3x3_dgrad_split).
+__global__ void rows_deinterleave_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long nvec, int rows, int vec_per_row) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / vec_per_row;
+        const int v = (int)(i - row * vec_per_row);
+        const long long g = row / rows;
+        const int r = (int)(row - g * rows);
+        const int sr = r < rows / 2 ? 2 * r : 2 * (r - rows / 2) + 1;
+        dst[i] = src[(g * rows + sr) * vec_per_row + v];
+    }
+}
+
 // ------------------------------------------------------------------------------------ column-block copy (torch.concat on C)
 template <class T>
 __global__ void copy_cols_kernel(const T* __restrict__ src, long long src_ld, int src_c0, T* __restrict__ dst, long long dst_ld,
@@ -1945,6 +1959,14 @@ int eel_add_interleave_bwd_bnsums(const void* dout, void* dab, void* de, long lo
         bn_bwd_finalize_raw_kernel<T><<<dim3(cdiv(C, 32), nbn), 1024, 0, st>>>(partial, pl.nrb, C, Q, b0, b1);
         return check_launch("add_interleave_bwd_bnsums.finalize");
     });
+}
+
+int eel_rows_deinterleave(const void* src, void* dst, long long groups, int rows, long long row_bytes, eel_stream s) {
+    EEL_REQUIRE(src && dst && groups > 0 && rows > 0 && rows % 2 == 0 && row_bytes > 0 && row_bytes % 16 == 0,
+                "rows_deinterleave: bad argument (even row count, rows of whole 16-byte vectors)");
+    const long long nvec = groups * rows * (row_bytes / 16);
+    rows_deinterleave_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)src, (uint4*)dst, nvec, rows, (int)(row_bytes / 16));
+    return check_launch("rows_deinterleave");
 }
 
 int eel_copy_cols(const void* src, long long src_ld, int src_c0, void* dst, long long dst_ld, int dst_c0, long long P, int ncols,

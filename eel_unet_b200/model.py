@@ -100,12 +100,21 @@ def _mlp_upconv_block(cin, cout):
 _PRECISIONS = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}
 
 
+class _Bridge:
+    """a skip bridge whose tensors have not been combined yet: (upconv BatchNorm, its input z, edge feature b, encoder skip e)"""
+    __slots__ = ("bn", "z", "b", "e")
+
+    def __init__(self, bn, z, b, e):
+        self.bn, self.z, self.b, self.e = bn, z, b, e
+
+
 class EELUnet(nn.Module):
     """B200-native EEL-UNet (reference models/EELUnet.py:228-471)."""
 
     # token MLP of ChannelAwarePatchedMLP as one kernel (False / EEL_FUSED_MLP=0: the three separate launches; kept for A/B runs)
     fused_mlp = __import__("os").environ.get("EEL_FUSED_MLP", "1") != "0"
     fused_shift = __import__("os").environ.get("EEL_FUSED_SHIFT", "1") != "0"
+    fused_bridge = __import__("os").environ.get("EEL_FUSED_BRIDGE", "1") != "0"
 
     def __init__(self, in_channels, out_channels, precision="fp32"):
         super().__init__()
@@ -156,6 +165,10 @@ class EELUnet(nn.Module):
     def _weight_packer(self):
         if self._packer is None or self._packer.stale():
             self._packer = ops.build_packer(self)
+            if EELUnet.fused_bridge:
+                for blk in (self.dec4, self.dec3, self.dec2, self.dec1):      # the convs that read a skip bridge (ops.BridgeConv3x3)
+                    if blk[0].weight.shape[1] // 2 >= ops.BridgeConv3x3.MIN_CHANNELS:
+                        self._packer.want_split(blk[0].weight)
         return self._packer
 
     def _composed_packer(self):
@@ -263,11 +276,19 @@ class EELUnet(nn.Module):
     def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False, shift_out=False):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
         f = ops.folded(conv.weight)
+        if isinstance(x, _Bridge) and (f is not None or not ops.BridgeConv3x3.supported(x.z, conv.weight)):
+            x = EELUnet._bn_add_interleave(x.bn, x.z, x.b, x.e)       # (not fusable after all: the interleaved tensor, then a plain conv)
         if f is not None:
             return ops.conv3x3_folded(x, f[0], f[1], relu)
         ops.expect_bn(bn.training or bn.running_mean is None)
         try:
-            z = ops.conv3x3(x, conv.weight, conv.bias, False)
+            if isinstance(x, _Bridge):
+                ub = x.bn
+                z = ops.BridgeConv3x3.apply(x.z, ub.weight, ub.bias, ub.running_mean, ub.running_var, EELUnet._bn_mode(ub),
+                                            ub.momentum if ub.momentum is not None else 0.1, ub.eps, x.b, x.e, True,
+                                            conv.weight, conv.bias)
+            else:
+                z = ops.conv3x3(x, conv.weight, conv.bias, False)
         finally:
             ops.expect_bn(False)
         if defer:
@@ -336,6 +357,8 @@ class EELUnet(nn.Module):
         """(upconv output + edge feature) interleaved with the encoder skip (reference models/EELUnet.py:422-426); `up` is
         either the finished upconv output or (pre-BatchNorm tensor, BatchNorm) when its BatchNorm is fused in here"""
         if isinstance(up, tuple):
+            if EELUnet.fused_bridge and up[0].dtype == torch.bfloat16:
+                return _Bridge(up[1], up[0], b, e)          # consumed by the decoder block's first conv (_conv_bn)
             return self._bn_add_interleave(up[1], up[0], b, e)
         return ops.AddInterleave.apply(up, b, e)
 

@@ -337,10 +337,19 @@ class WeightPacker:
         self.table = None
         self.ptrs = None
         self.versions = None
+        self.split_ids = set()
+        self.splits = []       # (param, dgrad operand, its de-interleaved copy)
 
     def add(self, param, dims, perm_fwd, perm_dgrad, owner=None):
         self.entries.append((param, tuple(int(d) for d in dims), perm_fwd, perm_dgrad))
         self.owners.append(owner)
+
+    def want_split(self, param):
+        """``param`` is the weight of a conv3x3 that reads a skip bridge: also keep its data-gradient operand with the input
+        channel rows de-interleaved (BridgeConv3x3, eel_tc_conv3x3_dgrad_split)"""
+        if id(param) not in self.split_ids:
+            self.split_ids.add(id(param))
+            self.table = None               # rebuild: the split buffers are allocated with the table
 
     def stale(self):
         """a module's ``weight`` was replaced by another Parameter object (torch.nn.utils.prune.remove, manual surgery):
@@ -363,6 +372,8 @@ class WeightPacker:
                 outs.append(dst)
             self.by_param[id(w)] = tuple(outs)
             keep.append(w)
+        self.splits = [(w, self.by_param[id(w)][1], torch.empty_like(self.by_param[id(w)][1]))
+                       for (w, dims, pf, pd) in self.entries if id(w) in self.split_ids]
         self.table = torch.from_numpy(rec.reshape(-1).view(np.uint8).copy()).to(device)
         self.ptrs = [w.data_ptr() for w in keep]
         self.versions = None
@@ -378,13 +389,19 @@ class WeightPacker:
         ver = [_WEIGHT_EPOCH] + [e[0]._version for e in self.entries]
         if ver == self.versions:
             return
-        _on_side_stream(lambda: call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream()))
+        def launch():
+            call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream())
+            for w, dg, sp in self.splits:      # [ky][kx][ci][co] -> ci rows de-interleaved
+                call("eel_rows_deinterleave", ptr(dg), ptr(sp), dg.shape[0] * dg.shape[1], dg.shape[2], dg.shape[3] * dg.element_size(), stream())
+        _on_side_stream(launch)
         self.versions = ver
         # publish on the parameters themselves: ops find the operands through the weight they are handed (forward and
         # backward, any thread, any number of models), and only while the weight is what was packed
         for e in self.entries:
             w = e[0]
             w._eel_packed = self.by_param[id(w)] + (_pack_key(w),)
+        for w, dg, sp in self.splits:
+            w._eel_packed_split = (sp, _pack_key(w))
 
     def get(self, w):
         return self.by_param.get(id(w))
@@ -679,6 +696,20 @@ def _packed(weight, which):
         return None
     _await_packed()
     return hit[which]
+
+
+def _packed_split(weight, dtype):
+    """the data-gradient operand of ``weight`` with its input-channel rows de-interleaved (published by a WeightPacker, or made here)"""
+    hit = getattr(weight, "_eel_packed_split", None)
+    if hit is not None and hit[1] == _pack_key(weight):
+        _await_packed()
+        return hit[0]
+    dg = _packed(weight, 1)
+    if dg is None:
+        dg = _pack(weight, (2, 3, 1, 0), dtype)
+    sp = torch.empty_like(dg)
+    call("eel_rows_deinterleave", ptr(dg), ptr(sp), dg.shape[0] * dg.shape[1], dg.shape[2], dg.shape[3] * dg.element_size(), stream())
+    return sp
 
 
 def conv3x3(x, weight, bias, relu):
@@ -1425,6 +1456,88 @@ class BNAddInterleave(Function):
         if dzsum is not None:
             _attach(dz, "_eel_colsum", dzsum)
         return dz, dgamma, dbeta, None, None, None, None, None, dab, de, None
+
+
+class BridgeConv3x3(Function):
+    """The skip bridge and the decoder block's first conv3x3 as ONE autograd node (bf16 tensor-core path):
+
+        x = interleave(BatchNorm(z) + b, e)      (BNAddInterleave: models/EELUnet.py:365/373, :422-426, :132-141)
+        y = conv3x3(x)                           (:338 of the decoder block; pre-BatchNorm, statistics from the epilogue)
+
+    The forward is the two launches of BNAddInterleave and Conv3x3.  The point is the backward: the conv's data gradient runs on
+    a weight operand whose input-channel rows were de-interleaved, so its epilogue stores d(BatchNorm(z) + b) and d(e) as two
+    tensors and accumulates the BatchNorm's backward sums over the first -- the interleaved gradient tensor, the de-interleaving
+    pass over it (eel_add_interleave_bwd) and the BatchNorm's reduction pass do not exist."""
+
+    # Measured on B200 (batch 64): against the plain data gradient + eel_add_interleave_bwd_bnsums the split launch saves
+    # 0.13 / 0.07 / 0.01 ms at 128 / 256 / 512 channels, but LOSES 0.3 ms at the 64-channel full-resolution bridge, whose
+    # data gradient (K = 64 per tap) is all epilogue: 0.44 -> 1.08 ms with the BatchNorm sums on half of its columns, and the
+    # edge branch's last BatchNorm would lose the sums the de-interleaving pass gives it there.  So: 128 channels and up.
+    MIN_CHANNELS = 128
+
+    @staticmethod
+    def supported(z, weight):
+        C = z.shape[-1]
+        return (z.dtype == BF16 and z.is_cuda and C % 64 == 0 and C >= BridgeConv3x3.MIN_CHANNELS
+                and tuple(weight.shape[1:]) == (2 * C, 3, 3) and weight.shape[0] % 64 == 0 and _stats_cols_ok(C))
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, momentum, eps, b, e, producer_bias, weight, bias):
+        z, b, e = _c(z), _c(b), _c(e)
+        N, H, W, C = z.shape
+        Cout = weight.shape[0]
+        st = stream()
+        mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
+        x = torch.empty((N, H, W, 2 * C), dtype=z.dtype, device=z.device)
+        call("eel_add_interleave_fwd", ptr(z), ptr(b), ptr(e), ptr(x), N * H * W, C, ptr(mean), ptr(rstd), ptr(gamma.detach()),
+             ptr(beta.detach()), dtype_code(z), st)
+        wk = _packed(weight, 0)
+        if wk is None:
+            wk = _pack(weight, (2, 3, 0, 1), x.dtype)
+        y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+        sums = _want_bn_sums(x, Cout)
+        bd = bias.detach() if bias is not None else None
+        call("eel_tc_conv3x3", ptr(x), ptr(wk), None if sums is not None else ptr(bd), ptr(y), N, H, W, 2 * C, Cout, 0, 0, ptr(sums), st)
+        if sums is not None:
+            _attach(y, "_eel_bn_sums", (sums, bd))
+        ctx.training, ctx.producer_bias = training, producer_bias
+        ctx.save_for_backward(z, mean, rstd, gamma, beta, x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma, beta, x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, C = z.shape
+        Cout = weight.shape[0]
+        P = N * H * W
+        st = stream()
+        dev = z.device
+        g, bt = gamma.detach(), beta.detach()
+        # data gradient in two halves + the BatchNorm's backward sums over the first
+        wsp = _packed_split(weight, x.dtype)
+        dab = torch.empty((N, H, W, C), dtype=x.dtype, device=dev)
+        de = torch.empty_like(dab)
+        sums = torch.empty((2, C), dtype=F32, device=dev)
+        cws = workspace(16 * C, dev, slot=1)
+        call("eel_tc_conv3x3_dgrad_split", ptr(dy), ptr(wsp), ptr(dab), ptr(de), N, H, W, Cout, 2 * C, ptr(z), ptr(mean), ptr(rstd), ptr(g),
+             ptr(bt), 0, ptr(sums), ptr(cws), st)
+        # weight gradient (side stream): the saved interleaved input, as Conv3x3.backward
+        on = _async_ok(weight)
+        dw = _grad_out(weight)
+        with _Wgrad(on, x, dy):
+            dwp = torch.empty((3, 3, 2 * C, Cout), dtype=F32, device=dev)
+            call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, 2 * C, Cout, stream())
+            _pack(dwp, (3, 2, 0, 1), F32, out=dw)
+        db = _colsum(dy, Cout)
+        # the BatchNorm's backward: one apply pass
+        dz = torch.empty_like(z)
+        dzsum = torch.empty(C, dtype=F32, device=dev) if ctx.producer_bias else None
+        call("eel_bn_act_bwd_apply", ptr(dab), ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(bt), ptr(sums), ptr(dz), ptr(dzsum), P, C, 0,
+             int(ctx.training), dtype_code(z), st)
+        if dzsum is not None:
+            _attach(dz, "_eel_colsum", dzsum)
+        return dz, sums[1], sums[0], None, None, None, None, None, dab, de, None, dw, db
 
 
 class Concat(Function):

@@ -126,6 +126,19 @@ int eel_tc_conv3x3(const void* x, const void* wk, const float* bias, void* y, in
 int eel_tc_conv3x3_dgrad_bnsums(const void* dy, const void* wk, void* dx, int N, int H, int W, int Cin, int Cout, const void* z,
                                 const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                                 float* sums, void* consts_ws, eel_stream s);
+/* The data gradient of the conv that reads a skip bridge (FeatureInterleaveBridge, models/EELUnet.py:132-141, then the decoder
+ * block's first conv, :338): wk_split is the data-gradient operand [ky][kx][ci][co] with its ci rows DE-INTERLEAVED (even input
+ * channels first: eel_rows_deinterleave), so the two halves of the result leave as two [N,H,W,Cout/2] tensors -- dx0 the gradient
+ * of (upconv + edge feature), dx1 the gradient of the encoder skip -- and no interleaved gradient tensor (nor
+ * eel_add_interleave_bwd) exists.  z != NULL: the epilogue also accumulates the BACKWARD sums {sum g, sum g * xhat} of the
+ * BatchNorm that produced the first half (the upconv block's, relu = 0) into sums:[2][Cout/2]; finish with eel_bn_act_bwd_apply.
+ * Here Cin = channels of dy (the conv's outputs), Cout = channels of the conv's input (both halves).  consts_ws: 8 * Cout bytes. */
+int eel_tc_conv3x3_dgrad_split(const void* dy, const void* wk_split, void* dx0, void* dx1, int N, int H, int W, int Cin, int Cout,
+                               const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                               int relu, float* sums, void* consts_ws, eel_stream s);
+/* dst[g][r'][:] = src[g][perm(r')][:] with perm(r') = 2 r' for r' < rows / 2, else 2 (r' - rows / 2) + 1; rows of row_bytes
+ * (a multiple of 16) bytes */
+int eel_rows_deinterleave(const void* src, void* dst, long long groups, int rows, long long row_bytes, eel_stream s);
 /* scatterH/scatterW > 0: rows are pixels of [*, scatterH, scatterW] images and every output row is stored through the
  * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,

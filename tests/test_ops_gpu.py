@@ -453,6 +453,47 @@ def test_bn_add_interleave(dtype, edge_bn, shape):
         assert "eel_bn_act_bwd" not in names and names.count("eel_bn_act_bwd_apply") == (2 if edge_bn else 1)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 40, 24, 64), (1, 128, 36, 20, 128), (1, 256, 16, 16, 256), (2, 512, 8, 8, 512),
+                                   (1, 64, 16, 16, 128)])
+def test_bridge_conv_backward_in_two_halves(shape):
+    """skip bridge + the decoder block's first conv3x3 as one node (ops.BridgeConv3x3; reference models/EELUnet.py:365/373,
+    :422-426, :132-141, :338).  The conv's data gradient runs on the de-interleaved operand (eel_rows_deinterleave) and stores
+    d(BatchNorm(z) + b) and d(e) as two tensors with the BatchNorm's backward sums from its epilogue
+    (eel_tc_conv3x3_dgrad_split): no eel_add_interleave_bwd, no BatchNorm reduction pass"""
+    from eel_unet_b200 import _lib, ops
+
+    n, c, h, w, cout = shape
+    dtype = torch.bfloat16
+    z = torch.randn(n, c, h, w, device=DEV) * 1.5 + 0.3
+    b = torch.randn(n, c, h, w, device=DEV) * 0.7
+    e = torch.randn(n, c, h, w, device=DEV)
+    g = torch.rand(c, device=DEV) + 0.5
+    bt = torch.randn(c, device=DEV) * 0.5
+    wt = torch.randn(cout, 2 * c, 3, 3, device=DEV) / math.sqrt(18 * c)
+    bias = torch.randn(cout, device=DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    assert ops.BridgeConv3x3.supported(nhwc(z).to(dtype), wt) == (c >= 128)      # (the model keeps 64 channels on the two-launch path)
+
+    def mine(a, p):
+        return ops.BridgeConv3x3.apply(a[0], p[0], p[1], rm, rv, True, 0.1, 1e-5, a[1], a[2], False, p[2], p[3])
+
+    def ref(a, p):
+        s = F.batch_norm(a[0], None, None, p[0], p[1], True, 0.1, 1e-5) + a[1]
+        x = torch.stack([s, a[2]], dim=2).reshape(n, 2 * c, h, w)
+        x = x + (x.to(dtype).double() - x).detach()               # the conv reads the interleaved tensor as stored
+        return F.conv2d(x, p[2], p[3], padding=1)
+
+    rec = []
+    _lib.set_profiler(rec)
+    try:
+        run_case(mine, ref, [z, b, e], [g, bt, wt, bias], dtype, atol_scale=2.0)
+    finally:
+        _lib.set_profiler(None)
+    names = [r[0] for r in rec]
+    assert "eel_tc_conv3x3_dgrad_split" in names and "eel_add_interleave_bwd" not in names and "eel_bn_act_bwd" not in names
+    assert names.count("eel_bn_act_bwd_apply") == 1
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("c", [64, 128, 1024])
 def test_pgr(dtype, c):

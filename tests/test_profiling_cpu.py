@@ -23,6 +23,7 @@ def _header_params():
 EXPECTED = {
     "eel_tc_conv3x3": {4: "N", 5: "H", 6: "W", 7: "Cin", 8: "Cout"},
     "eel_tc_conv3x3_dgrad_bnsums": {3: "N", 4: "H", 5: "W", 6: "Cin", 7: "Cout"},
+    "eel_tc_conv3x3_dgrad_split": {4: "N", 5: "H", 6: "W", 7: "Cin", 8: "Cout", 9: "z"},
     "eel_tc_linear": {4: "P", 5: "K", 6: "Nout"},
     "eel_tc_convt2x2_fwd": {4: "N", 5: "h", 6: "w", 7: "Cin", 8: "Cout"},
     "eel_tc_convt2x2_dgrad": {3: "N", 4: "h", 5: "w", 6: "Cin", 7: "Cout"},
