@@ -463,7 +463,7 @@ def run_ours(args):
         if top[0] == "tc_conv3x3":
             # the family holds two kinds of launch: plain implicit-GEMM convolutions, and data gradients whose epilogue also reads
             # the BatchNorm input z and accumulates that BatchNorm's backward sums (HBM work without FLOPs): both rates
-            for tag, names in (("plain_conv_launches", ("eel_tc_conv3x3",)), ("dgrad_with_bn_sums_launches", ("eel_tc_conv3x3_dgrad_bnsums", "eel_tc_conv3x3_dgrad_split"))):
+            for tag, names in (("plain_conv_launches", ("eel_tc_conv3x3", "eel_tc_conv3x3_2src")), ("dgrad_with_bn_sums_launches", ("eel_tc_conv3x3_dgrad_bnsums", "eel_tc_conv3x3_dgrad_split"))):
                 sel = [(profiling.cost(nm, a)[0], s0.elapsed_time(s1)) for nm, a, s0, s1 in rec if nm in names]
                 if sel:
                     fl, tm = sum(v[0] for v in sel), sum(v[1] for v in sel)

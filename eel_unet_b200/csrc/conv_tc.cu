@@ -44,6 +44,10 @@ struct ConvParams {
     // Fused BatchNorm-backward sums (STATS == 2) then cover the first half only (bz / bcst / bn_sums are [.., split]).
     bf16* out2;
     int split;
+    // kc1 < kchunks (forward of the conv that reads a skip bridge): the first kc1 K chunks come from the first input tensor
+    // (tensor map tmA), the rest from a second one (tmA2) -- the Cin axis of the weight operand was de-interleaved, the
+    // interleaved 2C-channel activation tensor is never built
+    int kc1;
 };
 
 constexpr int kMaxStages = 8;
@@ -128,7 +132,8 @@ __device__ __forceinline__ void conv_mma_loop(const ConvParams& p, uint8_t* sA, 
 
 template <int BN, int MT, bool RES, int EW, int STATS>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+               const ConvParams p) {
     typedef ConvCfg<BN, MT, RES> Cfg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -149,6 +154,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1);
@@ -182,7 +188,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < p.kchunks; ++c) {
                 mbar_wait(&emptyA[sa], pa ^ 1);
                 mbar_expect_tx(&fullA[sa], Cfg::A_TX);
-                tma_load_4d(sA + sa * Cfg::A_BYTES, &tmA, &fullA[sa], c * 64, c_w, c_h, c_n);
+                if (c < p.kc1) tma_load_4d(sA + sa * Cfg::A_BYTES, &tmA, &fullA[sa], c * 64, c_w, c_h, c_n);
+                else tma_load_4d(sA + sa * Cfg::A_BYTES, &tmA2, &fullA[sa], (c - p.kc1) * 64, c_w, c_h, c_n);
                 if (++sa == p.na) { sa = 0; pa ^= 1; }
                 if (!RES) {
                     for (int t = 0; t < 9; ++t) {
@@ -317,7 +324,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int MT, bool RES>
-static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int Cout, cudaStream_t st, const char* what) {
+static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int Cout, cudaStream_t st, const char* what,
+                       const void* x2 = nullptr, int Cin1 = 0) {
     typedef ConvCfg<BN, MT, RES> Cfg;
     const int b_bytes = (RES ? 9 * p.kchunks : Cfg::NB) * Cfg::B_TILE;
     // 8 epilogue warps (16 KB of transposition buffers) unless that would leave fewer than three activation stages
@@ -344,12 +352,23 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
         set_error("%s: cannot raise dynamic shared memory to %d", what, smem);
         return EEL_ERR_CUDA;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmA2, tmB;
+    const int Ca = x2 != nullptr ? Cin1 : Cin;      // channels of the first (or only) input tensor
     {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
-        uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)p.W * Cin, (uint64_t)p.H * p.W * Cin};
+        uint64_t dims[4] = {(uint64_t)Ca, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+        uint64_t str[4] = {1, (uint64_t)Ca, (uint64_t)p.W * Ca, (uint64_t)p.H * p.W * Ca};
         uint32_t box[4] = {64, 10, (uint32_t)(Cfg::TH + 2), 1};
         if (int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, what)) return rc;
+    }
+    tmA2 = tmA;
+    p.kc1 = p.kchunks;
+    if (x2 != nullptr) {
+        const int Cb = Cin - Cin1;
+        uint64_t dims[4] = {(uint64_t)Cb, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+        uint64_t str[4] = {1, (uint64_t)Cb, (uint64_t)p.W * Cb, (uint64_t)p.H * p.W * Cb};
+        uint32_t box[4] = {64, 10, (uint32_t)(Cfg::TH + 2), 1};
+        if (int rc = make_tmap_bf16(&tmA2, x2, 4, dims, str, box, what)) return rc;
+        p.kc1 = Cin1 / 64;
     }
     {
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
@@ -374,7 +393,7 @@ static int launch_conv(const void* x, const void* wk, ConvParams p, int Cin, int
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    void* args[3] = {(void*)&tmA, (void*)&tmB, (void*)&p};
+    void* args[4] = {(void*)&tmA, (void*)&tmA2, (void*)&tmB, (void*)&p};
     if (cudaLaunchKernel(fns[variant], dim3(grid), dim3(64 + 32 * ew), args, smem, st) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
         return EEL_ERR_CUDA;
@@ -405,7 +424,7 @@ __global__ void bn_sums_fix_kernel(float* __restrict__ sums, const float* __rest
 
 static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                             int relu, int flip, float* bn_sums, const bf16* bz, const float2* bcst, int brelu, cudaStream_t st,
-                            void* y2 = nullptr, int split = 0) {
+                            void* y2 = nullptr, int split = 0, const void* x2 = nullptr, int Cin1 = 0) {
     EEL_REQUIRE(x && wk && y && N > 0 && H > 0 && W > 0, "tc_conv3x3: bad argument");
     EEL_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_conv3x3: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
     EEL_REQUIRE((long long)N * H * W * Cout / 8 < (1LL << 32), "tc_conv3x3: output too large for 32-bit vector offsets");
@@ -420,17 +439,17 @@ static int conv3x3_dispatch(const void* x, const void* wk, const float* bias, vo
     p.out2 = (bf16*)y2; p.split = split;
     const bool tall = H > 16;                  // a 32-row tile would be half empty on 16-row maps
     if (Cin == 64 && Cout == 64)
-        return tall ? launch_conv<64, 2, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)")
-                    : launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)");
-    if (Cin == 128 && Cout == 64) return launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 128x64)");
-    if (Cin == 64 && Cout == 128) return launch_conv<128, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x128)");
+        return tall ? launch_conv<64, 2, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)", x2, Cin1)
+                    : launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x64)", x2, Cin1);
+    if (Cin == 128 && Cout == 64) return launch_conv<64, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 128x64)", x2, Cin1);
+    if (Cin == 64 && Cout == 128) return launch_conv<128, 1, true>(x, wk, p, Cin, Cout, st, "tc_conv3x3(res 64x128)", x2, Cin1);
     // N = 256 MMAs read the least shared memory per FLOP (A 4 KB + B 8 KB per 128 cycles): preferred when Cout allows
-    if (Cout % 256 == 0) return launch_conv<256, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(256x1)");
+    if (Cout % 256 == 0) return launch_conv<256, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(256x1)", x2, Cin1);
     if (Cout % 128 == 0)
-        return tall ? launch_conv<128, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x2)")
-                    : launch_conv<128, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x1)");
-    return tall ? launch_conv<64, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x2)")
-                : launch_conv<64, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x1)");
+        return tall ? launch_conv<128, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x2)", x2, Cin1)
+                    : launch_conv<128, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(128x1)", x2, Cin1);
+    return tall ? launch_conv<64, 2, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x2)", x2, Cin1)
+                : launch_conv<64, 1, false>(x, wk, p, Cin, Cout, st, "tc_conv3x3(64x1)", x2, Cin1);
 }
 
 extern "C" {
@@ -453,6 +472,15 @@ int eel_tc_conv3x3_dgrad_bnsums(const void* dy, const void* wk, void* dx, int N,
     if (int rc = conv3x3_dispatch(dy, wk, nullptr, dx, N, H, W, Cin, Cout, 0, 1, sums, (const bf16*)z, (const float2*)consts_ws, relu, st)) return rc;
     bn_sums_fix_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(sums, mean, rstd, Cout);
     return check_launch("tc_conv3x3_dgrad_bnsums.fix");
+}
+
+// conv3x3 whose input channels come from TWO tensors (x1: C1 channels, x2: C2): the forward of the conv that reads a skip bridge.
+// wk is the forward operand [ky][kx][co][ci] with its ci columns de-interleaved (eel_cols_deinterleave): x1 = the even input
+// channels (BatchNorm(upconv) + edge feature), x2 = the odd ones (the encoder skip).
+int eel_tc_conv3x3_2src(const void* x1, const void* x2, const void* wk, const float* bias, void* y, int N, int H, int W, int C1, int C2,
+                        int Cout, int relu, float* bn_sums, eel_stream s) {
+    EEL_REQUIRE(x1 && x2 && C1 > 0 && C2 > 0 && C1 % 64 == 0 && C2 % 64 == 0, "tc_conv3x3_2src: both inputs need multiples of 64 channels");
+    return conv3x3_dispatch(x1, wk, bias, y, N, H, W, C1 + C2, Cout, relu, 0, bn_sums, nullptr, nullptr, 0, (cudaStream_t)s, nullptr, 0, x2, C1);
 }
 
 // Data gradient of the conv that reads a skip bridge (channels interleaved as (upconv + edge feature, encoder skip), models/EELUnet.py:

@@ -1113,6 +1113,55 @@ __global__ void rows_deinterleave_kernel(const uint4* __restrict__ src, uint4* _
     }
 }
 
+// dst[r][c'] = src[r][perm(c')], perm(c') = 2 c' (c' < cols / 2) or 2 (c' - cols / 2) + 1 (2-byte elements): the forward operand
+// [ky][kx][co][ci] of a conv that reads a skip bridge, its input channels de-interleaved (eel_tc_conv3x3_2src)
+__global__ void cols_deinterleave_kernel(const unsigned short* __restrict__ src, unsigned short* __restrict__ dst, long long n, int cols) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        const int sc = c < cols / 2 ? 2 * c : 2 * (c - cols / 2) + 1;
+        dst[i] = src[r * cols + sc];
+    }
+}
+
+// dw[co][2 c + h][t] = dwp_h[t][c][co]: the two half weight gradients of a two-source conv (taps x C x Cout each, fp32) written
+// into the reference layout [Cout][2C][3][3] with the input channels interleaved again
+__global__ void dw_interleave_kernel(const float* __restrict__ dwp0, const float* __restrict__ dwp1, float* __restrict__ dw, int taps, int C,
+                                     int Cout) {
+    const long long n = (long long)Cout * 2 * C * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps);
+        long long r = i / taps;
+        const int ci = (int)(r % (2 * C));
+        const int co = (int)(r / (2 * C));
+        const float* srcp = (ci & 1) ? dwp1 : dwp0;
+        dw[i] = srcp[((long long)t * C + (ci >> 1)) * Cout + co];
+    }
+}
+
+// out = BatchNorm(z) + b  (the first half of a skip bridge that is never interleaved: eel_tc_conv3x3_2src reads it next to the skip)
+template <class T>
+__global__ void bn_add_fwd_kernel(const T* __restrict__ z, const T* __restrict__ b, T* __restrict__ out, long long nvec, int C,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta) {
+    constexpr int V = Vec16<T>::N;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float sc[V], sh[V];
+    const int c0 = (int)(i0 % (C / V)) * V;          // (the launch uses a multiple of C / V threads: a thread keeps its channel vector)
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = gamma[c0 + j] * rstd[c0 + j];
+        sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    }
+    for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const Vec16<T> vz = ld16(z + i * V), vb = ld16(b + i * V);
+        Vec16<T> o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.set(j, fmaf(vz.get(j), sc[j], sh[j]) + vb.get(j));
+        st16(out + i * V, o);
+    }
+}
+
 // ------------------------------------------------------------------------------------ column-block copy (torch.concat on C)
 template <class T>
 __global__ void copy_cols_kernel(const T* __restrict__ src, long long src_ld, int src_c0, T* __restrict__ dst, long long dst_ld,
@@ -1967,6 +2016,33 @@ int eel_rows_deinterleave(const void* src, void* dst, long long groups, int rows
     const long long nvec = groups * rows * (row_bytes / 16);
     rows_deinterleave_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)src, (uint4*)dst, nvec, rows, (int)(row_bytes / 16));
     return check_launch("rows_deinterleave");
+}
+
+int eel_cols_deinterleave(const void* src, void* dst, long long rows, int cols, eel_stream s) {
+    EEL_REQUIRE(src && dst && rows > 0 && cols > 0 && cols % 2 == 0, "cols_deinterleave: bad argument (even column count)");
+    const long long n = rows * cols;
+    cols_deinterleave_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>((const unsigned short*)src, (unsigned short*)dst, n, cols);
+    return check_launch("cols_deinterleave");
+}
+
+int eel_dw_interleave(const float* dwp0, const float* dwp1, float* dw, int taps, int C, int Cout, eel_stream s) {
+    EEL_REQUIRE(dwp0 && dwp1 && dw && taps > 0 && C > 0 && Cout > 0, "dw_interleave: bad argument");
+    const long long n = (long long)Cout * 2 * C * taps;
+    dw_interleave_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>(dwp0, dwp1, dw, taps, C, Cout);
+    return check_launch("dw_interleave");
+}
+
+int eel_bn_add_fwd(const void* z, const void* b, void* out, long long P, int C, const float* mean, const float* rstd,
+                   const float* gamma, const float* beta, int dtype, eel_stream s) {
+    EEL_REQUIRE(z && b && out && mean && rstd && gamma && beta && P > 0 && C > 0, "bn_add_fwd: bad argument");
+    EEL_DISPATCH_DTYPE(dtype, {
+        EEL_VEC_CHECK(T, C, "bn_add_fwd");
+        constexpr int V = Vec16<T>::N;
+        EEL_REQUIRE(256 % (C / V) == 0, "bn_add_fwd: C / %d must divide 256", V);
+        long long nvec = P * C / V;
+        bn_add_fwd_kernel<T><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const T*)z, (const T*)b, (T*)out, nvec, C, mean, rstd, gamma, beta);
+        return check_launch("bn_add_fwd");
+    });
 }
 
 int eel_copy_cols(const void* src, long long src_ld, int src_c0, void* dst, long long dst_ld, int dst_c0, long long P, int ncols,

@@ -167,8 +167,7 @@ class EELUnet(nn.Module):
             self._packer = ops.build_packer(self)
             if EELUnet.fused_bridge:
                 for blk in (self.dec4, self.dec3, self.dec2, self.dec1):      # the convs that read a skip bridge (ops.BridgeConv3x3)
-                    if blk[0].weight.shape[1] // 2 >= ops.BridgeConv3x3.MIN_CHANNELS:
-                        self._packer.want_split(blk[0].weight)
+                    self._packer.want_split(blk[0].weight)
         return self._packer
 
     def _composed_packer(self):

@@ -345,8 +345,8 @@ class WeightPacker:
         self.owners.append(owner)
 
     def want_split(self, param):
-        """``param`` is the weight of a conv3x3 that reads a skip bridge: also keep its data-gradient operand with the input
-        channel rows de-interleaved (BridgeConv3x3, eel_tc_conv3x3_dgrad_split)"""
+        """``param`` is the weight of a conv3x3 that reads a skip bridge: also keep its two operands with the input channels
+        de-interleaved (BridgeConv3x3: eel_tc_conv3x3_2src, eel_tc_conv3x3_dgrad_split)"""
         if id(param) not in self.split_ids:
             self.split_ids.add(id(param))
             self.table = None               # rebuild: the split buffers are allocated with the table
@@ -372,7 +372,8 @@ class WeightPacker:
                 outs.append(dst)
             self.by_param[id(w)] = tuple(outs)
             keep.append(w)
-        self.splits = [(w, self.by_param[id(w)][1], torch.empty_like(self.by_param[id(w)][1]))
+        self.splits = [(w, self.by_param[id(w)][0], torch.empty_like(self.by_param[id(w)][0]),
+                        self.by_param[id(w)][1], torch.empty_like(self.by_param[id(w)][1]))
                        for (w, dims, pf, pd) in self.entries if id(w) in self.split_ids]
         self.table = torch.from_numpy(rec.reshape(-1).view(np.uint8).copy()).to(device)
         self.ptrs = [w.data_ptr() for w in keep]
@@ -391,8 +392,8 @@ class WeightPacker:
             return
         def launch():
             call("eel_pack_batch", ptr(self.table), 2 * len(self.entries), 128, stream())
-            for w, dg, sp in self.splits:      # [ky][kx][ci][co] -> ci rows de-interleaved
-                call("eel_rows_deinterleave", ptr(dg), ptr(sp), dg.shape[0] * dg.shape[1], dg.shape[2], dg.shape[3] * dg.element_size(), stream())
+            for w, fw, fsp, dg, dsp in self.splits:
+                _deinterleave_operands(fw, fsp, dg, dsp)
         _on_side_stream(launch)
         self.versions = ver
         # publish on the parameters themselves: ops find the operands through the weight they are handed (forward and
@@ -400,8 +401,8 @@ class WeightPacker:
         for e in self.entries:
             w = e[0]
             w._eel_packed = self.by_param[id(w)] + (_pack_key(w),)
-        for w, dg, sp in self.splits:
-            w._eel_packed_split = (sp, _pack_key(w))
+        for w, fw, fsp, dg, dsp in self.splits:
+            w._eel_packed_split = (fsp, dsp, _pack_key(w))
 
     def get(self, w):
         return self.by_param.get(id(w))
@@ -698,18 +699,27 @@ def _packed(weight, which):
     return hit[which]
 
 
+def _deinterleave_operands(fw, fsp, dg, dsp):
+    """forward operand [ky][kx][co][ci] -> ci columns de-interleaved; data-gradient operand [ky][kx][ci][co] -> ci rows"""
+    call("eel_cols_deinterleave", ptr(fw), ptr(fsp), fw.shape[0] * fw.shape[1] * fw.shape[2], fw.shape[3], stream())
+    call("eel_rows_deinterleave", ptr(dg), ptr(dsp), dg.shape[0] * dg.shape[1], dg.shape[2], dg.shape[3] * dg.element_size(), stream())
+
+
 def _packed_split(weight, dtype):
-    """the data-gradient operand of ``weight`` with its input-channel rows de-interleaved (published by a WeightPacker, or made here)"""
+    """(forward, data-gradient) operands of ``weight`` with the input channels de-interleaved (even channels first): published by
+    a WeightPacker, or made here"""
     hit = getattr(weight, "_eel_packed_split", None)
-    if hit is not None and hit[1] == _pack_key(weight):
+    if hit is not None and hit[2] == _pack_key(weight):
         _await_packed()
-        return hit[0]
-    dg = _packed(weight, 1)
+        return hit[0], hit[1]
+    fw, dg = _packed(weight, 0), _packed(weight, 1)
+    if fw is None:
+        fw = _pack(weight, (2, 3, 0, 1), dtype)
     if dg is None:
         dg = _pack(weight, (2, 3, 1, 0), dtype)
-    sp = torch.empty_like(dg)
-    call("eel_rows_deinterleave", ptr(dg), ptr(sp), dg.shape[0] * dg.shape[1], dg.shape[2], dg.shape[3] * dg.element_size(), stream())
-    return sp
+    fsp, dsp = torch.empty_like(fw), torch.empty_like(dg)
+    _deinterleave_operands(fw, fsp, dg, dsp)
+    return fsp, dsp
 
 
 def conv3x3(x, weight, bias, relu):
@@ -1461,24 +1471,28 @@ class BNAddInterleave(Function):
 class BridgeConv3x3(Function):
     """The skip bridge and the decoder block's first conv3x3 as ONE autograd node (bf16 tensor-core path):
 
-        x = interleave(BatchNorm(z) + b, e)      (BNAddInterleave: models/EELUnet.py:365/373, :422-426, :132-141)
+        x = interleave(BatchNorm(z) + b, e)      (models/EELUnet.py:365/373, :422-426, :132-141)
         y = conv3x3(x)                           (:338 of the decoder block; pre-BatchNorm, statistics from the epilogue)
 
-    The forward is the two launches of BNAddInterleave and Conv3x3.  The point is the backward: the conv's data gradient runs on
-    a weight operand whose input-channel rows were de-interleaved, so its epilogue stores d(BatchNorm(z) + b) and d(e) as two
-    tensors and accumulates the BatchNorm's backward sums over the first -- the interleaved gradient tensor, the de-interleaving
-    pass over it (eel_add_interleave_bwd) and the BatchNorm's reduction pass do not exist."""
+    The interleaved 2C-channel tensor x is never built.  Forward: s = BatchNorm(z) + b (eel_bn_add_fwd), then the conv reads
+    its K chunks from the TWO tensors s and e through two tensor maps, on a forward operand whose input-channel columns were
+    de-interleaved (eel_tc_conv3x3_2src).  Backward, 128 channels and up: the data gradient runs on the operand with de-interleaved
+    rows, so its epilogue stores d(s) and d(e) as two tensors and accumulates the BatchNorm's backward sums over the first
+    (eel_tc_conv3x3_dgrad_split) -- no interleaved gradient tensor, no de-interleaving pass, no BatchNorm reduction pass.  At 64
+    channels (the full-resolution bridge) the data gradient is all epilogue, so there the plain launch writes the interleaved
+    gradient and the de-interleaving pass delivers the sums (eel_add_interleave_bwd_bnsums), also those of the BatchNorm + ReLU
+    that produced b when this bridge is its only consumer.  The weight gradient is two half launches (inputs s and e) whose
+    results eel_dw_interleave writes into the reference layout."""
 
     # Measured on B200 (batch 64): against the plain data gradient + eel_add_interleave_bwd_bnsums the split launch saves
     # 0.13 / 0.07 / 0.01 ms at 128 / 256 / 512 channels, but LOSES 0.3 ms at the 64-channel full-resolution bridge, whose
-    # data gradient (K = 64 per tap) is all epilogue: 0.44 -> 1.08 ms with the BatchNorm sums on half of its columns, and the
-    # edge branch's last BatchNorm would lose the sums the de-interleaving pass gives it there.  So: 128 channels and up.
-    MIN_CHANNELS = 128
+    # data gradient (K = 64 per tap) is all epilogue: 0.44 -> 1.08 ms with the BatchNorm sums on half of its columns.
+    MIN_SPLIT_CHANNELS = 128
 
     @staticmethod
     def supported(z, weight):
         C = z.shape[-1]
-        return (z.dtype == BF16 and z.is_cuda and C % 64 == 0 and C >= BridgeConv3x3.MIN_CHANNELS
+        return (z.dtype == BF16 and z.is_cuda and C % 64 == 0 and (C == 64 or C % 128 == 0) and 256 % (C // 8) == 0
                 and tuple(weight.shape[1:]) == (2 * C, 3, 3) and weight.shape[0] % 64 == 0 and _stats_cols_ok(C))
 
     @staticmethod
@@ -1488,25 +1502,27 @@ class BridgeConv3x3(Function):
         Cout = weight.shape[0]
         st = stream()
         mean, rstd = _bn_statistics(z, running_mean, running_var, training, momentum, eps)
-        x = torch.empty((N, H, W, 2 * C), dtype=z.dtype, device=z.device)
-        call("eel_add_interleave_fwd", ptr(z), ptr(b), ptr(e), ptr(x), N * H * W, C, ptr(mean), ptr(rstd), ptr(gamma.detach()),
-             ptr(beta.detach()), dtype_code(z), st)
-        wk = _packed(weight, 0)
-        if wk is None:
-            wk = _pack(weight, (2, 3, 0, 1), x.dtype)
-        y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
-        sums = _want_bn_sums(x, Cout)
+        s_t = torch.empty_like(z)
+        call("eel_bn_add_fwd", ptr(z), ptr(b), ptr(s_t), N * H * W, C, ptr(mean), ptr(rstd), ptr(gamma.detach()), ptr(beta.detach()),
+             dtype_code(z), st)
+        wf, _ = _packed_split(weight, z.dtype)
+        y = torch.empty((N, H, W, Cout), dtype=z.dtype, device=z.device)
+        sums = _want_bn_sums(z, Cout)
         bd = bias.detach() if bias is not None else None
-        call("eel_tc_conv3x3", ptr(x), ptr(wk), None if sums is not None else ptr(bd), ptr(y), N, H, W, 2 * C, Cout, 0, 0, ptr(sums), st)
+        call("eel_tc_conv3x3_2src", ptr(s_t), ptr(e), ptr(wf), None if sums is not None else ptr(bd), ptr(y), N, H, W, C, C, Cout, 0,
+             ptr(sums), st)
         if sums is not None:
             _attach(y, "_eel_bn_sums", (sums, bd))
         ctx.training, ctx.producer_bias = training, producer_bias
-        ctx.save_for_backward(z, mean, rstd, gamma, beta, x, weight)
+        # 64 channels: b = relu(bn(z_b)) with this bridge as its only consumer -> the de-interleaving pass of the backward also
+        # delivers THAT BatchNorm's sums (as BNAddInterleave)
+        ctx.b_bn = _take(b, "_eel_bn_out") if (ctx.needs_input_grad[8] and C < BridgeConv3x3.MIN_SPLIT_CHANNELS) else None
+        ctx.save_for_backward(z, mean, rstd, gamma, beta, s_t, e, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        z, mean, rstd, gamma, beta, x, weight = ctx.saved_tensors
+        z, mean, rstd, gamma, beta, s_t, e, weight = ctx.saved_tensors
         dy = _c(dy)
         N, H, W, C = z.shape
         Cout = weight.shape[0]
@@ -1514,21 +1530,40 @@ class BridgeConv3x3(Function):
         st = stream()
         dev = z.device
         g, bt = gamma.detach(), beta.detach()
-        # data gradient in two halves + the BatchNorm's backward sums over the first
-        wsp = _packed_split(weight, x.dtype)
-        dab = torch.empty((N, H, W, C), dtype=x.dtype, device=dev)
+        dab = torch.empty((N, H, W, C), dtype=z.dtype, device=dev)
         de = torch.empty_like(dab)
         sums = torch.empty((2, C), dtype=F32, device=dev)
-        cws = workspace(16 * C, dev, slot=1)
-        call("eel_tc_conv3x3_dgrad_split", ptr(dy), ptr(wsp), ptr(dab), ptr(de), N, H, W, Cout, 2 * C, ptr(z), ptr(mean), ptr(rstd), ptr(g),
-             ptr(bt), 0, ptr(sums), ptr(cws), st)
-        # weight gradient (side stream): the saved interleaved input, as Conv3x3.backward
+        if C >= BridgeConv3x3.MIN_SPLIT_CHANNELS:
+            # data gradient in two halves + the BatchNorm's backward sums over the first
+            _, wsp = _packed_split(weight, z.dtype)
+            cws = workspace(16 * C, dev, slot=1)
+            call("eel_tc_conv3x3_dgrad_split", ptr(dy), ptr(wsp), ptr(dab), ptr(de), N, H, W, Cout, 2 * C, ptr(z), ptr(mean), ptr(rstd),
+                 ptr(g), ptr(bt), 0, ptr(sums), ptr(cws), st)
+        else:
+            wk = _packed(weight, 1)
+            if wk is None:
+                wk = _pack(weight, (2, 3, 1, 0), z.dtype)
+            dx = torch.empty((N, H, W, 2 * C), dtype=z.dtype, device=dev)
+            call("eel_tc_conv3x3", ptr(dy), ptr(wk), None, ptr(dx), N, H, W, Cout, 2 * C, 0, 1, None, st)
+            other, ctx.b_bn = ctx.b_bn, None
+            sums1 = torch.empty((2, C), dtype=F32, device=dev) if other is not None else None
+            z1, m1, r1, g1, b1, relu1 = other if other is not None else (None, None, None, None, None, 0)
+            ws, n = _reduce_ws(dev, C, 4)
+            call("eel_add_interleave_bwd_bnsums", ptr(dx), ptr(dab), ptr(de), P, C, ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(bt), 0,
+                 ptr(sums), ptr(z1), ptr(m1), ptr(r1), ptr(g1.detach()) if g1 is not None else None,
+                 ptr(b1.detach()) if b1 is not None else None, int(relu1), ptr(sums1), ptr(ws), n, dtype_code(dx), st)
+            if other is not None:
+                _attach(dab, "_eel_bn_bwd_sums", (sums1, z1))
+        # weight gradient (side stream): one half launch per input tensor, interleaved into the reference layout
         on = _async_ok(weight)
         dw = _grad_out(weight)
-        with _Wgrad(on, x, dy):
-            dwp = torch.empty((3, 3, 2 * C, Cout), dtype=F32, device=dev)
-            call("eel_tc_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dwp), N, H, W, 2 * C, Cout, stream())
-            _pack(dwp, (3, 2, 0, 1), F32, out=dw)
+        with _Wgrad(on, s_t, e, dy):
+            sst = stream()
+            dwp0 = torch.empty((3, 3, C, Cout), dtype=F32, device=dev)
+            dwp1 = torch.empty((3, 3, C, Cout), dtype=F32, device=dev)
+            call("eel_tc_conv3x3_wgrad", ptr(s_t), ptr(dy), ptr(dwp0), N, H, W, C, Cout, sst)
+            call("eel_tc_conv3x3_wgrad", ptr(e), ptr(dy), ptr(dwp1), N, H, W, C, Cout, sst)
+            call("eel_dw_interleave", ptr(dwp0), ptr(dwp1), ptr(dw), 9, C, Cout, sst)
         db = _colsum(dy, Cout)
         # the BatchNorm's backward: one apply pass
         dz = torch.empty_like(z)

@@ -26,6 +26,13 @@ def cost(name, a):
         N, H, W, ci, co = a[3], a[4], a[5], a[6], a[7]
         P = N * H * W
         return 2.0 * P * 9 * ci * co, P * (ci + 2 * co) * 2 + 9 * ci * co * 2
+    if n == "tc_conv3x3_2src":
+        N, H, W, c1, c2, co = a[5], a[6], a[7], a[8], a[9], a[10]
+        P = N * H * W
+        return 2.0 * P * 9 * (c1 + c2) * co, P * (c1 + c2 + co) * 2 + 9 * (c1 + c2) * co * 2
+    if n == "bn_add_fwd":
+        P, C, dt = a[3], a[4], a[9]
+        return 3.0 * P * C, 3 * P * C * _esz(dt)
     if n == "tc_conv3x3_dgrad_split":      # the data-gradient launch (two output tensors) + one read of the BatchNorm input of the first half
         N, H, W, ci, co = a[4], a[5], a[6], a[7], a[8]
         P = N * H * W
@@ -174,7 +181,7 @@ def cost(name, a):
 
 
 # launches reported under another family's name
-ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "tc_conv3x3_dgrad_split": "tc_conv3x3", "gelu_bwd_colsum": "gelu_bwd", "add_interleave_bwd_bnsums": "add_interleave_bwd", "bn_act_shift_fwd": "bn_act_fwd"}
+ALIAS = {"tc_conv3x3_dgrad_bnsums": "tc_conv3x3", "tc_conv3x3_dgrad_split": "tc_conv3x3", "tc_conv3x3_2src": "tc_conv3x3", "bn_add_fwd": "add_interleave_fwd", "gelu_bwd_colsum": "gelu_bwd", "add_interleave_bwd_bnsums": "add_interleave_bwd", "bn_act_shift_fwd": "bn_act_fwd"}
 
 GEMM_CLASS = {"tc_conv3x3", "tc_linear", "tc_capmlp_fwd", "tc_convt2x2_fwd", "tc_convt2x2_dgrad", "tc_conv3x3_wgrad", "tc_wgrad", "conv3x3_fwd", "conv3x3_wgrad", "convt2x2_fwd", "convt2x2_dgrad", "convt2x2_wgrad", "linear_fwd",
               "linear_dgrad", "linear_wgrad", "hft_fwd", "hft_bwd"}

@@ -139,6 +139,19 @@ int eel_tc_conv3x3_dgrad_split(const void* dy, const void* wk_split, void* dx0, 
 /* dst[g][r'][:] = src[g][perm(r')][:] with perm(r') = 2 r' for r' < rows / 2, else 2 (r' - rows / 2) + 1; rows of row_bytes
  * (a multiple of 16) bytes */
 int eel_rows_deinterleave(const void* src, void* dst, long long groups, int rows, long long row_bytes, eel_stream s);
+/* The FORWARD of that conv without the interleaved tensor: input channels from two tensors, x1:[N,H,W,C1] = the even input
+ * channels (BatchNorm(upconv) + edge feature, eel_bn_add_fwd) and x2:[N,H,W,C2] = the odd ones (the encoder skip); wk is the
+ * forward operand [ky][kx][co][ci] with its ci columns de-interleaved (eel_cols_deinterleave).  Otherwise eel_tc_conv3x3. */
+int eel_tc_conv3x3_2src(const void* x1, const void* x2, const void* wk, const float* bias, void* y, int N, int H, int W, int C1,
+                        int C2, int Cout, int relu, float* bn_sums, eel_stream s);
+/* dst[r][c'] = src[r][perm(c')] with perm(c') = 2 c' for c' < cols / 2, else 2 (c' - cols / 2) + 1; 2-byte elements */
+int eel_cols_deinterleave(const void* src, void* dst, long long rows, int cols, eel_stream s);
+/* dw:[Cout][2C][taps] (reference layout, fp32) from the two half weight gradients dwp0 (even input channels) and dwp1 (odd),
+ * each [taps][C][Cout] as eel_tc_conv3x3_wgrad writes them */
+int eel_dw_interleave(const float* dwp0, const float* dwp1, float* dw, int taps, int C, int Cout, eel_stream s);
+/* out = BatchNorm(z) + b: the summed half of a skip bridge (models/EELUnet.py:365/373, :422) when the halves stay separate */
+int eel_bn_add_fwd(const void* z, const void* b, void* out, long long P, int C, const float* mean, const float* rstd,
+                   const float* gamma, const float* beta, int dtype, eel_stream s);
 /* scatterH/scatterW > 0: rows are pixels of [*, scatterH, scatterW] images and every output row is stored through the
  * ADJOINT of ShiftedChannel (models/EELUnet.py:88-97) -- the data gradient of a to_patch conv lands unshifted */
 int eel_tc_linear(const void* x, const void* w, const float* bias, void* y, long long P, int K, int Nout,

@@ -457,9 +457,10 @@ def test_bn_add_interleave(dtype, edge_bn, shape):
                                    (1, 64, 16, 16, 128)])
 def test_bridge_conv_backward_in_two_halves(shape):
     """skip bridge + the decoder block's first conv3x3 as one node (ops.BridgeConv3x3; reference models/EELUnet.py:365/373,
-    :422-426, :132-141, :338).  The conv's data gradient runs on the de-interleaved operand (eel_rows_deinterleave) and stores
-    d(BatchNorm(z) + b) and d(e) as two tensors with the BatchNorm's backward sums from its epilogue
-    (eel_tc_conv3x3_dgrad_split): no eel_add_interleave_bwd, no BatchNorm reduction pass"""
+    :422-426, :132-141, :338).  Forward: the conv reads BatchNorm(z) + b and e through two tensor maps on a de-interleaved
+    operand -- no interleaved tensor.  Backward at >= 128 channels: the data gradient stores d(BatchNorm(z) + b) and d(e) as two
+    tensors with the BatchNorm's backward sums from its epilogue (eel_tc_conv3x3_dgrad_split); at 64 channels the interleaved
+    gradient + the de-interleaving pass with the sums.  Weight gradient: two half launches interleaved into the reference layout"""
     from eel_unet_b200 import _lib, ops
 
     n, c, h, w, cout = shape
@@ -472,7 +473,7 @@ def test_bridge_conv_backward_in_two_halves(shape):
     wt = torch.randn(cout, 2 * c, 3, 3, device=DEV) / math.sqrt(18 * c)
     bias = torch.randn(cout, device=DEV)
     rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
-    assert ops.BridgeConv3x3.supported(nhwc(z).to(dtype), wt) == (c >= 128)      # (the model keeps 64 channels on the two-launch path)
+    assert ops.BridgeConv3x3.supported(nhwc(z).to(dtype), wt)
 
     def mine(a, p):
         return ops.BridgeConv3x3.apply(a[0], p[0], p[1], rm, rv, True, 0.1, 1e-5, a[1], a[2], False, p[2], p[3])
@@ -490,8 +491,9 @@ def test_bridge_conv_backward_in_two_halves(shape):
     finally:
         _lib.set_profiler(None)
     names = [r[0] for r in rec]
-    assert "eel_tc_conv3x3_dgrad_split" in names and "eel_add_interleave_bwd" not in names and "eel_bn_act_bwd" not in names
-    assert names.count("eel_bn_act_bwd_apply") == 1
+    assert "eel_tc_conv3x3_2src" in names and "eel_add_interleave_fwd" not in names          # the interleaved tensor is never built
+    assert ("eel_tc_conv3x3_dgrad_split" in names) == (c >= 128) and ("eel_add_interleave_bwd_bnsums" in names) == (c < 128)
+    assert "eel_bn_act_bwd" not in names and names.count("eel_bn_act_bwd_apply") == 1 and names.count("eel_tc_conv3x3_wgrad") == 2
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

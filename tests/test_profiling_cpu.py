@@ -24,6 +24,8 @@ EXPECTED = {
     "eel_tc_conv3x3": {4: "N", 5: "H", 6: "W", 7: "Cin", 8: "Cout"},
     "eel_tc_conv3x3_dgrad_bnsums": {3: "N", 4: "H", 5: "W", 6: "Cin", 7: "Cout"},
     "eel_tc_conv3x3_dgrad_split": {4: "N", 5: "H", 6: "W", 7: "Cin", 8: "Cout", 9: "z"},
+    "eel_tc_conv3x3_2src": {5: "N", 6: "H", 7: "W", 8: "C1", 9: "C2", 10: "Cout"},
+    "eel_bn_add_fwd": {3: "P", 4: "C", 9: "dtype"},
     "eel_tc_linear": {4: "P", 5: "K", 6: "Nout"},
     "eel_tc_convt2x2_fwd": {4: "N", 5: "h", 6: "w", 7: "Cin", 8: "Cout"},
     "eel_tc_convt2x2_dgrad": {3: "N", 4: "h", 5: "w", 6: "Cin", 7: "Cout"},
