@@ -197,6 +197,9 @@ class EELUnet(nn.Module):
                 if no % 64 == 0 and k % 64 == 0:
                     fp.composed.add(m.mlp[2], m.to_space, bn)
 
+            if EELUnet.fused_bridge:
+                for blk in (self.dec4, self.dec3, self.dec2, self.dec1):      # the convs that read a skip bridge
+                    fp.want_split(blk[0].weight)
             for blk in (self.enc1[0], self.enc2[0], self.dec2, self.dec1, self.edge_upconv_2[2], self.edge_upconv_1[2]):
                 conv(blk[0], blk[1]); conv(blk[3], blk[4])
             for blk in (self.enc3[0], self.enc4[0], self.dec4, self.dec3, self.edge_upconv_4[1], self.edge_upconv_3[1]):
@@ -275,8 +278,15 @@ class EELUnet(nn.Module):
     def _conv_bn(conv, bn, x, relu=True, defer=False, single_conv_consumer=False, shift_out=False):
         """conv3x3 -> BatchNorm[-> ReLU]; in training the conv's epilogue also delivers the BatchNorm sums"""
         f = ops.folded(conv.weight)
-        if isinstance(x, _Bridge) and (f is not None or not ops.BridgeConv3x3.supported(x.z, conv.weight)):
-            x = EELUnet._bn_add_interleave(x.bn, x.z, x.b, x.e)       # (not fusable after all: the interleaved tensor, then a plain conv)
+        if isinstance(x, _Bridge):
+            fs = ops.folded_split(conv.weight) if f is not None else None
+            if x.bn is None and fs is not None:
+                # inference: (upconv + edge feature) and the encoder skip go into the conv as two tensors
+                return ops.conv3x3_folded_2src(ops.add2(x.z, x.b), x.e, fs, f[1], relu)
+            if x.bn is None:
+                x = ops.AddInterleave.apply(x.z, x.b, x.e)
+            elif f is not None or not ops.BridgeConv3x3.supported(x.z, conv.weight):
+                x = EELUnet._bn_add_interleave(x.bn, x.z, x.b, x.e)   # (not fusable after all: the interleaved tensor, then a plain conv)
         if f is not None:
             return ops.conv3x3_folded(x, f[0], f[1], relu)
         ops.expect_bn(bn.training or bn.running_mean is None)
@@ -359,6 +369,8 @@ class EELUnet(nn.Module):
             if EELUnet.fused_bridge and up[0].dtype == torch.bfloat16:
                 return _Bridge(up[1], up[0], b, e)          # consumed by the decoder block's first conv (_conv_bn)
             return self._bn_add_interleave(up[1], up[0], b, e)
+        if EELUnet.fused_bridge and up.dtype == torch.bfloat16 and getattr(ops._TLS, "folded", None) is not None:
+            return _Bridge(None, up, b, e)                  # inference: the upconv's BatchNorm is already folded in (bn = None)
         return ops.AddInterleave.apply(up, b, e)
 
     @staticmethod

@@ -421,6 +421,8 @@ class FoldedPacker:
         self.by_weight = {}
         self.fold_table = self.pack_table = None
         self.ptrs = self.versions = None
+        self.split_ids = set()     # weights of the convs that read a skip bridge: also kept with de-interleaved input channels
+        self.split_by_weight = {}
         self.composed = ComposedPacker(BF16)       # (mlp[2], to_space, BatchNorm) triples: composed, then folded
 
     def bns(self):
@@ -445,7 +447,7 @@ class FoldedPacker:
         n = len(self.entries)
         fold = np.zeros((n, 8), dtype=np.int64)
         pack = np.zeros((n, 8), dtype=np.int64)
-        self.by_weight, self._keep = {}, []
+        self.by_weight, self._keep, self.split_by_weight = {}, [], {}
         for k, e in enumerate(self.entries):
             w, b, bn, dims, perm, spos = e
             C = bn.num_features
@@ -464,6 +466,8 @@ class FoldedPacker:
             r[7] = spos
             self.by_weight[id(w)] = (dst, fbias)
             self._keep.append((scale, fbias, dst))
+            if id(w) in self.split_ids:
+                self.split_by_weight[id(w)] = (dst, torch.empty_like(dst))
         to_dev = lambda a: torch.from_numpy(a.reshape(-1).view(np.uint8).copy()).to(device)
         self.fold_table, self.pack_table = to_dev(fold), to_dev(pack)
         self.ptrs = [t.data_ptr() for e in self.entries for t in self._tensors(e) if t is not None]
@@ -481,7 +485,19 @@ class FoldedPacker:
             return
         call("eel_bn_fold_batch", ptr(self.fold_table), len(self.entries), stream())
         call("eel_pack_batch", ptr(self.pack_table), len(self.entries), 128, stream())
+        for fw, fsp in self.split_by_weight.values():          # [ky][kx][co][ci] -> ci columns de-interleaved
+            call("eel_cols_deinterleave", ptr(fw), ptr(fsp), fw.shape[0] * fw.shape[1] * fw.shape[2], fw.shape[3], stream())
         self.versions = ver
+
+    def want_split(self, weight):
+        """conv3x3 that reads a skip bridge: keep its folded operand with de-interleaved input channels too (conv3x3_folded_2src)"""
+        if id(weight) not in self.split_ids:
+            self.split_ids.add(id(weight))
+            self.fold_table = None
+
+    def get_split(self, w):
+        hit = self.split_by_weight.get(id(w))
+        return None if hit is None else hit[1]
 
     def get(self, w):
         hit = self.by_weight.get(id(w))
@@ -605,6 +621,41 @@ def folded(weight):
     """(packed bf16 weight with the BatchNorm folded in, fp32 folded bias) or None"""
     f = getattr(_TLS, "folded", None)
     return None if f is None else f.get(weight)
+
+
+def folded_split(weight):
+    """the BatchNorm-folded forward operand of ``weight`` with de-interleaved input channels, or None"""
+    f = getattr(_TLS, "folded", None)
+    return None if f is None else f.get_split(weight)
+
+
+_IDENT = {}
+
+
+def add2(a, b):
+    """a + b on NHWC tensors (inference: the summed half of a skip bridge; eel_bn_add_fwd with identity constants)"""
+    a, b = _c(a), _c(b)
+    C = a.shape[-1]
+    key = (a.device, C)
+    cst = _IDENT.get(key)
+    if cst is None:
+        cst = _IDENT[key] = (torch.zeros(C, dtype=F32, device=a.device), torch.ones(C, dtype=F32, device=a.device))
+    zero, one = cst
+    out = torch.empty_like(a)
+    call("eel_bn_add_fwd", ptr(a), ptr(b), ptr(out), a.numel() // C, C, ptr(zero), ptr(one), ptr(one), ptr(zero), dtype_code(a), stream())
+    return out
+
+
+def conv3x3_folded_2src(x1, x2, wk_split, fbias, relu):
+    """inference: the conv that reads a skip bridge, its two halves as separate tensors (no interleaved tensor), + eval-mode
+    BatchNorm (+ ReLU) as ONE tensor-core kernel"""
+    x1, x2 = _c(x1), _c(x2)
+    N, H, W, C1 = x1.shape
+    C2 = x2.shape[-1]
+    Cout = wk_split.shape[2]
+    y = torch.empty((N, H, W, Cout), dtype=x1.dtype, device=x1.device)
+    call("eel_tc_conv3x3_2src", ptr(x1), ptr(x2), ptr(wk_split), ptr(fbias), ptr(y), N, H, W, C1, C2, Cout, int(relu), None, stream())
+    return y
 
 
 def conv3x3_folded(x, wk, fbias, relu):
