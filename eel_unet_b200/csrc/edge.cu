@@ -6,6 +6,8 @@
 // image once and writes a {0 none, 1 weak, 2 strong} byte per pixel into the OUTPUT image, appending
 // the sparse candidate pixels to a list.  Stage 2 is a lock-free union-find over that list only, so
 // the dense traffic stays at the algorithmic 3 B read + 1 B written per pixel.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eel {
@@ -392,6 +394,404 @@ __global__ void canny_merge_v2_kernel(const uint8_t* __restrict__ out, int* __re
     }
 }
 
+// ---- third generation (W % 32 == 0, W <= 512): no shared-memory tiles, no labels ------------------------------------------------
+// Stage 1: one WARP owns a band of BR image rows over the full row width: lane l holds pixels [16 l, 16 l + 16) of the current
+// row and slides down the band.  Two gray rows, two magnitude rows and the row being formed live in registers (the row loop is
+// unrolled by three so that the rotation is a renaming); the only horizontal exchange is one value per side of the vertical
+// smooth / difference sums and of the magnitude (6 shuffles per row of 512 pixels).  The replicated border needs no halo: a row
+// starts and ends inside the warp.  Pixels above the low threshold (a few per cent) branch into the direction test when their
+// magnitude is formed and into the suppression test one row later, everything else is ~25 instructions per pixel (the tile kernel
+// above: ~125).  Output: two BITMAPS per image (suppressed candidates; candidates above the high threshold), 16 bits per lane.
+// Stage 2: hysteresis = flood fill of the strong bitmap through the candidate bitmap, one CTA per image with both bitmaps in
+// shared memory (512 x 512: 2 x 32 KB).  A warp holds 32 rows (lane = row, 16 words = 512 pixels per lane): a whole row floods
+// in one carry-propagating pass per direction ((w & ~(w + s)) | s extends every seed through its run of candidates), rows
+// exchange through shuffles, 32-row bands through shared memory until nothing changes; the CTA then expands its bitmap into the
+// 0 / 255 byte image.  No global atomics, no memset, 0.25 bytes of workspace per pixel.
+struct RawRow { uint4 a, b, c; };
+
+template <bool RGB>
+__device__ __forceinline__ RawRow canny_load_row(const uint8_t* p) {
+    RawRow r;
+    r.a = __ldg(reinterpret_cast<const uint4*>(p));
+    if (RGB) {
+        r.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        r.c = __ldg(reinterpret_cast<const uint4*>(p) + 2);
+    } else {
+        r.b = r.a; r.c = r.a;
+    }
+    return r;
+}
+
+template <bool RGB>
+__device__ __forceinline__ void canny_gray16(const RawRow& r, int (&g)[16]) {
+    const uint32_t w[12] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w, r.c.x, r.c.y, r.c.z, r.c.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (RGB) {
+            const int i0 = 3 * j, i1 = 3 * j + 1, i2 = 3 * j + 2;
+            const int R = (int)((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xffu);
+            const int G = (int)((w[i1 >> 2] >> (8 * (i1 & 3))) & 0xffu);
+            const int B = (int)((w[i2 >> 2] >> (8 * (i2 & 3))) & 0xffu);
+            g[j] = gray_of(R, G, B);
+        } else {
+            g[j] = (int)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+        }
+    }
+}
+
+// per-row masks, bit j = pixel j of the lane: above the low / high threshold, gradient direction classes (horizontal: compare
+// left / right; vertical: up / down; otherwise a diagonal, `neg`: dx and dy of opposite sign = up-right / down-left), and the
+// comparisons of the row's magnitudes with the row above (gt_u: M[j] > up[j]; gt_ul / gt_ur: > up[j-1] / up[j+1]) and with the
+// left neighbour (gt_l, 17 bits: bit 16 belongs to the first pixel of the next lane)
+struct RowMasks { unsigned cand, strong, hor, ver, neg, gt_l, gt_u, gt_ul, gt_ur; };
+
+// one row step: gC (gray row t) is formed from `raw`; for t >= 2 the magnitude row MC (image row y0 + t - 3) from gA, gB, gC with
+// its masks mC; for t >= 4 the suppression of image row y0 + t - 4 (magnitudes MB, masks mB, row below MC) is stored.  Straight-line
+// code: every comparison is made for every pixel once and combined as 16-bit masks (a divergent per-pixel branch for the few
+// per cent above the low threshold runs for nearly every j of nearly every row, with two or three lanes in it).
+template <bool RGB>
+__device__ __forceinline__ void canny_row_step(const int t, const RawRow& raw, const int (&gA)[16], const int (&gB)[16], int (&gC)[16],
+                                               const int (&MB)[18], int (&MC)[18], const RowMasks& mB, RowMasks& mC,
+                                               const int y0, const int H, const int low, const int high, const bool first,
+                                               const bool last, const bool act, uint16_t* __restrict__ wrow,
+                                               uint16_t* __restrict__ srow, const int row_stride16) {
+    canny_gray16<RGB>(raw, gC);
+    if (t < 2) return;
+    int s[18], d[18];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        s[j + 1] = gA[j] + 2 * gB[j] + gC[j];
+        d[j + 1] = gC[j] - gA[j];
+    }
+    {
+        const int sl = __shfl_up_sync(0xffffffffu, s[16], 1), dl = __shfl_up_sync(0xffffffffu, d[16], 1);
+        const int sr = __shfl_down_sync(0xffffffffu, s[1], 1), dr = __shfl_down_sync(0xffffffffu, d[1], 1);
+        s[0] = first ? s[1] : sl;  d[0] = first ? d[1] : dl;          // BORDER_REPLICATE
+        s[17] = last ? s[16] : sr; d[17] = last ? d[16] : dr;
+    }
+    const int ry = y0 + t - 3;
+    const int rowmask = (ry >= 0 && ry < H) ? -1 : 0;                 // the magnitude is zero outside the image
+    // every mask is built by shifting the SIGN of a difference in at bit 0 (a > b  <=>  b - a < 0; all operands < 2^27), last
+    // pixel first, so that pixel j ends at bit j: two instructions per comparison
+#define EEL_PUSH(mask, diff) mask = __funnelshift_l((unsigned)(diff), mask, 1)
+    unsigned cand = 0, strong = 0, hor = 0, ver = 0, neg = 0;
+#pragma unroll
+    for (int j = 15; j >= 0; --j) {
+        const int dx = s[j + 2] - s[j];
+        const int dy = d[j] + 2 * d[j + 1] + d[j + 2];
+        const int ax = abs(dx), ay = abs(dy);
+        const int m = (ax + ay) & rowmask;
+        MC[j + 1] = m;
+        const int dh = (ay << 15) - ax * 13573;          // < 0: closer than 22.5 degrees to the x axis
+        const int dv = (ax << 16) - dh;                  // < 0: beyond 67.5 degrees  (t67 = t22 + (ax << 16))
+        EEL_PUSH(cand, low - m);
+        EEL_PUSH(strong, high - m);
+        EEL_PUSH(hor, dh);
+        EEL_PUSH(ver, dv);
+        EEL_PUSH(neg, dx ^ dy);
+    }
+    {
+        const int ml = __shfl_up_sync(0xffffffffu, MC[16], 1), mr = __shfl_down_sync(0xffffffffu, MC[1], 1);
+        MC[0] = first ? 0 : ml;
+        MC[17] = last ? 0 : mr;
+    }
+    unsigned gt_l = 0, gt_u = 0, gt_ul = 0, gt_ur = 0, gt_d = 0, gt_dl = 0, gt_dr = 0;
+#pragma unroll
+    for (int j = 16; j >= 0; --j) EEL_PUSH(gt_l, MC[j] - MC[j + 1]);
+#pragma unroll
+    for (int j = 15; j >= 0; --j) {
+        EEL_PUSH(gt_u, MB[j + 1] - MC[j + 1]);            // the new row against the row above it ...
+        EEL_PUSH(gt_ul, MB[j] - MC[j + 1]);
+        EEL_PUSH(gt_ur, MB[j + 2] - MC[j + 1]);
+        EEL_PUSH(gt_dl, MC[j] - MB[j + 1]);               // ... and the row above against the new row (strict on the diagonals)
+        EEL_PUSH(gt_dr, MC[j + 2] - MB[j + 1]);
+    }
+#undef EEL_PUSH
+    gt_d = gt_u;                                                       // bit j: below[j] > M[j], i.e. NOT (M[j] >= below[j])
+    mC.cand = cand; mC.strong = strong; mC.hor = hor; mC.ver = ver & ~hor; mC.neg = neg;
+    mC.gt_l = gt_l; mC.gt_u = gt_u; mC.gt_ul = gt_ul; mC.gt_ur = gt_ur;
+    if (t < 4) return;
+    const int rn = y0 + t - 4;
+    const unsigned keep_h = mB.gt_l & ~(mB.gt_l >> 1);                 // m > left  && m >= right
+    const unsigned keep_v = mB.gt_u & ~gt_d;                           // m > up    && m >= down
+    const unsigned keep_d2 = mB.gt_ul & gt_dr;                         // m > up-left  && m > down-right
+    const unsigned keep_d3 = mB.gt_ur & gt_dl;                         // m > up-right && m > down-left
+    const unsigned diag = ~(mB.hor | mB.ver);
+    const unsigned wk = mB.cand & 0xffffu &
+                        ((mB.hor & keep_h) | (mB.ver & keep_v) | (diag & ((~mB.neg & keep_d2) | (mB.neg & keep_d3))));
+    const unsigned st = wk & mB.strong;
+    if (act && rn < H) {
+        wrow[(size_t)rn * row_stride16] = (uint16_t)wk;
+        srow[(size_t)rn * row_stride16] = (uint16_t)st;
+    }
+}
+
+template <bool RGB>
+__global__ void __launch_bounds__(128) canny_rows_kernel(const uint8_t* __restrict__ src, uint16_t* __restrict__ weak,
+                                                       uint16_t* __restrict__ strong, int N, int H, int W, int BR, int bands,
+                                                       int low, int high) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= N * bands) return;                          // (the whole warp leaves together)
+    const int n = gw / bands, band = gw - n * bands;
+    const int y0 = band * BR;
+    const int nl = W >> 4;                                // lanes that hold pixels
+    const bool act = lane < nl;
+    const bool first = lane == 0, last = lane == nl - 1;
+    constexpr int bpp = RGB ? 3 : 1;
+    const size_t rowbytes = (size_t)W * bpp;
+    // lanes beyond the row re-read lane 0's pixels (they take part in the shuffles, their results are never used or stored)
+    const uint8_t* base = src + (size_t)n * H * rowbytes + (size_t)(act ? lane : 0) * 16 * bpp;
+    const int row_stride16 = W >> 4;
+    uint16_t* wrow = weak + (size_t)n * H * row_stride16 + lane;
+    uint16_t* srow = strong + (size_t)n * H * row_stride16 + lane;
+    const int T = BR + 4;                                 // gray rows y0 - 2 .. y0 + BR + 1 (clamped)
+
+    int g0[16], g1[16], g2[16], M0[18], M1[18];
+    RowMasks m0 = {}, m1 = {};
+#pragma unroll
+    for (int j = 0; j < 18; ++j) { M0[j] = 0; M1[j] = 0; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { g0[j] = 0; g1[j] = 0; g2[j] = 0; }
+
+    auto rowptr = [&](int t) { return base + (size_t)min(max(y0 - 2 + t, 0), H - 1) * rowbytes; };
+    RawRow nxt = canny_load_row<RGB>(rowptr(0));
+    // gray rows rotate through three register sets, magnitude rows and masks through two: six steps per trip
+#define EEL_CANNY_STEP(tt, GA, GB, GC, MB_, MC_, mB_, mC_)                                                                       \
+    {                                                                                                                            \
+        if ((tt) >= T) break;                                                                                                    \
+        const RawRow cur = nxt;                                                                                                  \
+        nxt = canny_load_row<RGB>(rowptr((tt) + 1)); /* (clamped: the last prefetch re-reads a valid row) */                     \
+        canny_row_step<RGB>((tt), cur, GA, GB, GC, MB_, MC_, mB_, mC_, y0, H, low, high, first, last, act, wrow, srow, row_stride16); \
+    }
+#pragma unroll 1
+    for (int t = 0; t < T; t += 6) {
+        EEL_CANNY_STEP(t, g1, g2, g0, M1, M0, m1, m0)
+        EEL_CANNY_STEP(t + 1, g2, g0, g1, M0, M1, m0, m1)
+        EEL_CANNY_STEP(t + 2, g0, g1, g2, M1, M0, m1, m0)
+        EEL_CANNY_STEP(t + 3, g1, g2, g0, M0, M1, m0, m1)
+        EEL_CANNY_STEP(t + 4, g2, g0, g1, M1, M0, m1, m0)
+        EEL_CANNY_STEP(t + 5, g0, g1, g2, M0, M1, m0, m1)
+    }
+#undef EEL_CANNY_STEP
+}
+
+constexpr int kHystWords = 16;        // words per lane = 512 pixels per row
+constexpr int kFloodWarps = 16;       // warps per CTA of the per-image fix-up kernel
+constexpr int kMaxBands = 1024;       // 32-row bands per image the fix-up kernel can track (H <= 32768)
+
+// one bitmap row of WW words into 16 registers (words beyond the row are zero); CG: bypass L1 (the row may have been rewritten by
+// another warp of this kernel)
+template <bool CG>
+__device__ __forceinline__ void bitmap_row_load(const uint32_t* __restrict__ p, const int WW, const bool valid, uint32_t (&v)[kHystWords]) {
+    if ((WW & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < kHystWords / 4; ++q) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && 4 * q < WW) t = CG ? __ldcg(reinterpret_cast<const uint4*>(p) + q) : __ldg(reinterpret_cast<const uint4*>(p) + q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kHystWords; ++k) v[k] = (valid && k < WW) ? (CG ? __ldcg(p + k) : __ldg(p + k)) : 0u;
+    }
+}
+
+__device__ __forceinline__ void bitmap_row_store(uint32_t* __restrict__ p, const int WW, const uint32_t (&v)[kHystWords]) {
+    if ((WW & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < kHystWords / 4; ++q)
+            if (4 * q < WW) __stcg(reinterpret_cast<uint4*>(p) + q, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < kHystWords; ++k)
+            if (k < WW) __stcg(p + k, v[k]);
+    }
+}
+
+// Flood step of a 32-row band held by one warp (lane = row, 16 words = 512 pixels per lane; w: candidates, rw: bit-reversed
+// candidates, s: set pixels, hu / hd: the rows just above lane 0 / below lane 31), repeated until nothing changes inside the band.
+// One step: seeds = candidates next to a set pixel (8-neighbourhood, across rows through shuffles, across words through the
+// neighbouring words' end bits), then every seed runs through its whole run of candidates INSIDE its word in both directions:
+// (w & ~(w + sd)) | sd towards higher x, the same on the bit-reversed word towards lower x.  The 16 words are independent (a run
+// that crosses a word border continues in the next step).  Returns the lane's changed bits (OR over the words).
+__device__ __forceinline__ uint32_t canny_flood_steps(const uint32_t (&w)[kHystWords], const uint32_t (&rw)[kHystWords],
+                                                      uint32_t (&s)[kHystWords], const uint32_t (&hu)[kHystWords],
+                                                      const uint32_t (&hd)[kHystWords], const int lane) {
+    uint32_t changed = 0u;
+    for (;;) {
+        uint32_t nb[kHystWords];
+#pragma unroll
+        for (int k = 0; k < kHystWords; ++k) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, s[k], 1), dn = __shfl_down_sync(0xffffffffu, s[k], 1);
+            if (lane == 0) up = hu[k];
+            if (lane == 31) dn = hd[k];
+            nb[k] = s[k] | up | dn;
+        }
+        uint32_t diff = 0u;
+#pragma unroll
+        for (int k = 0; k < kHystWords; ++k) {
+            uint32_t n3 = nb[k] | (nb[k] << 1) | (nb[k] >> 1);
+            if (k > 0) n3 |= nb[k - 1] >> 31;
+            if (k + 1 < kHystWords) n3 |= nb[k + 1] << 31;
+            const uint32_t sd = s[k] | (w[k] & n3);
+            const uint32_t f = (w[k] & ~(w[k] + sd)) | sd;               // towards higher x
+            const uint32_t rs = __brev(f);
+            const uint32_t rf = (rw[k] & ~(rw[k] + rs)) | rs;            // towards lower x
+            const uint32_t nf = __brev(rf);
+            diff |= nf ^ s[k];
+            s[k] = nf;
+        }
+        if (!__any_sync(0xffffffffu, diff != 0u)) break;
+        changed |= diff;
+    }
+    return changed;
+}
+
+// A warp floods the strong bitmap of one 32-row band in global memory through the candidate bitmap until nothing changes inside
+// the band; the rows just outside the band only seed it.  Returns (warp-uniform) a 2-bit code: bit 0: the band's first row
+// changed, bit 1: its last row changed.  Rows of other bands may be rewritten by other warps while they are read here: every value
+// read is a subset of the final answer (bits are only ever set), so the result can only be incomplete, never wrong, and the caller
+// iterates until nothing changes.
+__device__ __forceinline__ unsigned canny_flood_band(const uint32_t* __restrict__ weak, uint32_t* __restrict__ strong, const int H,
+                                                     const int WW, const int band, const int lane) {
+    const int row = band * 32 + lane;
+    const bool valid = row < H;
+    uint32_t w[kHystWords], s[kHystWords];
+    bitmap_row_load<false>(weak + (size_t)row * WW, WW, valid, w);
+    bitmap_row_load<true>(strong + (size_t)row * WW, WW, valid, s);
+    // (the rows just outside the band are requested together with the band: one memory round trip per visit)
+    uint32_t hu[kHystWords], hd[kHystWords];
+    bitmap_row_load<true>(strong + (size_t)(row - 1) * WW, WW, lane == 0 && row > 0, hu);
+    bitmap_row_load<true>(strong + (size_t)(row + 1) * WW, WW, lane == 31 && row + 1 < H, hd);
+    uint32_t open = 0u;
+#pragma unroll
+    for (int k = 0; k < kHystWords; ++k) open |= w[k] & ~s[k];
+    if (!__any_sync(0xffffffffu, open != 0u)) return 0u;                 // nothing left to grow into
+    uint32_t rw[kHystWords];
+#pragma unroll
+    for (int k = 0; k < kHystWords; ++k) rw[k] = __brev(w[k]);
+    const uint32_t changed = canny_flood_steps(w, rw, s, hu, hd, lane);
+    const unsigned rows_changed = __ballot_sync(0xffffffffu, changed != 0u);
+    if (rows_changed == 0u) return 0u;
+    if (changed != 0u) bitmap_row_store(strong + (size_t)row * WW, WW, s);
+    const int last_lane = min(31, H - 1 - band * 32);
+    return (rows_changed & 1u) | (((rows_changed >> last_lane) & 1u) << 1);
+}
+
+// H <= 512: one CTA per image, one warp per band, the band stays in REGISTERS from the first flood to the last; the bands'
+// first and last rows are exchanged through shared memory after every round (a round = every band floods until it stops changing)
+__global__ void __launch_bounds__(kFloodWarps * 32) canny_flood_image_reg_kernel(const uint32_t* __restrict__ weak, uint32_t* __restrict__ strong,
+                                                                                int H, int WW, int nbands) {
+    __shared__ uint32_t bnd[kFloodWarps][2][kHystWords];                  // [band][first row, last row]
+    __shared__ int flag;
+    volatile uint32_t (*vb)[2][kHystWords] = bnd;
+    const size_t img = (size_t)blockIdx.x * H * WW;
+    weak += img;
+    strong += img;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool mine = warp < nbands;
+    const int row = warp * 32 + lane;
+    const bool valid = mine && row < H;
+    const int last_lane = min(31, max(0, H - 1 - warp * 32));
+    uint32_t w[kHystWords], rw[kHystWords], s[kHystWords];
+    bitmap_row_load<false>(weak + (size_t)row * WW, WW, valid, w);
+    bitmap_row_load<false>(strong + (size_t)row * WW, WW, valid, s);
+#pragma unroll
+    for (int k = 0; k < kHystWords; ++k) rw[k] = __brev(w[k]);
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < kHystWords; ++k) {
+            if (lane == 0) vb[warp][0][k] = s[k];
+            if (lane == last_lane) vb[warp][1][k] = s[k];
+        }
+    }
+    uint32_t changed_total = 0u;
+    for (;;) {
+        __syncthreads();                       // published rows of the previous round are visible; the flag has been read
+        if (threadIdx.x == 0) flag = 0;
+        __syncthreads();
+        if (mine) {
+            uint32_t hu[kHystWords], hd[kHystWords];
+#pragma unroll
+            for (int k = 0; k < kHystWords; ++k) {
+                hu[k] = (lane == 0 && warp > 0) ? vb[warp - 1][1][k] : 0u;
+                hd[k] = (lane == 31 && warp + 1 < nbands) ? vb[warp + 1][0][k] : 0u;
+            }
+            const uint32_t changed = canny_flood_steps(w, rw, s, hu, hd, lane);
+            changed_total |= changed;
+            if (changed != 0u && lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kHystWords; ++k) vb[warp][0][k] = s[k];
+                if (warp > 0) flag = 1;
+            }
+            if (changed != 0u && lane == last_lane) {
+#pragma unroll
+                for (int k = 0; k < kHystWords; ++k) vb[warp][1][k] = s[k];
+                if (warp + 1 < nbands) flag = 1;
+            }
+        }
+        __syncthreads();
+        if (!flag) break;
+    }
+    if (valid && changed_total != 0u) bitmap_row_store(strong + (size_t)row * WW, WW, s);
+}
+
+// first pass over all SMs: every (image, band) once
+__global__ void __launch_bounds__(128) canny_flood_bands_kernel(const uint32_t* __restrict__ weak, uint32_t* __restrict__ strong, int N, int H,
+                                                              int WW, int nbands) {
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= N * nbands) return;
+    const int n = gw / nbands, band = gw - n * nbands;
+    const size_t img = (size_t)n * H * WW;
+    canny_flood_band(weak + img, strong + img, H, WW, band, threadIdx.x & 31);
+}
+
+// fix-up across band borders, one CTA per image: bands whose neighbouring rows changed are flooded again until nothing changes
+__global__ void __launch_bounds__(kFloodWarps * 32) canny_flood_image_kernel(const uint32_t* __restrict__ weak, uint32_t* __restrict__ strong,
+                                                                            int H, int WW, int nbands) {
+    __shared__ int dirty[2][kMaxBands];
+    __shared__ int flag;
+    const size_t img = (size_t)blockIdx.x * H * WW;
+    weak += img;
+    strong += img;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = threadIdx.x; b < nbands; b += kFloodWarps * 32) { dirty[0][b] = 1; dirty[1][b] = 0; }
+    for (int round = 0;; ++round) {
+        const int cur = round & 1, nxt = cur ^ 1;
+        __syncthreads();                       // bitmap writes (L2) and dirty marks of the previous round are visible; the flag has been read
+        if (threadIdx.x == 0) flag = 0;
+        __syncthreads();
+        for (int band = warp; band < nbands; band += kFloodWarps) {
+            if (!dirty[cur][band]) continue;                             // (warp-uniform)
+            __syncwarp();
+            if (lane == 0) dirty[cur][band] = 0;
+            const unsigned edge = canny_flood_band(weak, strong, H, WW, band, lane);
+            if (lane == 0) {
+                if ((edge & 1u) && band > 0) { dirty[nxt][band - 1] = 1; flag = 1; }
+                if ((edge & 2u) && band + 1 < nbands) { dirty[nxt][band + 1] = 1; flag = 1; }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (!flag) break;
+    }
+}
+
+// the final bitmap as 0 / 255 bytes, 16 pixels per thread and store
+__global__ void __launch_bounds__(256) canny_expand_kernel(const uint32_t* __restrict__ strong, uint8_t* __restrict__ out, long long groups) {
+    for (long long gidx = blockIdx.x * 256LL + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * 256) {
+        const uint32_t bits = (__ldcg(strong + (gidx >> 1)) >> ((int)(gidx & 1) * 16)) & 0xffffu;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t x = (bits >> (4 * q)) & 0xfu;
+            v[q] = ((x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u) * 255u;
+        }
+        reinterpret_cast<uint4*>(out)[gidx] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 __global__ void gray_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, long long npix) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x)
         gray[i] = (uint8_t)gray_of(rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2]);
@@ -463,6 +863,35 @@ static int canny_impl(const uint8_t* src, uint8_t* edges, int N, int H, int W, i
     if (P >= (1LL << 31)) { set_error("canny: more than 2^31 pixels in one call"); return EEL_ERR_INVALID; }
     size_t need = eel_canny_workspace_bytes(N, H, W);
     if (!ws || ws_bytes < need) { set_error("canny: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
+    // third generation: register-resident row bands + bitmap hysteresis (both bitmaps of an image must fit in shared memory)
+    const size_t bitmap_bytes = (size_t)H * (W / 32) * 4;
+    const int nbands = cdiv(H, 32);
+    if (W % 32 == 0 && W <= 32 * kHystWords && nbands <= kMaxBands && ((uintptr_t)src % 16) == 0 && ((uintptr_t)edges % 16) == 0 &&
+        ((uintptr_t)ws % 16) == 0) {
+        uint16_t* weak = (uint16_t*)ws;
+        uint16_t* strong = (uint16_t*)((uint8_t*)ws + (size_t)N * bitmap_bytes);
+        // rows per warp: every band costs 4 extra gray rows, so the bands are as long as still fills the GPU once (one wave)
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, canny_rows_kernel<RGB>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+        const long long capacity = (long long)kNumSMs * per_sm * 4;
+        int BR = 32;
+        while (BR > 8 && (long long)N * cdiv(H, BR / 2) <= capacity) BR >>= 1;
+        const int bands = cdiv(H, BR);
+        canny_rows_kernel<RGB><<<cdiv((long long)N * bands, 4), 128, 0, st>>>(src, weak, strong, N, H, W, BR, bands, low, high);
+        if (int rc = check_launch("canny.rows")) return rc;
+        if (nbands <= kFloodWarps) {
+            canny_flood_image_reg_kernel<<<N, kFloodWarps * 32, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, H, W / 32, nbands);
+            if (int rc = check_launch("canny.flood_image_reg")) return rc;
+        } else {
+            canny_flood_bands_kernel<<<cdiv((long long)N * nbands, 4), 128, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, N, H, W / 32, nbands);
+            if (int rc = check_launch("canny.flood_bands")) return rc;
+            canny_flood_image_kernel<<<N, kFloodWarps * 32, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, H, W / 32, nbands);
+            if (int rc = check_launch("canny.flood_image")) return rc;
+        }
+        const long long groups = P / 16;
+        canny_expand_kernel<<<(int)std::min<long long>(cdiv(groups, 256), (long long)kNumSMs * 16), 256, 0, st>>>((const uint32_t*)strong, edges, groups);
+        return check_launch("canny.expand");
+    }
     int* count = (int*)ws;
     int* labels = count + 4;
     int* list = labels + P;

@@ -12,7 +12,9 @@ def _cases():
 
     rng = np.random.default_rng(11)
     out = []
-    for (n, h, w) in [(3, 256, 256), (2, 37, 53), (1, 1, 1), (1, 2, 7), (2, 128, 300), (1, 16, 64), (1, 17, 65), (1, 600, 40)]:
+    for (n, h, w) in [(3, 256, 256), (2, 37, 53), (1, 1, 1), (1, 2, 7), (2, 128, 300), (1, 16, 64), (1, 17, 65), (1, 600, 40),
+                      # W % 32 == 0 and W <= 512: register-band stage 1 + bitmap hysteresis (third generation)
+                      (2, 100, 96), (1, 33, 32), (1, 5, 512), (1, 1, 32), (1, 600, 480), (1, 1700, 512), (5, 64, 512)]:
         imgs, _ = synth.tooth_images(n, h, w, seed=h * 7 + w)
         out.append(imgs)
         out.append(rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8))   # dense-edge stress
@@ -95,7 +97,15 @@ def test_canny_long_snake_component():
 
     from eel_unet_b200 import edges
 
-    h = w = 257
+    for h, w in ((257, 257), (256, 256), (300, 512)):     # 257: tile kernels + union-find; the others: bitmap flood fill
+        _snake(h, w)
+
+
+def _snake(h, w):
+    import cv2
+
+    from eel_unet_b200 import edges
+
     g = np.zeros((h, w), np.uint8)
     y0, x0, y1, x1 = 2, 2, h - 3, w - 3
     while y1 - y0 > 8 and x1 - x0 > 8:
