@@ -679,62 +679,111 @@ __device__ __forceinline__ unsigned canny_flood_band(const uint32_t* __restrict_
     return (rows_changed & 1u) | (((rows_changed >> last_lane) & 1u) << 1);
 }
 
-// H <= 512: one CTA per image, one warp per band, the band stays in REGISTERS from the first flood to the last; the bands'
-// first and last rows are exchanged through shared memory after every round (a round = every band floods until it stops changing)
-__global__ void __launch_bounds__(kFloodWarps * 32) canny_flood_image_reg_kernel(const uint32_t* __restrict__ weak, uint32_t* __restrict__ strong,
-                                                                                int H, int WW, int nbands) {
-    __shared__ uint32_t bnd[kFloodWarps][2][kHystWords];                  // [band][first row, last row]
-    __shared__ int flag;
-    volatile uint32_t (*vb)[2][kHystWords] = bnd;
+// H <= 512: one CTA per image, thread = (segment g of 16 rows, word column k): the thread keeps its 16 rows x 32 pixels of both
+// bitmaps in registers and sweeps them down and up (Gauss-Seidel: a chain runs through the whole column strip in one sweep, and
+// through each row's word in both directions by the carry trick); what crosses into another thread's strip -- the first / last row
+// of a strip and the first / last bit of every row -- is published in shared memory after each iteration (Jacobi between threads),
+// so the number of iterations is the number of strip borders the longest chain crosses (2-8 on the synthetic batches; the
+// row-per-lane flood above needs one step per ROW a chain climbs).  The converged strips leave directly as 0 / 255 bytes.
+constexpr int kSweepRows = 16;
+constexpr int kSweepSegs = 32;
+
+__global__ void __launch_bounds__(kSweepSegs * 16) canny_flood_sweep_kernel(const uint32_t* __restrict__ weak, const uint32_t* __restrict__ strong,
+                                                                           uint8_t* __restrict__ out, int H, int WW) {
+    constexpr int R = kSweepRows;
+    __shared__ uint32_t sT[kSweepSegs][16], sB[kSweepSegs][16];           // first / last row of every strip
+    __shared__ uint32_t sM[kSweepSegs][16], sL[kSweepSegs][16];           // bit r: last / first pixel of the strip's row r
+    __shared__ int flags[3];
+    volatile uint32_t (*T)[16] = sT;
+    volatile uint32_t (*B)[16] = sB;
+    volatile uint32_t (*Mm)[16] = sM;
+    volatile uint32_t (*Lm)[16] = sL;
+    volatile int* vflags = flags;
+    const int k = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const int nseg = (H + R - 1) / R;
     const size_t img = (size_t)blockIdx.x * H * WW;
-    weak += img;
-    strong += img;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool mine = warp < nbands;
-    const int row = warp * 32 + lane;
-    const bool valid = mine && row < H;
-    const int last_lane = min(31, max(0, H - 1 - warp * 32));
-    uint32_t w[kHystWords], rw[kHystWords], s[kHystWords];
-    bitmap_row_load<false>(weak + (size_t)row * WW, WW, valid, w);
-    bitmap_row_load<false>(strong + (size_t)row * WW, WW, valid, s);
+    uint32_t w[R], s[R];
 #pragma unroll
-    for (int k = 0; k < kHystWords; ++k) rw[k] = __brev(w[k]);
-    if (mine) {
+    for (int r = 0; r < R; ++r) {
+        const int y = g * R + r;
+        const bool in = y < H && k < WW;
+        w[r] = in ? __ldg(weak + img + (size_t)y * WW + k) : 0u;
+        s[r] = in ? __ldg(strong + img + (size_t)y * WW + k) : 0u;
+    }
+    auto publish = [&]() {
+        uint32_t mm = 0u, lm = 0u;
 #pragma unroll
-        for (int k = 0; k < kHystWords; ++k) {
-            if (lane == 0) vb[warp][0][k] = s[k];
-            if (lane == last_lane) vb[warp][1][k] = s[k];
+        for (int r = 0; r < R; ++r) {
+            mm |= (s[r] >> 31) << r;
+            lm |= (s[r] & 1u) << r;
+        }
+        T[g][k] = s[0];
+        B[g][k] = s[R - 1];
+        Mm[g][k] = mm;
+        Lm[g][k] = lm;
+    };
+    if (threadIdx.x < 3) flags[threadIdx.x] = 0;
+    publish();
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const bool hasU = g > 0, hasD = g + 1 < nseg, hasL = k > 0, hasR = k < 15;
+        const uint32_t up = hasU ? B[g - 1][k] : 0u;
+        const uint32_t dn = hasD ? T[g + 1][k] : 0u;
+        const uint32_t upL = (hasU && hasL) ? B[g - 1][k - 1] >> 31 : 0u, upR = (hasU && hasR) ? B[g - 1][k + 1] & 1u : 0u;
+        const uint32_t dnL = (hasD && hasL) ? T[g + 1][k - 1] >> 31 : 0u, dnR = (hasD && hasR) ? T[g + 1][k + 1] & 1u : 0u;
+        // bit r + 1: row r of the neighbouring column (bit 0: the row above the strip, bit R + 1: the row below);
+        // cL / cR bit r: any of rows r - 1, r, r + 1 there = the three neighbours of this strip's first / last pixel of row r
+        const uint32_t mLx = ((hasL ? Mm[g][k - 1] : 0u) << 1) | upL | (dnL << (R + 1));
+        const uint32_t mRx = ((hasR ? Lm[g][k + 1] : 0u) << 1) | upR | (dnR << (R + 1));
+        const uint32_t cL = mLx | (mLx >> 1) | (mLx >> 2);
+        const uint32_t cR = mRx | (mRx >> 1) | (mRx >> 2);
+        if (threadIdx.x == 0) vflags[(it + 1) % 3] = 0;                  // (last read two barriers ago)
+        uint32_t ch = 0u;
+#define EEL_SWEEP_ROW(r)                                                                                       \
+        {                                                                                                      \
+            const uint32_t above = (r) == 0 ? up : s[(r) > 0 ? (r) - 1 : 0];                                  \
+            const uint32_t below = (r) == R - 1 ? dn : s[(r) < R - 1 ? (r) + 1 : R - 1];                      \
+            const uint32_t nb = above | s[r] | below;                                                         \
+            const uint32_t n3 = nb | (nb << 1) | (nb >> 1) | ((cL >> (r)) & 1u) | (((cR >> (r)) & 1u) << 31); \
+            const uint32_t sd = s[r] | (w[r] & n3);                                                           \
+            const uint32_t f = (w[r] & ~(w[r] + sd)) | sd;                                                    \
+            const uint32_t rw = __brev(w[r]), rs = __brev(f);                                                 \
+            const uint32_t nf = __brev((rw & ~(rw + rs)) | rs);                                               \
+            ch |= nf ^ s[r];                                                                                  \
+            s[r] = nf;                                                                                        \
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) EEL_SWEEP_ROW(r)
+#pragma unroll
+        for (int r = R - 1; r >= 0; --r) EEL_SWEEP_ROW(r)
+#undef EEL_SWEEP_ROW
+        if (ch != 0u) {
+            publish();
+            vflags[it % 3] = 1;
+        }
+        __syncthreads();
+        if (!vflags[it % 3]) break;
+    }
+    // ---- the strip as 0 / 255 bytes: 32 pixels = two 16-byte stores per row (the 16 columns of a row are consecutive threads)
+    if (k < WW) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int y = g * R + r;
+            if (y < H) {
+                uint4* o = reinterpret_cast<uint4*>(out + ((size_t)blockIdx.x * H + y) * ((size_t)WW * 32) + k * 32);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t x = (s[r] >> (16 * h + 4 * q)) & 0xfu;
+                        v[q] = ((x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u) * 255u;
+                    }
+                    o[h] = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+            }
         }
     }
-    uint32_t changed_total = 0u;
-    for (;;) {
-        __syncthreads();                       // published rows of the previous round are visible; the flag has been read
-        if (threadIdx.x == 0) flag = 0;
-        __syncthreads();
-        if (mine) {
-            uint32_t hu[kHystWords], hd[kHystWords];
-#pragma unroll
-            for (int k = 0; k < kHystWords; ++k) {
-                hu[k] = (lane == 0 && warp > 0) ? vb[warp - 1][1][k] : 0u;
-                hd[k] = (lane == 31 && warp + 1 < nbands) ? vb[warp + 1][0][k] : 0u;
-            }
-            const uint32_t changed = canny_flood_steps(w, rw, s, hu, hd, lane);
-            changed_total |= changed;
-            if (changed != 0u && lane == 0) {
-#pragma unroll
-                for (int k = 0; k < kHystWords; ++k) vb[warp][0][k] = s[k];
-                if (warp > 0) flag = 1;
-            }
-            if (changed != 0u && lane == last_lane) {
-#pragma unroll
-                for (int k = 0; k < kHystWords; ++k) vb[warp][1][k] = s[k];
-                if (warp + 1 < nbands) flag = 1;
-            }
-        }
-        __syncthreads();
-        if (!flag) break;
-    }
-    if (valid && changed_total != 0u) bitmap_row_store(strong + (size_t)row * WW, WW, s);
 }
 
 // first pass over all SMs: every (image, band) once
@@ -879,15 +928,14 @@ static int canny_impl(const uint8_t* src, uint8_t* edges, int N, int H, int W, i
         const int bands = cdiv(H, BR);
         canny_rows_kernel<RGB><<<cdiv((long long)N * bands, 4), 128, 0, st>>>(src, weak, strong, N, H, W, BR, bands, low, high);
         if (int rc = check_launch("canny.rows")) return rc;
-        if (nbands <= kFloodWarps) {
-            canny_flood_image_reg_kernel<<<N, kFloodWarps * 32, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, H, W / 32, nbands);
-            if (int rc = check_launch("canny.flood_image_reg")) return rc;
-        } else {
-            canny_flood_bands_kernel<<<cdiv((long long)N * nbands, 4), 128, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, N, H, W / 32, nbands);
-            if (int rc = check_launch("canny.flood_bands")) return rc;
-            canny_flood_image_kernel<<<N, kFloodWarps * 32, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, H, W / 32, nbands);
-            if (int rc = check_launch("canny.flood_image")) return rc;
+        if (H <= kSweepRows * kSweepSegs) {
+            canny_flood_sweep_kernel<<<N, kSweepSegs * 16, 0, st>>>((const uint32_t*)weak, (const uint32_t*)strong, edges, H, W / 32);
+            return check_launch("canny.flood_sweep");
         }
+        canny_flood_bands_kernel<<<cdiv((long long)N * nbands, 4), 128, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, N, H, W / 32, nbands);
+        if (int rc = check_launch("canny.flood_bands")) return rc;
+        canny_flood_image_kernel<<<N, kFloodWarps * 32, 0, st>>>((const uint32_t*)weak, (uint32_t*)strong, H, W / 32, nbands);
+        if (int rc = check_launch("canny.flood_image")) return rc;
         const long long groups = P / 16;
         canny_expand_kernel<<<(int)std::min<long long>(cdiv(groups, 256), (long long)kNumSMs * 16), 256, 0, st>>>((const uint32_t*)strong, edges, groups);
         return check_launch("canny.expand");
