@@ -527,7 +527,7 @@ __device__ __forceinline__ void canny_row_step(const int t, const RawRow& raw, c
 }
 
 template <bool RGB>
-__global__ void __launch_bounds__(128) canny_rows_kernel(const uint8_t* __restrict__ src, uint16_t* __restrict__ weak,
+__global__ void __launch_bounds__(128, 4) canny_rows_kernel(const uint8_t* __restrict__ src, uint16_t* __restrict__ weak,
                                                        uint16_t* __restrict__ strong, int N, int H, int W, int BR, int bands,
                                                        int low, int high) {
     const int lane = threadIdx.x & 31;
@@ -556,7 +556,9 @@ __global__ void __launch_bounds__(128) canny_rows_kernel(const uint8_t* __restri
 
     auto rowptr = [&](int t) { return base + (size_t)min(max(y0 - 2 + t, 0), H - 1) * rowbytes; };
     RawRow nxt = canny_load_row<RGB>(rowptr(0));
-    // gray rows rotate through three register sets, magnitude rows and masks through two: six steps per trip
+    // two steps per trip: magnitude rows and masks alternate between two register sets, the gray rows are renamed by 32 moves
+    // per trip.  (Six steps per trip would make every rotation a pure renaming, but that loop body is 76 KB of code: with the
+    // warps of an SM at different places in it, 46 % of the stall samples were instruction-cache misses; two steps are 26 KB.)
 #define EEL_CANNY_STEP(tt, GA, GB, GC, MB_, MC_, mB_, mC_)                                                                       \
     {                                                                                                                            \
         if ((tt) >= T) break;                                                                                                    \
@@ -565,13 +567,11 @@ __global__ void __launch_bounds__(128) canny_rows_kernel(const uint8_t* __restri
         canny_row_step<RGB>((tt), cur, GA, GB, GC, MB_, MC_, mB_, mC_, y0, H, low, high, first, last, act, wrow, srow, row_stride16); \
     }
 #pragma unroll 1
-    for (int t = 0; t < T; t += 6) {
-        EEL_CANNY_STEP(t, g1, g2, g0, M1, M0, m1, m0)
-        EEL_CANNY_STEP(t + 1, g2, g0, g1, M0, M1, m0, m1)
-        EEL_CANNY_STEP(t + 2, g0, g1, g2, M1, M0, m1, m0)
-        EEL_CANNY_STEP(t + 3, g1, g2, g0, M0, M1, m0, m1)
-        EEL_CANNY_STEP(t + 4, g2, g0, g1, M1, M0, m1, m0)
-        EEL_CANNY_STEP(t + 5, g0, g1, g2, M0, M1, m0, m1)
+    for (int t = 0; t < T; t += 2) {
+        EEL_CANNY_STEP(t, g0, g1, g2, M1, M0, m1, m0)          // rows t-2, t-1 -> row t in g2
+        EEL_CANNY_STEP(t + 1, g1, g2, g0, M0, M1, m0, m1)      // rows t-1, t -> row t+1 in g0
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { g1[j] = g0[j]; g0[j] = g2[j]; }
     }
 #undef EEL_CANNY_STEP
 }
@@ -912,7 +912,7 @@ static int canny_impl(const uint8_t* src, uint8_t* edges, int N, int H, int W, i
     if (P >= (1LL << 31)) { set_error("canny: more than 2^31 pixels in one call"); return EEL_ERR_INVALID; }
     size_t need = eel_canny_workspace_bytes(N, H, W);
     if (!ws || ws_bytes < need) { set_error("canny: workspace too small (%zu > %zu)", need, ws_bytes); return EEL_ERR_WORKSPACE; }
-    // third generation: register-resident row bands + bitmap hysteresis (both bitmaps of an image must fit in shared memory)
+    // third generation: register-resident row bands + bitmap flood-fill hysteresis
     const size_t bitmap_bytes = (size_t)H * (W / 32) * 4;
     const int nbands = cdiv(H, 32);
     if (W % 32 == 0 && W <= 32 * kHystWords && nbands <= kMaxBands && ((uintptr_t)src % 16) == 0 && ((uintptr_t)edges % 16) == 0 &&
