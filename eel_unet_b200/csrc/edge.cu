@@ -2,10 +2,14 @@
 //   gray  = (9798 R + 19235 G + 3735 B + 16384) >> 15
 //   Canny = 3x3 Sobel (replicated border) -> L1 magnitude (zero outside) -> tangent-table
 //           non-maximum suppression -> hysteresis (8-connected components that contain a strong pixel)
-// Stage 1 is one fused shared-memory tile kernel (gray halo 2, magnitude halo 1) that reads the RGB
-// image once and writes a {0 none, 1 weak, 2 strong} byte per pixel into the OUTPUT image, appending
-// the sparse candidate pixels to a list.  Stage 2 is a lock-free union-find over that list only, so
-// the dense traffic stays at the algorithmic 3 B read + 1 B written per pixel.
+// Three generations live here, chosen by canny_impl from the image width:
+//   W % 32 == 0, W <= 512   register-resident row bands (one warp per band, no shared memory) writing two bitmaps, hysteresis as
+//                           a bitmap flood fill (column strips in registers for H <= 512, a warp per 32-row band above that)
+//   W % 4 == 0              fused shared-memory tile kernel (gray halo 2, magnitude halo 1) that reads the image once and writes a
+//                           {0 none, 1 weak, 2 strong} byte per pixel plus a sparse candidate list; hysteresis = lock-free union-find
+//                           over that list (tile-local in shared memory first, then across tile borders)
+//   otherwise               the first, byte-wise version of the tile kernel
+// The dense traffic stays at the algorithmic 3 B read + 1 B written per pixel in all of them.
 #include <algorithm>
 
 #include "common.cuh"
