@@ -689,6 +689,10 @@ __device__ __forceinline__ unsigned canny_flood_band(const uint32_t* __restrict_
 // of a strip and the first / last bit of every row -- is published in shared memory after each iteration (Jacobi between threads),
 // so the number of iterations is the number of strip borders the longest chain crosses (2-8 on the synthetic batches; the
 // row-per-lane flood above needs one step per ROW a chain climbs).  The converged strips leave directly as 0 / 255 bytes.
+// A thread may read a neighbour's published words while that neighbour is already publishing its next state: bits are only ever
+// set, so whatever it reads is a subset of the final answer, and any change raises the flag for another iteration (the loop ends
+// only after an iteration in which no thread changed anything, i.e. every thread has seen the final state of its neighbours).
+// tests/test_canny_design_cpu.py runs a thread-level transcription of this kernel against the oracle.
 constexpr int kSweepRows = 16;
 constexpr int kSweepSegs = 32;
 
