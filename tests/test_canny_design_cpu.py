@@ -160,7 +160,7 @@ def _snake(h, w):
     g = np.zeros((h, w), np.uint8)
     y0, x0, y1, x1 = 2, 2, h - 3, w - 3
     while y1 - y0 > 8 and x1 - x0 > 8:
-        g[y0, x0:x1] = 40; g[y0:y1, x1] = 40; g[y1, x0 + 4:x1 + 1] = 40; g[y0 + 4:y1 + 1, x0 + 4] = 40
+        g[y0, x0:x1] = 30; g[y0:y1, x1] = 30; g[y1, x0 + 4:x1 + 1] = 30; g[y0 + 4:y1 + 1, x0 + 4] = 30
         y0 += 4; x0 += 4; y1 -= 4; x1 -= 4
     g[2, 2:6] = 255
     return g
@@ -184,8 +184,8 @@ def test_flood_follows_a_long_weak_chain_across_strips():
     """a one-pixel spiral of WEAK candidates hanging on one strong run: the sweeps must follow it through every strip border"""
     g = _snake(96, 128)
     nms = edge_np.canny_nms(g, 100, 200)
-    assert (nms == 0).sum() > 20 * (nms == 2).sum() > 0            # the chain really is weak
+    assert (nms == 0).sum() > 100 * (nms == 2).sum() > 0           # the chain really is weak: magnitude 4 x 30 (corners 6 x 30) < 200
     wk, st = rows_kernel(g, 16, 100, 200)
     out, its = flood_sweep(wk, st, 96, 128)
     assert np.array_equal(out, edge_np.canny(g, 100, 200))
-    assert its > 3                                                 # it did have to cross strip borders
+    assert its > 30                                                # it did have to cross strip borders, one per iteration
