@@ -22,7 +22,7 @@ def _weak_spiral(h, w, level=30):
     return g
 
 
-@pytest.mark.parametrize("h,w", [(257, 257), (256, 256), (300, 512), (600, 512)])
+@pytest.mark.parametrize("h,w", [(257, 257), (260, 260), (256, 256), (300, 512), (600, 512)])   # generation 1, 2, 3 (strips), 3 (strips), 3 (bands)
 def test_hysteresis_walks_a_long_weak_chain(h, w):
     import cv2
 
